@@ -1,0 +1,70 @@
+"""ctypes binding of libtinysd_b200.so (the C ABI declared in include/tinysd_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtinysd_b200.so")
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m from_ddpm_to_stable_diffusion_b200.csrc.build` "
+                "(or __graft_entry__.build()); there is no CPU/PyTorch fallback for this path")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.tsd_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def _as_arg(a):
+    if a is None:
+        return ctypes.c_void_p(0)
+    if isinstance(a, torch.Tensor):
+        return ctypes.c_void_p(a.data_ptr())
+    if isinstance(a, bool):
+        return ctypes.c_int(int(a))
+    if isinstance(a, int):
+        return ctypes.c_int(a)
+    if isinstance(a, float):
+        return ctypes.c_float(a)
+    return a  # already a ctypes value
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    """Call `int name(void* stream, ...)` on the current torch CUDA stream."""
+    fn = getattr(lib(), name)
+    rc = fn(stream_ptr(), *[_as_arg(a) for a in args])
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib().tsd_last_error().decode()}")
+
+
+def call_nostream(name, *args):
+    fn = getattr(lib(), name)
+    rc = fn(*[_as_arg(a) for a in args])
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib().tsd_last_error().decode()}")
+
+
+def i64(v):
+    return ctypes.c_int64(int(v))
+
+
+def u64(v):
+    return ctypes.c_uint64(int(v) & 0xFFFFFFFFFFFFFFFF)
+
+
+def f32(v):
+    return ctypes.c_float(float(v))

@@ -1,0 +1,173 @@
+// C-ABI entry points for the dense contractions (linear / 1x1 conv / 3x3 conv; forward, data
+// gradient, weight gradient).  All of them route to the single tcgen05 GEMM core in gemm_tc.cu.
+#include "../../include/tinysd_b200.h"
+#include "gemm_tc.cuh"
+
+using namespace tsd;
+
+namespace {
+
+// Decompose P consecutive output pixels (P = 128 or 64) of an [n][Ho][Wo] grid into a TMA box.
+int pixel_box(int Ho, int Wo, int P, uint32_t* bw, uint32_t* bh, uint32_t* bn) {
+  if (Wo >= P) {
+    TSD_CHECK(Wo % P == 0, "conv: output width %d not a multiple of the %d-pixel tile", Wo, P);
+    *bw = P; *bh = 1; *bn = 1;
+    return 0;
+  }
+  TSD_CHECK(P % Wo == 0, "conv: output width %d must divide the %d-pixel tile", Wo, P);
+  const int rows = P / Wo;
+  if (Ho >= rows) {
+    TSD_CHECK(Ho % rows == 0, "conv: output height %d not a multiple of %d tile rows", Ho, rows);
+    *bw = Wo; *bh = rows; *bn = 1;
+    return 0;
+  }
+  TSD_CHECK(rows % Ho == 0, "conv: output height %d must divide %d tile rows", Ho, rows);
+  *bw = Wo; *bh = Ho; *bn = rows / Ho;
+  return 0;
+}
+
+void zero_params(GemmParams& p) { memset(&p, 0, sizeof(p)); p.splits = 1; p.b_cpt = 1 << 30; p.a_cpt = 1; }
+
+}  // namespace
+
+extern "C" int tsd_gemm_fwd(void* stream, const void* a0, const void* a1, int c0, int c1, int M,
+                            const void* w, int N, const float* bias, const float* row_bias,
+                            int rows_per_sample, const void* residual, int epi, void* d) {
+  const int K = c0 + c1;
+  TSD_CHECK(M > 0 && N % 128 == 0 && K % 64 == 0 && c0 % 64 == 0, "gemm_fwd: bad shape M=%d N=%d K=%d c0=%d", M, N, K, c0);
+  TSD_CHECK(c1 == 0 || a1 != nullptr, "gemm_fwd: second source missing");
+  CUtensorMap tA0, tA1, tB, tD;
+  if (make_tmap_2d(&tA0, a0, 2, M, c0, c0, 64, 128)) return 1;
+  if (c1 > 0) { if (make_tmap_2d(&tA1, a1, 2, M, c1, c1, 64, 128)) return 1; } else tA1 = tA0;
+  if (make_tmap_2d(&tB, w, 2, N, K, K, 64, 128)) return 1;
+  const int Nd = epi == EPI_GEGLU ? N / 2 : N;
+  if (make_tmap_2d(&tD, d, 2, M, Nd, Nd, 64, 128)) return 1;
+  GemmParams p; zero_params(p);
+  p.M = M; p.N = N; p.tiles_m = ceil_div(M, 128); p.tiles_n = N / 128;
+  p.num_kb = K / 64; p.kb_per_split = p.num_kb;
+  p.a_mode = A_K2D; p.a_c0 = c0; p.b_mode = B_K2D;
+  p.epi = epi; p.bias = bias; p.row_bias = row_bias; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+  p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = N;
+  TSD_CHECK(!(epi == EPI_GEGLU && (residual || row_bias)), "gemm_fwd: GEGLU epilogue takes no residual/row bias");
+  return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA0, tA1, tB, tB, tD, p);
+}
+
+extern "C" int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
+                               int H, int W, int stride, const void* w, int cout, const float* bias,
+                               const float* row_bias, const void* residual, void* d) {
+  const int cin = c0 + c1;
+  TSD_CHECK(stride == 1 || stride == 2, "conv3x3_fwd: stride must be 1 or 2");
+  TSD_CHECK(cin % 64 == 0 && c0 % 64 == 0 && cout % 128 == 0, "conv3x3_fwd: bad channels c0=%d c1=%d cout=%d", c0, c1, cout);
+  TSD_CHECK(H % stride == 0 && W % stride == 0, "conv3x3_fwd: H, W must be multiples of the stride");
+  const int Ho = H / stride, Wo = W / stride;
+  const int M = n_img * Ho * Wo;
+  uint32_t bw, bh, bn;
+  if (pixel_box(Ho, Wo, 128, &bw, &bh, &bn)) return 1;
+  CUtensorMap tA0, tA1, tB, tD;
+  if (make_tmap_nhwc(&tA0, x0, n_img, H, W, c0, 64, bw, bh, bn, stride)) return 1;
+  if (c1 > 0) { if (make_tmap_nhwc(&tA1, x1, n_img, H, W, c1, 64, bw, bh, bn, stride)) return 1; } else tA1 = tA0;
+  if (make_tmap_2d(&tB, w, 2, cout, 9 * cin, 9 * cin, 64, 128)) return 1;
+  if (make_tmap_2d(&tD, d, 2, M, cout, cout, 64, 128)) return 1;
+  GemmParams p; zero_params(p);
+  p.M = M; p.N = cout; p.tiles_m = ceil_div(M, 128); p.tiles_n = cout / 128;
+  p.a_mode = A_KCONV; p.a_c0 = c0; p.a_cpt = cin / 64;
+  p.num_kb = 9 * p.a_cpt; p.kb_per_split = p.num_kb;
+  p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.b_mode = B_K2D;
+  p.bias = bias; p.row_bias = row_bias; p.rows_per_sample = Ho * Wo;
+  p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = cout;
+  return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA0, tA1, tB, tB, tD, p);
+}
+
+// dX[M][K] = dY[M][N] * W[N][K] (+ residual): the packed forward weight is read as an MN-major B.
+extern "C" int tsd_gemm_dgrad(void* stream, const void* dy, int M, int N, const void* w, int K,
+                              const void* residual, void* dx) {
+  TSD_CHECK(M > 0 && N % 64 == 0 && K % 128 == 0, "gemm_dgrad: bad shape M=%d N=%d K=%d", M, N, K);
+  CUtensorMap tA, tB, tD;
+  if (make_tmap_2d(&tA, dy, 2, M, N, N, 64, 128)) return 1;
+  if (make_tmap_2d(&tB, w, 2, N, K, K, 64, 64)) return 1;
+  if (make_tmap_2d(&tD, dx, 2, M, K, K, 64, 128)) return 1;
+  GemmParams p; zero_params(p);
+  p.M = M; p.N = K; p.tiles_m = ceil_div(M, 128); p.tiles_n = K / 128;
+  p.num_kb = N / 64; p.kb_per_split = p.num_kb;
+  p.a_mode = A_K2D; p.a_c0 = N;
+  p.b_mode = B_MN2D; p.b_c0 = K; p.b_cpt = p.num_kb; p.b_ntaps = 1; p.b_tapstride = 0;
+  p.rows_per_sample = 1;
+  p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = K;
+  return launch_gemm((cudaStream_t)stream, 0, 1, 0, tA, tA, tB, tB, tD, p);
+}
+
+// Stride-1 3x3 data gradient: dX = conv3x3(dY, W mirrored and transposed), same implicit GEMM with
+// the forward weight [cout][9*cin] consumed as an MN-major operand, taps visited mirrored.
+extern "C" int tsd_conv3x3_dgrad(void* stream, const void* dy, int n_img, int H, int W, int cout,
+                                 const void* w, int cin, const void* residual, void* dx) {
+  TSD_CHECK(cout % 64 == 0 && cin % 128 == 0, "conv3x3_dgrad: bad channels cin=%d cout=%d", cin, cout);
+  const int M = n_img * H * W;
+  uint32_t bw, bh, bn;
+  if (pixel_box(H, W, 128, &bw, &bh, &bn)) return 1;
+  CUtensorMap tA, tB, tD;
+  if (make_tmap_nhwc(&tA, dy, n_img, H, W, cout, 64, bw, bh, bn, 1)) return 1;
+  if (make_tmap_2d(&tB, w, 2, cout, 9 * cin, 9 * cin, 64, 64)) return 1;
+  if (make_tmap_2d(&tD, dx, 2, M, cin, cin, 64, 128)) return 1;
+  GemmParams p; zero_params(p);
+  p.M = M; p.N = cin; p.tiles_m = ceil_div(M, 128); p.tiles_n = cin / 128;
+  p.a_mode = A_KCONV; p.a_c0 = cout; p.a_cpt = cout / 64;
+  p.num_kb = 9 * p.a_cpt; p.kb_per_split = p.num_kb;
+  p.Ho = H; p.Wo = W; p.stride = 1;
+  p.b_mode = B_MN2D; p.b_c0 = cin; p.b_cpt = cout / 64; p.b_ntaps = 9; p.b_flip = 1; p.b_tapstride = cin;
+  p.rows_per_sample = H * W;
+  p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = cin;
+  return launch_gemm((cudaStream_t)stream, 0, 1, 0, tA, tA, tB, tB, tD, p);
+}
+
+static void pick_splits(GemmParams& p) {
+  const int tiles = p.tiles_m * p.tiles_n;
+  int want = ceil_div(2 * num_sms(), tiles);
+  if (want < 1) want = 1;
+  if (want > p.num_kb) want = p.num_kb;
+  p.kb_per_split = ceil_div(p.num_kb, want);
+  p.splits = ceil_div(p.num_kb, p.kb_per_split);
+}
+
+// dW[N][K] (fp32, accumulated) += dY[M][N]^T * [X0 | X1][M][K]
+extern "C" int tsd_gemm_wgrad(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1,
+                              int M, int N, float* dw) {
+  const int K = c0 + c1;
+  TSD_CHECK(M % 64 == 0 && N % 64 == 0 && K % 128 == 0 && c0 % 128 == 0, "gemm_wgrad: bad shape M=%d N=%d K=%d c0=%d", M, N, K, c0);
+  CUtensorMap tA, tB0, tB1, tD;
+  if (make_tmap_2d(&tA, dy, 2, M, N, N, 64, 64)) return 1;
+  if (make_tmap_2d(&tB0, x0, 2, M, c0, c0, 64, 64)) return 1;
+  if (c1 > 0) { if (make_tmap_2d(&tB1, x1, 2, M, c1, c1, 64, 64)) return 1; } else tB1 = tB0;
+  if (make_tmap_2d(&tD, dw, 4, N, K, K, 32, 128)) return 1;
+  GemmParams p; zero_params(p);
+  p.M = N; p.N = K; p.tiles_m = ceil_div(N, 128); p.tiles_n = K / 128;
+  p.num_kb = M / 64;
+  p.a_mode = A_MN2D; p.b_mode = B_MN2D; p.b_c0 = c0; p.b_cpt = 1 << 30; p.b_ntaps = 1;
+  p.rows_per_sample = 1;
+  pick_splits(p);
+  return launch_gemm((cudaStream_t)stream, 1, 1, 1, tA, tA, tB0, tB1, tD, p);
+}
+
+// dW[cout][9*cin] (fp32, accumulated) += sum over output pixels of dY[p][co] * X[p*s + tap][ci]
+extern "C" int tsd_conv3x3_wgrad(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1,
+                                 int n_img, int H, int W, int stride, int cout, float* dw) {
+  const int cin = c0 + c1;
+  TSD_CHECK(stride == 1 || stride == 2, "conv3x3_wgrad: stride must be 1 or 2");
+  TSD_CHECK(cin % 128 == 0 && c0 % 128 == 0 && cout % 64 == 0, "conv3x3_wgrad: bad channels c0=%d c1=%d cout=%d", c0, c1, cout);
+  const int Ho = H / stride, Wo = W / stride;
+  const int M = n_img * Ho * Wo;
+  TSD_CHECK(M % 64 == 0, "conv3x3_wgrad: pixel count %d must be a multiple of 64", M);
+  uint32_t bw, bh, bn;
+  if (pixel_box(Ho, Wo, 64, &bw, &bh, &bn)) return 1;
+  CUtensorMap tA, tB0, tB1, tD;
+  if (make_tmap_2d(&tA, dy, 2, M, cout, cout, 64, 64)) return 1;
+  if (make_tmap_nhwc(&tB0, x0, n_img, H, W, c0, 64, bw, bh, bn, stride)) return 1;
+  if (c1 > 0) { if (make_tmap_nhwc(&tB1, x1, n_img, H, W, c1, 64, bw, bh, bn, stride)) return 1; } else tB1 = tB0;
+  if (make_tmap_2d(&tD, dw, 4, cout, 9 * cin, 9 * cin, 32, 128)) return 1;
+  GemmParams p; zero_params(p);
+  p.M = cout; p.N = 9 * cin; p.tiles_m = ceil_div(cout, 128); p.tiles_n = 9 * cin / 128;
+  p.num_kb = M / 64;
+  p.a_mode = A_MN2D; p.b_mode = B_MNCONV; p.b_c0 = c0; p.b_ctot = cin;
+  p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.rows_per_sample = 1;
+  pick_splits(p);
+  return launch_gemm((cudaStream_t)stream, 1, 1, 1, tA, tA, tB0, tB1, tD, p);
+}

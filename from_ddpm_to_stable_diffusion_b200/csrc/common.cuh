@@ -1,0 +1,109 @@
+// Shared host/device helpers for the tiny-SD B200 library.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace tsd {
+
+typedef __nv_bfloat16 bf16;
+
+// Error plumbing for the C ABI: every entry point returns 0 on success, non-zero otherwise, and
+// tsd_last_error() returns the message.
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define TSD_CHECK(cond, ...)        \
+  do {                              \
+    if (!(cond)) {                  \
+      tsd::set_error(__VA_ARGS__);  \
+      return 1;                     \
+    }                               \
+  } while (0)
+
+#define TSD_CUDA(expr)                                   \
+  do {                                                   \
+    if (tsd::check_cuda((expr), #expr)) return 2;        \
+  } while (0)
+
+#define TSD_LAUNCH_CHECK() TSD_CUDA(cudaGetLastError())
+
+int num_sms();
+
+// Tensor-map (TMA descriptor) builders; bf16 / f32 elements, SWIZZLE_128B, zero OOB fill.
+// 2-D: tensor [rows][cols] with cols contiguous; box = box_cols x box_rows.
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                 uint64_t row_stride_elems, uint32_t box_cols, uint32_t box_rows);
+// 4-D NHWC activation [N][H][W][C]; box = (box_c, bw, bh, bn) elements *loaded*; traversal stride s
+// along W and H (s = 2 gives the stride-2 convolution gather).
+int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W,
+                   uint64_t C, uint32_t box_c, uint32_t bw, uint32_t bh, uint32_t bn, uint32_t s);
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// d/dx silu(x) = s + x*s*(1-s), s = sigmoid(x)
+__device__ __forceinline__ float silu_grad_f(float x) {
+  float s = 1.f / (1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float gelu_f(float x) {  // exact erf form (F.gelu default)
+  return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+// Philox4x32-10 counter RNG (same generator family torch's CUDA RNG uses; the stream layout is ours).
+struct Philox {
+  uint32_t key0, key1;
+  __device__ __forceinline__ Philox(uint64_t seed) : key0((uint32_t)seed), key1((uint32_t)(seed >> 32)) {}
+  __device__ __forceinline__ uint4 operator()(uint64_t ctr_lo, uint64_t ctr_hi) const {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi,
+             c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+// Two uniform u32 -> two N(0,1) via Box-Muller.
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  float u1 = (a + 0.5f) * 2.3283064365386963e-10f;  // (0,1)
+  float u2 = (b + 0.5f) * 2.3283064365386963e-10f;
+  float r = sqrtf(-2.f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+}  // namespace tsd

@@ -1,0 +1,366 @@
+// tcgen05 / TMEM / TMA GEMM core (see gemm_tc.cuh for the operand modes).
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+namespace tsd {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 16 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+constexpr int TMEM_COLS = 256;  // two 128-column fp32 accumulators
+
+template <int OUT_F32>
+struct Cfg {
+  static constexpr int STAGES = OUT_F32 ? 5 : 6;
+  static constexpr int STAGING_BYTES = BM * BN * (OUT_F32 ? 4 : 2);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
+};
+
+template <int A_MN, int B_MN, int OUT_F32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+  constexpr int STAGES = Cfg<OUT_F32>::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_stage0 = smem_base;
+  const uint32_t smem_staging = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = smem_staging + Cfg<OUT_F32>::STAGING_BYTES;
+  // barrier map (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to aligned base
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB0);
+    tma_prefetch_desc(&tmB1);
+    tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_mn * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    // =========================================================== TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      // (m, n) tiles fastest, K split slowest: CTAs running together share operand tiles in L2.
+      const int split = tile / tiles_mn;
+      const int t2 = tile - split * tiles_mn;
+      const int n_blk = t2 % p.tiles_n;
+      const int m_blk = t2 / p.tiles_n;
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+
+      // Conv geometry of this M tile (A_KCONV): the 128 rows are a (bn, bh, bw) box of output pixels.
+      int a_n0 = 0, a_y0 = 0, a_x0 = 0;
+      if (p.a_mode == A_KCONV) {
+        const int hw = p.Ho * p.Wo;
+        a_n0 = m0 / hw;
+        const int rem = m0 - a_n0 * hw;
+        a_y0 = rem / p.Wo;
+        a_x0 = rem - a_y0 * p.Wo;
+      }
+      // B_MNCONV: the N tile is (tap, 128 channels of one source).
+      int b_tap = 0, b_c = n0;
+      const CUtensorMap* b_map = &tmB0;
+      if (p.b_mode == B_MNCONV) {
+        b_tap = n0 / p.b_ctot;
+        b_c = n0 - b_tap * p.b_ctot;
+      }
+      if (p.b_mode != B_K2D && b_c >= p.b_c0) {
+        b_c -= p.b_c0;
+        b_map = &tmB1;
+      }
+
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = smem_stage0 + stage * STAGE_BYTES;
+        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint32_t fb = full_bar(stage);
+        mbar_arrive_expect_tx(fb, STAGE_BYTES);
+        // ---- A
+        if (A_MN == 0) {
+          if (p.a_mode == A_K2D) {
+            int c = kb * BK;
+            const CUtensorMap* m = &tmA0;
+            if (c >= p.a_c0) { c -= p.a_c0; m = &tmA1; }
+            tma_load_2d(sa, m, fb, c, m0);
+          } else {  // A_KCONV
+            const int tap = kb / p.a_cpt;
+            int c = (kb - tap * p.a_cpt) * BK;
+            const CUtensorMap* m = &tmA0;
+            if (c >= p.a_c0) { c -= p.a_c0; m = &tmA1; }
+            const int dy = tap / 3, dx = tap - dy * 3;
+            tma_load_4d(sa, m, fb, c, a_x0 * p.stride + dx - 1, a_y0 * p.stride + dy - 1, a_n0);
+          }
+        } else {  // A_MN2D: [K][M], two 64-wide M chunks
+          tma_load_2d(sa, &tmA0, fb, m0, kb * BK);
+          tma_load_2d(sa + A_STAGE_BYTES / 2, &tmA0, fb, m0 + 64, kb * BK);
+        }
+        // ---- B
+        if (B_MN == 0) {
+          tma_load_2d(sb, &tmB0, fb, kb * BK, n0);
+        } else if (p.b_mode == B_MN2D) {
+          const int tap = kb / p.b_cpt;
+          const int row = (kb - tap * p.b_cpt) * BK;
+          const int t = p.b_flip ? (p.b_ntaps - 1 - tap) : tap;
+          const int col = b_c + t * p.b_tapstride;
+          tma_load_2d(sb, b_map, fb, col, row);
+          tma_load_2d(sb + B_STAGE_BYTES / 2, b_map, fb, col + 64, row);
+        } else {  // B_MNCONV: 64 output pixels starting at kb*64, shifted by the tap
+          const int p0 = kb * BK;
+          const int hw = p.Ho * p.Wo;
+          const int n_i = p0 / hw;
+          const int rem = p0 - n_i * hw;
+          const int y = rem / p.Wo, x = rem - (rem / p.Wo) * p.Wo;
+          const int dy = b_tap / 3, dx = b_tap - dy * 3;
+          const int xs = x * p.stride + dx - 1, ys = y * p.stride + dy - 1;
+          tma_load_4d(sb, b_map, fb, b_c, xs, ys, n_i);
+          tma_load_4d(sb + B_STAGE_BYTES / 2, b_map, fb, b_c + 64, xs, ys, n_i);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // =========================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    // K-major: 32 B per UMMA_K step inside the 128 B swizzle row; MN-major: 16 k-rows of 128 B.
+    constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32;
+    constexpr uint32_t B_KSTEP = B_MN ? 2048 : 32;
+    constexpr uint32_t A_LBO = A_MN ? (A_STAGE_BYTES / 2) : 0;
+    constexpr uint32_t B_LBO = B_MN ? (B_STAGE_BYTES / 2) : 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int split = tile / tiles_mn;
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_stage0 + stage * STAGE_BYTES;
+        const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = umma_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
+          const uint64_t db = umma_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
+          umma_bf16(d_tmem, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+    }
+  } else if (warp >= 4) {
+    // =========================================================== epilogue
+    const int ep_tid = threadIdx.x - 128;  // == TMEM lane == row inside the tile
+    const int ep_warp = warp - 4;          // TMEM sub-partition (warp % 4)
+    const uint32_t lane_off = static_cast<uint32_t>(ep_warp * 32) << 16;
+    uint8_t* staging = smem_gen + (smem_staging - smem_base);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int t2 = tile % tiles_mn;
+      const int n_blk = t2 % p.tiles_n;
+      const int m_blk = t2 / p.tiles_n;
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row = m0 + ep_tid;
+      const bool row_ok = row < p.M;
+      const int sample = p.row_bias ? (row_ok ? row / p.rows_per_sample : 0) : 0;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      // Staging buffer must have been fully read by the previous tile's TMA stores.
+      if (ep_tid == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, EPI_THREADS);
+
+      const uint32_t t_addr = tmem_base + lane_off + acc * BN;
+      const int r7 = ep_tid & 7;
+      if (OUT_F32) {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + ch * 32, v);
+          tmem_ld_wait();
+          uint8_t* dst = staging + ch * (BM * 128) + ep_tid * 128;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint4 o = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            *reinterpret_cast<uint4*>(dst + ((q ^ r7) << 4)) = o;
+          }
+        }
+      } else if (p.epi == EPI_GEGLU) {
+        // columns [0,64) = value half, [64,128) = gate half (weights are packed that way)
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t xv[32], gv[32];
+          tmem_ld32(t_addr + ch * 32, xv);
+          tmem_ld32(t_addr + 64 + ch * 32, gv);
+          tmem_ld_wait();
+          uint8_t* dst = staging + ep_tid * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = q * 8 + e * 2;
+              float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
+              float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
+              if (p.bias) {
+                x0 += __ldg(p.bias + n0 + ch * 32 + j);
+                x1 += __ldg(p.bias + n0 + ch * 32 + j + 1);
+                g0 += __ldg(p.bias + n0 + 64 + ch * 32 + j);
+                g1 += __ldg(p.bias + n0 + 64 + ch * 32 + j + 1);
+              }
+              o[e] = pack_bf16(x0 * gelu_f(g0), x1 * gelu_f(g1));
+            }
+            const int cj = ch * 4 + q;
+            *reinterpret_cast<uint4*>(dst + ((cj ^ r7) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + ch * 32, v);
+          tmem_ld_wait();
+          const int col0 = n0 + ch * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.row_bias) {
+            const float* rb = p.row_bias + (size_t)sample * p.N + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(rb + j);
+          }
+          if (p.residual && row_ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 r = __ldg(rp + q);
+              const float2 a = unpack_bf16(r.x), b = unpack_bf16(r.y), c = unpack_bf16(r.z),
+                           d = unpack_bf16(r.w);
+              f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+              f[q * 8 + 4] += c.x; f[q * 8 + 5] += c.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+            }
+          }
+          uint8_t* dst = staging + (ch >> 1) * (BM * 128) + ep_tid * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o = make_uint4(pack_bf16(f[q * 8 + 0], f[q * 8 + 1]), pack_bf16(f[q * 8 + 2], f[q * 8 + 3]),
+                                 pack_bf16(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16(f[q * 8 + 6], f[q * 8 + 7]));
+            const int cj = (ch & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(dst + ((cj ^ r7) << 4)) = o;
+          }
+        }
+      }
+      // TMEM accumulator drained -> hand it back to the MMA warp.
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      // smem writes (generic proxy) -> visible to the TMA engine (async proxy).
+      fence_proxy_async_smem();
+      named_bar_sync(1, EPI_THREADS);
+      if (ep_tid == 0) {
+        if (OUT_F32) {
+#pragma unroll
+          for (int ch = 0; ch < BN / 32; ++ch)
+            tma_reduce_add_2d(&tmD, smem_staging + ch * (BM * 128), n0 + ch * 32, m0);
+        } else if (p.epi == EPI_GEGLU) {
+          tma_store_2d(&tmD, smem_staging, n0 / 2, m0);
+        } else {
+          tma_store_2d(&tmD, smem_staging, n0, m0);
+          tma_store_2d(&tmD, smem_staging + BM * 128, n0 + 64, m0);
+        }
+        tma_store_commit();
+      }
+    }
+    if (ep_tid == 0) tma_store_wait_all<0>();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int A_MN, int B_MN, int OUT_F32>
+static int launch_t(cudaStream_t stream, const CUtensorMap& tmA0, const CUtensorMap& tmA1,
+                    const CUtensorMap& tmB0, const CUtensorMap& tmB1, const CUtensorMap& tmD,
+                    const GemmParams& p) {
+  auto kern = gemm_tc_kernel<A_MN, B_MN, OUT_F32>;
+  constexpr int smem = Cfg<OUT_F32>::SMEM_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  kern<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB0, tmB1, tmD, p);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUtensorMap& tmA0,
+                const CUtensorMap& tmA1, const CUtensorMap& tmB0, const CUtensorMap& tmB1,
+                const CUtensorMap& tmD, const GemmParams& p) {
+  TSD_CHECK(p.N % BN == 0, "gemm: N=%d must be a multiple of %d", p.N, BN);
+  TSD_CHECK(p.num_kb > 0 && p.splits > 0 && p.kb_per_split > 0, "gemm: empty K loop");
+  if (!a_mn && !b_mn && !out_f32) return launch_t<0, 0, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, p);
+  if (!a_mn && b_mn && !out_f32) return launch_t<0, 1, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, p);
+  if (a_mn && b_mn && out_f32) return launch_t<1, 1, 1>(stream, tmA0, tmA1, tmB0, tmB1, tmD, p);
+  set_error("gemm: unsupported operand-major / output combination (%d,%d,%d)", a_mn, b_mn, out_f32);
+  return 1;
+}
+
+}  // namespace tsd
