@@ -54,7 +54,7 @@ extern "C" int tsd_gemm_fwd(void* stream, const void* a0, const void* a1, int c0
 
 extern "C" int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
                                int H, int W, int stride, const void* w, int cout, const float* bias,
-                               const float* row_bias, const void* residual, void* d) {
+                               const float* row_bias, int rows_per_sample, const void* residual, void* d) {
   const int cin = c0 + c1;
   TSD_CHECK(stride == 1 || stride == 2, "conv3x3_fwd: stride must be 1 or 2");
   TSD_CHECK(cin % 64 == 0 && c0 % 64 == 0 && cout % 128 == 0, "conv3x3_fwd: bad channels c0=%d c1=%d cout=%d", c0, c1, cout);
@@ -73,7 +73,7 @@ extern "C" int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int
   p.a_mode = A_KCONV; p.a_c0 = c0; p.a_cpt = cin / 64;
   p.num_kb = 9 * p.a_cpt; p.kb_per_split = p.num_kb;
   p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.b_mode = B_K2D;
-  p.bias = bias; p.row_bias = row_bias; p.rows_per_sample = Ho * Wo;
+  p.bias = bias; p.row_bias = row_bias; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : Ho * Wo;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = cout;
   return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA0, tA1, tB, tB, tD, p);
 }
@@ -132,7 +132,7 @@ static void pick_splits(GemmParams& p) {
 extern "C" int tsd_gemm_wgrad(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1,
                               int M, int N, float* dw) {
   const int K = c0 + c1;
-  TSD_CHECK(M % 64 == 0 && N % 64 == 0 && K % 128 == 0 && c0 % 128 == 0, "gemm_wgrad: bad shape M=%d N=%d K=%d c0=%d", M, N, K, c0);
+  TSD_CHECK(M > 0 && N % 64 == 0 && K % 128 == 0 && c0 % 128 == 0, "gemm_wgrad: bad shape M=%d N=%d K=%d c0=%d", M, N, K, c0);
   CUtensorMap tA, tB0, tB1, tD;
   if (make_tmap_2d(&tA, dy, 2, M, N, N, 64, 64)) return 1;
   if (make_tmap_2d(&tB0, x0, 2, M, c0, c0, 64, 64)) return 1;
@@ -140,7 +140,7 @@ extern "C" int tsd_gemm_wgrad(void* stream, const void* dy, const void* x0, cons
   if (make_tmap_2d(&tD, dw, 4, N, K, K, 32, 128)) return 1;
   GemmParams p; zero_params(p);
   p.M = N; p.N = K; p.tiles_m = ceil_div(N, 128); p.tiles_n = K / 128;
-  p.num_kb = M / 64;
+  p.num_kb = ceil_div(M, 64);
   p.a_mode = A_MN2D; p.b_mode = B_MN2D; p.b_c0 = c0; p.b_cpt = 1 << 30; p.b_ntaps = 1;
   p.rows_per_sample = 1;
   pick_splits(p);
@@ -155,7 +155,6 @@ extern "C" int tsd_conv3x3_wgrad(void* stream, const void* dy, const void* x0, c
   TSD_CHECK(cin % 128 == 0 && c0 % 128 == 0 && cout % 64 == 0, "conv3x3_wgrad: bad channels c0=%d c1=%d cout=%d", c0, c1, cout);
   const int Ho = H / stride, Wo = W / stride;
   const int M = n_img * Ho * Wo;
-  TSD_CHECK(M % 64 == 0, "conv3x3_wgrad: pixel count %d must be a multiple of 64", M);
   uint32_t bw, bh, bn;
   if (pixel_box(Ho, Wo, 64, &bw, &bh, &bn)) return 1;
   CUtensorMap tA, tB0, tB1, tD;
@@ -165,7 +164,7 @@ extern "C" int tsd_conv3x3_wgrad(void* stream, const void* dy, const void* x0, c
   if (make_tmap_2d(&tD, dw, 4, cout, 9 * cin, 9 * cin, 32, 128)) return 1;
   GemmParams p; zero_params(p);
   p.M = cout; p.N = 9 * cin; p.tiles_m = ceil_div(cout, 128); p.tiles_n = 9 * cin / 128;
-  p.num_kb = M / 64;
+  p.num_kb = ceil_div(M, 64);
   p.a_mode = A_MN2D; p.b_mode = B_MNCONV; p.b_c0 = c0; p.b_ctot = cin;
   p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.rows_per_sample = 1;
   pick_splits(p);

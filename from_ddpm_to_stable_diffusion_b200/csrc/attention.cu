@@ -1,0 +1,556 @@
+// Fused single-pass self-attention (forward + backward) for head_dim 16 / 32.
+//
+// Reference: SelfAttention.forward, diffusion.py:46-58 -- softmax(q k^T / sqrt(dh)) v over 8 heads,
+// q, k, v = consecutive C-wide column blocks of the in_proj output, head h = channels [h*dh, (h+1)*dh).
+//
+// With dh = 16 the score GEMM has K = 16 and the kernel is bound by exp throughput (MUFU), not by
+// tensor throughput, so the contractions use warp-level mma.sync (m16n8k16, bf16 in,
+// fp32 accumulate) with operands staged by cp.async + ldmatrix; the online softmax runs in the
+// log2 domain with the 1/sqrt(dh) scale folded into one FFMA per score.
+//
+// Layout: qkv bf16 [B*L][3C]; out bf16 [B*L][C]; lse2 fp32 [B][heads][L] (log2-domain logsumexp).
+#include "../../include/tinysd_b200.h"
+#include "common.cuh"
+
+using namespace tsd;
+
+namespace {
+
+constexpr int KV_TILE = 64;
+
+__device__ __forceinline__ uint32_t smem_u32_(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// B fragments for two n-tiles (rows row0..row0+15 of a row-major [n][k] tile), k = cols col0..col0+15.
+// r[0],r[1] = (b0,b1) of n-tile row0; r[2],r[3] = n-tile row0+8.
+__device__ __forceinline__ void ldsm_nt(uint32_t* r, uint32_t base, int RS, int row0, int col0, int lane) {
+  const int mat = lane >> 3, rr = lane & 7;
+  const uint32_t addr = base + (row0 + 8 * (mat >> 1) + rr) * RS + (col0 + 8 * (mat & 1)) * 2;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// B fragments from a row-major [k][n] tile (transposed load): k = rows row0..row0+15, two n-tiles
+// cols col0..col0+7 and col0+8..col0+15.  r[0],r[1] = n-tile col0; r[2],r[3] = n-tile col0+8.
+__device__ __forceinline__ void ldsm_t(uint32_t* r, uint32_t base, int RS, int row0, int col0, int lane) {
+  const int mat = lane >> 3, rr = lane & 7;
+  const uint32_t addr = base + (row0 + 8 * (mat & 1) + rr) * RS + (col0 + 8 * (mat >> 1)) * 2;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// A fragment (16 rows x 16 cols at column col0) straight from global memory; rows >= row_limit read row 0.
+__device__ __forceinline__ void load_a_frag(uint32_t* a, const bf16* base, size_t ld, int row0, int row_limit,
+                                            int col0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  int r0 = row0 + g, r1 = row0 + g + 8;
+  if (r0 >= row_limit) r0 = 0;
+  if (r1 >= row_limit) r1 = 0;
+  const bf16* p0 = base + (size_t)r0 * ld + col0 + 2 * t;
+  const bf16* p1 = base + (size_t)r1 * ld + col0 + 2 * t;
+  a[0] = *reinterpret_cast<const uint32_t*>(p0);
+  a[1] = *reinterpret_cast<const uint32_t*>(p1);
+  a[2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+  a[3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
+}
+
+// Cooperative async load of a [64 rows][DH] bf16 tile (rows row0.. of a strided matrix) into padded smem.
+template <int DH>
+__device__ __forceinline__ void load_tile_async(uint32_t smem, const bf16* base, size_t ld, int row0, int row_limit) {
+  constexpr int RS = DH * 2 + 16;
+  constexpr int CH = DH / 8;  // 16-byte chunks per row
+  for (int i = threadIdx.x; i < KV_TILE * CH; i += blockDim.x) {
+    const int r = i / CH, c = i - r * CH;
+    const int row = row0 + r;
+    const bool ok = row < row_limit;
+    cp_async16(smem + r * RS + c * 16, base + (size_t)(ok ? row : 0) * ld + c * 8, ok ? 16 : 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward.  grid = (ceil(L / (warps*16*MT)), heads, B); each warp owns MT m-tiles of 16 query rows.
+// ------------------------------------------------------------------------------------------
+template <int DH, int MT>
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                       float* __restrict__ lse2, int L, int C, float scale_log2) {
+  constexpr int RS = DH * 2 + 16;
+  constexpr int KT = DH / 16;
+  constexpr int ND = DH / 8;
+  __shared__ __align__(16) uint8_t sK[2][KV_TILE * RS];
+  __shared__ __align__(16) uint8_t sV[2][KV_TILE * RS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const size_t ld = 3 * (size_t)C;
+  const bf16* qbase = qkv + (size_t)b * L * ld + h * DH;
+  const bf16* kbase = qbase + C;
+  const bf16* vbase = qbase + 2 * C;
+  const int q0 = (blockIdx.x * nwarps + warp) * 16 * MT;
+
+  uint32_t qf[MT][KT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) load_a_frag(qf[mt][kk], qbase, ld, q0 + mt * 16, L, kk * 16, lane);
+
+  float oacc[MT][ND][4];
+  float mrow[MT][2], lrow[MT][2];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    mrow[mt][0] = mrow[mt][1] = -INFINITY;
+    lrow[mt][0] = lrow[mt][1] = 0.f;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) oacc[mt][j][0] = oacc[mt][j][1] = oacc[mt][j][2] = oacc[mt][j][3] = 0.f;
+  }
+
+  const int ntiles = (L + KV_TILE - 1) / KV_TILE;
+  load_tile_async<DH>(smem_u32_(sK[0]), kbase, ld, 0, L);
+  load_tile_async<DH>(smem_u32_(sV[0]), vbase, ld, 0, L);
+  cp_async_commit();
+
+  for (int it = 0; it < ntiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < ntiles) {
+      load_tile_async<DH>(smem_u32_(sK[buf ^ 1]), kbase, ld, (it + 1) * KV_TILE, L);
+      load_tile_async<DH>(smem_u32_(sV[buf ^ 1]), vbase, ld, (it + 1) * KV_TILE, L);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t kS = smem_u32_(sK[buf]), vS = smem_u32_(sV[buf]);
+
+    float sacc[MT][8][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sacc[mt][j][0] = sacc[mt][j][1] = sacc[mt][j][2] = sacc[mt][j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t r[4];
+        ldsm_nt(r, kS, RS, 16 * jp, 16 * kk, lane);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16(sacc[mt][2 * jp], qf[mt][kk], r[0], r[1]);
+          mma_bf16(sacc[mt][2 * jp + 1], qf[mt][kk], r[2], r[3]);
+        }
+      }
+    const bool partial = (it + 1) * KV_TILE > L;
+    uint32_t pf[MT][4][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float s = sacc[mt][j][e] * scale_log2;
+          if (partial && (it * KV_TILE + 8 * j + 2 * t + (e & 1)) >= L) s = -INFINITY;
+          sacc[mt][j][e] = s;
+        }
+        mx0 = fmaxf(mx0, fmaxf(sacc[mt][j][0], sacc[mt][j][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[mt][j][2], sacc[mt][j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(mrow[mt][0], mx0), mn1 = fmaxf(mrow[mt][1], mx1);
+      const float c0 = ex2(mrow[mt][0] - mn0), c1 = ex2(mrow[mt][1] - mn1);
+      mrow[mt][0] = mn0; mrow[mt][1] = mn1;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = ex2(sacc[mt][j][0] - mn0), p1 = ex2(sacc[mt][j][1] - mn0);
+        const float p2 = ex2(sacc[mt][j][2] - mn1), p3 = ex2(sacc[mt][j][3] - mn1);
+        s0 += p0 + p1; s1 += p2 + p3;
+        // C fragments of n-tiles (2kk, 2kk+1) are the A fragment of k-step kk
+        pf[mt][j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
+        pf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+      lrow[mt][0] = lrow[mt][0] * c0 + s0;
+      lrow[mt][1] = lrow[mt][1] * c1 + s1;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        oacc[mt][j][0] *= c0; oacc[mt][j][1] *= c0; oacc[mt][j][2] *= c1; oacc[mt][j][3] *= c1;
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int jp = 0; jp < ND / 2; ++jp) {
+        uint32_t r[4];
+        ldsm_t(r, vS, RS, 16 * kk, 16 * jp, lane);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16(oacc[mt][2 * jp], pf[mt][kk], r[0], r[1]);
+          mma_bf16(oacc[mt][2 * jp + 1], pf[mt][kk], r[2], r[3]);
+        }
+      }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float l0 = lrow[mt][0], l1 = lrow[mt][1];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = q0 + mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      if (r0 < L)
+        *reinterpret_cast<uint32_t*>(out + ((size_t)b * L + r0) * C + h * DH + 8 * j + 2 * t) =
+            pack_bf16(oacc[mt][j][0] * i0, oacc[mt][j][1] * i0);
+      if (r1 < L)
+        *reinterpret_cast<uint32_t*>(out + ((size_t)b * L + r1) * C + h * DH + 8 * j + 2 * t) =
+            pack_bf16(oacc[mt][j][2] * i1, oacc[mt][j][3] * i1);
+    }
+    if (lse2 && t == 0) {
+      if (r0 < L) lse2[((size_t)b * H + h) * L + r0] = mrow[mt][0] + log2f(l0);
+      if (r1 < L) lse2[((size_t)b * H + h) * L + r1] = mrow[mt][1] + log2f(l1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward prep: delta[b][h][row] = sum_d dO * O
+// ------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
+                                     int B, int L, int C) {
+  const int H = C / DH;
+  const size_t total = (size_t)B * L * H;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i % H);
+    const size_t row = i / H;  // b*L + l
+    const bf16* po = o + row * C + h * DH;
+    const bf16* pd = dout + row * C + h * DH;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < DH; c += 8) {
+      const uint4 a = *reinterpret_cast<const uint4*>(po + c), d = *reinterpret_cast<const uint4*>(pd + c);
+      const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+      const float2 d0 = unpack_bf16(d.x), d1 = unpack_bf16(d.y), d2 = unpack_bf16(d.z), d3 = unpack_bf16(d.w);
+      acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+    }
+    const size_t b = row / L, l = row % L;
+    delta[(b * H + h) * L + l] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward dQ: query-outer, recompute P, dS = P * (dP - delta), dQ += dS K.  One m-tile per warp.
+// ------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                          const float* __restrict__ lse2, const float* __restrict__ delta,
+                                                          bf16* __restrict__ dqkv, int L, int C, float scale,
+                                                          float scale_log2) {
+  constexpr int RS = DH * 2 + 16;
+  constexpr int KT = DH / 16;
+  constexpr int ND = DH / 8;
+  __shared__ __align__(16) uint8_t sK[2][KV_TILE * RS];
+  __shared__ __align__(16) uint8_t sV[2][KV_TILE * RS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const size_t ld = 3 * (size_t)C;
+  const bf16* qbase = qkv + (size_t)b * L * ld + h * DH;
+  const bf16* kbase = qbase + C;
+  const bf16* vbase = qbase + 2 * C;
+  const bf16* dobase = dout + (size_t)b * L * C + h * DH;
+  const int q0 = (blockIdx.x * nwarps + warp) * 16;
+
+  uint32_t qf[KT][4], dof[KT][4];
+#pragma unroll
+  for (int kk = 0; kk < KT; ++kk) {
+    load_a_frag(qf[kk], qbase, ld, q0, L, kk * 16, lane);
+    load_a_frag(dof[kk], dobase, C, q0, L, kk * 16, lane);
+  }
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+  const size_t sbase = ((size_t)b * H + h) * L;
+  const float lse0 = r0 < L ? lse2[sbase + r0] : 0.f, lse1 = r1 < L ? lse2[sbase + r1] : 0.f;
+  const float dl0 = r0 < L ? delta[sbase + r0] : 0.f, dl1 = r1 < L ? delta[sbase + r1] : 0.f;
+
+  float dq[ND][4];
+#pragma unroll
+  for (int j = 0; j < ND; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+
+  const int ntiles = (L + KV_TILE - 1) / KV_TILE;
+  load_tile_async<DH>(smem_u32_(sK[0]), kbase, ld, 0, L);
+  load_tile_async<DH>(smem_u32_(sV[0]), vbase, ld, 0, L);
+  cp_async_commit();
+  for (int it = 0; it < ntiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < ntiles) {
+      load_tile_async<DH>(smem_u32_(sK[buf ^ 1]), kbase, ld, (it + 1) * KV_TILE, L);
+      load_tile_async<DH>(smem_u32_(sV[buf ^ 1]), vbase, ld, (it + 1) * KV_TILE, L);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t kS = smem_u32_(sK[buf]), vS = smem_u32_(sV[buf]);
+    float sacc[8][4], pacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+      pacc[j][0] = pacc[j][1] = pacc[j][2] = pacc[j][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t r[4];
+        ldsm_nt(r, kS, RS, 16 * jp, 16 * kk, lane);
+        mma_bf16(sacc[2 * jp], qf[kk], r[0], r[1]);
+        mma_bf16(sacc[2 * jp + 1], qf[kk], r[2], r[3]);
+        ldsm_nt(r, vS, RS, 16 * jp, 16 * kk, lane);
+        mma_bf16(pacc[2 * jp], dof[kk], r[0], r[1]);
+        mma_bf16(pacc[2 * jp + 1], dof[kk], r[2], r[3]);
+      }
+    const bool partial = (it + 1) * KV_TILE > L;
+    uint32_t dsf[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float ds[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lse = (e < 2) ? lse0 : lse1;
+        const float dl = (e < 2) ? dl0 : dl1;
+        float p = ex2(sacc[j][e] * scale_log2 - lse);
+        if (partial && (it * KV_TILE + 8 * j + 2 * t + (e & 1)) >= L) p = 0.f;
+        ds[e] = p * (pacc[j][e] - dl);
+      }
+      dsf[j >> 1][(j & 1) * 2] = pack_bf16(ds[0], ds[1]);
+      dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int jp = 0; jp < ND / 2; ++jp) {
+        uint32_t r[4];
+        ldsm_t(r, kS, RS, 16 * kk, 16 * jp, lane);
+        mma_bf16(dq[2 * jp], dsf[kk], r[0], r[1]);
+        mma_bf16(dq[2 * jp + 1], dsf[kk], r[2], r[3]);
+      }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < ND; ++j) {
+    if (r0 < L)
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r0) * ld + h * DH + 8 * j + 2 * t) =
+          pack_bf16(dq[j][0] * scale, dq[j][1] * scale);
+    if (r1 < L)
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r1) * ld + h * DH + 8 * j + 2 * t) =
+          pack_bf16(dq[j][2] * scale, dq[j][3] * scale);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward dK/dV: key-outer (each warp owns 16 keys), loops over query tiles of 64.
+//   S^T = K Q^T,  P^T = exp2(S^T*c - lse[q]),  dV += P^T dO,  dP^T = V dO^T,
+//   dS^T = P^T * (dP^T - delta[q]),  dK += dS^T Q   (scaled by 1/sqrt(dh) at the end)
+// ------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                           const float* __restrict__ lse2, const float* __restrict__ delta,
+                                                           bf16* __restrict__ dqkv, int L, int C, float scale,
+                                                           float scale_log2) {
+  constexpr int RS = DH * 2 + 16;
+  constexpr int KT = DH / 16;
+  constexpr int ND = DH / 8;
+  __shared__ __align__(16) uint8_t sQ[2][KV_TILE * RS];
+  __shared__ __align__(16) uint8_t sD[2][KV_TILE * RS];
+  __shared__ float sLse[2][KV_TILE], sDl[2][KV_TILE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const size_t ld = 3 * (size_t)C;
+  const bf16* qbase = qkv + (size_t)b * L * ld + h * DH;
+  const bf16* kbase = qbase + C;
+  const bf16* vbase = qbase + 2 * C;
+  const bf16* dobase = dout + (size_t)b * L * C + h * DH;
+  const size_t sbase = ((size_t)b * H + h) * L;
+  const int k0 = (blockIdx.x * nwarps + warp) * 16;
+
+  uint32_t kf[KT][4], vf[KT][4];
+#pragma unroll
+  for (int kk = 0; kk < KT; ++kk) {
+    load_a_frag(kf[kk], kbase, ld, k0, L, kk * 16, lane);
+    load_a_frag(vf[kk], vbase, ld, k0, L, kk * 16, lane);
+  }
+  const bool key_ok0 = (k0 + g) < L, key_ok1 = (k0 + g + 8) < L;
+  float dk[ND][4], dv[ND][4];
+#pragma unroll
+  for (int j = 0; j < ND; ++j) {
+    dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
+    dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
+  }
+  const int ntiles = (L + KV_TILE - 1) / KV_TILE;
+  auto load_stats = [&](int buf, int tile) {
+    for (int i = threadIdx.x; i < KV_TILE; i += blockDim.x) {
+      const int q = tile * KV_TILE + i;
+      // padded query rows: lse = +inf makes P = 0
+      sLse[buf][i] = q < L ? lse2[sbase + q] : INFINITY;
+      sDl[buf][i] = q < L ? delta[sbase + q] : 0.f;
+    }
+  };
+  load_tile_async<DH>(smem_u32_(sQ[0]), qbase, ld, 0, L);
+  load_tile_async<DH>(smem_u32_(sD[0]), dobase, C, 0, L);
+  cp_async_commit();
+  load_stats(0, 0);
+  for (int it = 0; it < ntiles; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < ntiles) {
+      load_tile_async<DH>(smem_u32_(sQ[buf ^ 1]), qbase, ld, (it + 1) * KV_TILE, L);
+      load_tile_async<DH>(smem_u32_(sD[buf ^ 1]), dobase, C, (it + 1) * KV_TILE, L);
+      cp_async_commit();
+      load_stats(buf ^ 1, it + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t qS = smem_u32_(sQ[buf]), dS_ = smem_u32_(sD[buf]);
+    float sacc[8][4], pacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+      pacc[j][0] = pacc[j][1] = pacc[j][2] = pacc[j][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        uint32_t r[4];
+        ldsm_nt(r, qS, RS, 16 * jp, 16 * kk, lane);
+        mma_bf16(sacc[2 * jp], kf[kk], r[0], r[1]);
+        mma_bf16(sacc[2 * jp + 1], kf[kk], r[2], r[3]);
+        ldsm_nt(r, dS_, RS, 16 * jp, 16 * kk, lane);
+        mma_bf16(pacc[2 * jp], vf[kk], r[0], r[1]);
+        mma_bf16(pacc[2 * jp + 1], vf[kk], r[2], r[3]);
+      }
+    uint32_t pf[4][4], dsf[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p[4], ds[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qi = 8 * j + 2 * t + (e & 1);
+        float pe = ex2(sacc[j][e] * scale_log2 - sLse[buf][qi]);
+        if (!((e < 2) ? key_ok0 : key_ok1)) pe = 0.f;
+        p[e] = pe;
+        ds[e] = pe * (pacc[j][e] - sDl[buf][qi]);
+      }
+      pf[j >> 1][(j & 1) * 2] = pack_bf16(p[0], p[1]);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
+      dsf[j >> 1][(j & 1) * 2] = pack_bf16(ds[0], ds[1]);
+      dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int jp = 0; jp < ND / 2; ++jp) {
+        uint32_t r[4];
+        ldsm_t(r, dS_, RS, 16 * kk, 16 * jp, lane);
+        mma_bf16(dv[2 * jp], pf[kk], r[0], r[1]);
+        mma_bf16(dv[2 * jp + 1], pf[kk], r[2], r[3]);
+        ldsm_t(r, qS, RS, 16 * kk, 16 * jp, lane);
+        mma_bf16(dk[2 * jp], dsf[kk], r[0], r[1]);
+        mma_bf16(dk[2 * jp + 1], dsf[kk], r[2], r[3]);
+      }
+    __syncthreads();
+  }
+  const int r0 = k0 + g, r1 = k0 + g + 8;
+#pragma unroll
+  for (int j = 0; j < ND; ++j) {
+    const int col = h * DH + 8 * j + 2 * t;
+    if (r0 < L) {
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r0) * ld + C + col) = pack_bf16(dk[j][0] * scale, dk[j][1] * scale);
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r0) * ld + 2 * C + col) = pack_bf16(dv[j][0], dv[j][1]);
+    }
+    if (r1 < L) {
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r1) * ld + C + col) = pack_bf16(dk[j][2] * scale, dk[j][3] * scale);
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r1) * ld + 2 * C + col) = pack_bf16(dv[j][2], dv[j][3]);
+    }
+  }
+}
+
+struct LaunchShape { int warps, mt, grid_x; };
+LaunchShape pick_shape(int L, bool allow_mt2) {
+  LaunchShape s;
+  if (allow_mt2 && L % 256 == 0) { s.warps = 8; s.mt = 2; }
+  else if (L >= 128) { s.warps = 8; s.mt = 1; }
+  else if (L >= 64) { s.warps = 4; s.mt = 1; }
+  else { s.warps = (L + 15) / 16; if (s.warps < 1) s.warps = 1; s.mt = 1; }
+  s.grid_x = ceil_div(L, s.warps * 16 * s.mt);
+  return s;
+}
+
+}  // namespace
+
+extern "C" int tsd_attn_fwd(void* stream, const void* qkv, void* out, float* lse2, int B, int L, int C, int heads) {
+  TSD_CHECK(C % heads == 0, "attn_fwd: C %% heads != 0");
+  const int dh = C / heads;
+  TSD_CHECK(dh == 16 || dh == 32, "attn_fwd: head_dim %d not in {16, 32}", dh);
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)dh);
+  const LaunchShape s = pick_shape(L, dh == 16);
+  dim3 grid(s.grid_x, heads, B), block(s.warps * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dh == 16 && s.mt == 2) attn_fwd_kernel<16, 2><<<grid, block, 0, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
+  else if (dh == 16) attn_fwd_kernel<16, 1><<<grid, block, 0, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
+  else attn_fwd_kernel<32, 1><<<grid, block, 0, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+// dqkv [B*L][3C] receives (dq, dk, dv); delta is scratch fp32 [B][heads][L].
+extern "C" int tsd_attn_bwd(void* stream, const void* qkv, const void* out, const void* dout, const float* lse2,
+                            float* delta, void* dqkv, int B, int L, int C, int heads) {
+  TSD_CHECK(C % heads == 0, "attn_bwd: C %% heads != 0");
+  const int dh = C / heads;
+  TSD_CHECK(dh == 16 || dh == 32, "attn_bwd: head_dim %d not in {16, 32}", dh);
+  const float scale = 1.f / sqrtf((float)dh);
+  const float scale_log2 = 1.4426950408889634f * scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)B * L * heads;
+  int pg = (int)((total + 255) / 256);
+  if (pg > num_sms() * 16) pg = num_sms() * 16;
+  if (dh == 16) attn_bwd_prep_kernel<16><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
+  else attn_bwd_prep_kernel<32><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
+  TSD_LAUNCH_CHECK();
+  const LaunchShape s = pick_shape(L, false);
+  dim3 grid(s.grid_x, heads, B), block(s.warps * 32);
+  if (dh == 16) {
+    attn_bwd_dq_kernel<16><<<grid, block, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+    TSD_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<16><<<grid, block, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+  } else {
+    attn_bwd_dq_kernel<32><<<grid, block, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+    TSD_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<32><<<grid, block, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+  }
+  TSD_LAUNCH_CHECK();
+  return 0;
+}

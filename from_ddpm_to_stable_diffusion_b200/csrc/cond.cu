@@ -1,0 +1,177 @@
+// Conditioning path (tiny, fp32 CUDA-core work): sinusoidal timestep embedding, label embedding
+// lookup and the small-M linears (time / label MLPs, per-ResBlock linear_time, the degenerate
+// cross-attention v_proj -> out_proj vectors).  Weights are read directly in the reference's
+// fp32 [out][in] layout, no packing.
+//
+// Reference: TimestepEmbedder diffusion.py:13-37; label_embedding :196-201; linear_time :101-104,
+// :112; CrossAttention :61-82 (one key/value token => out_proj(v_proj(ctx)) per sample).
+#include "../../include/tinysd_b200.h"
+#include "common.cuh"
+
+using namespace tsd;
+
+namespace {
+
+constexpr int ROWS = 8;  // rows of x handled per CTA (weight rows are re-used across them)
+
+// out[m][n] = sum_k f(x[m][k]) * w[n][k] + b[n],  f = SiLU if silu_in.  grid = (ceil(N/64), ceil(M/ROWS))
+__global__ void __launch_bounds__(256) small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ out,
+                                                               int M, int N, int K, int silu_in) {
+  extern __shared__ float sx[];  // [ROWS][K]
+  const int m0 = blockIdx.y * ROWS;
+  for (int i = threadIdx.x; i < ROWS * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    float v = (m0 + r) < M ? x[(size_t)(m0 + r) * K + k] : 0.f;
+    if (silu_in) v = v / (1.f + expf(-v));
+    sx[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = blockIdx.x * 64 + warp; n < min(N, blockIdx.x * 64 + 64); n += 8) {
+    float acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = w[(size_t)n * K + k];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) acc[r] += wv * sx[r * K + k];
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane == 0) {
+      const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+        if (m0 + r < M) out[(size_t)(m0 + r) * N + n] = acc[r] + bv;
+    }
+  }
+}
+
+// dx[m][k] (+)= f'(x[m][k]) * sum_n dy[m][n] * w[n][k].  grid = (ceil(K/256), ceil(M/ROWS))
+__global__ void __launch_bounds__(256) small_linear_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                 const float* __restrict__ x, float* __restrict__ dx,
+                                                                 int M, int N, int K, int silu_in, int accumulate) {
+  extern __shared__ float sdy[];  // [ROWS][N]
+  const int m0 = blockIdx.y * ROWS;
+  for (int i = threadIdx.x; i < ROWS * N; i += blockDim.x) {
+    const int r = i / N, n = i - r * N;
+    sdy[i] = (m0 + r) < M ? dy[(size_t)(m0 + r) * N + n] : 0.f;
+  }
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float acc[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float wv = w[(size_t)n * K + k];  // coalesced over k
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] += wv * sdy[r * N + n];
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    if (m0 + r >= M) break;
+    float v = acc[r];
+    if (silu_in) {
+      const float xv = x[(size_t)(m0 + r) * K + k];
+      const float s = 1.f / (1.f + expf(-xv));
+      v *= s * (1.f + xv * (1.f - s));
+    }
+    float* p = dx + (size_t)(m0 + r) * K + k;
+    *p = accumulate ? *p + v : v;
+  }
+}
+
+// dw[n][k] += sum_m dy[m][n] * f(x[m][k]);  db[n] += sum_m dy[m][n].  grid = (ceil(K/256), N)
+__global__ void __launch_bounds__(256) small_linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                 float* __restrict__ dw, float* __restrict__ db, int M,
+                                                                 int N, int K, int silu_in) {
+  const int n = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f, accb = 0.f;
+  if (k < K) {
+    for (int m = 0; m < M; ++m) {
+      const float d = dy[(size_t)m * N + n];
+      float v = x[(size_t)m * K + k];
+      if (silu_in) v = v / (1.f + expf(-v));
+      acc += d * v;
+      accb += d;
+    }
+    dw[(size_t)n * K + k] += acc;
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x == 0) db[n] += accb;
+}
+
+// emb[m][0:half] = cos(t*f_i), emb[m][half:] = sin(t*f_i), f_i = exp(-ln(10000) * i / half)  (diffusion.py:24-28)
+// freqs are passed in (built by the host shell with the reference's own torch expression).
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
+                                          float* __restrict__ emb, int M, int half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * half) return;
+  const int m = i / half, j = i - m * half;
+  const float a = (float)t[m] * freqs[j];
+  emb[(size_t)m * 2 * half + j] = cosf(a);
+  emb[(size_t)m * 2 * half + half + j] = sinf(a);
+}
+
+__global__ void embedding_fwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ table,
+                                     float* __restrict__ out, int M, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * D) return;
+  const int m = i / D, d = i - m * D;
+  out[i] = table[(size_t)idx[m] * D + d];
+}
+// dtable[idx[m]] += dy[m]; padding row (padding_idx) receives no gradient (diffusion.py:197)
+__global__ void embedding_bwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dy,
+                                     float* __restrict__ dtable, int M, int D, int padding_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * D) return;
+  const int m = i / D, d = i - m * D;
+  const int64_t r = idx[m];
+  if (r == padding_idx) return;
+  atomicAdd(&dtable[(size_t)r * D + d], dy[i]);
+}
+
+}  // namespace
+
+extern "C" int tsd_small_linear_fwd(void* stream, const float* x, const float* w, const float* bias, float* out, int M,
+                                    int N, int K, int silu_in) {
+  TSD_CHECK(K <= 4096, "small_linear_fwd: K=%d too large", K);
+  dim3 grid(ceil_div(N, 64), ceil_div(M, ROWS));
+  small_linear_fwd_kernel<<<grid, 256, ROWS * K * sizeof(float), (cudaStream_t)stream>>>(x, w, bias, out, M, N, K, silu_in);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_small_linear_bwd(void* stream, const float* dy, const float* x, const float* w, float* dx, float* dw,
+                                    float* db, int M, int N, int K, int silu_in, int accumulate_dx) {
+  TSD_CHECK(N <= 4096, "small_linear_bwd: N=%d too large", N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx) {
+    dim3 grid(ceil_div(K, 256), ceil_div(M, ROWS));
+    small_linear_dgrad_kernel<<<grid, 256, ROWS * N * sizeof(float), st>>>(dy, w, x, dx, M, N, K, silu_in, accumulate_dx);
+    TSD_LAUNCH_CHECK();
+  }
+  if (dw) {
+    dim3 grid(ceil_div(K, 256), N);
+    small_linear_wgrad_kernel<<<grid, 256, 0, st>>>(dy, x, dw, db, M, N, K, silu_in);
+    TSD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+extern "C" int tsd_timestep_embedding(void* stream, const int64_t* t, const float* freqs, float* emb, int M, int half) {
+  timestep_embedding_kernel<<<ceil_div(M * half, 256), 256, 0, (cudaStream_t)stream>>>(t, freqs, emb, M, half);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_embedding_fwd(void* stream, const int64_t* idx, const float* table, float* out, int M, int D) {
+  embedding_fwd_kernel<<<ceil_div(M * D, 256), 256, 0, (cudaStream_t)stream>>>(idx, table, out, M, D);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_embedding_bwd(void* stream, const int64_t* idx, const float* dy, float* dtable, int M, int D,
+                                 int padding_idx) {
+  embedding_bwd_kernel<<<ceil_div(M * D, 256), 256, 0, (cudaStream_t)stream>>>(idx, dy, dtable, M, D, padding_idx);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}

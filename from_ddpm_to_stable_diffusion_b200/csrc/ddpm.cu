@@ -1,0 +1,436 @@
+// DDPM process kernels and the two skinny convolutions that touch the fp32 NCHW image tensor.
+//
+//   head conv  channel_img -> 128, K = 27/36: not tensor-core shaped, CUDA cores     (diffusion.py:206)
+//   tail conv  128 -> channel_img, N = 3/4                                            (diffusion.py:260)
+//   q_sample + on-device Philox noise                                                 (utils.py:112-116)
+//   noise-MSE forward / backward                                                      (utils.py:118)
+//   CFG combine + posterior update + Philox z + NaN flag                              (utils.py:149-167)
+#include "../../include/tinysd_b200.h"
+#include "common.cuh"
+
+using namespace tsd;
+
+namespace {
+
+constexpr int MAX_CI = 4;    // image / latent channels supported (3 or 4)
+constexpr int HEAD_CO = 128;
+
+// ------------------------------------------------------------------------------------------ head conv
+// x fp32 NCHW [n][ci][H][W] -> out bf16 NHWC [n][H][W][co]; thread = (pixel, 8 output channels)
+__global__ void __launch_bounds__(256) head_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, bf16* __restrict__ out,
+                                                            int n_img, int ci, int H, int W, int co) {
+  extern __shared__ float sw[];  // [ci*9][co] (transposed for conflict-free reads) + bias[co]
+  float* sb = sw + ci * 9 * co;
+  for (int i = threadIdx.x; i < co * ci * 9; i += blockDim.x) {
+    const int o = i / (ci * 9), r = i - o * (ci * 9);  // OIHW: r = c*9 + tap
+    sw[r * co + o] = w[i];
+  }
+  for (int i = threadIdx.x; i < co; i += blockDim.x) sb[i] = bias[i];
+  __syncthreads();
+  const int groups = co / 8;
+  const size_t total = (size_t)n_img * H * W * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int gsel = (int)(i % groups);
+    size_t p = i / groups;
+    const int xx = (int)(p % W); p /= W;
+    const int yy = (int)(p % H);
+    const int n = (int)(p / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sb[gsel * 8 + j];
+    for (int c = 0; c < ci; ++c) {
+      const float* xp = x + ((size_t)n * ci + c) * H * W;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
+        if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
+        const float v = __ldg(xp + (size_t)y2 * W + x2);
+        const float* wr = sw + (c * 9 + tap) * co + gsel * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v * wr[j];
+      }
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) =
+        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+
+// dW[co][ci][3][3] += sum_p dy[p][co] * x[p+tap][ci], db[co] += sum_p dy[p][co].  thread = output channel.
+__global__ void __launch_bounds__(HEAD_CO) head_conv_wgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
+                                                                  float* __restrict__ dw, float* __restrict__ db,
+                                                                  int n_img, int ci, int H, int W, int co,
+                                                                  int pix_per_cta) {
+  const int o = threadIdx.x;
+  const size_t total = (size_t)n_img * H * W;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
+  const size_t p1 = p0 + pix_per_cta < total ? p0 + pix_per_cta : total;
+  float acc[MAX_CI * 9];
+#pragma unroll
+  for (int i = 0; i < MAX_CI * 9; ++i) acc[i] = 0.f;
+  float accb = 0.f;
+  for (size_t p = p0; p < p1; ++p) {
+    const int xx = (int)(p % W);
+    const int yy = (int)((p / W) % H);
+    const int n = (int)(p / ((size_t)W * H));
+    const float d = __bfloat162float(dy[p * co + o]);
+    accb += d;
+#pragma unroll
+    for (int c = 0; c < MAX_CI; ++c) {
+      if (c >= ci) break;
+      const float* xp = x + ((size_t)n * ci + c) * H * W;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
+        const float v = (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) ? 0.f : __ldg(xp + (size_t)y2 * W + x2);
+        acc[c * 9 + tap] += d * v;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAX_CI; ++c) {
+    if (c >= ci) break;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) atomicAdd(&dw[((size_t)o * ci + c) * 9 + tap], acc[c * 9 + tap]);
+  }
+  atomicAdd(&db[o], accb);
+}
+
+// ------------------------------------------------------------------------------------------ tail conv
+// a bf16 NHWC [n][H][W][128] (already GroupNorm+SiLU'ed) -> out fp32 NCHW [n][co][H][W], co <= 4.
+// One warp walks 32 consecutive pixels; lanes split the 128 input channels (4 each).
+template <int CO>
+__global__ void __launch_bounds__(256) tail_conv_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            int n_img, int H, int W) {
+  constexpr int C = 128;
+  __shared__ float sw[CO * 9 * C];  // [co][tap][c]
+  for (int i = threadIdx.x; i < CO * C * 9; i += blockDim.x) {
+    const int o = i / (C * 9), r = i - o * (C * 9), c = r / 9, tap = r - c * 9;  // OIHW
+    sw[(o * 9 + tap) * C + c] = w[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)n_img * H * W;
+  const size_t warp_global = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t base = warp_global * 32; base < total; base += nwarps * 32) {
+    float mine[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) mine[o] = 0.f;
+    for (int i = 0; i < 32; ++i) {
+      const size_t p = base + i;
+      if (p >= total) break;
+      const int xx = (int)(p % W);
+      const int yy = (int)((p / W) % H);
+      const size_t nbase = (p / ((size_t)W * H)) * H * W;
+      float acc[CO];
+#pragma unroll
+      for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
+        if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
+        const uint2 u = *reinterpret_cast<const uint2*>(a + (nbase + (size_t)y2 * W + x2) * C + lane * 4);
+        const float2 v0 = unpack_bf16(u.x), v1 = unpack_bf16(u.y);
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+          const float4 wv = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + lane * 4);
+          acc[o] += v0.x * wv.x + v0.y * wv.y + v1.x * wv.z + v1.y * wv.w;
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        const float s = warp_sum(acc[o]);
+        if (lane == i) mine[o] = s;
+      }
+    }
+    const size_t p = base + lane;
+    if (p < total) {
+      const size_t n = p / ((size_t)W * H), rem = p - n * (size_t)W * H;
+#pragma unroll
+      for (int o = 0; o < CO; ++o) out[(n * CO + o) * (size_t)H * W + rem] = mine[o] + bias[o];
+    }
+  }
+}
+
+// da[p][c] = sum_tap sum_co dy[p - off(tap)][co] * w[co][c][tap]; thread = (pixel, 8 channels)
+template <int CO>
+__global__ void __launch_bounds__(256) tail_conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                              bf16* __restrict__ da, int n_img, int H, int W) {
+  constexpr int C = 128;
+  __shared__ float sw[CO * 9 * C];  // [co][tap][c]
+  for (int i = threadIdx.x; i < CO * C * 9; i += blockDim.x) {
+    const int o = i / (C * 9), r = i - o * (C * 9), c = r / 9, tap = r - c * 9;
+    sw[(o * 9 + tap) * C + c] = w[i];
+  }
+  __syncthreads();
+  const size_t total = (size_t)n_img * H * W * (C / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % (C / 8)) * 8;
+    size_t p = i / (C / 8);
+    const int xx = (int)(p % W);
+    const int yy = (int)((p / W) % H);
+    const size_t n = p / ((size_t)W * H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      // forward: out[q] += a[q + off(tap)] * w[tap]  =>  da[p] += dy[p - off(tap)] * w[tap]
+      const int y2 = yy - (tap / 3 - 1), x2 = xx - (tap % 3 - 1);
+      if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        const float d = __ldg(dy + ((n * CO + o) * H + y2) * (size_t)W + x2);
+        const float* wr = sw + (o * 9 + tap) * C + cv;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += d * wr[j];
+      }
+    }
+    *reinterpret_cast<uint4*>(da + i * 8) =
+        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+  }
+}
+
+// dW[co][c][3][3] += sum_p dy[p][co] * a[p+off][c]; db[co] += sum dy.  thread = input channel c.
+template <int CO>
+__global__ void __launch_bounds__(128) tail_conv_wgrad_kernel(const float* __restrict__ dy, const bf16* __restrict__ a,
+                                                              float* __restrict__ dw, float* __restrict__ db, int n_img,
+                                                              int H, int W, int pix_per_cta) {
+  constexpr int C = 128;
+  const int c = threadIdx.x;
+  const size_t total = (size_t)n_img * H * W;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
+  const size_t p1 = p0 + pix_per_cta < total ? p0 + pix_per_cta : total;
+  float acc[CO * 9];
+#pragma unroll
+  for (int i = 0; i < CO * 9; ++i) acc[i] = 0.f;
+  float accb[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) accb[o] = 0.f;
+  for (size_t p = p0; p < p1; ++p) {
+    const int xx = (int)(p % W);
+    const int yy = (int)((p / W) % H);
+    const size_t n = p / ((size_t)W * H);
+    float d[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+      d[o] = __ldg(dy + ((n * CO + o) * H + yy) * (size_t)W + xx);
+      accb[o] += d[o];
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
+      if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
+      const float v = __bfloat162float(a[((n * H + y2) * (size_t)W + x2) * C + c]);
+#pragma unroll
+      for (int o = 0; o < CO; ++o) acc[o * 9 + tap] += d[o] * v;
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < CO; ++o)
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) atomicAdd(&dw[((size_t)o * C + c) * 9 + tap], acc[o * 9 + tap]);
+  if (c == 0) {
+#pragma unroll
+    for (int o = 0; o < CO; ++o) atomicAdd(&db[o], accb[o]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ DDPM elementwise
+// x_t = sqrt_ab[t_n] * x0 + sqrt_1mab[t_n] * noise (utils.py:115-116); noise ~ N(0,1) from Philox unless given.
+__global__ void q_sample_kernel(const float* __restrict__ x0, const int64_t* __restrict__ t,
+                                const float* __restrict__ sqrt_ab, const float* __restrict__ sqrt_1mab,
+                                const float* __restrict__ noise_in, uint64_t seed, uint64_t offset,
+                                float* __restrict__ x_t, float* __restrict__ noise_out, size_t per_sample, size_t total4) {
+  const Philox rng(seed);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    const int n = (int)(e / per_sample);
+    const int64_t tn = t[n];
+    const float a = sqrt_ab[tn], b = sqrt_1mab[tn];
+    const float4 x = *reinterpret_cast<const float4*>(x0 + e);
+    float4 z;
+    if (noise_in) {
+      z = *reinterpret_cast<const float4*>(noise_in + e);
+    } else {
+      const uint4 r = rng(offset + i, 0x71ULL);
+      const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
+      z = make_float4(z0.x, z0.y, z1.x, z1.y);
+    }
+    // same operation order as the reference (two products, one sum), no FMA contraction
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(a, x.x), __fmul_rn(b, z.x));
+    o.y = __fadd_rn(__fmul_rn(a, x.y), __fmul_rn(b, z.y));
+    o.z = __fadd_rn(__fmul_rn(a, x.z), __fmul_rn(b, z.z));
+    o.w = __fadd_rn(__fmul_rn(a, x.w), __fmul_rn(b, z.w));
+    *reinterpret_cast<float4*>(x_t + e) = o;
+    if (noise_out) *reinterpret_cast<float4*>(noise_out + e) = z;
+  }
+}
+
+__global__ void mse_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ noise, float* __restrict__ loss,
+                               size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = pred[i] - noise[i];
+    loss[i] = d * d;
+  }
+}
+__global__ void mse_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ noise,
+                               const float* __restrict__ gout, float* __restrict__ dpred, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    dpred[i] = 2.f * (pred[i] - noise[i]) * gout[i];
+}
+
+// One reverse-diffusion update (utils.py:149-167):
+//   eps = (1+w) eps_c - w eps_u;  mean = c1[t] x - c2[t] eps;  x' = mean + sigma[t] z  (z = 0 at t = 0)
+// eps holds [2B] images: the conditional batch first, then the unconditional batch.  The step
+// index is read from device memory so the same launch can be replayed from a CUDA graph.
+__global__ void sampler_update_kernel(const float* __restrict__ x, const float* __restrict__ eps, const int* __restrict__ step_ptr,
+                                      const float* __restrict__ c1, const float* __restrict__ c2,
+                                      const float* __restrict__ sigma, float w, const float* __restrict__ noise_in,
+                                      uint64_t seed, float* __restrict__ x_out, int* __restrict__ nan_flag, size_t total4,
+                                      int clip_last, int dup) {
+  const int step = *step_ptr;
+  const float k1 = c1[step], k2 = c2[step], sg = sigma[step];
+  const float w1 = 1.f + w;
+  const Philox rng(seed);
+  bool bad = false;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    const float4 xv = *reinterpret_cast<const float4*>(x + e);
+    const float4 ec = *reinterpret_cast<const float4*>(eps + e);
+    const float4 eu = *reinterpret_cast<const float4*>(eps + total4 * 4 + e);
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (step > 0) {
+      if (noise_in) {
+        z = *reinterpret_cast<const float4*>(noise_in + e);
+      } else {
+        const uint4 r = rng(i, (uint64_t)step + 1);  // fresh stream per step
+        const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
+        z = make_float4(z0.x, z0.y, z1.x, z1.y);
+      }
+    }
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs[4] = {ec.x, ec.y, ec.z, ec.w}, us[4] = {eu.x, eu.y, eu.z, eu.w},
+                zs[4] = {z.x, z.y, z.z, z.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float ep = __fsub_rn(__fmul_rn(w1, cs[j]), __fmul_rn(w, us[j]));
+      const float mean = __fsub_rn(__fmul_rn(k1, xs[j]), __fmul_rn(k2, ep));
+      float v = __fadd_rn(mean, __fmul_rn(sg, zs[j]));
+      bad |= (v != v);
+      if (clip_last && step == 0) v = fminf(fmaxf(v, -1.f), 1.f);
+      o[j] = v;
+    }
+    *reinterpret_cast<float4*>(x_out + e) = make_float4(o[0], o[1], o[2], o[3]);
+    if (dup) *reinterpret_cast<float4*>(x_out + total4 * 4 + e) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (bad) atomicOr(nan_flag, 1);
+}
+
+__global__ void step_counter_kernel(int* step_ptr, int delta) { *step_ptr += delta; }
+// out[0:len] = table[*step][0:len]  (per-step conditioning rows, indexed on the device so a CUDA graph can replay)
+__global__ void gather_row_kernel(const float* __restrict__ table, const int* __restrict__ step_ptr, int len,
+                                  float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) out[i] = table[(size_t)(*step_ptr) * len + i];
+}
+
+inline int ew_grid(size_t items) {
+  size_t g = (items + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int tsd_head_conv_fwd(void* stream, const float* x, const float* w, const float* bias, void* out, int n_img,
+                                 int ci, int H, int W, int co) {
+  TSD_CHECK(ci <= MAX_CI && co % 8 == 0, "head_conv_fwd: unsupported channels ci=%d co=%d", ci, co);
+  const size_t smem = (size_t)(ci * 9 * co + co) * sizeof(float);
+  head_conv_fwd_kernel<<<ew_grid((size_t)n_img * H * W * (co / 8)), 256, smem, (cudaStream_t)stream>>>(x, w, bias, (bf16*)out, n_img, ci, H, W, co);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_head_conv_wgrad(void* stream, const void* dy, const float* x, float* dw, float* db, int n_img, int ci,
+                                   int H, int W, int co) {
+  TSD_CHECK(ci <= MAX_CI && co == HEAD_CO, "head_conv_wgrad: unsupported channels ci=%d co=%d", ci, co);
+  const size_t total = (size_t)n_img * H * W;
+  int ppc = (int)((total + 4 * num_sms() - 1) / (4 * num_sms()));
+  if (ppc < 64) ppc = 64;
+  head_conv_wgrad_kernel<<<(int)((total + ppc - 1) / ppc), HEAD_CO, 0, (cudaStream_t)stream>>>((const bf16*)dy, x, dw, db, n_img, ci, H, W, co, ppc);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_tail_conv_fwd(void* stream, const void* a, const float* w, const float* bias, float* out, int n_img,
+                                 int H, int W, int c_in, int co) {
+  TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_fwd: unsupported channels c_in=%d co=%d", c_in, co);
+  const size_t total = (size_t)n_img * H * W;
+  int grid = (int)((total + 255) / 256);  // 8 warps x 32 pixels per CTA pass
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  if (co == 3) tail_conv_fwd_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, w, bias, out, n_img, H, W);
+  else tail_conv_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, w, bias, out, n_img, H, W);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_tail_conv_bwd(void* stream, const float* dy, const void* a, const float* w, void* da, float* dw,
+                                 float* db, int n_img, int H, int W, int c_in, int co) {
+  TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_bwd: unsupported channels c_in=%d co=%d", c_in, co);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)n_img * H * W;
+  const int g1 = ew_grid(total * 16);
+  int ppc = (int)((total + 4 * num_sms() - 1) / (4 * num_sms()));
+  if (ppc < 64) ppc = 64;
+  const int g2 = (int)((total + ppc - 1) / ppc);
+  if (co == 3) {
+    tail_conv_dgrad_kernel<3><<<g1, 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
+    TSD_LAUNCH_CHECK();
+    tail_conv_wgrad_kernel<3><<<g2, 128, 0, st>>>(dy, (const bf16*)a, dw, db, n_img, H, W, ppc);
+  } else {
+    tail_conv_dgrad_kernel<4><<<g1, 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
+    TSD_LAUNCH_CHECK();
+    tail_conv_wgrad_kernel<4><<<g2, 128, 0, st>>>(dy, (const bf16*)a, dw, db, n_img, H, W, ppc);
+  }
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_q_sample(void* stream, const float* x0, const int64_t* t, const float* sqrt_ab, const float* sqrt_1mab,
+                            const float* noise_in, uint64_t seed, uint64_t offset, float* x_t, float* noise_out,
+                            int n_img, int64_t per_sample) {
+  TSD_CHECK(per_sample % 4 == 0, "q_sample: per-sample element count must be a multiple of 4");
+  const size_t total4 = (size_t)n_img * per_sample / 4;
+  q_sample_kernel<<<ew_grid(total4), 256, 0, (cudaStream_t)stream>>>(x0, t, sqrt_ab, sqrt_1mab, noise_in, seed, offset, x_t, noise_out, per_sample, total4);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_mse_fwd(void* stream, const float* pred, const float* noise, float* loss, int64_t total) {
+  mse_fwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(pred, noise, loss, total);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_mse_bwd(void* stream, const float* pred, const float* noise, const float* gout, float* dpred,
+                           int64_t total) {
+  mse_bwd_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(pred, noise, gout, dpred, total);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_sampler_update(void* stream, const float* x, const float* eps, const int* step_ptr, const float* c1,
+                                  const float* c2, const float* sigma, float w, const float* noise_in, uint64_t seed,
+                                  float* x_out, int* nan_flag, int64_t total, int clip_last, int dup) {
+  TSD_CHECK(total % 4 == 0, "sampler_update: element count must be a multiple of 4");
+  sampler_update_kernel<<<ew_grid(total / 4), 256, 0, (cudaStream_t)stream>>>(x, eps, step_ptr, c1, c2, sigma, w, noise_in, seed, x_out, nan_flag, total / 4, clip_last, dup);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_step_add(void* stream, int* step_ptr, int delta) {
+  step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr, delta);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_gather_row_f32(void* stream, const float* table, const int* step_ptr, int len, float* out) {
+  gather_row_kernel<<<ceil_div(len, 256), 256, 0, (cudaStream_t)stream>>>(table, step_ptr, len, out);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,511 @@
+// GroupNorm(+SiLU,+dropout) and LayerNorm, forward and backward, on bf16 channels-last tensors.
+// These are the HBM-bound kernels of the path: 16-byte vector accesses, fp32 statistics,
+// warp-shuffle reductions, one atomic per (warp, statistic).
+//
+// Reference: nn.GroupNorm(32, C) + nn.SiLU (+ nn.Dropout) at diffusion.py:90-91, 95-97, 122, 258-259;
+// nn.LayerNorm(C) at diffusion.py:127, 130, 132.
+#include "../../include/tinysd_b200.h"
+#include "common.cuh"
+
+using namespace tsd;
+
+namespace {
+
+constexpr int GROUPS = 32;
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics.  grid = (chunks, n_img); each CTA reduces a slab of pixels of one image
+// over all channels of the (optionally concatenated) input and adds per-group partial sums.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1,
+                                                         int c0, int c1, int hw, int pix_per_cta,
+                                                         float* __restrict__ sums /* [n][32][2] */) {
+  const int C = c0 + c1;
+  const int cpg = C / GROUPS;
+  const int vec_per_pix = C / 8;
+  const int n = blockIdx.y;
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+  __shared__ float s_sum[GROUPS], s_sq[GROUPS];
+  if (threadIdx.x < GROUPS) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  // blockDim (256) is a multiple of vec_per_pix (C/8 in {8,16,32,64,128,256}), so every thread owns a
+  // fixed 8-channel slot: accumulate in registers over its pixels, one smem atomic per group at the end.
+  const int slots = blockDim.x / vec_per_pix;
+  const int cv = (threadIdx.x % vec_per_pix) * 8;
+  const int my_slot = threadIdx.x / vec_per_pix;
+  const int ng = cpg >= 8 ? 1 : 8 / cpg;  // groups covered by this vector
+  float ls[4] = {0.f, 0.f, 0.f, 0.f}, lq[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int pix = p_begin + my_slot; pix < p_end; pix += slots) {
+    const bf16* src = cv < c0 ? x0 + ((size_t)n * hw + pix) * c0 + cv : x1 + ((size_t)n * hw + pix) * c1 + (cv - c0);
+    const uint4 u = *reinterpret_cast<const uint4*>(src);
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    const float e[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+    if (cpg >= 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ls[0] += e[j]; lq[0] += e[j] * e[j]; }
+    } else if (cpg == 4) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ls[j >> 2] += e[j]; lq[j >> 2] += e[j] * e[j]; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ls[j >> 1] += e[j]; lq[j >> 1] += e[j] * e[j]; }
+    }
+  }
+  for (int g = 0; g < ng; ++g) {
+    atomicAdd(&s_sum[cv / cpg + g], ls[g]);
+    atomicAdd(&s_sq[cv / cpg + g], lq[g]);
+  }
+  __syncthreads();
+  if (threadIdx.x < GROUPS) {
+    atomicAdd(&sums[((size_t)n * GROUPS + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
+    atomicAdd(&sums[((size_t)n * GROUPS + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  }
+}
+
+// sums -> (mean, rstd); re-zeroes the scratch sums for the next call.
+__global__ void gn_finalize_kernel(float* __restrict__ sums, float* __restrict__ stats, int count, float inv_cnt,
+                                   float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float s = sums[2 * i], q = sums[2 * i + 1];
+  const float mean = s * inv_cnt;
+  const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+  stats[2 * i] = mean;
+  stats[2 * i + 1] = rsqrtf(var + eps);
+  sums[2 * i] = 0.f;
+  sums[2 * i + 1] = 0.f;
+}
+
+// Keep/scale factors for the 8 consecutive elements starting at flat index ebase (ebase % 8 == 0):
+// two Philox calls, one 32-bit word per element.  The backward kernels regenerate the same mask.
+__device__ __forceinline__ void dropout_scales8(const Philox& rng, uint64_t ebase, float p, float inv_keep,
+                                                float* sc) {
+  const uint4 r0 = rng(ebase >> 2, 0x5eedULL), r1 = rng((ebase >> 2) + 1, 0x5eedULL);
+  const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sc[j] = (w[j] * 2.3283064365386963e-10f) >= p ? inv_keep : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm apply: out = dropout(silu(gamma * (x - mean) * rstd + beta)).
+// grid = (chunks, n_img); thread = one 8-channel vector.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1, int c0,
+                                                       int c1, int hw, const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int act_silu, float drop_p, uint64_t seed,
+                                                       bf16* __restrict__ out) {
+  const int C = c0 + c1;
+  const int cpg = C / GROUPS;
+  const int vec_per_pix = C / 8;
+  const int n = blockIdx.y;
+  __shared__ float s_mean[GROUPS], s_rstd[GROUPS];
+  if (threadIdx.x < GROUPS) {
+    s_mean[threadIdx.x] = stats[((size_t)n * GROUPS + threadIdx.x) * 2];
+    s_rstd[threadIdx.x] = stats[((size_t)n * GROUPS + threadIdx.x) * 2 + 1];
+  }
+  __syncthreads();
+  const Philox rng(seed);
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int total = hw * vec_per_pix;
+  for (int v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += gridDim.x * blockDim.x) {
+    const int pix = v0 / vec_per_pix;
+    const int cv = (v0 - pix * vec_per_pix) * 8;
+    const bf16* src = cv < c0 ? x0 + ((size_t)n * hw + pix) * c0 + cv : x1 + ((size_t)n * hw + pix) * c1 + (cv - c0);
+    const uint4 u = *reinterpret_cast<const uint4*>(src);
+    float e[8];
+    { const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = d.x; e[7] = d.y; }
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + cv), g1 = *reinterpret_cast<const float4*>(gamma + cv + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + cv), b1 = *reinterpret_cast<const float4*>(beta + cv + 4);
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const size_t ebase = ((size_t)n * hw + pix) * C + cv;
+    float sc[8];
+    if (drop_p > 0.f) dropout_scales8(rng, ebase, drop_p, inv_keep, sc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (cv + j) / cpg;
+      float z = (e[j] - s_mean[g]) * s_rstd[g] * gm[j] + bt[j];
+      if (act_silu) z = silu_f(z);
+      if (drop_p > 0.f) z *= sc[j];
+      e[j] = z;
+    }
+    uint4 o = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+    *reinterpret_cast<uint4*>(out + ebase) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm backward, pass 1: per-(image, channel) sums  A = sum dz * xhat,  B = sum dz
+// where dz = dy * dropout_scale * silu'(z).  grid = (chunks, n_img).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_bwd_sums_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x0,
+                                                          const bf16* __restrict__ x1, int c0, int c1, int hw,
+                                                          int pix_per_cta, const float* __restrict__ stats,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          int act_silu, float drop_p, uint64_t seed,
+                                                          float* __restrict__ ab /* [n][C][2] */) {
+  const int C = c0 + c1;
+  const int cpg = C / GROUPS;
+  const int vec_per_pix = C / 8;
+  const int n = blockIdx.y;
+  extern __shared__ float s_ab[];  // [C][2]
+  __shared__ float s_mean[GROUPS], s_rstd[GROUPS];
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_ab[i] = 0.f;
+  if (threadIdx.x < GROUPS) {
+    s_mean[threadIdx.x] = stats[((size_t)n * GROUPS + threadIdx.x) * 2];
+    s_rstd[threadIdx.x] = stats[((size_t)n * GROUPS + threadIdx.x) * 2 + 1];
+  }
+  __syncthreads();
+  const Philox rng(seed);
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+  // thread -> fixed channel vector when blockDim % vec_per_pix == 0 (true for C <= 2048, C % 64 == 0 ... C/8 | 256)
+  const int slots = blockDim.x / vec_per_pix;  // pixels processed per sweep
+  const int my_vec = threadIdx.x % vec_per_pix;
+  const int my_slot = threadIdx.x / vec_per_pix;
+  if (my_slot < slots) {
+    const int cv = my_vec * 8;
+    float accA[8], accB[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
+    float gm[8], bt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gm[j] = gamma[cv + j]; bt[j] = beta[cv + j]; }
+    for (int pix = p_begin + my_slot; pix < p_end; pix += slots) {
+      const bf16* src = cv < c0 ? x0 + ((size_t)n * hw + pix) * c0 + cv : x1 + ((size_t)n * hw + pix) * c1 + (cv - c0);
+      const size_t ebase = ((size_t)n * hw + pix) * C + cv;
+      const uint4 u = *reinterpret_cast<const uint4*>(src);
+      const uint4 g = *reinterpret_cast<const uint4*>(dy + ebase);
+      float e[8], d[8];
+      { const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), dd = unpack_bf16(u.w);
+        e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = dd.x; e[7] = dd.y; }
+      { const float2 a = unpack_bf16(g.x), b = unpack_bf16(g.y), c = unpack_bf16(g.z), dd = unpack_bf16(g.w);
+        d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = dd.x; d[7] = dd.y; }
+      float sc[8];
+      if (drop_p > 0.f) dropout_scales8(rng, ebase, drop_p, inv_keep, sc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int grp = (cv + j) / cpg;
+        const float xhat = (e[j] - s_mean[grp]) * s_rstd[grp];
+        float dz = d[j];
+        if (drop_p > 0.f) dz *= sc[j];
+        if (act_silu) dz *= silu_grad_f(xhat * gm[j] + bt[j]);
+        accA[j] += dz * xhat;
+        accB[j] += dz;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_ab[(cv + j) * 2], accA[j]);
+      atomicAdd(&s_ab[(cv + j) * 2 + 1], accB[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&ab[(size_t)n * 2 * C + i], s_ab[i]);
+}
+
+// pass 2: dx = rstd * (gamma*dz - mean_g(gamma*dz) - xhat * mean_g(gamma*dz*xhat)) (+ radd), written to the
+// (optionally split) destinations dx0 [.., c0] and dx1 [.., c1].
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x0,
+                                                           const bf16* __restrict__ x1, int c0, int c1, int hw,
+                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, int act_silu, float drop_p,
+                                                           uint64_t seed, const float* __restrict__ ab,
+                                                           const bf16* __restrict__ radd, bf16* __restrict__ dx0,
+                                                           bf16* __restrict__ dx1) {
+  const int C = c0 + c1;
+  const int cpg = C / GROUPS;
+  const int vec_per_pix = C / 8;
+  const int n = blockIdx.y;
+  __shared__ float s_mean[GROUPS], s_rstd[GROUPS], s_m1[GROUPS], s_m2[GROUPS];
+  if (threadIdx.x < GROUPS) {
+    const int g = threadIdx.x;
+    s_mean[g] = stats[((size_t)n * GROUPS + g) * 2];
+    s_rstd[g] = stats[((size_t)n * GROUPS + g) * 2 + 1];
+    float m1 = 0.f, m2 = 0.f;
+    for (int j = 0; j < cpg; ++j) {
+      const int c = g * cpg + j;
+      m2 += gamma[c] * ab[((size_t)n * C + c) * 2];      // sum gamma*dz*xhat
+      m1 += gamma[c] * ab[((size_t)n * C + c) * 2 + 1];  // sum gamma*dz
+    }
+    const float inv = 1.f / (float)(cpg * hw);
+    s_m1[g] = m1 * inv;
+    s_m2[g] = m2 * inv;
+  }
+  __syncthreads();
+  const Philox rng(seed);
+  const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int total = hw * vec_per_pix;
+  for (int v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += gridDim.x * blockDim.x) {
+    const int pix = v0 / vec_per_pix;
+    const int cv = (v0 - pix * vec_per_pix) * 8;
+    const size_t prow = (size_t)n * hw + pix;
+    const bf16* src = cv < c0 ? x0 + prow * c0 + cv : x1 + prow * c1 + (cv - c0);
+    const size_t ebase = prow * C + cv;
+    const uint4 u = *reinterpret_cast<const uint4*>(src);
+    const uint4 g = *reinterpret_cast<const uint4*>(dy + ebase);
+    float e[8], d[8], r[8];
+    { const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), dd = unpack_bf16(u.w);
+      e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = dd.x; e[7] = dd.y; }
+    { const float2 a = unpack_bf16(g.x), b = unpack_bf16(g.y), c = unpack_bf16(g.z), dd = unpack_bf16(g.w);
+      d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = dd.x; d[7] = dd.y; }
+    if (radd) {
+      const uint4 q = *reinterpret_cast<const uint4*>(radd + ebase);
+      const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), dd = unpack_bf16(q.w);
+      r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y; r[6] = dd.x; r[7] = dd.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = 0.f;
+    }
+    float sc[8];
+    if (drop_p > 0.f) dropout_scales8(rng, ebase, drop_p, inv_keep, sc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int grp = (cv + j) / cpg;
+      const float gmj = gamma[cv + j];
+      const float xhat = (e[j] - s_mean[grp]) * s_rstd[grp];
+      float dz = d[j];
+      if (drop_p > 0.f) dz *= sc[j];
+      if (act_silu) dz *= silu_grad_f(xhat * gmj + beta[cv + j]);
+      e[j] = s_rstd[grp] * (gmj * dz - s_m1[grp] - xhat * s_m2[grp]) + r[j];
+    }
+    const uint4 o = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+    bf16* dst = cv < c0 ? dx0 + prow * c0 + cv : dx1 + prow * c1 + (cv - c0);
+    *reinterpret_cast<uint4*>(dst) = o;
+  }
+}
+
+// dgamma[c] += sum_n A[n][c];  dbeta[c] += sum_n B[n][c]
+__global__ void gn_bwd_params_kernel(const float* __restrict__ ab, int n_img, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int n = 0; n < n_img; ++n) {
+    a += ab[((size_t)n * C + c) * 2];
+    b += ab[((size_t)n * C + c) * 2 + 1];
+  }
+  dgamma[c] += a;
+  dbeta[c] += b;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over C (128 / 256 / 512): one warp per token row.
+// ------------------------------------------------------------------------------------------
+template <int VEC>  // VEC = C / 256 uint4 loads per lane ... we use C/32 elements per lane = 8*VEC... see below
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, int M, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, bf16* __restrict__ out) {
+  // C = 64 * VEC * ... : each lane handles VEC chunks of 4 channels (8 bytes): C = 32 * 4 * VEC
+  constexpr int C = 128 * VEC;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float v[4 * VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const uint2 u = *reinterpret_cast<const uint2*>(x + (size_t)row * C + (i * 32 + lane) * 4);
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
+    s += a.x + a.y + b.x + b.y;
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4 * VEC; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    const float o0 = (v[4 * i] - mean) * rstd * g.x + b.x, o1 = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
+    const float o2 = (v[4 * i + 2] - mean) * rstd * g.z + b.z, o3 = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
+    *reinterpret_cast<uint2*>(out + (size_t)row * C + c) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+  }
+}
+
+// LayerNorm backward: dx = rstd * (g*dy - mean(g*dy) - xhat*mean(g*dy*xhat)) (+ radd); dgamma/dbeta are
+// accumulated per CTA in shared memory then atomically added (fp32).
+template <int VEC>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, int M,
+                                                     const float* __restrict__ gamma, float eps,
+                                                     const bf16* __restrict__ radd, bf16* __restrict__ dx,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     int rows_per_cta) {
+  constexpr int C = 128 * VEC;
+  __shared__ float s_dg[C], s_db[C];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float adg[4 * VEC], adb[4 * VEC], gm[4 * VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+    gm[4 * i] = g.x; gm[4 * i + 1] = g.y; gm[4 * i + 2] = g.z; gm[4 * i + 3] = g.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4 * VEC; ++i) { adg[i] = 0.f; adb[i] = 0.f; }
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(M, r_begin + rows_per_cta);
+  for (int row = r_begin + warp; row < r_end; row += nwarps) {
+    float v[4 * VEC], d[4 * VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const size_t off = (size_t)row * C + (i * 32 + lane) * 4;
+      const uint2 u = *reinterpret_cast<const uint2*>(x + off);
+      const uint2 g = *reinterpret_cast<const uint2*>(dy + off);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(g.x), e = unpack_bf16(g.y);
+      v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
+      d[4 * i] = c.x; d[4 * i + 1] = c.y; d[4 * i + 2] = e.x; d[4 * i + 3] = e.y;
+      s += a.x + a.y + b.x + b.y;
+    }
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4 * VEC; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4 * VEC; ++i) {
+      v[i] *= rstd;  // xhat
+      adg[i] += d[i] * v[i];
+      adb[i] += d[i];
+      d[i] *= gm[i];
+      m1 += d[i];
+      m2 += d[i] * v[i];
+    }
+    m1 = warp_sum(m1) * (1.f / C);
+    m2 = warp_sum(m2) * (1.f / C);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const size_t off = (size_t)row * C + (i * 32 + lane) * 4;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = rstd * (d[4 * i + j] - m1 - v[4 * i + j] * m2);
+      if (radd) {
+        const uint2 r = *reinterpret_cast<const uint2*>(radd + off);
+        const float2 a = unpack_bf16(r.x), b = unpack_bf16(r.y);
+        o[0] += a.x; o[1] += a.y; o[2] += b.x; o[3] += b.y;
+      }
+      *reinterpret_cast<uint2*>(dx + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(&s_dg[(i * 32 + lane) * 4 + j], adg[4 * i + j]);
+      atomicAdd(&s_db[(i * 32 + lane) * 4 + j], adb[4 * i + j]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&dgamma[i], s_dg[i]);
+    atomicAdd(&dbeta[i], s_db[i]);
+  }
+}
+
+int gn_grid_x(int hw, int C, int n_img, int* pix_per_cta) {
+  // enough CTAs to fill the machine ~4x, at least 32 pixels per CTA
+  int want = ceil_div(4 * num_sms(), n_img);
+  if (want < 1) want = 1;
+  int ppc = ceil_div(hw, want);
+  const int min_pix = ceil_div(8192, C);  // >= 8K elements per CTA
+  if (ppc < min_pix) ppc = min_pix;
+  if (ppc > hw) ppc = hw;
+  *pix_per_cta = ppc;
+  return ceil_div(hw, ppc);
+}
+
+}  // namespace
+
+extern "C" int tsd_gn_stats(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int hw,
+                            float eps, float* scratch, float* stats) {
+  const int C = c0 + c1;
+  TSD_CHECK(C % 64 == 0 && c0 % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "gn_stats: unsupported channels c0=%d c1=%d", c0, c1);
+  int ppc;
+  const int gx = gn_grid_x(hw, C, n_img, &ppc);
+  gn_partial_kernel<<<dim3(gx, n_img), 256, 0, (cudaStream_t)stream>>>((const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc,
+                                                                      scratch);
+  TSD_LAUNCH_CHECK();
+  const int count = n_img * GROUPS;
+  gn_finalize_kernel<<<ceil_div(count, 256), 256, 0, (cudaStream_t)stream>>>(scratch, stats, count,
+                                                                            1.f / ((float)hw * (C / GROUPS)), eps);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tsd_gn_apply(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int hw,
+                            const float* stats, const float* gamma, const float* beta, int act_silu, float drop_p,
+                            uint64_t seed, void* out) {
+  const int C = c0 + c1;
+  TSD_CHECK(C % 64 == 0 && c0 % 8 == 0, "gn_apply: unsupported channels c0=%d c1=%d", c0, c1);
+  const int total = hw * (C / 8);
+  int gx = ceil_div(total, 256 * 4);
+  if (gx < 1) gx = 1;
+  gn_apply_kernel<<<dim3(gx, n_img), 256, 0, (cudaStream_t)stream>>>((const bf16*)x0, (const bf16*)x1, c0, c1, hw, stats,
+                                                                    gamma, beta, act_silu, drop_p, seed, (bf16*)out);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+// ab: scratch [n_img][C][2] fp32, must be zero on entry (the call leaves it dirty; zero it with tsd_zero_f32).
+extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1, int n_img,
+                          int hw, const float* stats, const float* gamma, const float* beta, int act_silu,
+                          float drop_p, uint64_t seed, float* ab, const void* radd, void* dx0, void* dx1,
+                          float* dgamma, float* dbeta) {
+  const int C = c0 + c1;
+  TSD_CHECK(C % 64 == 0 && c0 % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "gn_bwd: unsupported channels c0=%d c1=%d", c0, c1);
+  cudaStream_t st = (cudaStream_t)stream;
+  TSD_CUDA(cudaMemsetAsync(ab, 0, (size_t)n_img * C * 2 * sizeof(float), st));
+  int ppc;
+  const int gx = gn_grid_x(hw, C, n_img, &ppc);
+  gn_bwd_sums_kernel<<<dim3(gx, n_img), 256, 2 * C * sizeof(float), st>>>(
+      (const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc, stats, gamma, beta, act_silu, drop_p, seed, ab);
+  TSD_LAUNCH_CHECK();
+  const int total = hw * (C / 8);
+  int gx2 = ceil_div(total, 256 * 4);
+  if (gx2 < 1) gx2 = 1;
+  gn_bwd_apply_kernel<<<dim3(gx2, n_img), 256, 0, st>>>((const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, stats,
+                                                        gamma, beta, act_silu, drop_p, seed, ab, (const bf16*)radd,
+                                                        (bf16*)dx0, (bf16*)dx1);
+  TSD_LAUNCH_CHECK();
+  if (dgamma) {
+    gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ab, n_img, C, dgamma, dbeta);
+    TSD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int tsd_ln_fwd(void* stream, const void* x, int M, int C, const float* gamma, const float* beta, float eps,
+                          void* out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ceil_div(M, 8);
+  if (C == 128) ln_fwd_kernel<1><<<grid, 256, 0, st>>>((const bf16*)x, M, gamma, beta, eps, (bf16*)out);
+  else if (C == 256) ln_fwd_kernel<2><<<grid, 256, 0, st>>>((const bf16*)x, M, gamma, beta, eps, (bf16*)out);
+  else if (C == 512) ln_fwd_kernel<4><<<grid, 256, 0, st>>>((const bf16*)x, M, gamma, beta, eps, (bf16*)out);
+  else TSD_CHECK(false, "ln_fwd: C=%d not in {128,256,512}", C);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tsd_ln_bwd(void* stream, const void* dy, const void* x, int M, int C, const float* gamma, float eps,
+                          const void* radd, void* dx, float* dgamma, float* dbeta) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rows_per_cta = ceil_div(M, 2 * num_sms());
+  if (rows_per_cta < 8) rows_per_cta = 8;
+  const int grid = ceil_div(M, rows_per_cta);
+  if (C == 128)
+    ln_bwd_kernel<1><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, M, gamma, eps, (const bf16*)radd, (bf16*)dx, dgamma, dbeta, rows_per_cta);
+  else if (C == 256)
+    ln_bwd_kernel<2><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, M, gamma, eps, (const bf16*)radd, (bf16*)dx, dgamma, dbeta, rows_per_cta);
+  else if (C == 512)
+    ln_bwd_kernel<4><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, M, gamma, eps, (const bf16*)radd, (bf16*)dx, dgamma, dbeta, rows_per_cta);
+  else TSD_CHECK(false, "ln_bwd: C=%d not in {128,256,512}", C);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}

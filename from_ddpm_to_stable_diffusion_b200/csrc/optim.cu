@@ -1,0 +1,91 @@
+// Caller-side step body (02_train_direct.py:72-73): clip_grad_norm_(params, max_norm) + AdamW.step(),
+// as two passes over flat fp32 buffers: (1) global sum of squares, (2) clip + AdamW in one sweep.
+#include "../../include/tinysd_b200.h"
+#include "common.cuh"
+
+using namespace tsd;
+
+namespace {
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n4, size_t n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(g + i * 4);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t i = n4 * 4; i < n; ++i) acc += g[i] * g[i];
+  acc = warp_sum(acc);
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = s[threadIdx.x];
+    v += __shfl_xor_sync(0xffu, v, 4);
+    v += __shfl_xor_sync(0xffu, v, 2);
+    v += __shfl_xor_sync(0xffu, v, 1);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+// torch.optim.AdamW semantics (decoupled weight decay, bias-corrected), gradient pre-scaled by the
+// clip coefficient min(1, max_norm / (||g|| + 1e-6)) of torch.nn.utils.clip_grad_norm_.
+__global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                         float* __restrict__ v, size_t n, float lr, float beta1, float beta2,
+                                                         float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
+                                                         const float* __restrict__ sumsq, int write_clipped_grad) {
+  float coef = 1.f;
+  if (max_norm > 0.f) {
+    coef = max_norm / (sqrtf(*sumsq) + 1e-6f);
+    coef = coef > 1.f ? 1.f : coef;
+  }
+  const float step_size = lr / bc1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (write_clipped_grad) g[i] = gi;
+  }
+}
+
+__global__ void scale_kernel(float* __restrict__ x, size_t n, float s) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= s;
+}
+
+inline int ew_grid(size_t items) {
+  size_t g = (items + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+// out[0] += sum g^2   (out must be zeroed by the caller)
+extern "C" int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out) {
+  TSD_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: buffer must be 16-byte aligned");
+  sumsq_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(g, n / 4, n, out);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                              float beta2, float eps, float wd, int step, float max_norm, const float* sumsq,
+                              int write_clipped_grad) {
+  TSD_CHECK(step >= 1, "adamw: step must be >= 1");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adamw_clip_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt,
+                                                                 max_norm, sumsq, write_clipped_grad);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_scale_f32(void* stream, float* x, int64_t n, float s) {
+  scale_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, s);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}

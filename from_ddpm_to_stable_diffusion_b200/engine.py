@@ -1,0 +1,487 @@
+"""Kernel schedule of the UNet forward / backward (host side, Python like the reference).
+
+Replaces Diffusion.forward (06_tiny_stable_diffusion/diffusion.py:263-276) and what torch autograd
+derives from it (02_train_direct.py:71).  One autograd node spans the whole network: forward saves
+the activations it needs in a plain Python record, backward walks the blocks in reverse and writes
+parameter gradients straight into ``p.grad`` (views of one flat fp32 buffer).
+
+Data layout in HBM: activations bf16 channels-last as [n*h*w, c]; GEMM weights packed bf16
+[n_out][k] (3x3: k = tap*cin + ci); norm affine, biases, conditioning path and x_t / eps fp32.
+"""
+import math
+
+import torch
+
+from . import ops
+
+F32 = torch.float32
+
+
+class _Rec:
+    """Saved tensors of one block (forward -> backward)."""
+    __slots__ = ("kind", "key", "d")
+
+    def __init__(self, kind, key, **d):
+        self.kind, self.key, self.d = kind, key, d
+
+    def __getattr__(self, k):
+        try:
+            return self.d[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+class UNetEngine:
+    def __init__(self, model):
+        # weak-ish back reference (the engine is owned by the model)
+        object.__setattr__(self, "_model_ref", model)
+        self._packed = {}
+        self._packed_sig = None
+        self._epoch = 0
+        self._scratch = None
+        self._freqs = None
+        self._flat_grad = None
+        self._grad_views = None
+        self._fn = None
+        self.seed = 0x1234ABCD
+        self._drop_calls = 0
+
+    # ------------------------------------------------------------------ parameters
+    @property
+    def model(self):
+        return self._model_ref
+
+    def invalidate(self):
+        self._packed_sig = None
+        self._flat_grad = None
+        self._grad_views = None
+        self._scratch = None
+        self._freqs = None
+
+    def bump(self):
+        """Call after parameters were modified through raw pointers (fused optimiser)."""
+        self._epoch += 1
+
+    def params(self):
+        return dict(self.model.named_parameters())
+
+    def _signature(self, P):
+        return (self._epoch,) + tuple((p.data_ptr(), p._version) for p in P.values())
+
+    def _block_list(self):
+        m = self.model
+        out = []
+        for i, st in enumerate(m._enc):
+            for j, b in enumerate(st):
+                out.append((f"encoders.{i}.{j}", b))
+        for j, b in enumerate(m._mid):
+            out.append((f"bottleneck.{j}", b))
+        for i, st in enumerate(m._dec):
+            for j, b in enumerate(st):
+                out.append((f"decoders.{i}.{j}", b))
+        return out
+
+    def packed(self, P):
+        """bf16 GEMM-layout copies of the weights, refreshed when any parameter changed."""
+        sig = self._signature(P)
+        if sig == self._packed_sig:
+            return self._packed
+        W = {}
+        for key, b in self._block_list():
+            if b[0] == "conv":
+                if b[1] % 64 == 0:  # the head conv (3/4 input channels) runs on CUDA cores from fp32
+                    W[key] = ops.pack_conv3x3(P[key + ".weight"])
+            elif b[0] == "up":
+                W[key + ".conv"] = ops.pack_conv3x3(P[key + ".conv.weight"])
+            elif b[0] == "res":
+                W[key + ".conv_1.2"] = ops.pack_conv3x3(P[key + ".conv_1.2.weight"])
+                W[key + ".conv_2.3"] = ops.pack_conv3x3(P[key + ".conv_2.3.weight"])
+                if b[1] != b[2]:
+                    W[key + ".residual_layer"] = ops.pack_linear(P[key + ".residual_layer.weight"])
+            else:
+                for n in ("conv_1.1", "atten_1.1.in_proj", "atten_1.1.out_proj", "linear_1", "linear_2", "conv_output"):
+                    W[key + "." + n] = ops.pack_linear(P[f"{key}.{n}.weight"])
+                W[key + ".linear_1.geglu"] = ops.pack_linear(P[key + ".linear_1.weight"], geglu=True)
+                W[key + ".linear_1.geglu_bias"] = ops.pack_geglu_bias(P[key + ".linear_1.bias"])
+        self._packed, self._packed_sig = W, sig
+        return W
+
+    def _get_scratch(self, n_img, dev):
+        need = n_img * 64
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
+            self._scratch = torch.zeros(max(need, 4096), device=dev, dtype=F32)
+        return self._scratch
+
+    def _get_freqs(self, dev):
+        if self._freqs is None or self._freqs.device != dev:
+            half = self.model.d_model // 2
+            # the reference's own expression (diffusion.py:26), evaluated on the host in fp32
+            self._freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half) / half).to(dev)
+        return self._freqs
+
+    # ------------------------------------------------------------------ autograd entry
+    def apply(self, x, t, labels):
+        P = self.params()
+        plist = list(P.values())
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
+        if not need_grad:
+            with torch.no_grad():
+                eps, _ = self.forward(x, t, labels, save=False)
+            return eps
+        return _UNetFn.apply(self, x, t, labels, *plist)
+
+    # ------------------------------------------------------------------ conditioning (diffusion.py:265-266)
+    def conditioning(self, P, t, labels, save):
+        m = self.model
+        rec = {}
+        t_freq = ops.timestep_embedding(t, self._get_freqs(t.device))
+        h1 = ops.small_linear(t_freq, P["time_embedding.mlp.0.weight"], P["time_embedding.mlp.0.bias"])
+        temb = ops.small_linear(h1, P["time_embedding.mlp.2.weight"], P["time_embedding.mlp.2.bias"], silu_in=True)
+        emb = ops.embedding_fwd(labels, P["label_embedding.0.weight"])
+        c1 = ops.small_linear(emb, P["label_embedding.1.weight"], P["label_embedding.1.bias"])
+        ctx = ops.small_linear(c1, P["label_embedding.3.weight"], P["label_embedding.3.bias"], silu_in=True)
+        if save:
+            rec.update(t_freq=t_freq, h1=h1, temb=temb, emb=emb, c1=c1, ctx=ctx, labels=labels)
+        return temb, ctx, rec
+
+    def time_bias(self, P, key, temb):
+        """linear_time = Linear(SiLU(temb)) (diffusion.py:101-104, 112) -> [B, Cout] fp32"""
+        return ops.small_linear(temb, P[key + ".linear_time.1.weight"], P[key + ".linear_time.1.bias"], silu_in=True)
+
+    def cross_bias(self, P, key, ctx):
+        """CrossAttention with one key/value token == out_proj(v_proj(ctx)) per sample (diffusion.py:71-82)"""
+        vv = ops.small_linear(ctx, P[key + ".atten_2.v_proj.weight"])
+        cb = ops.small_linear(vv, P[key + ".atten_2.out_proj.weight"], P[key + ".atten_2.out_proj.bias"])
+        return vv, cb
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, t, labels, save, tb_override=None, cb_override=None, eps_out=None, taps=None):
+        """Returns (eps fp32 NCHW, tape).  tb_override / cb_override: precomputed per-block conditioning
+        (sampling: one shared time row for the whole batch, constant label vectors)."""
+        m = self.model
+        P = self.params()
+        W = self.packed(P)
+        n, ci, H, Wd = x.shape
+        assert ci == m.channel_img
+        dev = x.device
+        scratch = self._get_scratch(n, dev)
+        training = m.training
+        tape = []
+        x = x.contiguous().float()
+
+        if tb_override is None:
+            temb, ctx, crec = self.conditioning(P, t.contiguous(), labels.contiguous(), save)
+        else:
+            temb = ctx = None
+            crec = {}
+
+        def run_res(key, b, x0, x1, h, w):
+            ci_, co = b[1], b[2]
+            hw = h * w
+            if tb_override is None:
+                tb, rps = self.time_bias(P, key, temb), hw
+            else:
+                tb, rps = tb_override[key]
+            p_drop = m.dropout if (b[3] and training) else 0.0
+            st1 = ops.gn_stats(x0, n, hw, 1e-5, scratch, x1=x1)
+            a1 = ops.gn_apply(x0, n, hw, st1, P[key + ".conv_1.0.weight"], P[key + ".conv_1.0.bias"], True, x1=x1)
+            # row_bias row = output row / rps: per image in training, one shared time row when sampling
+            hmid = ops.conv3x3(a1, n, h, w, W[key + ".conv_1.2"], co, bias=P[key + ".conv_1.2.bias"],
+                               row_bias=tb, rows_per_sample=rps)
+            st2 = ops.gn_stats(hmid, n, hw, 1e-5, scratch)
+            seed = 0
+            if p_drop > 0.0:
+                self._drop_calls += 1
+                seed = (self.seed * 1000003 + self._drop_calls) & 0xFFFFFFFFFFFFFFFF
+            a2 = ops.gn_apply(hmid, n, hw, st2, P[key + ".conv_2.0.weight"], P[key + ".conv_2.0.bias"], True,
+                              drop_p=p_drop, seed=seed)
+            if ci_ != co:
+                sc = ops.gemm(x0, W[key + ".residual_layer"], co, a1=x1, bias=P[key + ".residual_layer.bias"])
+            else:
+                sc = x0
+            out = ops.conv3x3(a2, n, h, w, W[key + ".conv_2.3"], co, bias=P[key + ".conv_2.3.bias"], residual=sc)
+            if save:
+                tape.append(_Rec("res", key, b=b, x0=x0, x1=x1, st1=st1, a1=a1, hmid=hmid, st2=st2, a2=a2,
+                                 p_drop=p_drop, seed=seed, h=h, w=w))
+            return out
+
+        def run_attn(key, b, x0, h, w):
+            C = b[1]
+            L = h * w
+            if cb_override is None:
+                vv, cb = self.cross_bias(P, key, ctx)
+            else:
+                vv, cb = None, cb_override[key]
+            st = ops.gn_stats(x0, n, L, 1e-6, scratch)
+            g = ops.gn_apply(x0, n, L, st, P[key + ".conv_1.0.weight"], P[key + ".conv_1.0.bias"], False)
+            t0 = ops.gemm(g, W[key + ".conv_1.1"], C, bias=P[key + ".conv_1.1.bias"])
+            l1 = ops.ln_fwd(t0, P[key + ".atten_1.0.weight"], P[key + ".atten_1.0.bias"])
+            qkv = ops.gemm(l1, W[key + ".atten_1.1.in_proj"], 3 * C)
+            o, lse = ops.attn_fwd(qkv, n, L, C, m.N_HEAD, need_lse=save)
+            t2 = ops.gemm(o, W[key + ".atten_1.1.out_proj"], C, bias=P[key + ".atten_1.1.out_proj.bias"],
+                          row_bias=cb, rows_per_sample=L, residual=t0)
+            l3 = ops.ln_fwd(t2, P[key + ".norm_3.weight"], P[key + ".norm_3.bias"])
+            if save:
+                h8 = ops.gemm(l3, W[key + ".linear_1"], 8 * C, bias=P[key + ".linear_1.bias"])
+                gg = ops.geglu_fwd(h8)
+            else:
+                h8 = None
+                gg = ops.gemm(l3, W[key + ".linear_1.geglu"], 8 * C, bias=W[key + ".linear_1.geglu_bias"], geglu=True)
+            t3 = ops.gemm(gg, W[key + ".linear_2"], C, bias=P[key + ".linear_2.bias"], residual=t2)
+            out = ops.gemm(t3, W[key + ".conv_output"], C, bias=P[key + ".conv_output.bias"], residual=x0)
+            if save:
+                tape.append(_Rec("attn", key, b=b, x0=x0, st=st, g=g, t0=t0, l1=l1, qkv=qkv, o=o, lse=lse, t2=t2, l3=l3,
+                                 h8=h8, gg=gg, t3=t3, vv=vv, h=h, w=w))
+            return out
+
+        def run_block(key, b, x0, x1, h, w):
+            """returns (out, h, w)"""
+            if b[0] == "conv":
+                if b[1] % 64 != 0:  # head conv on the fp32 NCHW image
+                    out = ops.head_conv_fwd(x, P[key + ".weight"], P[key + ".bias"])
+                    if save:
+                        tape.append(_Rec("head", key, b=b))
+                    return out, h, w
+                out = ops.conv3x3(x0, n, h, w, W[key], b[2], stride=b[3], bias=P[key + ".bias"])
+                if save:
+                    tape.append(_Rec("conv", key, b=b, x0=x0, h=h, w=w))
+                return out, h // b[3], w // b[3]
+            if b[0] == "up":
+                u = ops.upsample2_fwd(x0, n, h, w)
+                out = ops.conv3x3(u, n, 2 * h, 2 * w, W[key + ".conv"], b[1], bias=P[key + ".conv.bias"])
+                if save:
+                    tape.append(_Rec("up", key, b=b, u=u, h=h, w=w))
+                return out, 2 * h, 2 * w
+            if b[0] == "res":
+                return run_res(key, b, x0, x1, h, w), h, w
+            return run_attn(key, b, x0, h, w), h, w
+
+        h, w = H, Wd
+        cur = None
+        skips = []
+        for i, st in enumerate(m._enc):
+            for j, b in enumerate(st):
+                cur, h, w = run_block(f"encoders.{i}.{j}", b, cur, None, h, w)
+                if taps is not None:
+                    taps[f"encoders.{i}.{j}"] = (cur, h, w)
+            skips.append(cur)
+            if save:
+                tape.append(_Rec("skip_push", ""))
+        for j, b in enumerate(m._mid):
+            cur, h, w = run_block(f"bottleneck.{j}", b, cur, None, h, w)
+            if taps is not None:
+                taps[f"bottleneck.{j}"] = (cur, h, w)
+        for i, st in enumerate(m._dec):
+            skip = skips.pop()
+            if save:
+                tape.append(_Rec("skip_pop", ""))
+            for j, b in enumerate(st):
+                cur, h, w = run_block(f"decoders.{i}.{j}", b, cur, skip if j == 0 else None, h, w)
+                if taps is not None:
+                    taps[f"decoders.{i}.{j}"] = (cur, h, w)
+        # tail: GroupNorm -> SiLU -> conv3x3 C -> channel_img (diffusion.py:257-261)
+        hw = h * w
+        stt = ops.gn_stats(cur, n, hw, 1e-5, scratch)
+        at = ops.gn_apply(cur, n, hw, stt, P["tail.0.weight"], P["tail.0.bias"], True)
+        eps = ops.tail_conv_fwd(at, P["tail.2.weight"], P["tail.2.bias"], n, h, w, out=eps_out)
+        if save:
+            tape.append(_Rec("tail", "tail", xin=cur, st=stt, a=at, h=h, w=w))
+            return eps, dict(tape=tape, crec=crec, x=x, n=n, P=P, W=W, scratch=scratch)
+        return eps, None
+
+    # ------------------------------------------------------------------ gradients
+    def _grad_buffers(self, P):
+        """p.grad tensors as views into one flat fp32 buffer (zeroed when freshly attached)."""
+        plist = list(P.values())
+        dev = plist[0].device
+        total = sum(p.numel() for p in plist)
+        if self._flat_grad is None or self._flat_grad.device != dev or self._flat_grad.numel() != _aligned_total(plist):
+            self._flat_grad = torch.zeros(_aligned_total(plist), device=dev, dtype=F32)
+            views, off = {}, 0
+            for k, p in P.items():
+                views[k] = self._flat_grad[off:off + p.numel()].view_as(p)
+                off += (p.numel() + 3) // 4 * 4
+            self._grad_views = views
+        G = {}
+        fresh = all(p.grad is None for p in plist)
+        if fresh:
+            self._flat_grad.zero_()
+        for k, p in P.items():
+            v = self._grad_views[k]
+            if p.grad is None:
+                if not fresh:
+                    v.zero_()
+                p.grad = v
+                G[k] = v
+            elif p.grad.data_ptr() == v.data_ptr():
+                G[k] = v
+            else:  # foreign grad tensor: accumulate through a temporary
+                G[k] = torch.zeros_like(p)
+        return G, total
+
+    def backward(self, saved, deps):
+        m = self.model
+        P, W, n, scratch = saved["P"], saved["W"], saved["n"], saved["scratch"]
+        x = saved["x"]
+        tape = saved["tape"]
+        crec = saved["crec"]
+        G, _ = self._grad_buffers(P)
+        dev = x.device
+        d_temb = torch.zeros(n, m.time_emb_dim, device=dev, dtype=F32)
+        d_ctx = torch.zeros(n, m.time_emb_dim, device=dev, dtype=F32)
+        temb, ctx = crec["temb"], crec["ctx"]
+        packed_wgrads = []  # (packed fp32 grad, OIHW grad view) to unpack at the end
+
+        def conv_wgrad(dy, x0, key_w, hh, ww, x1=None, stride=1):
+            gw = G[key_w]
+            tmp = torch.zeros(gw.shape[0], 9 * gw.shape[1], device=dev, dtype=F32)
+            ops.conv3x3_wgrad(dy, x0, n, hh, ww, tmp, x1=x1, stride=stride)
+            ops.unpack_conv3x3_grad(tmp, gw)
+
+        dcur = None
+        skip_grads = []
+        for rec in reversed(tape):
+            kind, key = rec.kind, rec.key
+            if kind == "tail":
+                hh, ww = rec.h, rec.w
+                da = ops.tail_conv_bwd(deps.contiguous().float(), rec.a, P["tail.2.weight"], G["tail.2.weight"],
+                                       G["tail.2.bias"], n, hh, ww)
+                dcur, _ = ops.gn_bwd(da, rec.xin, n, hh * ww, rec.st, P["tail.0.weight"], P["tail.0.bias"], True,
+                                     G["tail.0.weight"], G["tail.0.bias"])
+            elif kind == "skip_pop":
+                # forward popped a skip here: the block list after it consumed cat(cur, skip); dcur currently
+                # holds (dx0, dx1) from that stage's first ResBlock
+                dcur, dskip = dcur
+                skip_grads.append(dskip)
+            elif kind == "skip_push":
+                # forward pushed `cur` as a skip: its gradient gains the matching decoder's concat gradient
+                dskip = skip_grads.pop()
+                dcur = ops.add(dcur, dskip) if dcur is not None else dskip
+            elif kind == "res":
+                dcur = self._res_bwd(rec, dcur, P, W, G, n, temb, d_temb, conv_wgrad)
+            elif kind == "attn":
+                dcur = self._attn_bwd(rec, dcur, P, W, G, n, ctx, d_ctx)
+            elif kind == "conv":
+                b, hh, ww = rec.b, rec.h, rec.w
+                s = b[3]
+                ops.bias_grad(dcur, n, (hh // s) * (ww // s), G[key + ".bias"])
+                conv_wgrad(dcur, rec.x0, key + ".weight", hh, ww, stride=s)
+                if s == 2:
+                    zs = ops.zero_stuff2(dcur, n, hh // 2, ww // 2)
+                    dcur = ops.conv3x3_dgrad(zs, n, hh, ww, W[key], b[1])
+                else:
+                    dcur = ops.conv3x3_dgrad(dcur, n, hh, ww, W[key], b[1])
+            elif kind == "up":
+                hh, ww = rec.h, rec.w
+                ops.bias_grad(dcur, n, 4 * hh * ww, G[key + ".conv.bias"])
+                conv_wgrad(dcur, rec.u, key + ".conv.weight", 2 * hh, 2 * ww)
+                du = ops.conv3x3_dgrad(dcur, n, 2 * hh, 2 * ww, W[key + ".conv"], rec.b[1])
+                dcur = ops.upsample2_bwd(du, n, hh, ww)
+            elif kind == "head":
+                ops.head_conv_wgrad(dcur, x, G[key + ".weight"], G[key + ".bias"])
+                dcur = None
+        assert not skip_grads
+        # conditioning backward (time / label MLPs, embedding)
+        dh1 = torch.empty_like(crec["h1"])
+        ops.small_linear_bwd(d_temb, crec["h1"], P["time_embedding.mlp.2.weight"], dh1, G["time_embedding.mlp.2.weight"],
+                             G["time_embedding.mlp.2.bias"], silu_in=True)
+        ops.small_linear_bwd(dh1, crec["t_freq"], P["time_embedding.mlp.0.weight"], None, G["time_embedding.mlp.0.weight"],
+                             G["time_embedding.mlp.0.bias"])
+        dc1 = torch.empty_like(crec["c1"])
+        ops.small_linear_bwd(d_ctx, crec["c1"], P["label_embedding.3.weight"], dc1, G["label_embedding.3.weight"],
+                             G["label_embedding.3.bias"], silu_in=True)
+        demb = torch.empty_like(crec["emb"])
+        ops.small_linear_bwd(dc1, crec["emb"], P["label_embedding.1.weight"], demb, G["label_embedding.1.weight"],
+                             G["label_embedding.1.bias"])
+        ops.embedding_bwd(crec["labels"], demb, G["label_embedding.0.weight"], padding_idx=0)
+        # foreign grad tensors
+        for k, p in P.items():
+            if p.grad is not None and p.grad.data_ptr() != G[k].data_ptr():
+                p.grad.add_(G[k])
+
+    def _res_bwd(self, rec, dout, P, W, G, n, temb, d_temb, conv_wgrad):
+        key, b = rec.key, rec.b
+        ci, co = b[1], b[2]
+        hh, ww = rec.h, rec.w
+        hw = hh * ww
+        # conv_2 (+ shortcut bias share the same column sums of dout)
+        per = ops.bias_grad(dout, n, hw, G[key + ".conv_2.3.bias"])
+        conv_wgrad(dout, rec.a2, key + ".conv_2.3.weight", hh, ww)
+        da2 = ops.conv3x3_dgrad(dout, n, hh, ww, W[key + ".conv_2.3"], co)
+        dh, _ = ops.gn_bwd(da2, rec.hmid, n, hw, rec.st2, P[key + ".conv_2.0.weight"], P[key + ".conv_2.0.bias"], True,
+                           G[key + ".conv_2.0.weight"], G[key + ".conv_2.0.bias"], drop_p=rec.p_drop, seed=rec.seed)
+        # time bias: per-sample column sums of dh feed linear_time; their sum over samples is conv_1's bias grad
+        dtb = ops.bias_grad(dh, n, hw, G[key + ".conv_1.2.bias"])
+        ops.small_linear_bwd(dtb, temb, P[key + ".linear_time.1.weight"], d_temb, G[key + ".linear_time.1.weight"],
+                             G[key + ".linear_time.1.bias"], silu_in=True, accumulate_dx=True)
+        conv_wgrad(dh, rec.a1, key + ".conv_1.2.weight", hh, ww)
+        da1 = ops.conv3x3_dgrad(dh, n, hh, ww, W[key + ".conv_1.2"], ci)
+        if ci != co:
+            ops.reduce_rows_into(per, G[key + ".residual_layer.bias"])
+            ops.gemm_wgrad(dout, rec.x0, G[key + ".residual_layer.weight"].view(co, ci), x1=rec.x1)
+            radd = ops.gemm_dgrad(dout, W[key + ".residual_layer"], ci)
+        else:
+            radd = dout
+        dx0, dx1 = ops.gn_bwd(da1, rec.x0, n, hw, rec.st1, P[key + ".conv_1.0.weight"], P[key + ".conv_1.0.bias"], True,
+                              G[key + ".conv_1.0.weight"], G[key + ".conv_1.0.bias"], x1=rec.x1, radd=radd)
+        return (dx0, dx1) if rec.x1 is not None else dx0
+
+    def _attn_bwd(self, rec, dout, P, W, G, n, ctx, d_ctx):
+        key, b = rec.key, rec.b
+        C = b[1]
+        L = rec.h * rec.w
+        k = key
+        # conv_output (1x1) + long residual
+        ops.bias_grad(dout, n, L, G[k + ".conv_output.bias"])
+        ops.gemm_wgrad(dout, rec.t3, G[k + ".conv_output.weight"].view(C, C))
+        dt3 = ops.gemm_dgrad(dout, W[k + ".conv_output"], C)
+        # linear_2 (+ short residual to t2)
+        ops.bias_grad(dt3, n, L, G[k + ".linear_2.bias"])
+        ops.gemm_wgrad(dt3, rec.gg, G[k + ".linear_2.weight"])
+        dgg = ops.gemm_dgrad(dt3, W[k + ".linear_2"], 4 * C)
+        dh8 = ops.geglu_bwd(rec.h8, dgg)
+        ops.bias_grad(dh8, n, L, G[k + ".linear_1.bias"])
+        ops.gemm_wgrad(dh8, rec.l3, G[k + ".linear_1.weight"])
+        dl3 = ops.gemm_dgrad(dh8, W[k + ".linear_1"], C)
+        dt2 = ops.ln_bwd(dl3, rec.t2, P[k + ".norm_3.weight"], G[k + ".norm_3.weight"], G[k + ".norm_3.bias"], radd=dt3)
+        # out_proj (+ cross-attention vector + residual t0)
+        dcb = ops.bias_grad(dt2, n, L, G[k + ".atten_1.1.out_proj.bias"])  # per-sample sums = grad of the cross vector
+        ops.gemm_wgrad(dt2, rec.o, G[k + ".atten_1.1.out_proj.weight"])
+        do = ops.gemm_dgrad(dt2, W[k + ".atten_1.1.out_proj"], C)
+        dqkv = ops.attn_bwd(rec.qkv, rec.o, do, rec.lse, n, L, C, self.model.N_HEAD)
+        ops.gemm_wgrad(dqkv, rec.l1, G[k + ".atten_1.1.in_proj.weight"])
+        dl1 = ops.gemm_dgrad(dqkv, W[k + ".atten_1.1.in_proj"], C)
+        dt0 = ops.ln_bwd(dl1, rec.t0, P[k + ".atten_1.0.weight"], G[k + ".atten_1.0.weight"], G[k + ".atten_1.0.bias"],
+                         radd=dt2)
+        # conv_1.1 (1x1) and GroupNorm (eps 1e-6, no activation), + long residual
+        ops.bias_grad(dt0, n, L, G[k + ".conv_1.1.bias"])
+        ops.gemm_wgrad(dt0, rec.g, G[k + ".conv_1.1.weight"].view(C, C))
+        dg = ops.gemm_dgrad(dt0, W[k + ".conv_1.1"], C)
+        dx, _ = ops.gn_bwd(dg, rec.x0, n, L, rec.st, P[k + ".conv_1.0.weight"], P[k + ".conv_1.0.bias"], False,
+                           G[k + ".conv_1.0.weight"], G[k + ".conv_1.0.bias"], radd=dout)
+        # degenerate cross attention: cb = out_proj(v_proj(ctx)) + bias   (norm_2, q_proj, k_proj get exact zeros)
+        dvv = torch.empty_like(rec.vv)
+        ops.small_linear_bwd(dcb, rec.vv, P[k + ".atten_2.out_proj.weight"], dvv, G[k + ".atten_2.out_proj.weight"],
+                             G[k + ".atten_2.out_proj.bias"])
+        ops.small_linear_bwd(dvv, ctx, P[k + ".atten_2.v_proj.weight"], d_ctx, G[k + ".atten_2.v_proj.weight"], None,
+                             accumulate_dx=True)
+        return dx
+
+
+def _aligned_total(plist):
+    return sum((p.numel() + 3) // 4 * 4 for p in plist)
+
+
+class _UNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, t, labels, *params):
+        eps, saved = engine.forward(x, t, labels, save=True)
+        ctx.engine = engine
+        ctx.saved = saved
+        return eps
+
+    @staticmethod
+    def backward(ctx, deps):
+        ctx.engine.backward(ctx.saved, deps)
+        ctx.saved = None
+        return (None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 4)

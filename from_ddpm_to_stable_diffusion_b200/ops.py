@@ -1,0 +1,320 @@
+"""Thin tensor-level wrappers over the C ABI (include/tinysd_b200.h).
+
+PyTorch is used here only as the device allocator and stream provider; every computation below is
+a kernel in libtinysd_b200.so.  Activations are bf16 channels-last, stored as 2-D [n*h*w, c].
+"""
+import torch
+
+from . import _lib
+from ._lib import call, f32, i64, u64
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _chk(t, dtype):
+    assert t.is_cuda and t.is_contiguous() and t.dtype == dtype, (t.device, t.is_contiguous(), t.dtype, dtype)
+    return t
+
+
+def empty_bf16(*shape, like):
+    return torch.empty(shape, device=like.device, dtype=BF16)
+
+
+# ------------------------------------------------------------------ dense contractions (tcgen05)
+def gemm(a0, w, n_out, a1=None, bias=None, row_bias=None, rows_per_sample=1, residual=None, geglu=False):
+    M, c0 = a0.shape
+    c1 = a1.shape[1] if a1 is not None else 0
+    d = empty_bf16(M, n_out // 2 if geglu else n_out, like=a0)
+    call("tsd_gemm_fwd", _chk(a0, BF16), a1, c0, c1, M, _chk(w, BF16), n_out, bias, row_bias, rows_per_sample,
+         residual, 1 if geglu else 0, d)
+    return d
+
+
+def conv3x3(x0, n_img, H, W, w, cout, x1=None, stride=1, bias=None, row_bias=None, rows_per_sample=0, residual=None):
+    c0 = x0.shape[1]
+    c1 = x1.shape[1] if x1 is not None else 0
+    d = empty_bf16(n_img * (H // stride) * (W // stride), cout, like=x0)
+    call("tsd_conv3x3_fwd", _chk(x0, BF16), x1, c0, c1, n_img, H, W, stride, _chk(w, BF16), cout, bias, row_bias,
+         rows_per_sample, residual, d)
+    return d
+
+
+def gemm_dgrad(dy, w, k_in, residual=None):
+    M, N = dy.shape
+    dx = empty_bf16(M, k_in, like=dy)
+    call("tsd_gemm_dgrad", _chk(dy, BF16), M, N, _chk(w, BF16), k_in, residual, dx)
+    return dx
+
+
+def conv3x3_dgrad(dy, n_img, H, W, w, cin, residual=None):
+    cout = dy.shape[1]
+    dx = empty_bf16(n_img * H * W, cin, like=dy)
+    call("tsd_conv3x3_dgrad", _chk(dy, BF16), n_img, H, W, cout, _chk(w, BF16), cin, residual, dx)
+    return dx
+
+
+def gemm_wgrad(dy, x0, dw, x1=None):
+    M, N = dy.shape
+    c0 = x0.shape[1]
+    c1 = x1.shape[1] if x1 is not None else 0
+    call("tsd_gemm_wgrad", _chk(dy, BF16), _chk(x0, BF16), x1, c0, c1, M, N, _chk(dw, F32))
+
+
+def conv3x3_wgrad(dy, x0, n_img, H, W, dw_packed, x1=None, stride=1):
+    cout = dy.shape[1]
+    c0 = x0.shape[1]
+    c1 = x1.shape[1] if x1 is not None else 0
+    call("tsd_conv3x3_wgrad", _chk(dy, BF16), _chk(x0, BF16), x1, c0, c1, n_img, H, W, stride, cout, _chk(dw_packed, F32))
+
+
+# ------------------------------------------------------------------ norms
+def gn_stats(x0, n_img, hw, eps, scratch, x1=None):
+    c0 = x0.shape[1]
+    c1 = x1.shape[1] if x1 is not None else 0
+    stats = torch.empty(n_img, 32, 2, device=x0.device, dtype=F32)
+    call("tsd_gn_stats", _chk(x0, BF16), x1, c0, c1, n_img, hw, f32(eps), scratch, stats)
+    return stats
+
+
+def gn_apply(x0, n_img, hw, stats, gamma, beta, silu, x1=None, drop_p=0.0, seed=0):
+    c0 = x0.shape[1]
+    c1 = x1.shape[1] if x1 is not None else 0
+    out = empty_bf16(n_img * hw, c0 + c1, like=x0)
+    call("tsd_gn_apply", x0, x1, c0, c1, n_img, hw, stats, gamma, beta, int(silu), f32(drop_p), u64(seed), out)
+    return out
+
+
+def gn_bwd(dy, x0, n_img, hw, stats, gamma, beta, silu, dgamma, dbeta, x1=None, drop_p=0.0, seed=0, radd=None):
+    c0 = x0.shape[1]
+    c1 = x1.shape[1] if x1 is not None else 0
+    ab = torch.empty(n_img, c0 + c1, 2, device=x0.device, dtype=F32)
+    dx0 = empty_bf16(n_img * hw, c0, like=x0)
+    dx1 = empty_bf16(n_img * hw, c1, like=x0) if c1 else None
+    call("tsd_gn_bwd", _chk(dy, BF16), x0, x1, c0, c1, n_img, hw, stats, gamma, beta, int(silu), f32(drop_p), u64(seed),
+         ab, radd, dx0, dx1, dgamma, dbeta)
+    return dx0, dx1
+
+
+def ln_fwd(x, gamma, beta, eps=1e-5):
+    M, C = x.shape
+    out = torch.empty_like(x)
+    call("tsd_ln_fwd", _chk(x, BF16), M, C, gamma, beta, f32(eps), out)
+    return out
+
+
+def ln_bwd(dy, x, gamma, dgamma, dbeta, eps=1e-5, radd=None):
+    M, C = x.shape
+    dx = torch.empty_like(x)
+    call("tsd_ln_bwd", _chk(dy, BF16), x, M, C, gamma, f32(eps), radd, dx, dgamma, dbeta)
+    return dx
+
+
+# ------------------------------------------------------------------ attention
+def attn_fwd(qkv, B, L, C, heads=8, need_lse=False):
+    out = empty_bf16(B * L, C, like=qkv)
+    lse = torch.empty(B, heads, L, device=qkv.device, dtype=F32) if need_lse else None
+    call("tsd_attn_fwd", _chk(qkv, BF16), out, lse, B, L, C, heads)
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, B, L, C, heads=8):
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, heads, L, device=qkv.device, dtype=F32)
+    call("tsd_attn_bwd", qkv, out, _chk(dout, BF16), lse, delta, dqkv, B, L, C, heads)
+    return dqkv
+
+
+# ------------------------------------------------------------------ elementwise
+def add(a, b):
+    out = torch.empty_like(a)
+    call("tsd_add_bf16", _chk(a, BF16), _chk(b, BF16), out, i64(a.numel()))
+    return out
+
+
+def geglu_fwd(h8):
+    M, H2 = h8.shape
+    out = empty_bf16(M, H2 // 2, like=h8)
+    call("tsd_geglu_fwd", h8, out, i64(M), H2 // 2)
+    return out
+
+
+def geglu_bwd(h8, dout):
+    dh8 = torch.empty_like(h8)
+    call("tsd_geglu_bwd", h8, _chk(dout, BF16), dh8, i64(h8.shape[0]), h8.shape[1] // 2)
+    return dh8
+
+
+def upsample2_fwd(x, n_img, H, W):
+    C = x.shape[1]
+    out = empty_bf16(n_img * 4 * H * W, C, like=x)
+    call("tsd_upsample2_fwd", x, out, n_img, H, W, C)
+    return out
+
+
+def upsample2_bwd(dout, n_img, H, W):
+    C = dout.shape[1]
+    din = empty_bf16(n_img * H * W, C, like=dout)
+    call("tsd_upsample2_bwd", _chk(dout, BF16), din, n_img, H, W, C)
+    return din
+
+
+def zero_stuff2(x, n_img, H, W):
+    C = x.shape[1]
+    out = empty_bf16(n_img * 4 * H * W, C, like=x)
+    call("tsd_zero_stuff2", _chk(x, BF16), out, n_img, H, W, C)
+    return out
+
+
+def colsum(x, n_samples, rows_per_sample):
+    """[n_samples*rows_per_sample, C] bf16 -> fp32 [n_samples, C]"""
+    C = x.shape[1]
+    out = torch.zeros(n_samples, C, device=x.device, dtype=F32)
+    call("tsd_colsum", _chk(x, BF16), n_samples, rows_per_sample, C, out)
+    return out
+
+
+def reduce_rows_into(src, dst):
+    """dst[c] += sum_n src[n][c]"""
+    call("tsd_reduce_rows_f32", _chk(src, F32), src.shape[0], src.shape[1], _chk(dst, F32))
+
+
+def bias_grad(dy, n_samples, rows_per_sample, db):
+    """db[c] += sum over all rows of dy; returns the per-sample sums."""
+    per = colsum(dy, n_samples, rows_per_sample)
+    reduce_rows_into(per, db)
+    return per
+
+
+# ------------------------------------------------------------------ conditioning (fp32, small)
+def small_linear(x, w, bias=None, silu_in=False):
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=x.device, dtype=F32)
+    call("tsd_small_linear_fwd", _chk(x, F32), _chk(w, F32), bias, out, M, N, K, int(silu_in))
+    return out
+
+
+def small_linear_bwd(dy, x, w, dx, dw, db, silu_in=False, accumulate_dx=False):
+    M, N = dy.shape
+    K = x.shape[1]
+    call("tsd_small_linear_bwd", _chk(dy, F32), _chk(x, F32), _chk(w, F32), dx, dw, db, M, N, K, int(silu_in),
+         int(accumulate_dx))
+
+
+def timestep_embedding(t, freqs):
+    M = t.shape[0]
+    half = freqs.shape[0]
+    emb = torch.empty(M, 2 * half, device=t.device, dtype=F32)
+    call("tsd_timestep_embedding", _chk(t, torch.int64), _chk(freqs, F32), emb, M, half)
+    return emb
+
+
+def embedding_fwd(idx, table):
+    M, D = idx.shape[0], table.shape[1]
+    out = torch.empty(M, D, device=table.device, dtype=F32)
+    call("tsd_embedding_fwd", _chk(idx, torch.int64), _chk(table, F32), out, M, D)
+    return out
+
+
+def embedding_bwd(idx, dy, dtable, padding_idx=0):
+    call("tsd_embedding_bwd", idx, _chk(dy, F32), _chk(dtable, F32), idx.shape[0], dtable.shape[1], padding_idx)
+
+
+# ------------------------------------------------------------------ image-side convs and DDPM process
+def head_conv_fwd(x, w, bias):
+    n, ci, H, W = x.shape
+    co = w.shape[0]
+    out = torch.empty(n * H * W, co, device=x.device, dtype=BF16)
+    call("tsd_head_conv_fwd", _chk(x, F32), _chk(w, F32), bias, out, n, ci, H, W, co)
+    return out
+
+
+def head_conv_wgrad(dy, x, dw, db):
+    n, ci, H, W = x.shape
+    call("tsd_head_conv_wgrad", _chk(dy, BF16), x, _chk(dw, F32), db, n, ci, H, W, dw.shape[0])
+
+
+def tail_conv_fwd(a, w, bias, n, H, W, out=None):
+    co = w.shape[0]
+    if out is None:
+        out = torch.empty(n, co, H, W, device=a.device, dtype=F32)
+    call("tsd_tail_conv_fwd", _chk(a, BF16), _chk(w, F32), bias, out, n, H, W, a.shape[1], co)
+    return out
+
+
+def tail_conv_bwd(dy, a, w, dw, db, n, H, W):
+    da = torch.empty_like(a)
+    call("tsd_tail_conv_bwd", _chk(dy, F32), a, w, da, dw, db, n, H, W, a.shape[1], w.shape[0])
+    return da
+
+
+def q_sample(x0, t, sqrt_ab, sqrt_1mab, seed=0, offset=0, noise=None):
+    n = x0.shape[0]
+    x_t = torch.empty_like(x0)
+    noise_out = torch.empty_like(x0) if noise is None else None
+    call("tsd_q_sample", _chk(x0, F32), _chk(t, torch.int64), sqrt_ab, sqrt_1mab, noise, u64(seed), u64(offset), x_t,
+         noise_out, n, i64(x0.numel() // n))
+    return x_t, (noise if noise is not None else noise_out)
+
+
+def mse_fwd(pred, noise):
+    loss = torch.empty_like(pred)
+    call("tsd_mse_fwd", _chk(pred, F32), _chk(noise, F32), loss, i64(pred.numel()))
+    return loss
+
+
+def mse_bwd(pred, noise, gout):
+    dpred = torch.empty_like(pred)
+    call("tsd_mse_bwd", pred, noise, _chk(gout, F32), dpred, i64(pred.numel()))
+    return dpred
+
+
+def sampler_update(x, eps, step_ptr, c1, c2, sigma, w, x_out, nan_flag, noise=None, seed=0, clip_last=True, dup=False):
+    total = eps.numel() // 2
+    call("tsd_sampler_update", _chk(x, F32), _chk(eps, F32), step_ptr, c1, c2, sigma, f32(w), noise, u64(seed), x_out,
+         nan_flag, i64(total), int(clip_last), int(dup))
+
+
+def step_add(step_ptr, delta):
+    call("tsd_step_add", step_ptr, delta)
+
+
+def gather_row(table, step_ptr, out):
+    call("tsd_gather_row_f32", _chk(table, F32), step_ptr, table.shape[1], out)
+
+
+# ------------------------------------------------------------------ weight packing / optimiser
+def pack_linear(w, geglu=False):
+    rows = w.shape[0]
+    cols = w.numel() // rows
+    out = torch.empty(rows, cols, device=w.device, dtype=BF16)
+    call("tsd_pack_linear", _chk(w, F32), out, rows, cols, int(geglu))
+    return out
+
+
+def pack_geglu_bias(b):
+    out = torch.empty_like(b)
+    call("tsd_pack_geglu_bias", _chk(b, F32), out, b.shape[0])
+    return out
+
+
+def pack_conv3x3(w):
+    co, ci = w.shape[:2]
+    out = torch.empty(co, 9 * ci, device=w.device, dtype=BF16)
+    call("tsd_pack_conv3x3", _chk(w, F32), out, co, ci)
+    return out
+
+
+def unpack_conv3x3_grad(src_packed, dst_oihw):
+    co, ci = dst_oihw.shape[:2]
+    call("tsd_unpack_conv3x3_grad", _chk(src_packed, F32), _chk(dst_oihw, F32), co, ci)
+
+
+def sumsq(g, out):
+    call("tsd_sumsq_f32", _chk(g, F32), i64(g.numel()), out)
+
+
+def adamw_clip(p, g, m, v, lr, beta1, beta2, eps, wd, step, max_norm, sumsq_buf, write_clipped_grad=True):
+    call("tsd_adamw_clip", p, g, m, v, i64(p.numel()), f32(lr), f32(beta1), f32(beta2), f32(eps), f32(wd), int(step),
+         f32(max_norm), sumsq_buf, int(write_clipped_grad))

@@ -48,12 +48,12 @@ int tsd_gemm_fwd(void* stream, const void* a0, const void* a1, int c0, int c1, i
                  int epi, void* d);
 
 /* 3x3 convolution, padding 1, stride 1 or 2, NHWC bf16, implicit GEMM (9 shifted TMA boxes, OOB
- * zero fill = padding).  x = channel concat of x0 (c0) and x1 (c1).  row_bias is per image
- * ([n_img][cout], the time-embedding bias of diffusion.py:113).
+ * zero fill = padding).  x = channel concat of x0 (c0) and x1 (c1).  row_bias[row / rows_per_sample][cout]
+ * is the time-embedding bias of diffusion.py:113 (rows_per_sample <= 0 means one row per image).
  * Replaces nn.Conv2d(k=3) at diffusion.py:92,98,164,210,214,218. */
 int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int H, int W,
                     int stride, const void* w, int cout, const float* bias, const float* row_bias,
-                    const void* residual, void* d);
+                    int rows_per_sample, const void* residual, void* d);
 
 /* dx[M][K] = dy[M][N] * w[N][K] + residual[M][K]   (autograd of the ops above; reference relies on
  * torch autograd, 02_train_direct.py:71) */

@@ -85,7 +85,7 @@ def test_conv3x3_fwd(cuda, n, H, W, c0, c1, cout, stride):
     Ho, Wo = H // stride, W // stride
     res = _bf(torch.randn(n, Ho, Wo, cout, device=cuda, generator=g))
     d = torch.empty(n, Ho, Wo, cout, device=cuda, dtype=torch.bfloat16)
-    _lib.call("tsd_conv3x3_fwd", x0, x1, c0, c1, n, H, W, stride, pack_conv(w), cout, bias, rb, res, d)
+    _lib.call("tsd_conv3x3_fwd", x0, x1, c0, c1, n, H, W, stride, pack_conv(w), cout, bias, rb, 0, res, d)
     ref = F.conv2d(xh.float().permute(0, 3, 1, 2), _bf(w).float(), bias, stride=stride, padding=1)
     ref = ref.permute(0, 2, 3, 1) + rb[:, None, None, :] + res.float()
     torch.cuda.synchronize()
