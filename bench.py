@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the tiny-SD DDPM hot path on B200 (contract: see the task's bench.py section).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference path
+
+Workload (BASELINE.json configs[1]): one DDPM training step of the tiny UNet on synthetic 3x64x64
+images, batch 256 per GPU, bf16 activations / fp32 accumulate, dropout 0.1, AdamW + grad clip -- the
+reference's step body 02_train_direct.py:64-74.  A "step" = zero_grad, trainer (q_sample + UNet forward
++ noise-MSE), backward, [gradient all-reduce], clip + AdamW.  The same line also carries the sampling
+throughput (DDPM 64x64 images/s at T=1000, CFG w=1.8) under "sampling".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(channel_img=3, channel_multy=[1, 2, 2, 2], channel_base=128, num_class=3, dropout=0.1,
+           T=1000, beta_1=0.0015, beta_T=0.0195, w=1.8, lr=2e-6, weight_decay=1e-5, grad_clip=1.0, img=64)
+FWD_GF_PER_SAMPLE = 62.60  # necessary forward work, SURVEY 8(d)
+TRAIN_GF_PER_SAMPLE = 187.8
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for i, nm in enumerate(names):
+                    if r[2 + i].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_train_sample(n_img, steps, warmup, threads):
+    """The reference path (oracle port, torch CPU fp32) on a bounded sample: `n_img` images per step."""
+    from oracle import ref_unet as R
+    torch.set_num_threads(threads)
+    sd = R.init_state_dict(0, CFG["channel_img"], CFG["channel_multy"], CFG["channel_base"], CFG["num_class"])
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=CFG["lr"], weight_decay=CFG["weight_decay"])
+    sched = R.make_schedule(CFG["beta_1"], CFG["beta_T"], CFG["T"])
+    g = torch.Generator().manual_seed(1234)
+    x0 = torch.randn(n_img, CFG["channel_img"], CFG["img"], CFG["img"], generator=g)
+    y = torch.randint(1, CFG["num_class"] + 1, (n_img,), generator=g)
+
+    def step():
+        opt.zero_grad()
+        t = torch.randint(CFG["T"], (n_img,))
+        noise = torch.randn_like(x0)
+        loss = R.trainer_loss(params, sched, x0, y, t, noise, CFG["channel_multy"], CFG["channel_base"],
+                              use_sdpa=True).sum() / n_img ** 2
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), CFG["grad_clip"])
+        opt.step()
+        return loss.item()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n_img / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_img = 2
+    steps = max(1, min(args.steps, 3))
+    warmup = 1 if args.warmup > 0 else 0
+    val, dt = cpu_train_sample(n_img, steps, warmup, threads)
+    line = {
+        "impl": "reference", "metric": "train_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "tiny UNet DDPM training step 3x64x64 (reference CPU path, oracle port), "
+                               f"bounded sample: batch {n_img} per step", "global_batch": n_img, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} training step(s) of batch {n_img} (fwd+bwd+clip+AdamW), torch CPU fp32"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from from_ddpm_to_stable_diffusion_b200 import Diffusion, SamplerDDPM, TrainerDDPM, _lib
+    from from_ddpm_to_stable_diffusion_b200.optim import FusedClipAdamW
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(0)
+    model = Diffusion(CFG["channel_img"], CFG["channel_multy"], CFG["channel_base"], num_class=CFG["num_class"],
+                      dropout=CFG["dropout"]).to(dev).train()
+    trainer = TrainerDDPM(model, CFG["beta_1"], CFG["beta_T"], CFG["T"]).to(dev)
+    opt = FusedClipAdamW(model, lr=CFG["lr"], weight_decay=CFG["weight_decay"], max_norm=CFG["grad_clip"])
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, CFG["channel_img"], CFG["img"], CFG["img"], generator=g).pin_memory()
+    y_host = torch.randint(1, CFG["num_class"] + 1, (B,), generator=g).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    global_b = B * world
+
+    def step(x, y):
+        opt.zero_grad()
+        loss = trainer(x, y).sum() / global_b ** 2  # reference normalisation with the GLOBAL batch (02_train_direct.py:70)
+        loss.backward()
+        if world > 1:
+            opt.all_reduce_grads()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    lib = _lib.lib()
+    lib.tsd_launch_count.restype = __import__("ctypes").c_ulonglong
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    clocks = ClockSampler(local)
+    clocks.start()
+    n0 = lib.tsd_launch_count()
+    ms = timed(lambda: step(x_dev, y_dev), args.steps)
+    launches = lib.tsd_launch_count() - n0
+    clk = clocks.stop()
+    ms_per_step = ms / args.steps
+    value = global_b / (ms_per_step / 1e3)
+
+    # end-to-end: pinned host inputs -> H2D every step, loss read back every step (02_train_direct.py:66-74)
+    def e2e_step():
+        x = x_host.to(dev, non_blocking=True)
+        y = y_host.to(dev, non_blocking=True)
+        return step(x, y).item()
+
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_val = global_b / (e2e_ms / 1e3)
+
+    # roofline of the dominant kernel family: the dense contractions (tensor pipe).  Measured live with CUDA
+    # events around one isolated launch set is not separable inside the step, so the figure reported here is
+    # the whole step's necessary FLOPs over the step time (lower bound on the GEMM kernels' own rate).
+    hbm, tf, how = peaks()
+    ach_tf = TRAIN_GF_PER_SAMPLE * B / (ms_per_step / 1e3) / 1e3
+    roof = {"bound": "tensor", "achieved": ach_tf, "peak": tf, "unit": "TFLOP/s", "frac": ach_tf / tf, "traffic": None,
+            "peak_source": how + " (bf16_tflops_sustained)",
+            "note": "necessary train FLOPs per GPU (187.8 GF/sample) / step time; per-kernel figures in profiles/"}
+
+    # sampling throughput (same model, eval mode): DDPM 64x64 images/s at T=1000, CFG w=1.8, 2 forwards per step
+    sampling = None
+    if args.sample_steps > 0:
+        model.eval()
+        Bs = args.sample_batch
+        sampler = SamplerDDPM(model, CFG["beta_1"], CFG["beta_T"], CFG["T"], w=CFG["w"]).to(dev)
+        xT = torch.randn(Bs, CFG["channel_img"], CFG["img"], CFG["img"], device=dev)
+        ys = torch.randint(1, CFG["num_class"] + 1, (Bs,), device=dev)
+        k = args.sample_steps
+        sampler(xT, ys, steps=range(CFG["T"] - 1, CFG["T"] - 1 - 4, -1))  # capture + warm-up
+        s_ms = timed(lambda: sampler(xT, ys, steps=range(CFG["T"] - 1, CFG["T"] - 1 - k, -1)), 1) / k
+        sampling = {"images_per_s": Bs * world / (s_ms / 1e3 * CFG["T"]), "ms_per_reverse_step": s_ms,
+                    "batch_per_gpu": Bs, "T": CFG["T"], "w": CFG["w"], "timed_reverse_steps": k,
+                    "tflops": 2 * FWD_GF_PER_SAMPLE * Bs / (s_ms / 1e3) / 1e3}
+        model.train()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_train_sample(2, 1, 1, threads)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": "1 warm-up + 1 timed training step of batch 2 (fwd+bwd+clip+AdamW), oracle port on torch CPU fp32"}
+
+    if rank == 0:
+        line = {
+            "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"tiny UNet DDPM training step bf16 3x64x64, batch {B} per GPU (BASELINE configs[1])",
+                       "global_batch": global_b, "parallelism": f"dp{world}", "dropout": CFG["dropout"],
+                       "optimizer": "clip_grad_norm(1.0)+AdamW fused", "l2": "inputs larger than L2 (activations >> 126 MB)"},
+            "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "sampling": sampling,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="training batch per GPU")
+    ap.add_argument("--sample-batch", type=int, default=256, help="images per GPU for the sampling figure")
+    ap.add_argument("--sample-steps", type=int, default=8, help="timed reverse steps (0 = skip sampling figure)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

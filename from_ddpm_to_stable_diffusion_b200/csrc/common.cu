@@ -16,6 +16,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return 0;
   set_error("CUDA error %s: %s (%s)", cudaGetErrorName(e), cudaGetErrorString(e), what);
@@ -89,3 +92,5 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, u
 
 extern "C" const char* tsd_last_error() { return tsd::g_err; }
 extern "C" int tsd_abi_version() { return 1; }
+// number of kernel launches issued by this library so far (host-side counter)
+extern "C" unsigned long long tsd_launch_count() { return tsd::g_launches; }

@@ -28,7 +28,12 @@ int check_cuda(cudaError_t e, const char* what);
     if (tsd::check_cuda((expr), #expr)) return 2;        \
   } while (0)
 
-#define TSD_LAUNCH_CHECK() TSD_CUDA(cudaGetLastError())
+void count_launch();
+#define TSD_LAUNCH_CHECK()          \
+  do {                              \
+    tsd::count_launch();            \
+    TSD_CUDA(cudaGetLastError());   \
+  } while (0)
 
 int num_sms();
 

@@ -1,0 +1,65 @@
+"""Caller-side step body of the reference training loop as two fused passes.
+
+Reference: 02_train_direct.py:72-73 -- ``clip_grad_norm_(params, grad_clip)`` then ``AdamW.step()``
+(torch defaults: betas (0.9, 0.999), eps 1e-8; lr and weight_decay as given at :52).  Parameters and
+gradients live in flat fp32 buffers, so the global norm is one reduction kernel and clip + AdamW one
+sweep; for data-parallel training the flat gradient buffer is what gets all-reduced (NCCL, sum).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class FusedClipAdamW:
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=0.0):
+        self.model = model
+        self.engine = model._engine
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.param_groups = [{"lr": lr, "weight_decay": weight_decay, "params": list(model.parameters())}]
+        self.step_count = 0
+        self._flatten()
+
+    def _flatten(self):
+        """Re-home every parameter into one flat fp32 buffer (same 16-byte-aligned offsets as the grad buffer)."""
+        P = self.engine.params()
+        plist = list(P.values())
+        dev = plist[0].device
+        total = sum((p.numel() + 3) // 4 * 4 for p in plist)
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for p in plist:
+            v = flat[off:off + p.numel()].view_as(p)
+            v.copy_(p.data)
+            p.data = v
+            off += (p.numel() + 3) // 4 * 4
+        self.flat_p = flat
+        self.m = torch.zeros_like(flat)
+        self.v = torch.zeros_like(flat)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.engine.invalidate()
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.model.parameters():
+            p.grad = None
+
+    def all_reduce_grads(self, group=None):
+        """Data-parallel exchange: sum the flat gradient buffer over ranks (NCCL over NVLink)."""
+        g = self.engine._flat_grad
+        if g is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+
+    def grad_norm(self):
+        return float(self.sumsq.sqrt().item())
+
+    def step(self):
+        g = self.engine._flat_grad
+        if g is None:
+            raise RuntimeError("FusedClipAdamW.step() called before any backward pass")
+        self.step_count += 1
+        lr = self.param_groups[0]["lr"]
+        self.sumsq.zero_()
+        ops.sumsq(g, self.sumsq)
+        ops.adamw_clip(self.flat_p, g, self.m, self.v, lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                       self.step_count, self.max_norm, self.sumsq)
+        self.engine.bump()  # parameters changed through raw pointers: packed bf16 copies are stale

@@ -201,7 +201,7 @@ def _res_block(sd, key, x, temb, drop_mask: Optional[Tensor], p_drop: float):
     return h + x
 
 
-def _attn_block(sd, key, x, ctx, n_head: int = 8):
+def _attn_block(sd, key, x, ctx, n_head: int = 8, use_sdpa: bool = False):
     """diffusion.py:138-158 (SelfAttention :46-58, CrossAttention :69-82)"""
     res_long = x
     n, c, hh, ww = x.shape
@@ -217,7 +217,10 @@ def _attn_block(sd, key, x, ctx, n_head: int = 8):
     q = q.reshape(n, L, n_head, dh).transpose(1, 2)
     k = k.reshape(n, L, n_head, dh).transpose(1, 2)
     v = v.reshape(n, L, n_head, dh).transpose(1, 2)
-    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1) @ v
+    if use_sdpa:  # the reference's own call (diffusion.py:55); used for the timed CPU baseline
+        att = F.scaled_dot_product_attention(q, k, v)
+    else:
+        att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1) @ v
     att = att.transpose(1, 2).reshape(n, L, c)
     h = F.linear(att, sd[key + ".atten_1.1.out_proj.weight"], sd[key + ".atten_1.1.out_proj.bias"]) + h
     # cross attention: ctx [n, d_context] is viewed as ONE key/value token per head, so the softmax
@@ -240,7 +243,8 @@ def _attn_block(sd, key, x, ctx, n_head: int = 8):
 
 def unet_forward(sd: Dict[str, Tensor], x: Tensor, t: Tensor, labels: Tensor, channel_multy: List[int],
                  channel_base: int = 128, dropout: float = 0.0,
-                 drop_masks: Optional[Dict[str, Tensor]] = None, taps: Optional[Dict[str, Tensor]] = None):
+                 drop_masks: Optional[Dict[str, Tensor]] = None, taps: Optional[Dict[str, Tensor]] = None,
+                 use_sdpa: bool = False):
     """eps = Diffusion.forward(x, t, labels)  (diffusion.py:263-276), NCHW in / NCHW out.
 
     drop_masks: optional {res-block key: keep mask [n, c, h, w]} to replay a training-mode dropout
@@ -250,7 +254,7 @@ def unet_forward(sd: Dict[str, Tensor], x: Tensor, t: Tensor, labels: Tensor, ch
     channel_img = sd["tail.2.weight"].shape[0]
     enc, mid, dec, _ = stage_table(channel_img, channel_multy, channel_base)
     x = x.to(dtype)
-    emb = sd["label_embedding.0.weight"][labels]
+    emb = F.embedding(labels, sd["label_embedding.0.weight"], padding_idx=0)  # row 0 gets no gradient (:197)
     ctx = _mlp(sd, "label_embedding.1", "label_embedding.3", emb)
     temb = _mlp(sd, "time_embedding.mlp.0", "time_embedding.mlp.2",
                 timestep_embedding(t, sd["time_embedding.mlp.0.weight"].shape[1], dtype))
@@ -266,7 +270,7 @@ def unet_forward(sd: Dict[str, Tensor], x: Tensor, t: Tensor, labels: Tensor, ch
             mask = drop_masks.get(key) if (drop_masks is not None and block[4]) else None
             x = _res_block(sd, key, x, temb, mask, dropout)
         else:
-            x = _attn_block(sd, key, x, ctx)
+            x = _attn_block(sd, key, x, ctx, use_sdpa=use_sdpa)
         if taps is not None:
             taps[key] = x
         return x
@@ -324,22 +328,23 @@ def q_sample(sched, x0: Tensor, t: Tensor, noise: Tensor) -> Tensor:
             + extract(sched["sqrt_one_minus_alphas_bar"], t, x0.shape) * noise)
 
 
-def trainer_loss(sd, sched, x0, labels, t, noise, channel_multy, channel_base=128, dropout=0.0, drop_masks=None):
+def trainer_loss(sd, sched, x0, labels, t, noise, channel_multy, channel_base=128, dropout=0.0, drop_masks=None,
+                 use_sdpa=False):
     """utils.py:111-119 with t and noise injected: returns the un-reduced MSE [B,C,H,W]."""
     x_t = q_sample(sched, x0, t, noise)
-    pred = unet_forward(sd, x_t, t, labels, channel_multy, channel_base, dropout, drop_masks)
+    pred = unet_forward(sd, x_t, t, labels, channel_multy, channel_base, dropout, drop_masks, use_sdpa=use_sdpa)
     return (pred - noise.to(pred.dtype)) ** 2
 
 
 def sampler_step(sd, sched, x_t, labels, time_step: int, noise: Optional[Tensor], w: float,
-                 channel_multy, channel_base=128):
+                 channel_multy, channel_base=128, use_sdpa=False):
     """One iteration of utils.py:159-166 (two forwards, CFG combine, posterior mean, + sigma*z).
     Returns (x_{t-1}, eps_cond, eps_uncond)."""
     B = x_t.shape[0]
     t = torch.full((B,), time_step, dtype=torch.long)
     var = extract(sampler_variance(sched), t, x_t.shape)
-    eps_c = unet_forward(sd, x_t, t, labels, channel_multy, channel_base).float()
-    eps_u = unet_forward(sd, x_t, t, torch.zeros_like(labels), channel_multy, channel_base).float()
+    eps_c = unet_forward(sd, x_t, t, labels, channel_multy, channel_base, use_sdpa=use_sdpa).float()
+    eps_u = unet_forward(sd, x_t, t, torch.zeros_like(labels), channel_multy, channel_base, use_sdpa=use_sdpa).float()
     eps = (1.0 + w) * eps_c - w * eps_u
     mean = extract(sched["coeff1"], t, x_t.shape) * x_t - extract(sched["coeff2"], t, x_t.shape) * eps
     z = noise if time_step > 0 else 0
