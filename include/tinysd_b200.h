@@ -69,6 +69,118 @@ int tsd_gemm_wgrad(void* stream, const void* dy, const void* x0, const void* x1,
 int tsd_conv3x3_wgrad(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1, int n_img,
                       int H, int W, int stride, int cout, float* dw);
 
+/* ------------------------------------------------------------------------------------------
+ * Normalisation (HBM-bound, vectorised, fp32 statistics).
+ * ------------------------------------------------------------------------------------------ */
+
+/* GroupNorm(32 groups) statistics of x = cat(x0 [.., c0], x1 [.., c1]) per image: stats[n][32][2] =
+ * (mean, rstd).  scratch: fp32 [n_img*64], all zero on entry, left all zero on exit.
+ * nn.GroupNorm at diffusion.py:90,95 (eps 1e-5), :122 (eps 1e-6), :258. */
+int tsd_gn_stats(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int hw, float eps,
+                 float* scratch, float* stats);
+/* out = dropout_p(silu?(gamma * (x - mean) * rstd + beta)), bf16 [n*hw][c0+c1].  The dropout mask is a
+ * counter-based Philox function of (seed, element index); nn.SiLU / nn.Dropout at diffusion.py:91,96-97. */
+int tsd_gn_apply(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int hw, const float* stats,
+                 const float* gamma, const float* beta, int act_silu, float drop_p, uint64_t seed, void* out);
+/* Backward of tsd_gn_apply (+ optional residual add `radd` [n*hw][c0+c1]); dx is written split as dx0 [.., c0],
+ * dx1 [.., c1]; dgamma/dbeta (fp32 [c0+c1]) are accumulated.  ab: fp32 scratch [n_img][c0+c1][2]. */
+int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1, int n_img, int hw,
+               const float* stats, const float* gamma, const float* beta, int act_silu, float drop_p, uint64_t seed,
+               float* ab, const void* radd, void* dx0, void* dx1, float* dgamma, float* dbeta);
+/* LayerNorm over C in {128, 256, 512} per token row; nn.LayerNorm at diffusion.py:127,132 */
+int tsd_ln_fwd(void* stream, const void* x, int M, int C, const float* gamma, const float* beta, float eps, void* out);
+int tsd_ln_bwd(void* stream, const void* dy, const void* x, int M, int C, const float* gamma, float eps,
+               const void* radd, void* dx, float* dgamma, float* dbeta);
+
+/* ------------------------------------------------------------------------------------------
+ * Self-attention, head_dim 16 / 32 (SelfAttention.forward, diffusion.py:46-58).
+ * qkv bf16 [B*L][3C] (q | k | v, head h = columns [h*dh, (h+1)*dh)); out bf16 [B*L][C];
+ * lse2 fp32 [B][heads][L] = log2-domain logsumexp (NULL when no backward is needed).
+ * ------------------------------------------------------------------------------------------ */
+int tsd_attn_fwd(void* stream, const void* qkv, void* out, float* lse2, int B, int L, int C, int heads);
+/* dqkv [B*L][3C] receives (dq | dk | dv); delta: fp32 scratch [B][heads][L] */
+int tsd_attn_bwd(void* stream, const void* qkv, const void* out, const void* dout, const float* lse2, float* delta,
+                 void* dqkv, int B, int L, int C, int heads);
+
+/* ------------------------------------------------------------------------------------------
+ * Elementwise / small reductions on bf16 channels-last tensors.
+ * ------------------------------------------------------------------------------------------ */
+int tsd_add_bf16(void* stream, const void* a, const void* b, void* out, int64_t numel);
+/* GEGLU: out[M][H] = h8[:, :H] * gelu(h8[:, H:]) (exact erf GELU; diffusion.py:151-152) and its backward */
+int tsd_geglu_fwd(void* stream, const void* h8, void* out, int64_t M, int H);
+int tsd_geglu_bwd(void* stream, const void* h8, const void* dout, void* dh8, int64_t M, int H);
+/* nearest x2 upsample (F.interpolate, diffusion.py:167) and its adjoint (2x2 block sums) */
+int tsd_upsample2_fwd(void* stream, const void* in, void* out, int n_img, int H, int W, int C);
+int tsd_upsample2_bwd(void* stream, const void* dout, void* din, int n_img, int H, int W, int C);
+/* zero-stuffing [n][H][W][C] -> [n][2H][2W][C]: turns the stride-2 conv data gradient into a stride-1 one */
+int tsd_zero_stuff2(void* stream, const void* in, void* out, int n_img, int H, int W, int C);
+/* out[n][C] += column sums of sample n's rows (bias gradients, time-bias gradient); out[C] += sum_n in[n][C] */
+int tsd_colsum(void* stream, const void* x, int n_samples, int rows_per_sample, int C, float* out);
+int tsd_reduce_rows_f32(void* stream, const float* in, int n_rows, int C, float* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Conditioning path, fp32 (TimestepEmbedder diffusion.py:13-37, label_embedding :196-201, linear_time
+ * :101-104, degenerate CrossAttention :61-82).  Weights in the reference's [out][in] fp32 layout.
+ * ------------------------------------------------------------------------------------------ */
+/* out[M][N] = f(x)[M][K] * w[N][K]^T + bias, f = SiLU when silu_in */
+int tsd_small_linear_fwd(void* stream, const float* x, const float* w, const float* bias, float* out, int M, int N,
+                         int K, int silu_in);
+/* dx (=|+=) f'(x) * (dy * w); dw += dy^T f(x); db += colsum(dy).  dx, dw, db may each be NULL. */
+int tsd_small_linear_bwd(void* stream, const float* dy, const float* x, const float* w, float* dx, float* dw,
+                         float* db, int M, int N, int K, int silu_in, int accumulate_dx);
+/* emb[m] = [cos(t_m * freqs), sin(t_m * freqs)] (cos first, diffusion.py:28); freqs built by the host shell */
+int tsd_timestep_embedding(void* stream, const int64_t* t, const float* freqs, float* emb, int M, int half);
+int tsd_embedding_fwd(void* stream, const int64_t* idx, const float* table, float* out, int M, int D);
+int tsd_embedding_bwd(void* stream, const int64_t* idx, const float* dy, float* dtable, int M, int D, int padding_idx);
+
+/* ------------------------------------------------------------------------------------------
+ * Image-side convolutions (fp32 NCHW image <-> bf16 NHWC features) and the DDPM process.
+ * ------------------------------------------------------------------------------------------ */
+/* head conv channel_img(<=4) -> co (diffusion.py:206); weights OIHW fp32 */
+int tsd_head_conv_fwd(void* stream, const float* x, const float* w, const float* bias, void* out, int n_img, int ci,
+                      int H, int W, int co);
+int tsd_head_conv_wgrad(void* stream, const void* dy, const float* x, float* dw, float* db, int n_img, int ci, int H,
+                        int W, int co);
+/* tail conv 128 -> co in {3,4} on the GroupNorm+SiLU'ed features (diffusion.py:260); out fp32 NCHW */
+int tsd_tail_conv_fwd(void* stream, const void* a, const float* w, const float* bias, float* out, int n_img, int H,
+                      int W, int c_in, int co);
+int tsd_tail_conv_bwd(void* stream, const float* dy, const void* a, const float* w, void* da, float* dw, float* db,
+                      int n_img, int H, int W, int c_in, int co);
+/* x_t = sqrt_ab[t_n] x0 + sqrt_1mab[t_n] noise (utils.py:115-116); noise_in NULL => Philox N(0,1), written to
+ * noise_out.  Tables are the fp32 casts of the reference's fp64 buffers (what extract() returns). */
+int tsd_q_sample(void* stream, const float* x0, const int64_t* t, const float* sqrt_ab, const float* sqrt_1mab,
+                 const float* noise_in, uint64_t seed, uint64_t offset, float* x_t, float* noise_out, int n_img,
+                 int64_t per_sample);
+/* loss = (pred - noise)^2 un-reduced (utils.py:118); dpred = 2 (pred - noise) gout */
+int tsd_mse_fwd(void* stream, const float* pred, const float* noise, float* loss, int64_t total);
+int tsd_mse_bwd(void* stream, const float* pred, const float* noise, const float* gout, float* dpred, int64_t total);
+/* One reverse step (utils.py:149-166): eps = (1+w) eps[0:total] - w eps[total:2 total]; x' = c1[t] x - c2[t] eps +
+ * sigma[t] z; z = 0 at t = 0, Philox keyed by (seed, t) unless noise_in; t = *step_ptr (device memory, so a CUDA
+ * graph can replay the launch); NaN sets *nan_flag (utils.py:167); clip_last clamps to [-1,1] at t = 0 (:171);
+ * dup also writes x' to x_out[total:2 total] (the unconditional copy of the 2B batch). */
+int tsd_sampler_update(void* stream, const float* x, const float* eps, const int* step_ptr, const float* c1,
+                       const float* c2, const float* sigma, float w, const float* noise_in, uint64_t seed,
+                       float* x_out, int* nan_flag, int64_t total, int clip_last, int dup);
+int tsd_step_add(void* stream, int* step_ptr, int delta);
+/* out[0:len] = table[*step_ptr][0:len] (per-step time-embedding rows, indexed on the device) */
+int tsd_gather_row_f32(void* stream, const float* table, const int* step_ptr, int len, float* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight packing and the caller-side optimiser step (02_train_direct.py:72-73).
+ * ------------------------------------------------------------------------------------------ */
+int tsd_pack_linear(void* stream, const float* src, void* dst, int rows, int cols, int geglu);
+int tsd_pack_geglu_bias(void* stream, const float* src, float* dst, int rows);
+int tsd_pack_conv3x3(void* stream, const float* src, void* dst, int co, int ci);          /* OIHW -> [co][tap][ci] */
+int tsd_unpack_conv3x3_grad(void* stream, const float* src, float* dst, int co, int ci);  /* dst(OIHW) += src */
+/* out[0] += sum g^2 */
+int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out);
+/* clip_grad_norm_(max_norm) + torch.optim.AdamW step over flat fp32 buffers; sumsq = squared global grad norm */
+int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float wd, int step, float max_norm, const float* sumsq, int write_clipped_grad);
+int tsd_scale_f32(void* stream, float* x, int64_t n, float s);
+/* number of kernel launches issued by this library so far (host-side counter, for bench.py's gpu_launches) */
+unsigned long long tsd_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif
