@@ -43,12 +43,35 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+PROFILE = bool(int(os.environ.get("TSD_PROFILE", "0")))
+_prof = []
+
+
 def call(name, *args):
     """Call `int name(void* stream, ...)` on the current torch CUDA stream."""
     fn = getattr(lib(), name)
+    if PROFILE:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = fn(stream_ptr(), *[_as_arg(a) for a in args])
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib().tsd_last_error().decode()}")
+    if PROFILE:
+        e1.record()
+        _prof.append((name, tuple(a for a in args if isinstance(a, int) and not isinstance(a, bool)), e0, e1))
+
+
+def profile_report(reset=True):
+    """Per (entry point, integer arguments) device time, from CUDA events (TSD_PROFILE=1 only)."""
+    torch.cuda.synchronize()
+    agg = {}
+    for name, key, e0, e1 in _prof:
+        t = e0.elapsed_time(e1)
+        n, tot = agg.get((name, key), (0, 0.0))
+        agg[(name, key)] = (n + 1, tot + t)
+    if reset:
+        _prof.clear()
+    return agg
 
 
 def call_nostream(name, *args):
