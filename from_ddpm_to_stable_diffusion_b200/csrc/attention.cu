@@ -11,6 +11,7 @@
 // Layout: qkv bf16 [B*L][3C]; out bf16 [B*L][C]; lse2 fp32 [B][heads][L] (log2-domain logsumexp).
 #include "../../include/tinysd_b200.h"
 #include "common.cuh"
+#include <cstdlib>
 
 using namespace tsd;
 
@@ -82,17 +83,35 @@ __device__ __forceinline__ void load_tile_async(uint32_t smem, const bf16* base,
   }
 }
 
+// Same, for an arbitrary number of rows (a stage of several 64-key tiles).
+template <int DH>
+__device__ __forceinline__ void load_rows_async(uint32_t smem, const bf16* base, size_t ld, int row0, int row_limit,
+                                                int nrows) {
+  constexpr int RS = DH * 2 + 16;
+  constexpr int CH = DH / 8;
+  for (int i = threadIdx.x; i < nrows * CH; i += blockDim.x) {
+    const int r = i / CH, c = i - r * CH;
+    const int row = row0 + r;
+    const bool ok = row < row_limit;
+    cp_async16(smem + r * RS + c * 16, base + (size_t)(ok ? row : 0) * ld + c * 8, ok ? 16 : 0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Forward.  grid = (ceil(L / (warps*16*MT)), heads, B); each warp owns MT m-tiles of 16 query rows.
+// K/V arrive in stages of NSUB*64 keys (cp.async, double buffered): one barrier pair per stage, so the
+// warps of a CTA drift apart inside a stage and MUFU / FMA / tensor work of different warps overlap.
+// Softmax: running max on the raw scores, p = ex2(fma(s, c, -m*c)) with c = log2(e)/sqrt(dh).
 // ------------------------------------------------------------------------------------------
-template <int DH, int MT>
+template <int DH, int MT, int NSUB>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                        float* __restrict__ lse2, int L, int C, float scale_log2) {
   constexpr int RS = DH * 2 + 16;
   constexpr int KT = DH / 16;
   constexpr int ND = DH / 8;
-  __shared__ __align__(16) uint8_t sK[2][KV_TILE * RS];
-  __shared__ __align__(16) uint8_t sV[2][KV_TILE * RS];
+  constexpr int STAGE_KEYS = KV_TILE * NSUB;
+  constexpr int STAGE_BYTES = STAGE_KEYS * RS;  // per operand
+  extern __shared__ __align__(16) uint8_t smem_dyn[];  // [2][K | V]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
@@ -101,6 +120,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ 
   const bf16* kbase = qbase + C;
   const bf16* vbase = qbase + 2 * C;
   const int q0 = (blockIdx.x * nwarps + warp) * 16 * MT;
+  const uint32_t smem0 = smem_u32_(smem_dyn);
 
   uint32_t qf[MT][KT][4];
 #pragma unroll
@@ -118,93 +138,107 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ 
     for (int j = 0; j < ND; ++j) oacc[mt][j][0] = oacc[mt][j][1] = oacc[mt][j][2] = oacc[mt][j][3] = 0.f;
   }
 
-  const int ntiles = (L + KV_TILE - 1) / KV_TILE;
-  load_tile_async<DH>(smem_u32_(sK[0]), kbase, ld, 0, L);
-  load_tile_async<DH>(smem_u32_(sV[0]), vbase, ld, 0, L);
+  const int nstages = (L + STAGE_KEYS - 1) / STAGE_KEYS;
+  load_rows_async<DH>(smem0, kbase, ld, 0, L, STAGE_KEYS);
+  load_rows_async<DH>(smem0 + STAGE_BYTES, vbase, ld, 0, L, STAGE_KEYS);
   cp_async_commit();
 
-  for (int it = 0; it < ntiles; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < ntiles) {
-      load_tile_async<DH>(smem_u32_(sK[buf ^ 1]), kbase, ld, (it + 1) * KV_TILE, L);
-      load_tile_async<DH>(smem_u32_(sV[buf ^ 1]), vbase, ld, (it + 1) * KV_TILE, L);
+  for (int st = 0; st < nstages; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nstages) {
+      const uint32_t nb = smem0 + (buf ^ 1) * 2 * STAGE_BYTES;
+      load_rows_async<DH>(nb, kbase, ld, (st + 1) * STAGE_KEYS, L, STAGE_KEYS);
+      load_rows_async<DH>(nb + STAGE_BYTES, vbase, ld, (st + 1) * STAGE_KEYS, L, STAGE_KEYS);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
-    const uint32_t kS = smem_u32_(sK[buf]), vS = smem_u32_(sV[buf]);
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+      const int key0 = st * STAGE_KEYS + sub * KV_TILE;
+      if (key0 >= L) break;
+      const uint32_t kS = smem0 + buf * 2 * STAGE_BYTES + sub * KV_TILE * RS;
+      const uint32_t vS = kS + STAGE_BYTES;
 
-    float sacc[MT][8][4];
+      float sacc[MT][8][4];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sacc[mt][j][0] = sacc[mt][j][1] = sacc[mt][j][2] = sacc[mt][j][3] = 0.f;
+        for (int j = 0; j < 8; ++j) sacc[mt][j][0] = sacc[mt][j][1] = sacc[mt][j][2] = sacc[mt][j][3] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < KT; ++kk)
+      for (int kk = 0; kk < KT; ++kk)
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        uint32_t r[4];
-        ldsm_nt(r, kS, RS, 16 * jp, 16 * kk, lane);
+        for (int jp = 0; jp < 4; ++jp) {
+          uint32_t r[4];
+          ldsm_nt(r, kS, RS, 16 * jp, 16 * kk, lane);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(sacc[mt][2 * jp], qf[mt][kk], r[0], r[1]);
+            mma_bf16(sacc[mt][2 * jp + 1], qf[mt][kk], r[2], r[3]);
+          }
+        }
+      const bool partial = key0 + KV_TILE > L;
+      float msc[MT][2];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (partial) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (key0 + 8 * j + 2 * t + (e & 1) >= L) sacc[mt][j][e] = -INFINITY;
+          }
+          mx0 = fmaxf(mx0, fmaxf(sacc[mt][j][0], sacc[mt][j][1]));
+          mx1 = fmaxf(mx1, fmaxf(sacc[mt][j][2], sacc[mt][j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(mrow[mt][0], mx0), mn1 = fmaxf(mrow[mt][1], mx1);
+        const float c0 = ex2((mrow[mt][0] - mn0) * scale_log2), c1 = ex2((mrow[mt][1] - mn1) * scale_log2);
+        mrow[mt][0] = mn0; mrow[mt][1] = mn1;
+        msc[mt][0] = mn0 * scale_log2; msc[mt][1] = mn1 * scale_log2;
+        lrow[mt][0] *= c0; lrow[mt][1] *= c1;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) {
+          oacc[mt][j][0] *= c0; oacc[mt][j][1] *= c0; oacc[mt][j][2] *= c1; oacc[mt][j][3] *= c1;
+        }
+      }
+      // exponentials of k-step kk (two n-tiles) are produced right before the PV MMAs that consume them
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pf[MT][4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          mma_bf16(sacc[mt][2 * jp], qf[mt][kk], r[0], r[1]);
-          mma_bf16(sacc[mt][2 * jp + 1], qf[mt][kk], r[2], r[3]);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * kk + jj;
+            const float p0 = ex2(fmaf(sacc[mt][j][0], scale_log2, -msc[mt][0]));
+            const float p1 = ex2(fmaf(sacc[mt][j][1], scale_log2, -msc[mt][0]));
+            const float p2 = ex2(fmaf(sacc[mt][j][2], scale_log2, -msc[mt][1]));
+            const float p3 = ex2(fmaf(sacc[mt][j][3], scale_log2, -msc[mt][1]));
+            lrow[mt][0] += p0 + p1;
+            lrow[mt][1] += p2 + p3;
+            pf[mt][jj * 2] = pack_bf16(p0, p1);
+            pf[mt][jj * 2 + 1] = pack_bf16(p2, p3);
+          }
         }
-      }
-    const bool partial = (it + 1) * KV_TILE > L;
-    uint32_t pf[MT][4][4];
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+        for (int jp = 0; jp < ND / 2; ++jp) {
+          uint32_t r[4];
+          ldsm_t(r, vS, RS, 16 * kk, 16 * jp, lane);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float s = sacc[mt][j][e] * scale_log2;
-          if (partial && (it * KV_TILE + 8 * j + 2 * t + (e & 1)) >= L) s = -INFINITY;
-          sacc[mt][j][e] = s;
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(oacc[mt][2 * jp], pf[mt], r[0], r[1]);
+            mma_bf16(oacc[mt][2 * jp + 1], pf[mt], r[2], r[3]);
+          }
         }
-        mx0 = fmaxf(mx0, fmaxf(sacc[mt][j][0], sacc[mt][j][1]));
-        mx1 = fmaxf(mx1, fmaxf(sacc[mt][j][2], sacc[mt][j][3]));
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(mrow[mt][0], mx0), mn1 = fmaxf(mrow[mt][1], mx1);
-      const float c0 = ex2(mrow[mt][0] - mn0), c1 = ex2(mrow[mt][1] - mn1);
-      mrow[mt][0] = mn0; mrow[mt][1] = mn1;
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float p0 = ex2(sacc[mt][j][0] - mn0), p1 = ex2(sacc[mt][j][1] - mn0);
-        const float p2 = ex2(sacc[mt][j][2] - mn1), p3 = ex2(sacc[mt][j][3] - mn1);
-        s0 += p0 + p1; s1 += p2 + p3;
-        // C fragments of n-tiles (2kk, 2kk+1) are the A fragment of k-step kk
-        pf[mt][j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
-        pf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
-      }
-      lrow[mt][0] = lrow[mt][0] * c0 + s0;
-      lrow[mt][1] = lrow[mt][1] * c1 + s1;
-#pragma unroll
-      for (int j = 0; j < ND; ++j) {
-        oacc[mt][j][0] *= c0; oacc[mt][j][1] *= c0; oacc[mt][j][2] *= c1; oacc[mt][j][3] *= c1;
       }
     }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-      for (int jp = 0; jp < ND / 2; ++jp) {
-        uint32_t r[4];
-        ldsm_t(r, vS, RS, 16 * kk, 16 * jp, lane);
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          mma_bf16(oacc[mt][2 * jp], pf[mt][kk], r[0], r[1]);
-          mma_bf16(oacc[mt][2 * jp + 1], pf[mt][kk], r[2], r[3]);
-        }
-      }
     __syncthreads();
   }
 
@@ -225,8 +259,235 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const bf16* __restrict__ 
             pack_bf16(oacc[mt][j][2] * i1, oacc[mt][j][3] * i1);
     }
     if (lse2 && t == 0) {
-      if (r0 < L) lse2[((size_t)b * H + h) * L + r0] = mrow[mt][0] + log2f(l0);
-      if (r1 < L) lse2[((size_t)b * H + h) * L + r1] = mrow[mt][1] + log2f(l1);
+      if (r0 < L) lse2[((size_t)b * H + h) * L + r0] = mrow[mt][0] * scale_log2 + log2f(l0);
+      if (r1 < L) lse2[((size_t)b * H + h) * L + r1] = mrow[mt][1] * scale_log2 + log2f(l1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward, tuned variant (one m-tile per warp, more CTAs per SM).  Differences from attn_fwd_kernel:
+//   * row sums come out of the PV MMA: every V row carries a bf16 1.0 in its 16-byte pad, read as one
+//     extra n-tile, so sum_k P[q][k] accumulates in the tensor pipe on exactly the bf16 P the numerator uses;
+//   * 3-input max (FMNMX3) and packed fp32 FMA (FFMA2) halve the softmax instruction count;
+//   * POLY of the 8 n-tiles per 64-key tile evaluate 2^x with a cubic on the FMA pipe instead of MUFU
+//     (Cody-Waite split, magic-number rounding), because MUFU.EX2 (16/clk/SM) is the binding unit.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for a packed pair, x <= 0 (clamped at -126): cubic on [-0.5, 0.5], |rel err| < 2e-4 (bf16 P needs 4e-3)
+__device__ __forceinline__ void exp2_poly2(uint64_t x, float& o0, float& o1) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  const uint64_t xc = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t r = fadd2(xc, pack2(12582912.f, 12582912.f));
+  const uint64_t fl = fadd2(r, pack2(-12582912.f, -12582912.f));
+  const uint64_t f = ffma2(fl, pack2(-1.f, -1.f), xc);
+  uint64_t pv = ffma2(f, pack2(0.05550411f, 0.05550411f), pack2(0.24022651f, 0.24022651f));
+  pv = ffma2(pv, f, pack2(0.69314718f, 0.69314718f));
+  pv = ffma2(pv, f, pack2(1.f, 1.f));
+  float r0, r1, p0, p1;
+  unpack2(r, r0, r1);
+  unpack2(pv, p0, p1);
+  o0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+__device__ __forceinline__ void ldsm_t2(uint32_t* r, uint32_t base, int RS, int row0, int col0, int lane) {
+  const uint32_t addr = base + (row0 + (lane & 15)) * RS + col0 * 2;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+
+template <int DH, int MT, int NSUB, int POLY, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB) attn_fwd2_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                               float* __restrict__ lse2, int L, int C, float scale_log2) {
+  constexpr int RS = DH * 2 + 16;
+  constexpr int KT = DH / 16;
+  constexpr int ND = DH / 8;
+  constexpr int STAGE_KEYS = KV_TILE * NSUB;
+  constexpr int STAGE_BYTES = STAGE_KEYS * RS;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const size_t ld = 3 * (size_t)C;
+  const bf16* qbase = qkv + (size_t)b * L * ld + h * DH;
+  const bf16* kbase = qbase + C;
+  const bf16* vbase = qbase + 2 * C;
+  const int q0 = (blockIdx.x * nwarps + warp) * 16 * MT;
+  const uint32_t smem0 = smem_u32_(smem_dyn);
+  // B fragment of the constant "ones" n-tile (column 0 = 1): b0 = b1 = {1, 1} on lanes with g == 0
+  const uint32_t ones = g == 0 ? 0x3f803f80u : 0u;
+
+  uint32_t qf[MT][KT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) load_a_frag(qf[mt][kk], qbase, ld, q0 + mt * 16, L, kk * 16, lane);
+
+  float oacc[MT][ND + 1][4];
+  float m0[MT], m1[MT];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    m0[mt] = m1[mt] = -INFINITY;
+#pragma unroll
+    for (int j = 0; j <= ND; ++j) oacc[mt][j][0] = oacc[mt][j][1] = oacc[mt][j][2] = oacc[mt][j][3] = 0.f;
+  }
+  const uint64_t c2 = pack2(scale_log2, scale_log2);
+
+  const int nstages = (L + STAGE_KEYS - 1) / STAGE_KEYS;
+  load_rows_async<DH>(smem0, kbase, ld, 0, L, STAGE_KEYS);
+  load_rows_async<DH>(smem0 + STAGE_BYTES, vbase, ld, 0, L, STAGE_KEYS);
+  cp_async_commit();
+
+  for (int st = 0; st < nstages; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nstages) {
+      const uint32_t nb = smem0 + (buf ^ 1) * 2 * STAGE_BYTES;
+      load_rows_async<DH>(nb, kbase, ld, (st + 1) * STAGE_KEYS, L, STAGE_KEYS);
+      load_rows_async<DH>(nb + STAGE_BYTES, vbase, ld, (st + 1) * STAGE_KEYS, L, STAGE_KEYS);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+      const int key0 = st * STAGE_KEYS + sub * KV_TILE;
+      if (key0 >= L) break;
+      const uint32_t kS = smem0 + buf * 2 * STAGE_BYTES + sub * KV_TILE * RS;
+      const uint32_t vS = kS + STAGE_BYTES;
+      float sacc[MT][8][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sacc[mt][j][0] = sacc[mt][j][1] = sacc[mt][j][2] = sacc[mt][j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          uint32_t r[4];
+          ldsm_nt(r, kS, RS, 16 * jp, 16 * kk, lane);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(sacc[mt][2 * jp], qf[mt][kk], r[0], r[1]);
+            mma_bf16(sacc[mt][2 * jp + 1], qf[mt][kk], r[2], r[3]);
+          }
+        }
+      uint64_t nm0[MT], nm1[MT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        if (key0 + KV_TILE > L) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (key0 + 8 * j + 2 * t + (e & 1) >= L) sacc[mt][j][e] = -INFINITY;
+        }
+        float mx0 = m0[mt], mx1 = m1[mt];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          mx0 = max3(mx0, sacc[mt][j][0], sacc[mt][j][1]);
+          mx1 = max3(mx1, sacc[mt][j][2], sacc[mt][j][3]);
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float cr0 = ex2((m0[mt] - mx0) * scale_log2), cr1 = ex2((m1[mt] - mx1) * scale_log2);
+        m0[mt] = mx0; m1[mt] = mx1;
+        nm0[mt] = pack2(-mx0 * scale_log2, -mx0 * scale_log2);
+        nm1[mt] = pack2(-mx1 * scale_log2, -mx1 * scale_log2);
+#pragma unroll
+        for (int j = 0; j <= ND; ++j) {
+          oacc[mt][j][0] *= cr0; oacc[mt][j][1] *= cr0; oacc[mt][j][2] *= cr1; oacc[mt][j][3] *= cr1;
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pf[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = 2 * kk + jj;
+            const uint64_t x01 = ffma2(pack2(sacc[mt][j][0], sacc[mt][j][1]), c2, nm0[mt]);
+            const uint64_t x23 = ffma2(pack2(sacc[mt][j][2], sacc[mt][j][3]), c2, nm1[mt]);
+            float p0, p1, p2, p3;
+            const bool use_poly = POLY > 0 && ((j + 1) % (8 / (POLY > 0 ? POLY : 1)) == 0);
+            if (use_poly) {
+              exp2_poly2(x01, p0, p1);
+              exp2_poly2(x23, p2, p3);
+            } else {
+              float a0, a1, a2, a3;
+              unpack2(x01, a0, a1);
+              unpack2(x23, a2, a3);
+              p0 = ex2(a0); p1 = ex2(a1); p2 = ex2(a2); p3 = ex2(a3);
+            }
+            pf[mt][jj * 2] = pack_bf16(p0, p1);
+            pf[mt][jj * 2 + 1] = pack_bf16(p2, p3);
+          }
+#pragma unroll
+        for (int jp = 0; jp < ND / 2; ++jp) {
+          uint32_t r[4];
+          ldsm_t(r, vS, RS, 16 * kk, 16 * jp, lane);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(oacc[mt][2 * jp], pf[mt], r[0], r[1]);
+            mma_bf16(oacc[mt][2 * jp + 1], pf[mt], r[2], r[3]);
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) mma_bf16(oacc[mt][ND], pf[mt], ones, ones);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    // row sums sit in column 0 of the extra n-tile (threads with t == 0): broadcast over the quad
+    const float l0 = __shfl_sync(0xffffffffu, oacc[mt][ND][0], lane & ~3);
+    const float l1 = __shfl_sync(0xffffffffu, oacc[mt][ND][2], lane & ~3);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int r0 = q0 + mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      if (r0 < L)
+        *reinterpret_cast<uint32_t*>(out + ((size_t)b * L + r0) * C + h * DH + 8 * j + 2 * t) =
+            pack_bf16(oacc[mt][j][0] * i0, oacc[mt][j][1] * i0);
+      if (r1 < L)
+        *reinterpret_cast<uint32_t*>(out + ((size_t)b * L + r1) * C + h * DH + 8 * j + 2 * t) =
+            pack_bf16(oacc[mt][j][2] * i1, oacc[mt][j][3] * i1);
+    }
+    if (lse2 && t == 0) {
+      if (r0 < L) lse2[((size_t)b * H + h) * L + r0] = m0[mt] * scale_log2 + log2f(l0);
+      if (r1 < L) lse2[((size_t)b * H + h) * L + r1] = m1[mt] * scale_log2 + log2f(l1);
     }
   }
 }
@@ -260,16 +521,18 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __r
 // ------------------------------------------------------------------------------------------
 // Backward dQ: query-outer, recompute P, dS = P * (dP - delta), dQ += dS K.  One m-tile per warp.
 // ------------------------------------------------------------------------------------------
-template <int DH>
-__global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+template <int DH, int NSUB, int MINB>
+__global__ void __launch_bounds__(256, MINB) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                           const float* __restrict__ lse2, const float* __restrict__ delta,
                                                           bf16* __restrict__ dqkv, int L, int C, float scale,
                                                           float scale_log2) {
   constexpr int RS = DH * 2 + 16;
   constexpr int KT = DH / 16;
   constexpr int ND = DH / 8;
-  __shared__ __align__(16) uint8_t sK[2][KV_TILE * RS];
-  __shared__ __align__(16) uint8_t sV[2][KV_TILE * RS];
+  constexpr int STAGE_KEYS = KV_TILE * NSUB;
+  constexpr int STAGE_BYTES = STAGE_KEYS * RS;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];  // [2][K | V]
+  const uint32_t smem0 = smem_u32_(smem_dyn);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
@@ -295,22 +558,27 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const bf16* __restrict
 #pragma unroll
   for (int j = 0; j < ND; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
 
-  const int ntiles = (L + KV_TILE - 1) / KV_TILE;
-  load_tile_async<DH>(smem_u32_(sK[0]), kbase, ld, 0, L);
-  load_tile_async<DH>(smem_u32_(sV[0]), vbase, ld, 0, L);
+  const int nstages = (L + STAGE_KEYS - 1) / STAGE_KEYS;
+  load_rows_async<DH>(smem0, kbase, ld, 0, L, STAGE_KEYS);
+  load_rows_async<DH>(smem0 + STAGE_BYTES, vbase, ld, 0, L, STAGE_KEYS);
   cp_async_commit();
-  for (int it = 0; it < ntiles; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < ntiles) {
-      load_tile_async<DH>(smem_u32_(sK[buf ^ 1]), kbase, ld, (it + 1) * KV_TILE, L);
-      load_tile_async<DH>(smem_u32_(sV[buf ^ 1]), vbase, ld, (it + 1) * KV_TILE, L);
+  for (int st = 0; st < nstages; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nstages) {
+      const uint32_t nb = smem0 + (buf ^ 1) * 2 * STAGE_BYTES;
+      load_rows_async<DH>(nb, kbase, ld, (st + 1) * STAGE_KEYS, L, STAGE_KEYS);
+      load_rows_async<DH>(nb + STAGE_BYTES, vbase, ld, (st + 1) * STAGE_KEYS, L, STAGE_KEYS);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
-    const uint32_t kS = smem_u32_(sK[buf]), vS = smem_u32_(sV[buf]);
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+    const int key0 = st * STAGE_KEYS + sub * KV_TILE;
+    if (key0 >= L) break;
+    const uint32_t kS = smem0 + buf * 2 * STAGE_BYTES + sub * KV_TILE * RS, vS = kS + STAGE_BYTES;
     float sacc[8][4], pacc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -329,7 +597,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const bf16* __restrict
         mma_bf16(pacc[2 * jp], dof[kk], r[0], r[1]);
         mma_bf16(pacc[2 * jp + 1], dof[kk], r[2], r[3]);
       }
-    const bool partial = (it + 1) * KV_TILE > L;
+    const bool partial = key0 + KV_TILE > L;
     uint32_t dsf[4][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -339,7 +607,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const bf16* __restrict
         const float lse = (e < 2) ? lse0 : lse1;
         const float dl = (e < 2) ? dl0 : dl1;
         float p = ex2(sacc[j][e] * scale_log2 - lse);
-        if (partial && (it * KV_TILE + 8 * j + 2 * t + (e & 1)) >= L) p = 0.f;
+        if (partial && (key0 + 8 * j + 2 * t + (e & 1)) >= L) p = 0.f;
         ds[e] = p * (pacc[j][e] - dl);
       }
       dsf[j >> 1][(j & 1) * 2] = pack_bf16(ds[0], ds[1]);
@@ -354,6 +622,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const bf16* __restrict
         mma_bf16(dq[2 * jp], dsf[kk], r[0], r[1]);
         mma_bf16(dq[2 * jp + 1], dsf[kk], r[2], r[3]);
       }
+    }
     __syncthreads();
   }
 #pragma unroll
@@ -372,17 +641,20 @@ __global__ void __launch_bounds__(256) attn_bwd_dq_kernel(const bf16* __restrict
 //   S^T = K Q^T,  P^T = exp2(S^T*c - lse[q]),  dV += P^T dO,  dP^T = V dO^T,
 //   dS^T = P^T * (dP^T - delta[q]),  dK += dS^T Q   (scaled by 1/sqrt(dh) at the end)
 // ------------------------------------------------------------------------------------------
-template <int DH>
-__global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+template <int DH, int NSUB, int MINB>
+__global__ void __launch_bounds__(256, MINB) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                            const float* __restrict__ lse2, const float* __restrict__ delta,
                                                            bf16* __restrict__ dqkv, int L, int C, float scale,
                                                            float scale_log2) {
   constexpr int RS = DH * 2 + 16;
   constexpr int KT = DH / 16;
   constexpr int ND = DH / 8;
-  __shared__ __align__(16) uint8_t sQ[2][KV_TILE * RS];
-  __shared__ __align__(16) uint8_t sD[2][KV_TILE * RS];
-  __shared__ float sLse[2][KV_TILE], sDl[2][KV_TILE];
+  constexpr int STAGE_Q = KV_TILE * NSUB;
+  constexpr int STAGE_BYTES = STAGE_Q * RS;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];  // [2][Q | dO] then lse[2][STAGE_Q], delta[2][STAGE_Q]
+  const uint32_t smem0 = smem_u32_(smem_dyn);
+  float* sLse = reinterpret_cast<float*>(smem_dyn + 4 * STAGE_BYTES);
+  float* sDl = sLse + 2 * STAGE_Q;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
@@ -407,32 +679,38 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const bf16* __restric
     dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f;
     dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f;
   }
-  const int ntiles = (L + KV_TILE - 1) / KV_TILE;
-  auto load_stats = [&](int buf, int tile) {
-    for (int i = threadIdx.x; i < KV_TILE; i += blockDim.x) {
-      const int q = tile * KV_TILE + i;
+  const int nstages = (L + STAGE_Q - 1) / STAGE_Q;
+  auto load_stats = [&](int buf, int stage) {
+    for (int i = threadIdx.x; i < STAGE_Q; i += blockDim.x) {
+      const int q = stage * STAGE_Q + i;
       // padded query rows: lse = +inf makes P = 0
-      sLse[buf][i] = q < L ? lse2[sbase + q] : INFINITY;
-      sDl[buf][i] = q < L ? delta[sbase + q] : 0.f;
+      sLse[buf * STAGE_Q + i] = q < L ? lse2[sbase + q] : INFINITY;
+      sDl[buf * STAGE_Q + i] = q < L ? delta[sbase + q] : 0.f;
     }
   };
-  load_tile_async<DH>(smem_u32_(sQ[0]), qbase, ld, 0, L);
-  load_tile_async<DH>(smem_u32_(sD[0]), dobase, C, 0, L);
+  load_rows_async<DH>(smem0, qbase, ld, 0, L, STAGE_Q);
+  load_rows_async<DH>(smem0 + STAGE_BYTES, dobase, C, 0, L, STAGE_Q);
   cp_async_commit();
   load_stats(0, 0);
-  for (int it = 0; it < ntiles; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < ntiles) {
-      load_tile_async<DH>(smem_u32_(sQ[buf ^ 1]), qbase, ld, (it + 1) * KV_TILE, L);
-      load_tile_async<DH>(smem_u32_(sD[buf ^ 1]), dobase, C, (it + 1) * KV_TILE, L);
+  for (int st = 0; st < nstages; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nstages) {
+      const uint32_t nb = smem0 + (buf ^ 1) * 2 * STAGE_BYTES;
+      load_rows_async<DH>(nb, qbase, ld, (st + 1) * STAGE_Q, L, STAGE_Q);
+      load_rows_async<DH>(nb + STAGE_BYTES, dobase, C, (st + 1) * STAGE_Q, L, STAGE_Q);
       cp_async_commit();
-      load_stats(buf ^ 1, it + 1);
+      load_stats(buf ^ 1, st + 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
-    const uint32_t qS = smem_u32_(sQ[buf]), dS_ = smem_u32_(sD[buf]);
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+    if (st * STAGE_Q + sub * KV_TILE >= L) break;
+    const uint32_t qS = smem0 + buf * 2 * STAGE_BYTES + sub * KV_TILE * RS, dS_ = qS + STAGE_BYTES;
+    const float* lseS = sLse + buf * STAGE_Q + sub * KV_TILE;
+    const float* dlS = sDl + buf * STAGE_Q + sub * KV_TILE;
     float sacc[8][4], pacc[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -458,10 +736,10 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const bf16* __restric
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int qi = 8 * j + 2 * t + (e & 1);
-        float pe = ex2(sacc[j][e] * scale_log2 - sLse[buf][qi]);
+        float pe = ex2(sacc[j][e] * scale_log2 - lseS[qi]);
         if (!((e < 2) ? key_ok0 : key_ok1)) pe = 0.f;
         p[e] = pe;
-        ds[e] = pe * (pacc[j][e] - sDl[buf][qi]);
+        ds[e] = pe * (pacc[j][e] - dlS[qi]);
       }
       pf[j >> 1][(j & 1) * 2] = pack_bf16(p[0], p[1]);
       pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
@@ -480,6 +758,7 @@ __global__ void __launch_bounds__(256) attn_bwd_dkv_kernel(const bf16* __restric
         mma_bf16(dk[2 * jp], dsf[kk], r[0], r[1]);
         mma_bf16(dk[2 * jp + 1], dsf[kk], r[2], r[3]);
       }
+    }
     __syncthreads();
   }
   const int r0 = k0 + g, r1 = k0 + g + 8;
@@ -510,17 +789,107 @@ LaunchShape pick_shape(int L, bool allow_mt2) {
 
 }  // namespace
 
+template <int DH, int MT, int NSUB>
+static int launch_fwd(cudaStream_t st, dim3 grid, dim3 block, const void* qkv, void* out, float* lse2, int L, int C,
+                      float scale_log2) {
+  auto kern = attn_fwd_kernel<DH, MT, NSUB>;
+  constexpr int smem = 2 * 2 * KV_TILE * NSUB * (DH * 2 + 16);
+  static bool configured = false;
+  if (!configured) {
+    TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, block, smem, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int DH, int MT, int NSUB, int POLY, int NTHR, int MINB>
+static int launch_fwd2(cudaStream_t st, int B, int heads, const void* qkv, void* out, float* lse2, int L, int C,
+                       float scale_log2) {
+  auto kern = attn_fwd2_kernel<DH, MT, NSUB, POLY, NTHR, MINB>;
+  constexpr int smem = 2 * 2 * KV_TILE * NSUB * (DH * 2 + 16);
+  static bool configured = false;
+  if (!configured) {
+    TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(L, (NTHR / 32) * 16 * MT), heads, B);
+  kern<<<grid, NTHR, smem, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+static int g_attn_variant = -1;  // experiment knob: TSD_ATTN_FWD = mt*10 + nsub
+
 extern "C" int tsd_attn_fwd(void* stream, const void* qkv, void* out, float* lse2, int B, int L, int C, int heads) {
   TSD_CHECK(C % heads == 0, "attn_fwd: C %% heads != 0");
   const int dh = C / heads;
   TSD_CHECK(dh == 16 || dh == 32, "attn_fwd: head_dim %d not in {16, 32}", dh);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)dh);
-  const LaunchShape s = pick_shape(L, dh == 16);
-  dim3 grid(s.grid_x, heads, B), block(s.warps * 32);
+  if (g_attn_variant < 0) {
+    const char* e = getenv("TSD_ATTN_FWD");
+    g_attn_variant = e ? atoi(e) : 112;
+  }
+  LaunchShape s = pick_shape(L, dh == 16);
+  int nsub = L >= 256 ? 4 : 1;
+  if (g_attn_variant > 0 && dh == 16 && L % 256 == 0) {
+    s.mt = g_attn_variant / 10; nsub = g_attn_variant % 10; s.warps = 8;
+    s.grid_x = ceil_div(L, s.warps * 16 * s.mt);
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  if (dh == 16 && s.mt == 2) attn_fwd_kernel<16, 2><<<grid, block, 0, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
-  else if (dh == 16) attn_fwd_kernel<16, 1><<<grid, block, 0, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
-  else attn_fwd_kernel<32, 1><<<grid, block, 0, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
+  if (g_attn_variant >= 100 && dh == 16 && L % 256 == 0) {
+#define TSD_F2(MT, NS, P, NT, MB) return launch_fwd2<16, MT, NS, P, NT, MB>(st, B, heads, qkv, out, lse2, L, C, scale_log2)
+    switch (g_attn_variant) {
+      case 100: TSD_F2(1, 4, 0, 256, 4);
+      case 101: TSD_F2(1, 4, 1, 256, 4);
+      case 110: TSD_F2(2, 4, 0, 256, 2);
+      case 111: TSD_F2(2, 4, 1, 256, 2);
+      case 112: TSD_F2(2, 4, 2, 256, 2);
+      case 120: TSD_F2(2, 4, 0, 128, 4);
+      case 121: TSD_F2(2, 4, 1, 128, 4);
+      case 122: TSD_F2(2, 4, 2, 128, 4);
+      case 130: TSD_F2(2, 2, 0, 128, 4);
+      case 140: TSD_F2(1, 4, 0, 128, 8);
+      default: break;
+    }
+#undef TSD_F2
+  }
+  dim3 grid(s.grid_x, heads, B), block(s.warps * 32);
+  if (dh == 16) {
+    if (s.mt == 2 && nsub == 4) return launch_fwd<16, 2, 4>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+    if (s.mt == 2 && nsub == 2) return launch_fwd<16, 2, 2>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+    if (s.mt == 2 && nsub == 1) return launch_fwd<16, 2, 1>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+    if (s.mt == 1 && nsub == 4) return launch_fwd<16, 1, 4>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+    if (s.mt == 1 && nsub == 2) return launch_fwd<16, 1, 2>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+    return launch_fwd<16, 1, 1>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+  }
+  if (nsub == 4) return launch_fwd<32, 1, 4>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+  return launch_fwd<32, 1, 1>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+}
+
+template <int NSUB>
+static int launch_bwd(cudaStream_t st, dim3 grid, dim3 block, int dh, const void* qkv, const void* dout, const float* lse2,
+                      const float* delta, void* dqkv, int L, int C, float scale, float scale_log2) {
+  const int smem_dq16 = 4 * KV_TILE * NSUB * 48, smem_dq32 = 4 * KV_TILE * NSUB * 80;
+  const int smem_kv16 = smem_dq16 + 4 * KV_TILE * NSUB * 4, smem_kv32 = smem_dq32 + 4 * KV_TILE * NSUB * 4;
+  static bool configured = false;
+  if (!configured) {
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<16, NSUB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq16));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<32, NSUB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq32));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<16, NSUB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv16));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<32, NSUB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv32));
+    configured = true;
+  }
+  if (dh == 16) {
+    attn_bwd_dq_kernel<16, NSUB, 3><<<grid, block, smem_dq16, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+    TSD_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<16, NSUB, 3><<<grid, block, smem_kv16, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+  } else {
+    attn_bwd_dq_kernel<32, NSUB, 2><<<grid, block, smem_dq32, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+    TSD_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<32, NSUB, 2><<<grid, block, smem_kv32, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+  }
   TSD_LAUNCH_CHECK();
   return 0;
 }
@@ -542,15 +911,9 @@ extern "C" int tsd_attn_bwd(void* stream, const void* qkv, const void* out, cons
   TSD_LAUNCH_CHECK();
   const LaunchShape s = pick_shape(L, false);
   dim3 grid(s.grid_x, heads, B), block(s.warps * 32);
-  if (dh == 16) {
-    attn_bwd_dq_kernel<16><<<grid, block, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
-    TSD_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<16><<<grid, block, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
-  } else {
-    attn_bwd_dq_kernel<32><<<grid, block, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
-    TSD_LAUNCH_CHECK();
-    attn_bwd_dkv_kernel<32><<<grid, block, 0, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
-  }
+  const int rc = L >= 256 ? launch_bwd<4>(st, grid, block, dh, qkv, dout, lse2, delta, dqkv, L, C, scale, scale_log2)
+                          : launch_bwd<1>(st, grid, block, dh, qkv, dout, lse2, delta, dqkv, L, C, scale, scale_log2);
+  if (rc) return rc;
   TSD_LAUNCH_CHECK();
   return 0;
 }
