@@ -29,13 +29,13 @@ __global__ void __launch_bounds__(256) head_conv_fwd_kernel(const float* __restr
   for (int i = threadIdx.x; i < co; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
   const int groups = co / 8;
-  const size_t total = (size_t)n_img * H * W * groups;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int gsel = (int)(i % groups);
-    size_t p = i / groups;
-    const int xx = (int)(p % W); p /= W;
-    const int yy = (int)(p % H);
-    const int n = (int)(p / H);
+  const int total = n_img * H * W * groups;  // < 2^31 for any batch that fits the GPU
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int gsel = i % groups;
+    int p = i / groups;
+    const int xx = p % W; p /= W;
+    const int yy = p % H;
+    const int n = p / H;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = sb[gsel * 8 + j];
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) head_conv_fwd_kernel(const float* __restr
         for (int j = 0; j < 8; ++j) acc[j] += v * wr[j];
       }
     }
-    *reinterpret_cast<uint4*>(out + i * 8) =
+    *reinterpret_cast<uint4*>(out + (size_t)i * 8) =
         make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
   }
 }
@@ -111,19 +111,19 @@ __global__ void __launch_bounds__(256) tail_conv_fwd_kernel(const bf16* __restri
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const size_t total = (size_t)n_img * H * W;
-  const size_t warp_global = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  for (size_t base = warp_global * 32; base < total; base += nwarps * 32) {
+  const int total = n_img * H * W;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = warp_global * 32; base < total; base += nwarps * 32) {
     float mine[CO];
 #pragma unroll
     for (int o = 0; o < CO; ++o) mine[o] = 0.f;
     for (int i = 0; i < 32; ++i) {
-      const size_t p = base + i;
+      const int p = base + i;
       if (p >= total) break;
-      const int xx = (int)(p % W);
-      const int yy = (int)((p / W) % H);
-      const size_t nbase = (p / ((size_t)W * H)) * H * W;
+      const int xx = p % W;
+      const int yy = (p / W) % H;
+      const size_t nbase = (size_t)(p / (W * H)) * H * W;
       float acc[CO];
 #pragma unroll
       for (int o = 0; o < CO; ++o) acc[o] = 0.f;
@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(256) tail_conv_fwd_kernel(const bf16* __restri
         if (lane == i) mine[o] = s;
       }
     }
-    const size_t p = base + lane;
+    const int p = base + lane;
     if (p < total) {
-      const size_t n = p / ((size_t)W * H), rem = p - n * (size_t)W * H;
+      const size_t n = p / (W * H), rem = p - n * (size_t)W * H;
 #pragma unroll
       for (int o = 0; o < CO; ++o) out[(n * CO + o) * (size_t)H * W + rem] = mine[o] + bias[o];
     }

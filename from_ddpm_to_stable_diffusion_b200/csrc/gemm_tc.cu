@@ -9,14 +9,16 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_THREADS = 128;
+constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int EPI_THREADS = 256;
 constexpr int TMEM_COLS = 256;  // two 128-column fp32 accumulators
 
 template <int OUT_F32>
 struct Cfg {
-  static constexpr int STAGES = OUT_F32 ? 5 : 6;
-  static constexpr int STAGING_BYTES = BM * BN * (OUT_F32 ? 4 : 2);
+  static constexpr int STAGES = 5;
+  // fp32 out: one 64 KB staging tile; bf16 out: two 32 KB staging tiles (double buffered; a tile's residual is
+  // TMA-prefetched into the buffer its result will be stored from)
+  static constexpr int STAGING_BYTES = 64 * 1024;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
 };
@@ -25,7 +27,8 @@ template <int A_MN, int B_MN, int OUT_F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-               const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+               const GemmParams p) {
   constexpr int STAGES = Cfg<OUT_F32>::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -38,7 +41,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto res_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 6);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to aligned base
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -52,6 +56,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmB0);
     tma_prefetch_desc(&tmB1);
     tma_prefetch_desc(&tmD);
+    tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -61,6 +66,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), EPI_THREADS);
+      mbar_init(res_bar(s), 1);
     }
     fence_mbar_init();
   }
@@ -195,12 +201,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp >= 4) {
     // =========================================================== epilogue
-    const int ep_tid = threadIdx.x - 128;  // == TMEM lane == row inside the tile
-    const int ep_warp = warp - 4;          // TMEM sub-partition (warp % 4)
+    // Eight epilogue warps: warps w and w+4 share TMEM sub-partition (w % 4) and split the 128 columns.
+    const int ep_warp = (warp - 4) & 3;      // TMEM sub-partition
+    const int half = (warp - 4) >> 2;        // column half handled by this warp
+    const int ep_tid = ep_warp * 32 + lane;  // == TMEM lane == row inside the tile
+    const bool ep_leader = (warp == 4 && lane == 0);
     const uint32_t lane_off = static_cast<uint32_t>(ep_warp * 32) << 16;
-    uint8_t* staging = smem_gen + (smem_staging - smem_base);
+    uint8_t* staging0 = smem_gen + (smem_staging - smem_base);
+    const bool has_res = (!OUT_F32) && p.residual != nullptr;
+    // residual tile of (m0, n0): two 64-column boxes, prefetched by TMA into a staging buffer
+    auto prefetch_residual = [&](int tile_idx, int bufsel) {
+      const int t2r = tile_idx % tiles_mn;
+      const int nb = t2r % p.tiles_n, mb = t2r / p.tiles_n;
+      const uint32_t dst = smem_staging + bufsel * (BM * BN * 2);
+      mbar_arrive_expect_tx(res_bar(bufsel), BM * BN * 2);
+      tma_load_2d(dst, &tmR, res_bar(bufsel), nb * BN, mb * BM);
+      tma_load_2d(dst + BM * 128, &tmR, res_bar(bufsel), nb * BN + 64, mb * BM);
+    };
+    if (has_res && ep_leader && (int)blockIdx.x < total_tiles) prefetch_residual(blockIdx.x, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int sbuf = OUT_F32 ? 0 : (it & 1);
+      uint8_t* staging = staging0 + sbuf * (BM * BN * 2);
+      const uint32_t staging_s = smem_staging + sbuf * (BM * BN * 2);
       const int t2 = tile % tiles_mn;
       const int n_blk = t2 % p.tiles_n;
       const int m_blk = t2 / p.tiles_n;
@@ -209,19 +232,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m0 + ep_tid;
       const bool row_ok = row < p.M;
-      const int sample = p.row_bias ? (row_ok ? row / p.rows_per_sample : 0) : 0;
+      const int sample = (p.row_bias && row_ok) ? row / p.rows_per_sample : 0;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      // Staging buffer must have been fully read by the previous tile's TMA stores.
-      if (ep_tid == 0) tma_store_wait_read<0>();
-      named_bar_sync(1, EPI_THREADS);
+      if (OUT_F32) {
+        // single staging tile: it must have been fully read by the previous tile's TMA reduce-add
+        if (ep_leader) tma_store_wait_read<0>();
+        named_bar_sync(1, EPI_THREADS);
+      } else if (has_res) {
+        mbar_wait(res_bar(sbuf), (it >> 1) & 1);  // residual tile has landed in this staging buffer
+      }
 
       const uint32_t t_addr = tmem_base + lane_off + acc * BN;
       const int r7 = ep_tid & 7;
       if (OUT_F32) {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
           uint32_t v[32];
           tmem_ld32(t_addr + ch * 32, v);
           tmem_ld_wait();
@@ -234,8 +261,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       } else if (p.epi == EPI_GEGLU) {
         // columns [0,64) = value half, [64,128) = gate half (weights are packed that way)
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
+        {
+          const int ch = half;
           uint32_t xv[32], gv[32];
           tmem_ld32(t_addr + ch * 32, xv);
           tmem_ld32(t_addr + 64 + ch * 32, gv);
@@ -263,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       } else {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
           uint32_t v[32];
           tmem_ld32(t_addr + ch * 32, v);
           tmem_ld_wait();
@@ -280,11 +307,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += __ldg(rb + j);
           }
-          if (p.residual && row_ok) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col0);
+          if (has_res) {
+            const uint8_t* rsrc = staging + (ch >> 1) * (BM * 128) + ep_tid * 128;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 r = __ldg(rp + q);
+              const int cjr = (ch & 1) * 4 + q;
+              const uint4 r = *reinterpret_cast<const uint4*>(rsrc + ((cjr ^ r7) << 4));
               const float2 a = unpack_bf16(r.x), b = unpack_bf16(r.y), c = unpack_bf16(r.z),
                            d = unpack_bf16(r.w);
               f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
@@ -306,22 +334,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_arrive(tempty_bar(acc));
       // smem writes (generic proxy) -> visible to the TMA engine (async proxy).
       fence_proxy_async_smem();
+      // bf16: before anyone moves on, the store of tile it-1 must have finished reading the OTHER staging buffer
+      // (the next tile's residual prefetch and, one tile later, its result are written there)
+      if (!OUT_F32 && ep_leader) tma_store_wait_read<0>();
       named_bar_sync(1, EPI_THREADS);
-      if (ep_tid == 0) {
+      if (ep_leader) {
         if (OUT_F32) {
 #pragma unroll
           for (int ch = 0; ch < BN / 32; ++ch)
             tma_reduce_add_2d(&tmD, smem_staging + ch * (BM * 128), n0 + ch * 32, m0);
-        } else if (p.epi == EPI_GEGLU) {
-          tma_store_2d(&tmD, smem_staging, n0 / 2, m0);
         } else {
-          tma_store_2d(&tmD, smem_staging, n0, m0);
-          tma_store_2d(&tmD, smem_staging + BM * 128, n0 + 64, m0);
+          // the other staging buffer was the source of tile it-1's store: once that has been read it can take
+          // the next tile's residual (prefetch) and, one tile later, the next result
+          if (has_res && tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + gridDim.x, sbuf ^ 1);
+          if (p.epi == EPI_GEGLU) {
+            tma_store_2d(&tmD, staging_s, n0 / 2, m0);
+          } else {
+            tma_store_2d(&tmD, staging_s, n0, m0);
+            tma_store_2d(&tmD, staging_s + BM * 128, n0 + 64, m0);
+          }
         }
         tma_store_commit();
       }
     }
-    if (ep_tid == 0) tma_store_wait_all<0>();
+    if (ep_leader) tma_store_wait_all<0>();
   }
 
   __syncwarp();
@@ -336,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 template <int A_MN, int B_MN, int OUT_F32>
 static int launch_t(cudaStream_t stream, const CUtensorMap& tmA0, const CUtensorMap& tmA1,
                     const CUtensorMap& tmB0, const CUtensorMap& tmB1, const CUtensorMap& tmD,
-                    const GemmParams& p) {
+                    const CUtensorMap& tmR, const GemmParams& p) {
   auto kern = gemm_tc_kernel<A_MN, B_MN, OUT_F32>;
   constexpr int smem = Cfg<OUT_F32>::SMEM_BYTES;
   static bool configured = false;
@@ -346,7 +382,7 @@ static int launch_t(cudaStream_t stream, const CUtensorMap& tmA0, const CUtensor
   }
   const int total = p.tiles_m * p.tiles_n * p.splits;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB0, tmB1, tmD, p);
+  kern<<<grid, NUM_THREADS, smem, stream>>>(tmA0, tmA1, tmB0, tmB1, tmD, tmR, p);
   TSD_LAUNCH_CHECK();
   return 0;
 }
@@ -354,11 +390,16 @@ static int launch_t(cudaStream_t stream, const CUtensorMap& tmA0, const CUtensor
 int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUtensorMap& tmA0,
                 const CUtensorMap& tmA1, const CUtensorMap& tmB0, const CUtensorMap& tmB1,
                 const CUtensorMap& tmD, const GemmParams& p) {
+  // residual [M][ldr] bf16 is read through its own tensor map (same tiling as D)
+  CUtensorMap tmR = tmD;
+  if (p.residual && !out_f32) {
+    if (make_tmap_2d(&tmR, p.residual, 2, p.M, p.N, p.ldr, 64, 128)) return 1;
+  }
   TSD_CHECK(p.N % BN == 0, "gemm: N=%d must be a multiple of %d", p.N, BN);
   TSD_CHECK(p.num_kb > 0 && p.splits > 0 && p.kb_per_split > 0, "gemm: empty K loop");
-  if (!a_mn && !b_mn && !out_f32) return launch_t<0, 0, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, p);
-  if (!a_mn && b_mn && !out_f32) return launch_t<0, 1, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, p);
-  if (a_mn && b_mn && out_f32) return launch_t<1, 1, 1>(stream, tmA0, tmA1, tmB0, tmB1, tmD, p);
+  if (!a_mn && !b_mn && !out_f32) return launch_t<0, 0, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p);
+  if (!a_mn && b_mn && !out_f32) return launch_t<0, 1, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p);
+  if (a_mn && b_mn && out_f32) return launch_t<1, 1, 1>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p);
   set_error("gemm: unsupported operand-major / output combination (%d,%d,%d)", a_mn, b_mn, out_f32);
   return 1;
 }

@@ -92,7 +92,7 @@ __device__ __forceinline__ void dropout_scales8(const Philox& rng, uint64_t ebas
 // grid = (chunks, n_img); thread = one 8-channel vector.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1, int c0,
-                                                       int c1, int hw, const float* __restrict__ stats,
+                                                       int c1, int hw, int pix_per_cta, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int act_silu, float drop_p, uint64_t seed,
                                                        bf16* __restrict__ out) {
@@ -100,40 +100,61 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   const int cpg = C / GROUPS;
   const int vec_per_pix = C / 8;
   const int n = blockIdx.y;
-  __shared__ float s_mean[GROUPS], s_rstd[GROUPS];
-  if (threadIdx.x < GROUPS) {
-    s_mean[threadIdx.x] = stats[((size_t)n * GROUPS + threadIdx.x) * 2];
-    s_rstd[threadIdx.x] = stats[((size_t)n * GROUPS + threadIdx.x) * 2 + 1];
+  // per-channel affine of this image folded with the statistics: z = x * a[c] + b[c]
+  extern __shared__ float s_ab[];  // a[C] then b[C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = stats[((size_t)n * GROUPS + g) * 2], rstd = stats[((size_t)n * GROUPS + g) * 2 + 1];
+    const float a = rstd * gamma[c];
+    s_ab[c] = a;
+    s_ab[C + c] = beta[c] - mean * a;
   }
   __syncthreads();
+  // blockDim is a multiple of vec_per_pix: each thread owns one 8-channel slot, keeps its affine in registers
+  const int slots = blockDim.x / vec_per_pix;
+  const int cv = (threadIdx.x % vec_per_pix) * 8;
+  const int my_slot = threadIdx.x / vec_per_pix;
+  float fa[8], fb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { fa[j] = s_ab[cv + j]; fb[j] = s_ab[C + cv + j]; }
   const Philox rng(seed);
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const int total = hw * vec_per_pix;
-  for (int v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += gridDim.x * blockDim.x) {
-    const int pix = v0 / vec_per_pix;
-    const int cv = (v0 - pix * vec_per_pix) * 8;
-    const bf16* src = cv < c0 ? x0 + ((size_t)n * hw + pix) * c0 + cv : x1 + ((size_t)n * hw + pix) * c1 + (cv - c0);
-    const uint4 u = *reinterpret_cast<const uint4*>(src);
-    float e[8];
-    { const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = d.x; e[7] = d.y; }
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + cv), g1 = *reinterpret_cast<const float4*>(gamma + cv + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(beta + cv), b1 = *reinterpret_cast<const float4*>(beta + cv + 4);
-    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const size_t ebase = ((size_t)n * hw + pix) * C + cv;
-    float sc[8];
-    if (drop_p > 0.f) dropout_scales8(rng, ebase, drop_p, inv_keep, sc);
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+  const bool from0 = cv < c0;
+  const bf16* src_base = from0 ? x0 + (size_t)n * hw * c0 + cv : x1 + (size_t)n * hw * c1 + (cv - c0);
+  const int src_ld = from0 ? c0 : c1;
+  bf16* dst_base = out + (size_t)n * hw * C + cv;
+  constexpr int UNROLL = 4;
+  for (int pix0 = p_begin + my_slot; pix0 < p_end; pix0 += slots * UNROLL) {
+    uint4 u[UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (cv + j) / cpg;
-      float z = (e[j] - s_mean[g]) * s_rstd[g] * gm[j] + bt[j];
-      if (act_silu) z = silu_f(z);
-      if (drop_p > 0.f) z *= sc[j];
-      e[j] = z;
+    for (int k = 0; k < UNROLL; ++k) {
+      const int pix = pix0 + k * slots;
+      if (pix < p_end) u[k] = *reinterpret_cast<const uint4*>(src_base + (size_t)pix * src_ld);
     }
-    uint4 o = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
-    *reinterpret_cast<uint4*>(out + ebase) = o;
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) {
+      const int pix = pix0 + k * slots;
+      if (pix >= p_end) break;
+      float e[8];
+      { const float2 a = unpack_bf16(u[k].x), b = unpack_bf16(u[k].y), c = unpack_bf16(u[k].z), d = unpack_bf16(u[k].w);
+        e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = d.x; e[7] = d.y; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float z = fmaf(e[j], fa[j], fb[j]);
+        if (act_silu) z = silu_f(z);
+        e[j] = z;
+      }
+      if (drop_p > 0.f) {
+        float sc[8];
+        dropout_scales8(rng, ((size_t)n * hw + pix) * C + cv, drop_p, inv_keep, sc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] *= sc[j];
+      }
+      *reinterpret_cast<uint4*>(dst_base + (size_t)pix * C) =
+          make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+    }
   }
 }
 
@@ -411,10 +432,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 
 int gn_grid_x(int hw, int C, int n_img, int* pix_per_cta) {
   // enough CTAs to fill the machine ~4x, at least 32 pixels per CTA
-  int want = ceil_div(4 * num_sms(), n_img);
+  int want = ceil_div(8 * num_sms(), n_img);
   if (want < 1) want = 1;
   int ppc = ceil_div(hw, want);
-  const int min_pix = ceil_div(8192, C);  // >= 8K elements per CTA
+  const int min_pix = ceil_div(16384, C);  // >= 16K elements per CTA
   if (ppc < min_pix) ppc = min_pix;
   if (ppc > hw) ppc = hw;
   *pix_per_cta = ppc;
@@ -444,11 +465,11 @@ extern "C" int tsd_gn_apply(void* stream, const void* x0, const void* x1, int c0
                             uint64_t seed, void* out) {
   const int C = c0 + c1;
   TSD_CHECK(C % 64 == 0 && c0 % 8 == 0, "gn_apply: unsupported channels c0=%d c1=%d", c0, c1);
-  const int total = hw * (C / 8);
-  int gx = ceil_div(total, 256 * 4);
-  if (gx < 1) gx = 1;
-  gn_apply_kernel<<<dim3(gx, n_img), 256, 0, (cudaStream_t)stream>>>((const bf16*)x0, (const bf16*)x1, c0, c1, hw, stats,
-                                                                    gamma, beta, act_silu, drop_p, seed, (bf16*)out);
+  TSD_CHECK(C <= 2048 && 256 % (C / 8) == 0, "gn_apply: unsupported channel count %d", C);
+  int ppc;
+  const int gx = gn_grid_x(hw, C, n_img, &ppc);
+  gn_apply_kernel<<<dim3(gx, n_img), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc, stats, gamma, beta, act_silu, drop_p, seed, (bf16*)out);
   TSD_LAUNCH_CHECK();
   return 0;
 }
