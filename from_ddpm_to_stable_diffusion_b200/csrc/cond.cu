@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) small_linear_fwd_kernel(const float* __re
 }
 
 // dx[m][k] (+)= f'(x[m][k]) * sum_n dy[m][n] * w[n][k].  grid = (ceil(K/256), ceil(M/ROWS))
-__global__ void __launch_bounds__(256) small_linear_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+__global__ void __launch_bounds__(64) small_linear_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                  const float* __restrict__ x, float* __restrict__ dx,
                                                                  int M, int N, int K, int silu_in, int accumulate) {
   extern __shared__ float sdy[];  // [ROWS][N]
@@ -83,24 +83,45 @@ __global__ void __launch_bounds__(256) small_linear_dgrad_kernel(const float* __
   }
 }
 
-// dw[n][k] += sum_m dy[m][n] * f(x[m][k]);  db[n] += sum_m dy[m][n].  grid = (ceil(K/256), N)
-__global__ void __launch_bounds__(256) small_linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+// dw[n][k] += sum_m dy[m][n] * f(x[m][k]);  db[n] += sum_m dy[m][n].  grid = (ceil(K/256), ceil(N/NT)):
+// a thread owns one k and NT consecutive n, so f(x[m][k]) is evaluated once per (m, k) and dy rows are broadcast.
+constexpr int NT = 16;
+__global__ void __launch_bounds__(64) small_linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                  float* __restrict__ dw, float* __restrict__ db, int M,
                                                                  int N, int K, int silu_in) {
-  const int n = blockIdx.y;
+  const int n0 = blockIdx.y * NT;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  float acc = 0.f, accb = 0.f;
-  if (k < K) {
-    for (int m = 0; m < M; ++m) {
-      const float d = dy[(size_t)m * N + n];
-      float v = x[(size_t)m * K + k];
-      if (silu_in) v = v / (1.f + expf(-v));
-      acc += d * v;
-      accb += d;
+  __shared__ float sdy[32][NT];
+  float acc[NT], accb[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { acc[j] = 0.f; accb[j] = 0.f; }
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * NT; i += blockDim.x) {
+      const int mm = i / NT, j = i - mm * NT;
+      sdy[mm][j] = (m0 + mm < M && n0 + j < N) ? dy[(size_t)(m0 + mm) * N + n0 + j] : 0.f;
     }
-    dw[(size_t)n * K + k] += acc;
+    __syncthreads();
+    if (k < K) {
+      const int mend = min(32, M - m0);
+      for (int mm = 0; mm < mend; ++mm) {
+        float v = x[(size_t)(m0 + mm) * K + k];
+        if (silu_in) v = v / (1.f + expf(-v));
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[j] += sdy[mm][j] * v;
+      }
+    }
+    if (db && blockIdx.x == 0 && threadIdx.x < NT) {
+      const int mend = min(32, M - m0);
+      for (int mm = 0; mm < mend; ++mm) accb[0] += sdy[mm][threadIdx.x];
+    }
   }
-  if (db && blockIdx.x == 0 && threadIdx.x == 0) db[n] += accb;
+  if (k < K) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+      if (n0 + j < N) dw[(size_t)(n0 + j) * K + k] += acc[j];
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x < NT && n0 + threadIdx.x < N) db[n0 + threadIdx.x] += accb[0];
 }
 
 // emb[m][0:half] = cos(t*f_i), emb[m][half:] = sin(t*f_i), f_i = exp(-ln(10000) * i / half)  (diffusion.py:24-28)
@@ -148,13 +169,13 @@ extern "C" int tsd_small_linear_bwd(void* stream, const float* dy, const float* 
   TSD_CHECK(N <= 4096, "small_linear_bwd: N=%d too large", N);
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {
-    dim3 grid(ceil_div(K, 256), ceil_div(M, ROWS));
-    small_linear_dgrad_kernel<<<grid, 256, ROWS * N * sizeof(float), st>>>(dy, w, x, dx, M, N, K, silu_in, accumulate_dx);
+    dim3 grid(ceil_div(K, 64), ceil_div(M, ROWS));
+    small_linear_dgrad_kernel<<<grid, 64, ROWS * N * sizeof(float), st>>>(dy, w, x, dx, M, N, K, silu_in, accumulate_dx);
     TSD_LAUNCH_CHECK();
   }
   if (dw) {
-    dim3 grid(ceil_div(K, 256), N);
-    small_linear_wgrad_kernel<<<grid, 256, 0, st>>>(dy, x, dw, db, M, N, K, silu_in);
+    dim3 grid(ceil_div(K, 64), ceil_div(N, NT));
+    small_linear_wgrad_kernel<<<grid, 64, 0, st>>>(dy, x, dw, db, M, N, K, silu_in);
     TSD_LAUNCH_CHECK();
   }
   return 0;

@@ -62,18 +62,18 @@ __global__ void __launch_bounds__(HEAD_CO) head_conv_wgrad_kernel(const bf16* __
                                                                   int n_img, int ci, int H, int W, int co,
                                                                   int pix_per_cta) {
   const int o = threadIdx.x;
-  const size_t total = (size_t)n_img * H * W;
-  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
-  const size_t p1 = p0 + pix_per_cta < total ? p0 + pix_per_cta : total;
+  const int total = n_img * H * W;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, total);
   float acc[MAX_CI * 9];
 #pragma unroll
   for (int i = 0; i < MAX_CI * 9; ++i) acc[i] = 0.f;
   float accb = 0.f;
-  for (size_t p = p0; p < p1; ++p) {
-    const int xx = (int)(p % W);
-    const int yy = (int)((p / W) % H);
-    const int n = (int)(p / ((size_t)W * H));
-    const float d = __bfloat162float(dy[p * co + o]);
+  for (int p = p0; p < p1; ++p) {
+    const int xx = p % W;
+    const int yy = (p / W) % H;
+    const int n = p / (W * H);
+    const float d = __bfloat162float(dy[(size_t)p * co + o]);
     accb += d;
 #pragma unroll
     for (int c = 0; c < MAX_CI; ++c) {
@@ -165,13 +165,13 @@ __global__ void __launch_bounds__(256) tail_conv_dgrad_kernel(const float* __res
     sw[(o * 9 + tap) * C + c] = w[i];
   }
   __syncthreads();
-  const size_t total = (size_t)n_img * H * W * (C / 8);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % (C / 8)) * 8;
-    size_t p = i / (C / 8);
-    const int xx = (int)(p % W);
-    const int yy = (int)((p / W) % H);
-    const size_t n = p / ((size_t)W * H);
+  const int total = n_img * H * W * (C / 8);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = (i % (C / 8)) * 8;
+    const int p = i / (C / 8);
+    const int xx = p % W;
+    const int yy = (p / W) % H;
+    const size_t n = p / (W * H);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) tail_conv_dgrad_kernel(const float* __res
         for (int j = 0; j < 8; ++j) acc[j] += d * wr[j];
       }
     }
-    *reinterpret_cast<uint4*>(da + i * 8) =
+    *reinterpret_cast<uint4*>(da + (size_t)i * 8) =
         make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
   }
 }
@@ -198,19 +198,19 @@ __global__ void __launch_bounds__(128) tail_conv_wgrad_kernel(const float* __res
                                                               int H, int W, int pix_per_cta) {
   constexpr int C = 128;
   const int c = threadIdx.x;
-  const size_t total = (size_t)n_img * H * W;
-  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
-  const size_t p1 = p0 + pix_per_cta < total ? p0 + pix_per_cta : total;
+  const int total = n_img * H * W;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, total);
   float acc[CO * 9];
 #pragma unroll
   for (int i = 0; i < CO * 9; ++i) acc[i] = 0.f;
   float accb[CO];
 #pragma unroll
   for (int o = 0; o < CO; ++o) accb[o] = 0.f;
-  for (size_t p = p0; p < p1; ++p) {
-    const int xx = (int)(p % W);
-    const int yy = (int)((p / W) % H);
-    const size_t n = p / ((size_t)W * H);
+  for (int p = p0; p < p1; ++p) {
+    const int xx = p % W;
+    const int yy = (p / W) % H;
+    const size_t n = p / (W * H);
     float d[CO];
 #pragma unroll
     for (int o = 0; o < CO; ++o) {

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 // GroupNorm backward, pass 1: per-(image, channel) sums  A = sum dz * xhat,  B = sum dz
 // where dz = dy * dropout_scale * silu'(z).  grid = (chunks, n_img).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_bwd_sums_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x0,
+__global__ void __launch_bounds__(256, 2) gn_bwd_sums_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x0,
                                                           const bf16* __restrict__ x1, int c0, int c1, int hw,
                                                           int pix_per_cta, const float* __restrict__ stats,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -173,57 +173,72 @@ __global__ void __launch_bounds__(256) gn_bwd_sums_kernel(const bf16* __restrict
   const int vec_per_pix = C / 8;
   const int n = blockIdx.y;
   extern __shared__ float s_ab[];  // [C][2]
-  __shared__ float s_mean[GROUPS], s_rstd[GROUPS];
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_ab[i] = 0.f;
-  if (threadIdx.x < GROUPS) {
-    s_mean[threadIdx.x] = stats[((size_t)n * GROUPS + threadIdx.x) * 2];
-    s_rstd[threadIdx.x] = stats[((size_t)n * GROUPS + threadIdx.x) * 2 + 1];
-  }
   __syncthreads();
   const Philox rng(seed);
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(hw, p_begin + pix_per_cta);
-  // thread -> fixed channel vector when blockDim % vec_per_pix == 0 (true for C <= 2048, C % 64 == 0 ... C/8 | 256)
-  const int slots = blockDim.x / vec_per_pix;  // pixels processed per sweep
-  const int my_vec = threadIdx.x % vec_per_pix;
+  // thread -> fixed 8-channel slot (blockDim % vec_per_pix == 0): all per-channel constants live in registers
+  const int slots = blockDim.x / vec_per_pix;
+  const int cv = (threadIdx.x % vec_per_pix) * 8;
   const int my_slot = threadIdx.x / vec_per_pix;
-  if (my_slot < slots) {
-    const int cv = my_vec * 8;
-    float accA[8], accB[8];
+  float fa[8], fb[8], rs[8], ms[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
-    float gm[8], bt[8];
+  for (int j = 0; j < 8; ++j) {
+    const int g = (cv + j) / cpg;
+    const float mean = stats[((size_t)n * GROUPS + g) * 2], rstd = stats[((size_t)n * GROUPS + g) * 2 + 1];
+    rs[j] = rstd;
+    ms[j] = -mean * rstd;
+    fa[j] = rstd * gamma[cv + j];
+    fb[j] = beta[cv + j] - mean * fa[j];
+  }
+  float accA[8], accB[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { gm[j] = gamma[cv + j]; bt[j] = beta[cv + j]; }
-    for (int pix = p_begin + my_slot; pix < p_end; pix += slots) {
-      const bf16* src = cv < c0 ? x0 + ((size_t)n * hw + pix) * c0 + cv : x1 + ((size_t)n * hw + pix) * c1 + (cv - c0);
-      const size_t ebase = ((size_t)n * hw + pix) * C + cv;
-      const uint4 u = *reinterpret_cast<const uint4*>(src);
-      const uint4 g = *reinterpret_cast<const uint4*>(dy + ebase);
-      float e[8], d[8];
-      { const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), dd = unpack_bf16(u.w);
-        e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = dd.x; e[7] = dd.y; }
-      { const float2 a = unpack_bf16(g.x), b = unpack_bf16(g.y), c = unpack_bf16(g.z), dd = unpack_bf16(g.w);
-        d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = dd.x; d[7] = dd.y; }
-      float sc[8];
-      if (drop_p > 0.f) dropout_scales8(rng, ebase, drop_p, inv_keep, sc);
+  for (int j = 0; j < 8; ++j) { accA[j] = 0.f; accB[j] = 0.f; }
+  const bool from0 = cv < c0;
+  const bf16* src_base = from0 ? x0 + (size_t)n * hw * c0 + cv : x1 + (size_t)n * hw * c1 + (cv - c0);
+  const int src_ld = from0 ? c0 : c1;
+  const bf16* dy_base = dy + (size_t)n * hw * C + cv;
+  constexpr int UNROLL = 2;
+  for (int pix0 = p_begin + my_slot; pix0 < p_end; pix0 += slots * UNROLL) {
+    uint4 u[UNROLL], gq[UNROLL];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int grp = (cv + j) / cpg;
-        const float xhat = (e[j] - s_mean[grp]) * s_rstd[grp];
-        float dz = d[j];
-        if (drop_p > 0.f) dz *= sc[j];
-        if (act_silu) dz *= silu_grad_f(xhat * gm[j] + bt[j]);
-        accA[j] += dz * xhat;
-        accB[j] += dz;
+    for (int k = 0; k < UNROLL; ++k) {
+      const int pix = pix0 + k * slots;
+      if (pix < p_end) {
+        u[k] = *reinterpret_cast<const uint4*>(src_base + (size_t)pix * src_ld);
+        gq[k] = *reinterpret_cast<const uint4*>(dy_base + (size_t)pix * C);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_ab[(cv + j) * 2], accA[j]);
-      atomicAdd(&s_ab[(cv + j) * 2 + 1], accB[j]);
+    for (int k = 0; k < UNROLL; ++k) {
+      const int pix = pix0 + k * slots;
+      if (pix >= p_end) break;
+      float e[8], d[8];
+      { const float2 a = unpack_bf16(u[k].x), b = unpack_bf16(u[k].y), c = unpack_bf16(u[k].z), dd = unpack_bf16(u[k].w);
+        e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = dd.x; e[7] = dd.y; }
+      { const float2 a = unpack_bf16(gq[k].x), b = unpack_bf16(gq[k].y), c = unpack_bf16(gq[k].z), dd = unpack_bf16(gq[k].w);
+        d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = dd.x; d[7] = dd.y; }
+      if (drop_p > 0.f) {
+        float sc[8];
+        dropout_scales8(rng, ((size_t)n * hw + pix) * C + cv, drop_p, inv_keep, sc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] *= sc[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dz = d[j];
+        if (act_silu) dz *= silu_grad_f(fmaf(e[j], fa[j], fb[j]));
+        accA[j] = fmaf(dz, fmaf(e[j], rs[j], ms[j]), accA[j]);
+        accB[j] += dz;
+      }
     }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_ab[(cv + j) * 2], accA[j]);
+    atomicAdd(&s_ab[(cv + j) * 2 + 1], accB[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&ab[(size_t)n * 2 * C + i], s_ab[i]);
@@ -231,22 +246,20 @@ __global__ void __launch_bounds__(256) gn_bwd_sums_kernel(const bf16* __restrict
 
 // pass 2: dx = rstd * (gamma*dz - mean_g(gamma*dz) - xhat * mean_g(gamma*dz*xhat)) (+ radd), written to the
 // (optionally split) destinations dx0 [.., c0] and dx1 [.., c1].
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x0,
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x0,
                                                            const bf16* __restrict__ x1, int c0, int c1, int hw,
-                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, int act_silu, float drop_p,
-                                                           uint64_t seed, const float* __restrict__ ab,
-                                                           const bf16* __restrict__ radd, bf16* __restrict__ dx0,
-                                                           bf16* __restrict__ dx1) {
+                                                           int pix_per_cta, const float* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int act_silu, float drop_p, uint64_t seed,
+                                                           const float* __restrict__ ab, const bf16* __restrict__ radd,
+                                                           bf16* __restrict__ dx0, bf16* __restrict__ dx1) {
   const int C = c0 + c1;
   const int cpg = C / GROUPS;
   const int vec_per_pix = C / 8;
   const int n = blockIdx.y;
-  __shared__ float s_mean[GROUPS], s_rstd[GROUPS], s_m1[GROUPS], s_m2[GROUPS];
+  __shared__ float s_m1[GROUPS], s_m2[GROUPS];
   if (threadIdx.x < GROUPS) {
     const int g = threadIdx.x;
-    s_mean[g] = stats[((size_t)n * GROUPS + g) * 2];
-    s_rstd[g] = stats[((size_t)n * GROUPS + g) * 2 + 1];
     float m1 = 0.f, m2 = 0.f;
     for (int j = 0; j < cpg; ++j) {
       const int c = g * cpg + j;
@@ -260,43 +273,69 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const bf16* __restric
   __syncthreads();
   const Philox rng(seed);
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const int total = hw * vec_per_pix;
-  for (int v0 = blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += gridDim.x * blockDim.x) {
-    const int pix = v0 / vec_per_pix;
-    const int cv = (v0 - pix * vec_per_pix) * 8;
-    const size_t prow = (size_t)n * hw + pix;
-    const bf16* src = cv < c0 ? x0 + prow * c0 + cv : x1 + prow * c1 + (cv - c0);
-    const size_t ebase = prow * C + cv;
-    const uint4 u = *reinterpret_cast<const uint4*>(src);
-    const uint4 g = *reinterpret_cast<const uint4*>(dy + ebase);
-    float e[8], d[8], r[8];
-    { const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), dd = unpack_bf16(u.w);
-      e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = dd.x; e[7] = dd.y; }
-    { const float2 a = unpack_bf16(g.x), b = unpack_bf16(g.y), c = unpack_bf16(g.z), dd = unpack_bf16(g.w);
-      d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = dd.x; d[7] = dd.y; }
-    if (radd) {
-      const uint4 q = *reinterpret_cast<const uint4*>(radd + ebase);
-      const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), dd = unpack_bf16(q.w);
-      r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y; r[6] = dd.x; r[7] = dd.y;
-    } else {
+  const int slots = blockDim.x / vec_per_pix;
+  const int cv = (threadIdx.x % vec_per_pix) * 8;
+  const int my_slot = threadIdx.x / vec_per_pix;
+  // dx = g1*dz - (k1 + xhat*k2), z = x*fa + fb, xhat = x*rs + ms
+  float fa[8], fb[8], rs[8], ms[8], k1[8], k2[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = 0.f;
-    }
-    float sc[8];
-    if (drop_p > 0.f) dropout_scales8(rng, ebase, drop_p, inv_keep, sc);
+  for (int j = 0; j < 8; ++j) {
+    const int g = (cv + j) / cpg;
+    const float mean = stats[((size_t)n * GROUPS + g) * 2], rstd = stats[((size_t)n * GROUPS + g) * 2 + 1];
+    const float gm = gamma[cv + j];
+    rs[j] = rstd;
+    ms[j] = -mean * rstd;
+    fa[j] = rstd * gm;
+    fb[j] = beta[cv + j] - mean * fa[j];
+    k1[j] = rstd * s_m1[g];
+    k2[j] = rstd * s_m2[g];
+  }
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(hw, p_begin + pix_per_cta);
+  const bool from0 = cv < c0;
+  const bf16* src_base = from0 ? x0 + (size_t)n * hw * c0 + cv : x1 + (size_t)n * hw * c1 + (cv - c0);
+  bf16* dst_base = from0 ? dx0 + (size_t)n * hw * c0 + cv : dx1 + (size_t)n * hw * c1 + (cv - c0);
+  const int src_ld = from0 ? c0 : c1;
+  const size_t full_base = (size_t)n * hw * C + cv;
+  constexpr int UNROLL = 2;
+  for (int pix0 = p_begin + my_slot; pix0 < p_end; pix0 += slots * UNROLL) {
+    uint4 u[UNROLL], gq[UNROLL], rq[UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int grp = (cv + j) / cpg;
-      const float gmj = gamma[cv + j];
-      const float xhat = (e[j] - s_mean[grp]) * s_rstd[grp];
-      float dz = d[j];
-      if (drop_p > 0.f) dz *= sc[j];
-      if (act_silu) dz *= silu_grad_f(xhat * gmj + beta[cv + j]);
-      e[j] = s_rstd[grp] * (gmj * dz - s_m1[grp] - xhat * s_m2[grp]) + r[j];
+    for (int k = 0; k < UNROLL; ++k) {
+      const int pix = pix0 + k * slots;
+      if (pix < p_end) {
+        u[k] = *reinterpret_cast<const uint4*>(src_base + (size_t)pix * src_ld);
+        gq[k] = *reinterpret_cast<const uint4*>(dy + full_base + (size_t)pix * C);
+        rq[k] = radd ? *reinterpret_cast<const uint4*>(radd + full_base + (size_t)pix * C) : make_uint4(0, 0, 0, 0);
+      }
     }
-    const uint4 o = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
-    bf16* dst = cv < c0 ? dx0 + prow * c0 + cv : dx1 + prow * c1 + (cv - c0);
-    *reinterpret_cast<uint4*>(dst) = o;
+#pragma unroll
+    for (int k = 0; k < UNROLL; ++k) {
+      const int pix = pix0 + k * slots;
+      if (pix >= p_end) break;
+      float e[8], d[8], r[8];
+      { const float2 a = unpack_bf16(u[k].x), b = unpack_bf16(u[k].y), c = unpack_bf16(u[k].z), dd = unpack_bf16(u[k].w);
+        e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = dd.x; e[7] = dd.y; }
+      { const float2 a = unpack_bf16(gq[k].x), b = unpack_bf16(gq[k].y), c = unpack_bf16(gq[k].z), dd = unpack_bf16(gq[k].w);
+        d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = dd.x; d[7] = dd.y; }
+      { const float2 a = unpack_bf16(rq[k].x), b = unpack_bf16(rq[k].y), c = unpack_bf16(rq[k].z), dd = unpack_bf16(rq[k].w);
+        r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y; r[6] = dd.x; r[7] = dd.y; }
+      if (drop_p > 0.f) {
+        float sc[8];
+        dropout_scales8(rng, full_base + (size_t)pix * C, drop_p, inv_keep, sc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] *= sc[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dz = d[j];
+        if (act_silu) dz *= silu_grad_f(fmaf(e[j], fa[j], fb[j]));
+        const float xhat = fmaf(e[j], rs[j], ms[j]);
+        e[j] = fmaf(fa[j], dz, r[j]) - fmaf(xhat, k2[j], k1[j]);
+      }
+      *reinterpret_cast<uint4*>(dst_base + (size_t)pix * src_ld) =
+          make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+    }
   }
 }
 
@@ -488,12 +527,9 @@ extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const vo
   gn_bwd_sums_kernel<<<dim3(gx, n_img), 256, 2 * C * sizeof(float), st>>>(
       (const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc, stats, gamma, beta, act_silu, drop_p, seed, ab);
   TSD_LAUNCH_CHECK();
-  const int total = hw * (C / 8);
-  int gx2 = ceil_div(total, 256 * 4);
-  if (gx2 < 1) gx2 = 1;
-  gn_bwd_apply_kernel<<<dim3(gx2, n_img), 256, 0, st>>>((const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, stats,
-                                                        gamma, beta, act_silu, drop_p, seed, ab, (const bf16*)radd,
-                                                        (bf16*)dx0, (bf16*)dx1);
+  gn_bwd_apply_kernel<<<dim3(gx, n_img), 256, 0, st>>>((const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc,
+                                                       stats, gamma, beta, act_silu, drop_p, seed, ab, (const bf16*)radd,
+                                                       (bf16*)dx0, (bf16*)dx1);
   TSD_LAUNCH_CHECK();
   if (dgamma) {
     gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ab, n_img, C, dgamma, dbeta);

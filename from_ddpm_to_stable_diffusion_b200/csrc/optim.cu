@@ -40,15 +40,34 @@ __global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, 
     coef = coef > 1.f ? 1.f : coef;
   }
   const float step_size = lr / bc1;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float gi = g[i] * coef;
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= step_size * (mi / denom);
-    p[i] = pi; m[i] = mi; v[i] = vi;
-    if (write_clipped_grad) g[i] = gi;
+  const float decay = 1.f - lr * wd, ib1 = 1.f - beta1, ib2 = 1.f - beta2, inv_bc2 = 1.f / bc2_sqrt;
+  // flat buffers are 16-byte aligned and padded to a multiple of 4 elements: 128-bit accesses throughout
+  const size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i], gv = reinterpret_cast<float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = &pv.x; float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gi = gp[j] * coef;
+      mp[j] = beta1 * mp[j] + ib1 * gi;
+      vp[j] = beta2 * vp[j] + ib2 * gi * gi;
+      pp[j] = pp[j] * decay - step_size * (mp[j] / (sqrtf(vp[j]) * inv_bc2 + eps));
+      gp[j] = gi;
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (write_clipped_grad) reinterpret_cast<float4*>(g)[i] = gv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (size_t i = n4 * 4; i < n; ++i) {
+      const float gi = g[i] * coef;
+      const float mi = beta1 * m[i] + ib1 * gi, vi = beta2 * v[i] + ib2 * gi * gi;
+      p[i] = p[i] * decay - step_size * (mi / (sqrtf(vi) * inv_bc2 + eps));
+      m[i] = mi; v[i] = vi;
+      if (write_clipped_grad) g[i] = gi;
+    }
   }
 }
 
@@ -58,7 +77,7 @@ __global__ void scale_kernel(float* __restrict__ x, size_t n, float s) {
 
 inline int ew_grid(size_t items) {
   size_t g = (items + 255) / 256;
-  const size_t cap = (size_t)num_sms() * 8;
+  const size_t cap = (size_t)num_sms() * 16;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -79,7 +98,7 @@ extern "C" int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float*
   TSD_CHECK(step >= 1, "adamw: step must be >= 1");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-  adamw_clip_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt,
+  adamw_clip_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt,
                                                                  max_norm, sumsq, write_clipped_grad);
   TSD_LAUNCH_CHECK();
   return 0;
