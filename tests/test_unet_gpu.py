@@ -140,3 +140,56 @@ def test_sampler_graph_matches_eager(cuda):
     # GroupNorm statistics are reduced with float atomics, so replay and eager runs differ in the last bits
     assert torch.isfinite(a).all()
     assert (a - b).abs().max().item() < 5e-3
+
+
+def test_fused_clip_adamw_matches_torch(cuda):
+    """tsd_sumsq_f32 + tsd_adamw_clip == clip_grad_norm_(1.0) + torch.optim.AdamW.step() (02_train_direct.py:72-73)."""
+    from from_ddpm_to_stable_diffusion_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 1000003
+    p0 = torch.randn(n + 1, device=cuda, generator=g)[:n].clone()
+    flat = torch.zeros((n + 3) // 4 * 4, device=cuda)
+    flat[:n] = p0
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=1e-2)
+    m = torch.zeros_like(flat)
+    v = torch.zeros_like(flat)
+    ss = torch.zeros(1, device=cuda)
+    for step in range(1, 4):
+        grad = torch.randn(n, device=cuda, generator=g) * 3.0
+        ref.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 1.0)
+        opt.step()
+        gflat = torch.zeros_like(flat)
+        gflat[:n] = grad
+        ss.zero_()
+        ops.sumsq(gflat, ss)
+        assert abs(ss.sqrt().item() - grad.norm().item()) / grad.norm().item() < 1e-5
+        ops.adamw_clip(flat, gflat, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step, 1.0, ss)
+        torch.cuda.synchronize()
+        assert (flat[:n] - ref.data).abs().max().item() < 2e-6, step
+
+
+def test_data_parallel_gradient_additivity(cuda):
+    """Two 'ranks' (half batches, loss scaled by the GLOBAL batch) sum to the single-process gradient -- what the
+    NCCL all-reduce of the flat gradient buffer relies on (run sequentially on one GPU)."""
+    from from_ddpm_to_stable_diffusion_b200 import TrainerDDPM
+    from from_ddpm_to_stable_diffusion_b200.parallel import dp_loss_scale, shard_range
+    m, _ = _model(cuda)
+    m.train()
+    B = 4
+    x0, t, y = _inputs(B, 3, 32, seed=5)
+    noise = torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(6))
+    tr = TrainerDDPM(m, 0.0015, 0.0195, 1000).to(cuda)
+
+    def grads(sl):
+        for p in m.parameters():
+            p.grad = None
+        loss = tr(x0[sl].to(cuda), y[sl].to(cuda), t=t[sl].to(cuda), noise=noise[sl].to(cuda)).sum() * dp_loss_scale(B)
+        loss.backward()
+        return m._engine._flat_grad.clone()
+
+    full = grads(slice(0, B))
+    parts = sum(grads(slice(*shard_range(B, r, 2))) for r in range(2))
+    rel = ((parts - full).norm() / full.norm()).item()
+    assert rel < 2e-2, rel  # bf16 wgrad partial sums are re-associated, nothing else differs
