@@ -328,6 +328,103 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
   if (bad) atomicOr(nan_flag, 1);
 }
 
+// Fused sampling tail (north star K7): final conv 128 -> CO on the GroupNorm+SiLU'ed features of BOTH halves of the
+// 2B batch (conditional rows n, unconditional rows n + B), and in the epilogue, per pixel and channel,
+//   eps = (1+w) eps_c - w eps_u;  x' = c1[t] x - c2[t] eps + sigma[t] z;  NaN flag;  clip at t = 0
+// with z from Philox keyed by (seed, t, element).  x (fp32 NCHW, [2B] with both halves equal) is read once and
+// written once per step; eps never goes to HBM.
+template <int CO>
+__global__ void __launch_bounds__(256) tail_conv_sample_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ x,
+                                                               const int* __restrict__ step_ptr, const float* __restrict__ c1,
+                                                               const float* __restrict__ c2, const float* __restrict__ sigma,
+                                                               float wcfg, const float* __restrict__ noise_in, uint64_t seed,
+                                                               int* __restrict__ nan_flag, float* __restrict__ eps_out,
+                                                               int B, int H, int W, int clip_last) {
+  constexpr int C = 128;
+  __shared__ float sw[CO * 9 * C];  // [co][tap][c]
+  for (int i = threadIdx.x; i < CO * C * 9; i += blockDim.x) {
+    const int o = i / (C * 9), r = i - o * (C * 9), c = r / 9, tap = r - c * 9;  // OIHW
+    sw[(o * 9 + tap) * C + c] = w[i];
+  }
+  __syncthreads();
+  const int step = *step_ptr;
+  const float k1 = c1[step], k2 = c2[step], sg = sigma[step], w1 = 1.f + wcfg;
+  const Philox rng(seed);
+  const int lane = threadIdx.x & 31;
+  const int HW = H * W;
+  const int total = B * HW;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  bool bad = false;
+  for (int base = warp_global * 32; base < total; base += nwarps * 32) {
+    float mine[2][CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) mine[0][o] = mine[1][o] = 0.f;
+    for (int i = 0; i < 32; ++i) {
+      const int p = base + i;
+      if (p >= total) break;
+      const int xx = p % W;
+      const int yy = (p / W) % H;
+      const int n = p / HW;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const size_t nbase = (size_t)(n + half * B) * HW;
+        float acc[CO];
+#pragma unroll
+        for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
+          if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
+          const uint2 u = *reinterpret_cast<const uint2*>(a + (nbase + (size_t)y2 * W + x2) * C + lane * 4);
+          const float2 v0 = unpack_bf16(u.x), v1 = unpack_bf16(u.y);
+#pragma unroll
+          for (int o = 0; o < CO; ++o) {
+            const float4 wv = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + lane * 4);
+            acc[o] += v0.x * wv.x + v0.y * wv.y + v1.x * wv.z + v1.y * wv.w;
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+          const float s = warp_sum(acc[o]);
+          if (lane == i) mine[half][o] = s;
+        }
+      }
+    }
+    const int p = base + lane;
+    if (p < total) {
+      const int n = p / HW, rem = p - n * HW;
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        const size_t e = ((size_t)n * CO + o) * HW + rem;  // element index inside the [B, CO, H, W] image tensor
+        const float ec = mine[0][o] + bias[o], eu = mine[1][o] + bias[o];
+        if (eps_out) {
+          eps_out[e] = ec;
+          eps_out[(size_t)B * CO * HW + e] = eu;
+        }
+        float z = 0.f;
+        if (step > 0) {
+          if (noise_in) {
+            z = noise_in[e];
+          } else {
+            const uint4 r = rng(e, (uint64_t)step + 1);
+            z = box_muller(r.x, r.y).x;
+          }
+        }
+        const float ep = __fsub_rn(__fmul_rn(w1, ec), __fmul_rn(wcfg, eu));
+        const float mean = __fsub_rn(__fmul_rn(k1, x[e]), __fmul_rn(k2, ep));
+        float v = __fadd_rn(mean, __fmul_rn(sg, z));
+        bad |= (v != v);
+        if (clip_last && step == 0) v = fminf(fmaxf(v, -1.f), 1.f);
+        x[e] = v;
+        x[(size_t)B * CO * HW + e] = v;  // the unconditional copy of the 2B batch
+      }
+    }
+  }
+  if (bad) atomicOr(nan_flag, 1);
+}
+
 __global__ void step_counter_kernel(int* step_ptr, int delta) { *step_ptr += delta; }
 // out[0:len] = table[*step][0:len]  (per-step conditioning rows, indexed on the device so a CUDA graph can replay)
 __global__ void gather_row_kernel(const float* __restrict__ table, const int* __restrict__ step_ptr, int len,
@@ -431,6 +528,22 @@ extern "C" int tsd_step_add(void* stream, int* step_ptr, int delta) {
 }
 extern "C" int tsd_gather_row_f32(void* stream, const float* table, const int* step_ptr, int len, float* out) {
   gather_row_kernel<<<ceil_div(len, 256), 256, 0, (cudaStream_t)stream>>>(table, step_ptr, len, out);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_tail_conv_sample(void* stream, const void* a, const float* w, const float* bias, float* x,
+                                    const int* step_ptr, const float* c1, const float* c2, const float* sigma, float wcfg,
+                                    const float* noise_in, uint64_t seed, int* nan_flag, float* eps_out, int B, int H, int W,
+                                    int c_in, int co, int clip_last) {
+  TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_sample: unsupported channels c_in=%d co=%d", c_in, co);
+  const size_t total = (size_t)B * H * W;
+  int grid = (int)((total + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (co == 3)
+    tail_conv_sample_kernel<3><<<grid, 256, 0, st>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
+  else
+    tail_conv_sample_kernel<4><<<grid, 256, 0, st>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -155,7 +155,7 @@ class UNetEngine:
         return vv, cb
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x, t, labels, save, tb_override=None, cb_override=None, eps_out=None, taps=None):
+    def forward(self, x, t, labels, save, tb_override=None, cb_override=None, eps_out=None, taps=None, sample_tail=None):
         """Returns (eps fp32 NCHW, tape).  tb_override / cb_override: precomputed per-block conditioning
         (sampling: one shared time row for the whole batch, constant label vectors)."""
         m = self.model
@@ -283,6 +283,10 @@ class UNetEngine:
         hw = h * w
         stt = ops.gn_stats(cur, n, hw, 1e-5, scratch)
         at = ops.gn_apply(cur, n, hw, stt, P["tail.0.weight"], P["tail.0.bias"], True)
+        if sample_tail is not None:
+            # sampling: final conv + CFG combine + posterior update + Philox noise in one kernel (x updated in place)
+            ops.tail_conv_sample(at, P["tail.2.weight"], P["tail.2.bias"], x, n // 2, h, w, **sample_tail)
+            return None, None
         eps = ops.tail_conv_fwd(at, P["tail.2.weight"], P["tail.2.bias"], n, h, w, out=eps_out)
         if save:
             tape.append(_Rec("tail", "tail", xin=cur, st=stt, a=at, h=h, w=w))

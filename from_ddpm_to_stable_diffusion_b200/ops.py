@@ -276,6 +276,12 @@ def sampler_update(x, eps, step_ptr, c1, c2, sigma, w, x_out, nan_flag, noise=No
          nan_flag, i64(total), int(clip_last), int(dup))
 
 
+def tail_conv_sample(a, w, bias, x, B, H, W, step_ptr, c1, c2, sigma, wcfg, nan_flag, noise=None, seed=0, eps_out=None,
+                     clip_last=True):
+    call("tsd_tail_conv_sample", _chk(a, BF16), _chk(w, F32), bias, _chk(x, F32), step_ptr, c1, c2, sigma, f32(wcfg), noise,
+         u64(seed), nan_flag, eps_out, B, H, W, a.shape[1], w.shape[0], int(clip_last))
+
+
 def step_add(step_ptr, delta):
     call("tsd_step_add", step_ptr, delta)
 

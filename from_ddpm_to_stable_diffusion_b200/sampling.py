@@ -32,7 +32,7 @@ class SamplingPlan:
         self.graph = None
         self.tb_table = None
         self.cond_sig = None
-        self.n_launch_graph_steps = 0
+        self.fused_tail = getattr(sampler, "fused_tail", True)
 
     def matches(self, x_T, model):
         return tuple(x_T.shape) == self.shape and x_T.device == self.device and model is self.sampler.model
@@ -77,10 +77,16 @@ class SamplingPlan:
     def _one_step(self, noise=None):
         model = self.sampler.model
         ops.gather_row(self.tb_table, self.step, self.tb_cur)
-        model._engine.forward(self.x2, None, None, save=False, tb_override=self.tb_override,
-                              cb_override=self.cb_override, eps_out=self.eps)
-        ops.sampler_update(self.x2, self.eps, self.step, self.c1, self.c2, self.sigma, float(self.sampler.w), self.x2,
-                           self.nan_flag, noise=noise, seed=self.sampler.seed, clip_last=True, dup=True)
+        if self.fused_tail:
+            tail = dict(step_ptr=self.step, c1=self.c1, c2=self.c2, sigma=self.sigma, wcfg=float(self.sampler.w),
+                        nan_flag=self.nan_flag, noise=noise, seed=self.sampler.seed, clip_last=True)
+            model._engine.forward(self.x2, None, None, save=False, tb_override=self.tb_override,
+                                  cb_override=self.cb_override, sample_tail=tail)
+        else:
+            model._engine.forward(self.x2, None, None, save=False, tb_override=self.tb_override,
+                                  cb_override=self.cb_override, eps_out=self.eps)
+            ops.sampler_update(self.x2, self.eps, self.step, self.c1, self.c2, self.sigma, float(self.sampler.w), self.x2,
+                               self.nan_flag, noise=noise, seed=self.sampler.seed, clip_last=True, dup=True)
         ops.step_add(self.step, -1)
 
     def run(self, x_T, labels, steps=None, noise_fn=None):

@@ -86,6 +86,7 @@ class SamplerDDPM(nn.Module):
         self.register_buffer('posterior_var', self.betas * (1. - alphas_bar_prev) / (1. - alphas_bar))
         self.seed = 0x5EED0002
         self.use_cuda_graph = True
+        self.fused_tail = True  # final conv + CFG + posterior update + noise as one kernel
         self._plan = None
 
     # reference helpers kept for API parity (utils.py:143-155) ------------------------------------

@@ -161,6 +161,14 @@ int tsd_mse_bwd(void* stream, const float* pred, const float* noise, const float
 int tsd_sampler_update(void* stream, const float* x, const float* eps, const int* step_ptr, const float* c1,
                        const float* c2, const float* sigma, float w, const float* noise_in, uint64_t seed,
                        float* x_out, int* nan_flag, int64_t total, int clip_last, int dup);
+/* Fused sampling tail: final conv 128 -> co over BOTH halves of the 2B batch `a` (rows [0,B) conditional, [B,2B)
+ * unconditional; diffusion.py:260) with the reverse-step update above in its epilogue: x ([2B,co,H,W] fp32, both
+ * halves identical) is read once and overwritten once per step and eps never reaches HBM (eps_out != NULL dumps
+ * eps_c | eps_u for tests).  Replaces utils.py:151-166 after the UNet body. */
+int tsd_tail_conv_sample(void* stream, const void* a, const float* w, const float* bias, float* x, const int* step_ptr,
+                         const float* c1, const float* c2, const float* sigma, float wcfg, const float* noise_in,
+                         uint64_t seed, int* nan_flag, float* eps_out, int B, int H, int W, int c_in, int co,
+                         int clip_last);
 int tsd_step_add(void* stream, int* step_ptr, int delta);
 /* out[0:len] = table[*step_ptr][0:len] (per-step time-embedding rows, indexed on the device) */
 int tsd_gather_row_f32(void* stream, const float* table, const int* step_ptr, int len, float* out);

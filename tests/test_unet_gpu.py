@@ -193,3 +193,19 @@ def test_data_parallel_gradient_additivity(cuda):
     parts = sum(grads(slice(*shard_range(B, r, 2))) for r in range(2))
     rel = ((parts - full).norm() / full.norm()).item()
     assert rel < 2e-2, rel  # bf16 wgrad partial sums are re-associated, nothing else differs
+
+
+def test_fused_sampling_tail_matches_unfused(cuda):
+    """tail conv + CFG + posterior update fused (tsd_tail_conv_sample) == tail conv kernel followed by the update kernel."""
+    from from_ddpm_to_stable_diffusion_b200 import SamplerDDPM
+    m, _ = _model(cuda)
+    g = torch.Generator().manual_seed(21)
+    xT = torch.randn(2, 3, 64, 64, generator=g).to(cuda)
+    z = torch.randn(2, 3, 64, 64, generator=g).to(cuda)
+    y = torch.tensor([3, 1]).to(cuda)
+    outs = []
+    for fused in (True, False):
+        s = SamplerDDPM(m, 0.0015, 0.0195, 1000, w=1.8).to(cuda)
+        s.fused_tail = fused
+        outs.append(s(xT, y, steps=[700, 699], noise_fn=lambda ts: z))
+    assert (outs[0] - outs[1]).abs().max().item() < 2e-3
