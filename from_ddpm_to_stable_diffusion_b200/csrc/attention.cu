@@ -776,6 +776,300 @@ __global__ void __launch_bounds__(256, MINB) attn_bwd_dkv_kernel(const bf16* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward dK/dV, register-blocked variant: each warp owns MT*16 keys and walks the query stage in sub-tiles of
+// QT = 64/MT queries, so every ldmatrix of Q / dO feeds MT m-tiles (half the shared-memory traffic per MMA,
+// which is what bounds the one-m-tile kernel above: ncu shows its smem pipe at 63 %).
+// ------------------------------------------------------------------------------------------
+template <int DH, int MT, int NSUB, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dkv2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                   const float* __restrict__ lse2, const float* __restrict__ delta,
+                                                                   bf16* __restrict__ dqkv, int L, int C, float scale,
+                                                                   float scale_log2) {
+  constexpr int RS = DH * 2 + 16;
+  constexpr int KT = DH / 16;
+  constexpr int ND = DH / 8;
+  constexpr int QT = KV_TILE / MT;   // queries per sub-tile
+  constexpr int NJ = QT / 8;         // n-tiles per sub-tile
+  constexpr int STAGE_Q = KV_TILE * NSUB;
+  constexpr int STAGE_BYTES = STAGE_Q * RS;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  const uint32_t smem0 = smem_u32_(smem_dyn);
+  float* sLse = reinterpret_cast<float*>(smem_dyn + 4 * STAGE_BYTES);
+  float* sDl = sLse + 2 * STAGE_Q;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const size_t ld = 3 * (size_t)C;
+  const bf16* qbase = qkv + (size_t)b * L * ld + h * DH;
+  const bf16* kbase = qbase + C;
+  const bf16* vbase = qbase + 2 * C;
+  const bf16* dobase = dout + (size_t)b * L * C + h * DH;
+  const size_t sbase = ((size_t)b * H + h) * L;
+  const int k0 = (blockIdx.x * nwarps + warp) * 16 * MT;
+
+  uint32_t kf[MT][KT][4], vf[MT][KT][4];
+  bool key_ok[MT][2];
+  float dk[MT][ND][4], dv[MT][ND][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      load_a_frag(kf[mt][kk], kbase, ld, k0 + 16 * mt, L, kk * 16, lane);
+      load_a_frag(vf[mt][kk], vbase, ld, k0 + 16 * mt, L, kk * 16, lane);
+    }
+    key_ok[mt][0] = (k0 + 16 * mt + g) < L;
+    key_ok[mt][1] = (k0 + 16 * mt + g + 8) < L;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      dk[mt][j][0] = dk[mt][j][1] = dk[mt][j][2] = dk[mt][j][3] = 0.f;
+      dv[mt][j][0] = dv[mt][j][1] = dv[mt][j][2] = dv[mt][j][3] = 0.f;
+    }
+  }
+  const int nstages = (L + STAGE_Q - 1) / STAGE_Q;
+  auto load_stats = [&](int buf, int stage) {
+    for (int i = threadIdx.x; i < STAGE_Q; i += blockDim.x) {
+      const int q = stage * STAGE_Q + i;
+      sLse[buf * STAGE_Q + i] = q < L ? lse2[sbase + q] : INFINITY;  // padded queries: P = 0
+      sDl[buf * STAGE_Q + i] = q < L ? delta[sbase + q] : 0.f;
+    }
+  };
+  load_rows_async<DH>(smem0, qbase, ld, 0, L, STAGE_Q);
+  load_rows_async<DH>(smem0 + STAGE_BYTES, dobase, C, 0, L, STAGE_Q);
+  cp_async_commit();
+  load_stats(0, 0);
+  for (int st = 0; st < nstages; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nstages) {
+      const uint32_t nb = smem0 + (buf ^ 1) * 2 * STAGE_BYTES;
+      load_rows_async<DH>(nb, qbase, ld, (st + 1) * STAGE_Q, L, STAGE_Q);
+      load_rows_async<DH>(nb + STAGE_BYTES, dobase, C, (st + 1) * STAGE_Q, L, STAGE_Q);
+      cp_async_commit();
+      load_stats(buf ^ 1, st + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int sub = 0; sub < STAGE_Q / QT; ++sub) {
+      if (st * STAGE_Q + sub * QT >= L) break;
+      const uint32_t qS = smem0 + buf * 2 * STAGE_BYTES + sub * QT * RS, dS_ = qS + STAGE_BYTES;
+      const float* lseS = sLse + buf * STAGE_Q + sub * QT;
+      const float* dlS = sDl + buf * STAGE_Q + sub * QT;
+      float sacc[MT][NJ][4], pacc[MT][NJ][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          sacc[mt][j][0] = sacc[mt][j][1] = sacc[mt][j][2] = sacc[mt][j][3] = 0.f;
+          pacc[mt][j][0] = pacc[mt][j][1] = pacc[mt][j][2] = pacc[mt][j][3] = 0.f;
+        }
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+        for (int jp = 0; jp < NJ / 2; ++jp) {
+          uint32_t r[4], r2[4];
+          ldsm_nt(r, qS, RS, 16 * jp, 16 * kk, lane);
+          ldsm_nt(r2, dS_, RS, 16 * jp, 16 * kk, lane);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(sacc[mt][2 * jp], kf[mt][kk], r[0], r[1]);
+            mma_bf16(sacc[mt][2 * jp + 1], kf[mt][kk], r[2], r[3]);
+            mma_bf16(pacc[mt][2 * jp], vf[mt][kk], r2[0], r2[1]);
+            mma_bf16(pacc[mt][2 * jp + 1], vf[mt][kk], r2[2], r2[3]);
+          }
+        }
+      uint32_t pf[MT][NJ / 2][4], dsf[MT][NJ / 2][4];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float2 ls = *reinterpret_cast<const float2*>(lseS + 8 * j + 2 * t);
+        const float2 dl = *reinterpret_cast<const float2*>(dlS + 8 * j + 2 * t);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          float p[4], ds[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float pe = ex2(fmaf(sacc[mt][j][e], scale_log2, -((e & 1) ? ls.y : ls.x)));
+            if (!key_ok[mt][e >> 1]) pe = 0.f;
+            p[e] = pe;
+            ds[e] = pe * (pacc[mt][j][e] - ((e & 1) ? dl.y : dl.x));
+          }
+          pf[mt][j >> 1][(j & 1) * 2] = pack_bf16(p[0], p[1]);
+          pf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
+          dsf[mt][j >> 1][(j & 1) * 2] = pack_bf16(ds[0], ds[1]);
+          dsf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < NJ / 2; ++kk)
+#pragma unroll
+        for (int jp = 0; jp < ND / 2; ++jp) {
+          uint32_t r[4], r2[4];
+          ldsm_t(r, dS_, RS, 16 * kk, 16 * jp, lane);
+          ldsm_t(r2, qS, RS, 16 * kk, 16 * jp, lane);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(dv[mt][2 * jp], pf[mt][kk], r[0], r[1]);
+            mma_bf16(dv[mt][2 * jp + 1], pf[mt][kk], r[2], r[3]);
+            mma_bf16(dk[mt][2 * jp], dsf[mt][kk], r2[0], r2[1]);
+            mma_bf16(dk[mt][2 * jp + 1], dsf[mt][kk], r2[2], r2[3]);
+          }
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r0 = k0 + 16 * mt + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      const int col = h * DH + 8 * j + 2 * t;
+      if (r0 < L) {
+        *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r0) * ld + C + col) = pack_bf16(dk[mt][j][0] * scale, dk[mt][j][1] * scale);
+        *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r0) * ld + 2 * C + col) = pack_bf16(dv[mt][j][0], dv[mt][j][1]);
+      }
+      if (r1 < L) {
+        *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r1) * ld + C + col) = pack_bf16(dk[mt][j][2] * scale, dk[mt][j][3] * scale);
+        *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r1) * ld + 2 * C + col) = pack_bf16(dv[mt][j][2], dv[mt][j][3]);
+      }
+    }
+  }
+}
+
+// Same idea for dQ: each warp owns MT*16 query rows and walks the key stage in sub-tiles of 64/MT keys.
+template <int DH, int MT, int NSUB, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dq2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                                  const float* __restrict__ lse2, const float* __restrict__ delta,
+                                                                  bf16* __restrict__ dqkv, int L, int C, float scale,
+                                                                  float scale_log2) {
+  constexpr int RS = DH * 2 + 16;
+  constexpr int KT = DH / 16;
+  constexpr int ND = DH / 8;
+  constexpr int KTILE = KV_TILE / MT;  // keys per sub-tile
+  constexpr int NJ = KTILE / 8;
+  constexpr int STAGE_KEYS = KV_TILE * NSUB;
+  constexpr int STAGE_BYTES = STAGE_KEYS * RS;
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  const uint32_t smem0 = smem_u32_(smem_dyn);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const size_t ld = 3 * (size_t)C;
+  const bf16* qbase = qkv + (size_t)b * L * ld + h * DH;
+  const bf16* kbase = qbase + C;
+  const bf16* vbase = qbase + 2 * C;
+  const bf16* dobase = dout + (size_t)b * L * C + h * DH;
+  const int q0 = (blockIdx.x * nwarps + warp) * 16 * MT;
+  const size_t sbase = ((size_t)b * H + h) * L;
+
+  uint32_t qf[MT][KT][4], dof[MT][KT][4];
+  float nlse[MT][2], dl[MT][2], dq[MT][ND][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      load_a_frag(qf[mt][kk], qbase, ld, q0 + 16 * mt, L, kk * 16, lane);
+      load_a_frag(dof[mt][kk], dobase, C, q0 + 16 * mt, L, kk * 16, lane);
+    }
+    const int r0 = q0 + 16 * mt + g, r1 = r0 + 8;
+    nlse[mt][0] = r0 < L ? -lse2[sbase + r0] : 0.f;
+    nlse[mt][1] = r1 < L ? -lse2[sbase + r1] : 0.f;
+    dl[mt][0] = r0 < L ? delta[sbase + r0] : 0.f;
+    dl[mt][1] = r1 < L ? delta[sbase + r1] : 0.f;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) dq[mt][j][0] = dq[mt][j][1] = dq[mt][j][2] = dq[mt][j][3] = 0.f;
+  }
+  const int nstages = (L + STAGE_KEYS - 1) / STAGE_KEYS;
+  load_rows_async<DH>(smem0, kbase, ld, 0, L, STAGE_KEYS);
+  load_rows_async<DH>(smem0 + STAGE_BYTES, vbase, ld, 0, L, STAGE_KEYS);
+  cp_async_commit();
+  for (int st = 0; st < nstages; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nstages) {
+      const uint32_t nb = smem0 + (buf ^ 1) * 2 * STAGE_BYTES;
+      load_rows_async<DH>(nb, kbase, ld, (st + 1) * STAGE_KEYS, L, STAGE_KEYS);
+      load_rows_async<DH>(nb + STAGE_BYTES, vbase, ld, (st + 1) * STAGE_KEYS, L, STAGE_KEYS);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int sub = 0; sub < STAGE_KEYS / KTILE; ++sub) {
+      const int key0 = st * STAGE_KEYS + sub * KTILE;
+      if (key0 >= L) break;
+      const uint32_t kS = smem0 + buf * 2 * STAGE_BYTES + sub * KTILE * RS, vS = kS + STAGE_BYTES;
+      float sacc[MT][NJ][4], pacc[MT][NJ][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          sacc[mt][j][0] = sacc[mt][j][1] = sacc[mt][j][2] = sacc[mt][j][3] = 0.f;
+          pacc[mt][j][0] = pacc[mt][j][1] = pacc[mt][j][2] = pacc[mt][j][3] = 0.f;
+        }
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk)
+#pragma unroll
+        for (int jp = 0; jp < NJ / 2; ++jp) {
+          uint32_t r[4], r2[4];
+          ldsm_nt(r, kS, RS, 16 * jp, 16 * kk, lane);
+          ldsm_nt(r2, vS, RS, 16 * jp, 16 * kk, lane);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(sacc[mt][2 * jp], qf[mt][kk], r[0], r[1]);
+            mma_bf16(sacc[mt][2 * jp + 1], qf[mt][kk], r[2], r[3]);
+            mma_bf16(pacc[mt][2 * jp], dof[mt][kk], r2[0], r2[1]);
+            mma_bf16(pacc[mt][2 * jp + 1], dof[mt][kk], r2[2], r2[3]);
+          }
+        }
+      const bool partial = key0 + KTILE > L;
+      uint32_t dsf[MT][NJ / 2][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          float ds[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float pe = ex2(fmaf(sacc[mt][j][e], scale_log2, nlse[mt][e >> 1]));
+            if (partial && (key0 + 8 * j + 2 * t + (e & 1)) >= L) pe = 0.f;
+            ds[e] = pe * (pacc[mt][j][e] - dl[mt][e >> 1]);
+          }
+          dsf[mt][j >> 1][(j & 1) * 2] = pack_bf16(ds[0], ds[1]);
+          dsf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+        }
+#pragma unroll
+      for (int kk = 0; kk < NJ / 2; ++kk)
+#pragma unroll
+        for (int jp = 0; jp < ND / 2; ++jp) {
+          uint32_t r[4];
+          ldsm_t(r, kS, RS, 16 * kk, 16 * jp, lane);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(dq[mt][2 * jp], dsf[mt][kk], r[0], r[1]);
+            mma_bf16(dq[mt][2 * jp + 1], dsf[mt][kk], r[2], r[3]);
+          }
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r0 = q0 + 16 * mt + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      if (r0 < L)
+        *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r0) * ld + h * DH + 8 * j + 2 * t) =
+            pack_bf16(dq[mt][j][0] * scale, dq[mt][j][1] * scale);
+      if (r1 < L)
+        *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r1) * ld + h * DH + 8 * j + 2 * t) =
+            pack_bf16(dq[mt][j][2] * scale, dq[mt][j][3] * scale);
+    }
+  }
+}
+
 struct LaunchShape { int warps, mt, grid_x; };
 LaunchShape pick_shape(int L, bool allow_mt2) {
   LaunchShape s;
@@ -909,6 +1203,30 @@ extern "C" int tsd_attn_bwd(void* stream, const void* qkv, const void* out, cons
   if (dh == 16) attn_bwd_prep_kernel<16><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
   else attn_bwd_prep_kernel<32><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
   TSD_LAUNCH_CHECK();
+  static int bwd_variant = -1;
+  if (bwd_variant < 0) { const char* e = getenv("TSD_ATTN_BWD"); bwd_variant = e ? atoi(e) : 44; }
+  if (bwd_variant > 0 && dh == 16 && L % 256 == 0) {
+    const int vq = bwd_variant / 10, vk = bwd_variant % 10;
+    const int smem_q = 4 * KV_TILE * 4 * 48, smem_k = smem_q + 4 * KV_TILE * 4 * 4;
+#define TSD_BWD_LAUNCH(KERN, MT, NT, SM)                                                                          \
+    do {                                                                                                          \
+      static bool cfgd = false;                                                                                   \
+      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); cfgd = true; } \
+      dim3 gr(ceil_div(L, (NT / 32) * 16 * MT), heads, B);                                                        \
+      KERN<<<gr, NT, SM, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2); \
+      TSD_LAUNCH_CHECK();                                                                                         \
+    } while (0)
+    if (vq == 1) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 1>), 2, 256, smem_q);
+    else if (vq == 2) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 128, 3>), 2, 128, smem_q);
+    else if (vq == 3) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 1, 4, 256, 3>), 1, 256, smem_q);
+    else TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 2>), 2, 256, smem_q);
+    if (vk == 1) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 1>), 2, 256, smem_k);
+    else if (vk == 2) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 128, 3>), 2, 128, smem_k);
+    else if (vk == 3) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 1, 4, 256, 3>), 1, 256, smem_k);
+    else TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 2>), 2, 256, smem_k);
+#undef TSD_BWD_LAUNCH
+    return 0;
+  }
   const LaunchShape s = pick_shape(L, false);
   dim3 grid(s.grid_x, heads, B), block(s.warps * 32);
   const int rc = L >= 256 ? launch_bwd<4>(st, grid, block, dh, qkv, dout, lse2, delta, dqkv, L, C, scale, scale_log2)
