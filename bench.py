@@ -121,8 +121,8 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_img = 2
-    steps = max(1, min(args.steps, 3))
+    n_img = 8
+    steps = max(1, min(args.steps, 5))
     warmup = 1 if args.warmup > 0 else 0
     val, dt = cpu_train_sample(n_img, steps, warmup, threads)
     line = {
@@ -281,9 +281,9 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        v, dt = cpu_train_sample(2, 1, 1, threads)
+        v, dt = cpu_train_sample(8, 3, 1, threads)
         cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": "1 warm-up + 1 timed training step of batch 2 (fwd+bwd+clip+AdamW), oracle port on torch CPU fp32"}
+               "sample": "1 warm-up + 3 timed training steps of batch 8 (fwd+bwd+clip+AdamW), oracle port on torch CPU fp32, all host threads"}
 
     if rank == 0:
         line = {

@@ -120,8 +120,10 @@ extern "C" int tsd_conv3x3_dgrad(void* stream, const void* dy, int n_img, int H,
 }
 
 static void pick_splits(GemmParams& p) {
+  // Work items = tiles * splits are dealt round-robin to one persistent CTA per SM: aim for (just under) two full
+  // rounds so that no CTA runs a third item alone (wave quantisation), never more splits than k-blocks.
   const int tiles = p.tiles_m * p.tiles_n;
-  int want = ceil_div(2 * num_sms(), tiles);
+  int want = (2 * num_sms()) / tiles;
   if (want < 1) want = 1;
   if (want > p.num_kb) want = p.num_kb;
   p.kb_per_split = ceil_div(p.num_kb, want);

@@ -553,7 +553,7 @@ extern "C" int tsd_ln_fwd(void* stream, const void* x, int M, int C, const float
 extern "C" int tsd_ln_bwd(void* stream, const void* dy, const void* x, int M, int C, const float* gamma, float eps,
                           const void* radd, void* dx, float* dgamma, float* dbeta) {
   cudaStream_t st = (cudaStream_t)stream;
-  int rows_per_cta = ceil_div(M, 2 * num_sms());
+  int rows_per_cta = ceil_div(M, 8 * num_sms());  // 8 CTAs (64 warps) per SM: the per-row shuffle chains are latency bound
   if (rows_per_cta < 8) rows_per_cta = 8;
   const int grid = ceil_div(M, rows_per_cta);
   if (C == 128)
