@@ -19,22 +19,19 @@ constexpr int GROUPS = 32;
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x0, const bf16* __restrict__ x1,
                                                          int c0, int c1, int hw, int pix_per_cta,
-                                                         float* __restrict__ sums /* [n][32][2] */) {
+                                                         float* __restrict__ part /* [n][chunks][32][2] */) {
   const int C = c0 + c1;
   const int cpg = C / GROUPS;
   const int vec_per_pix = C / 8;
   const int n = blockIdx.y;
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(hw, p_begin + pix_per_cta);
-  __shared__ float s_sum[GROUPS], s_sq[GROUPS];
-  if (threadIdx.x < GROUPS) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
   // blockDim (256) is a multiple of vec_per_pix (C/8 in {8,16,32,64,128,256}), so every thread owns a
-  // fixed 8-channel slot: accumulate in registers over its pixels, one smem atomic per group at the end.
+  // fixed 8-channel slot: accumulate in registers over its pixels, then reduce in a FIXED order (no atomics:
+  // the statistics, hence the whole forward pass, are bit-reproducible run to run).
   const int slots = blockDim.x / vec_per_pix;
   const int cv = (threadIdx.x % vec_per_pix) * 8;
   const int my_slot = threadIdx.x / vec_per_pix;
-  const int ng = cpg >= 8 ? 1 : 8 / cpg;  // groups covered by this vector
   float ls[4] = {0.f, 0.f, 0.f, 0.f}, lq[4] = {0.f, 0.f, 0.f, 0.f};
   for (int pix = p_begin + my_slot; pix < p_end; pix += slots) {
     const bf16* src = cv < c0 ? x0 + ((size_t)n * hw + pix) * c0 + cv : x1 + ((size_t)n * hw + pix) * c1 + (cv - c0);
@@ -52,29 +49,43 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
       for (int j = 0; j < 8; ++j) { ls[j >> 1] += e[j]; lq[j >> 1] += e[j] * e[j]; }
     }
   }
-  for (int g = 0; g < ng; ++g) {
-    atomicAdd(&s_sum[cv / cpg + g], ls[g]);
-    atomicAdd(&s_sq[cv / cpg + g], lq[g]);
-  }
+  __shared__ float s_ps[256][4], s_pq[256][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s_ps[threadIdx.x][k] = ls[k]; s_pq[threadIdx.x][k] = lq[k]; }
   __syncthreads();
   if (threadIdx.x < GROUPS) {
-    atomicAdd(&sums[((size_t)n * GROUPS + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
-    atomicAdd(&sums[((size_t)n * GROUPS + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    const int g = threadIdx.x;
+    float s = 0.f, q = 0.f;
+    if (cpg >= 8) {  // the group spans cpg/8 whole vectors, partial index 0
+      const int v0 = g * cpg / 8, nv = cpg / 8;
+      for (int sl = 0; sl < slots; ++sl)
+        for (int v = 0; v < nv; ++v) { s += s_ps[sl * vec_per_pix + v0 + v][0]; q += s_pq[sl * vec_per_pix + v0 + v][0]; }
+    } else {         // the group is the k-th sub-block of one vector
+      const int v0 = g * cpg / 8, k = (g * cpg % 8) / cpg;
+      for (int sl = 0; sl < slots; ++sl) { s += s_ps[sl * vec_per_pix + v0][k]; q += s_pq[sl * vec_per_pix + v0][k]; }
+    }
+    float* dst = part + (((size_t)n * gridDim.x + blockIdx.x) * GROUPS + g) * 2;
+    dst[0] = s;
+    dst[1] = q;
   }
 }
 
-// sums -> (mean, rstd); re-zeroes the scratch sums for the next call.
-__global__ void gn_finalize_kernel(float* __restrict__ sums, float* __restrict__ stats, int count, float inv_cnt,
-                                   float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// per-CTA partials (fixed order over chunks) -> (mean, rstd)
+__global__ void gn_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int count, int chunks,
+                                   float inv_cnt, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n * GROUPS + g
   if (i >= count) return;
-  const float s = sums[2 * i], q = sums[2 * i + 1];
+  const int n = i / GROUPS, g = i - n * GROUPS;
+  float s = 0.f, q = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    const float* src = part + (((size_t)n * chunks + c) * GROUPS + g) * 2;
+    s += src[0];
+    q += src[1];
+  }
   const float mean = s * inv_cnt;
   const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
   stats[2 * i] = mean;
   stats[2 * i + 1] = rsqrtf(var + eps);
-  sums[2 * i] = 0.f;
-  sums[2 * i + 1] = 0.f;
 }
 
 // Keep/scale factors for the 8 consecutive elements starting at flat index ebase (ebase % 8 == 0):
@@ -483,6 +494,8 @@ int gn_grid_x(int hw, int C, int n_img, int* pix_per_cta) {
 
 }  // namespace
 
+extern "C" int64_t tsd_gn_scratch_floats(int n_img) { return ((int64_t)8 * num_sms() + n_img) * 64 + 64; }
+
 extern "C" int tsd_gn_stats(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int hw,
                             float eps, float* scratch, float* stats) {
   const int C = c0 + c1;
@@ -493,7 +506,7 @@ extern "C" int tsd_gn_stats(void* stream, const void* x0, const void* x1, int c0
                                                                       scratch);
   TSD_LAUNCH_CHECK();
   const int count = n_img * GROUPS;
-  gn_finalize_kernel<<<ceil_div(count, 256), 256, 0, (cudaStream_t)stream>>>(scratch, stats, count,
+  gn_finalize_kernel<<<ceil_div(count, 256), 256, 0, (cudaStream_t)stream>>>(scratch, stats, count, gx,
                                                                             1.f / ((float)hw * (C / GROUPS)), eps);
   TSD_LAUNCH_CHECK();
   return 0;

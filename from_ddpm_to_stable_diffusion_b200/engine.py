@@ -107,7 +107,7 @@ class UNetEngine:
         return W
 
     def _get_scratch(self, n_img, dev):
-        need = n_img * 64
+        need = (8 * 160 + n_img) * 64 + 64  # >= tsd_gn_scratch_floats(n_img): per-CTA GroupNorm partials
         if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
             self._scratch = torch.zeros(max(need, 4096), device=dev, dtype=F32)
         return self._scratch

@@ -74,8 +74,10 @@ int tsd_conv3x3_wgrad(void* stream, const void* dy, const void* x0, const void* 
  * ------------------------------------------------------------------------------------------ */
 
 /* GroupNorm(32 groups) statistics of x = cat(x0 [.., c0], x1 [.., c1]) per image: stats[n][32][2] =
- * (mean, rstd).  scratch: fp32 [n_img*64], all zero on entry, left all zero on exit.
+ * (mean, rstd).  scratch: fp32 workspace of at least tsd_gn_scratch_floats(n_img) elements (per-CTA partial sums,
+ * reduced in a fixed order: the statistics are bit-reproducible).
  * nn.GroupNorm at diffusion.py:90,95 (eps 1e-5), :122 (eps 1e-6), :258. */
+int64_t tsd_gn_scratch_floats(int n_img);
 int tsd_gn_stats(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int hw, float eps,
                  float* scratch, float* stats);
 /* out = dropout_p(silu?(gamma * (x - mean) * rstd + beta)), bf16 [n*hw][c0+c1].  The dropout mask is a
