@@ -53,6 +53,7 @@ class UNetEngine:
 
     def invalidate(self):
         self._packed_sig = None
+        self._dgrad_sig = None
         self._flat_grad = None
         self._grad_views = None
         self._scratch = None
@@ -105,6 +106,23 @@ class UNetEngine:
                 W[key + ".linear_1.geglu_bias"] = ops.pack_geglu_bias(P[key + ".linear_1.bias"])
         self._packed, self._packed_sig = W, sig
         return W
+
+    def packed_dgrad(self, P):
+        """bf16 data-gradient weights of the 3x3 convs ([ci][mirrored tap][co]); training only."""
+        sig = self._signature(P)
+        if sig == getattr(self, "_dgrad_sig", None):
+            return self._dgrad
+        D = {}
+        for key, b in self._block_list():
+            if b[0] == "conv" and b[1] % 64 == 0:
+                D[key] = ops.pack_conv3x3_dgrad(P[key + ".weight"])
+            elif b[0] == "up":
+                D[key + ".conv"] = ops.pack_conv3x3_dgrad(P[key + ".conv.weight"])
+            elif b[0] == "res":
+                D[key + ".conv_1.2"] = ops.pack_conv3x3_dgrad(P[key + ".conv_1.2.weight"])
+                D[key + ".conv_2.3"] = ops.pack_conv3x3_dgrad(P[key + ".conv_2.3.weight"])
+        self._dgrad, self._dgrad_sig = D, sig
+        return D
 
     def _get_scratch(self, n_img, dev):
         need = (8 * 160 + n_img) * 64 + 64  # >= tsd_gn_scratch_floats(n_img): per-CTA GroupNorm partials
@@ -330,6 +348,8 @@ class UNetEngine:
         tape = saved["tape"]
         crec = saved["crec"]
         G, _ = self._grad_buffers(P)
+        D = self.packed_dgrad(P)
+        saved["D"] = D
         dev = x.device
         d_temb = torch.zeros(n, m.time_emb_dim, device=dev, dtype=F32)
         d_ctx = torch.zeros(n, m.time_emb_dim, device=dev, dtype=F32)
@@ -362,7 +382,7 @@ class UNetEngine:
                 dskip = skip_grads.pop()
                 dcur = ops.add(dcur, dskip) if dcur is not None else dskip
             elif kind == "res":
-                dcur = self._res_bwd(rec, dcur, P, W, G, n, temb, d_temb, conv_wgrad)
+                dcur = self._res_bwd(rec, dcur, P, W, G, n, temb, d_temb, conv_wgrad, D)
             elif kind == "attn":
                 dcur = self._attn_bwd(rec, dcur, P, W, G, n, ctx, d_ctx)
             elif kind == "conv":
@@ -372,14 +392,14 @@ class UNetEngine:
                 conv_wgrad(dcur, rec.x0, key + ".weight", hh, ww, stride=s)
                 if s == 2:
                     zs = ops.zero_stuff2(dcur, n, hh // 2, ww // 2)
-                    dcur = ops.conv3x3_dgrad(zs, n, hh, ww, W[key], b[1])
+                    dcur = ops.conv3x3(zs, n, hh, ww, D[key], b[1])
                 else:
-                    dcur = ops.conv3x3_dgrad(dcur, n, hh, ww, W[key], b[1])
+                    dcur = ops.conv3x3(dcur, n, hh, ww, D[key], b[1])
             elif kind == "up":
                 hh, ww = rec.h, rec.w
                 ops.bias_grad(dcur, n, 4 * hh * ww, G[key + ".conv.bias"])
                 conv_wgrad(dcur, rec.u, key + ".conv.weight", 2 * hh, 2 * ww)
-                du = ops.conv3x3_dgrad(dcur, n, 2 * hh, 2 * ww, W[key + ".conv"], rec.b[1])
+                du = ops.conv3x3(dcur, n, 2 * hh, 2 * ww, D[key + ".conv"], rec.b[1])
                 dcur = ops.upsample2_bwd(du, n, hh, ww)
             elif kind == "head":
                 ops.head_conv_wgrad(dcur, x, G[key + ".weight"], G[key + ".bias"])
@@ -403,7 +423,7 @@ class UNetEngine:
             if p.grad is not None and p.grad.data_ptr() != G[k].data_ptr():
                 p.grad.add_(G[k])
 
-    def _res_bwd(self, rec, dout, P, W, G, n, temb, d_temb, conv_wgrad):
+    def _res_bwd(self, rec, dout, P, W, G, n, temb, d_temb, conv_wgrad, D):
         key, b = rec.key, rec.b
         ci, co = b[1], b[2]
         hh, ww = rec.h, rec.w
@@ -411,7 +431,7 @@ class UNetEngine:
         # conv_2 (+ shortcut bias share the same column sums of dout)
         per = ops.bias_grad(dout, n, hw, G[key + ".conv_2.3.bias"])
         conv_wgrad(dout, rec.a2, key + ".conv_2.3.weight", hh, ww)
-        da2 = ops.conv3x3_dgrad(dout, n, hh, ww, W[key + ".conv_2.3"], co)
+        da2 = ops.conv3x3(dout, n, hh, ww, D[key + ".conv_2.3"], co)
         dh, _ = ops.gn_bwd(da2, rec.hmid, n, hw, rec.st2, P[key + ".conv_2.0.weight"], P[key + ".conv_2.0.bias"], True,
                            G[key + ".conv_2.0.weight"], G[key + ".conv_2.0.bias"], drop_p=rec.p_drop, seed=rec.seed)
         # time bias: per-sample column sums of dh feed linear_time; their sum over samples is conv_1's bias grad
@@ -419,7 +439,7 @@ class UNetEngine:
         ops.small_linear_bwd(dtb, temb, P[key + ".linear_time.1.weight"], d_temb, G[key + ".linear_time.1.weight"],
                              G[key + ".linear_time.1.bias"], silu_in=True, accumulate_dx=True)
         conv_wgrad(dh, rec.a1, key + ".conv_1.2.weight", hh, ww)
-        da1 = ops.conv3x3_dgrad(dh, n, hh, ww, W[key + ".conv_1.2"], ci)
+        da1 = ops.conv3x3(dh, n, hh, ww, D[key + ".conv_1.2"], ci)
         if ci != co:
             ops.reduce_rows_into(per, G[key + ".residual_layer.bias"])
             ops.gemm_wgrad(dout, rec.x0, G[key + ".residual_layer.weight"].view(co, ci), x1=rec.x1)

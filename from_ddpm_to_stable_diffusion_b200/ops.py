@@ -312,6 +312,13 @@ def pack_conv3x3(w):
     return out
 
 
+def pack_conv3x3_dgrad(w):
+    co, ci = w.shape[:2]
+    out = torch.empty(ci, 9 * co, device=w.device, dtype=BF16)
+    call("tsd_pack_conv3x3_dgrad", _chk(w, F32), out, co, ci)
+    return out
+
+
 def unpack_conv3x3_grad(src_packed, dst_oihw):
     co, ci = dst_oihw.shape[:2]
     call("tsd_unpack_conv3x3_grad", _chk(src_packed, F32), _chk(dst_oihw, F32), co, ci)

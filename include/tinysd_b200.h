@@ -181,6 +181,8 @@ int tsd_gather_row_f32(void* stream, const float* table, const int* step_ptr, in
 int tsd_pack_linear(void* stream, const float* src, void* dst, int rows, int cols, int geglu);
 int tsd_pack_geglu_bias(void* stream, const float* src, float* dst, int rows);
 int tsd_pack_conv3x3(void* stream, const float* src, void* dst, int co, int ci);          /* OIHW -> [co][tap][ci] */
+/* OIHW -> [ci][8-tap][co]: the data gradient of a stride-1 3x3 conv is tsd_conv3x3_fwd(dy, this weight) */
+int tsd_pack_conv3x3_dgrad(void* stream, const float* src, void* dst, int co, int ci);
 int tsd_unpack_conv3x3_grad(void* stream, const float* src, float* dst, int co, int ci);  /* dst(OIHW) += src */
 /* out[0] += sum g^2 */
 int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out);
