@@ -425,6 +425,51 @@ __global__ void __launch_bounds__(256) tail_conv_sample_kernel(const bf16* __res
   if (bad) atomicOr(nan_flag, 1);
 }
 
+// im2col of the fp32 NCHW image for the head-conv weight gradient: patch[p][k], k = c*9 + tap (< ci*9), zero-padded
+// to KP columns, bf16 -> the reduction over all pixels runs on the tensor cores (tsd_gemm_wgrad).
+__global__ void im2col_head_kernel(const float* __restrict__ x, bf16* __restrict__ patch, int n_img, int ci, int H, int W,
+                                   int KP) {
+  const int vec = KP / 8;
+  const int total = n_img * H * W * vec;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kv = (i % vec) * 8;
+    int p = i / vec;
+    const int xx = p % W; p /= W;
+    const int yy = p % H;
+    const int n = p / H;
+    float e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kv + j;
+      float v = 0.f;
+      if (k < ci * 9) {
+        const int c = k / 9, tap = k - c * 9;
+        const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) v = __ldg(x + (((size_t)n * ci + c) * H + y2) * W + x2);
+      }
+      e[j] = v;
+    }
+    *reinterpret_cast<uint4*>(patch + (size_t)i * 8) =
+        make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+  }
+}
+// fp32 NCHW [n][co][H][W] -> bf16 NHWC padded to CP channels (zeros beyond co): operand of the tail-conv weight gradient
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int n_img, int co, int HW,
+                                        int CP) {
+  const int vec = CP / 8;
+  const int total = n_img * HW * vec;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = (i % vec) * 8;
+    const int p = i / vec;
+    const int n = p / HW, r = p - n * HW;
+    float e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = (cv + j) < co ? __ldg(src + ((size_t)n * co + cv + j) * HW + r) : 0.f;
+    *reinterpret_cast<uint4*>(dst + (size_t)i * 8) =
+        make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+  }
+}
+
 __global__ void step_counter_kernel(int* step_ptr, int delta) { *step_ptr += delta; }
 // out[0:len] = table[*step][0:len]  (per-step conditioning rows, indexed on the device so a CUDA graph can replay)
 __global__ void gather_row_kernel(const float* __restrict__ table, const int* __restrict__ step_ptr, int len,
@@ -544,6 +589,28 @@ extern "C" int tsd_tail_conv_sample(void* stream, const void* a, const float* w,
     tail_conv_sample_kernel<3><<<grid, 256, 0, st>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
   else
     tail_conv_sample_kernel<4><<<grid, 256, 0, st>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_im2col_head(void* stream, const float* x, void* patch, int n_img, int ci, int H, int W, int KP) {
+  TSD_CHECK(KP % 8 == 0 && ci * 9 <= KP, "im2col_head: KP=%d too small for ci=%d", KP, ci);
+  im2col_head_kernel<<<ew_grid((size_t)n_img * H * W * (KP / 8)), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)patch, n_img, ci, H, W, KP);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_nchw_to_nhwc_pad(void* stream, const float* src, void* dst, int n_img, int co, int HW, int CP) {
+  TSD_CHECK(CP % 8 == 0 && co <= CP, "nchw_to_nhwc_pad: CP=%d too small for co=%d", CP, co);
+  nchw_to_nhwc_pad_kernel<<<ew_grid((size_t)n_img * HW * (CP / 8)), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n_img, co, HW, CP);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_tail_conv_dgrad(void* stream, const float* dy, const float* w, void* da, int n_img, int H, int W,
+                                   int c_in, int co) {
+  TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_dgrad: unsupported channels c_in=%d co=%d", c_in, co);
+  const size_t total = (size_t)n_img * H * W;
+  const int g1 = ew_grid(total * 16);
+  if (co == 3) tail_conv_dgrad_kernel<3><<<g1, 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
+  else tail_conv_dgrad_kernel<4><<<g1, 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
   TSD_LAUNCH_CHECK();
   return 0;
 }

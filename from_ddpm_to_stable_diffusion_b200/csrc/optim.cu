@@ -71,6 +71,14 @@ __global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, 
   }
 }
 
+// dst[r][c] += src[r][c] for c < cols (dst row pitch ldd, src row pitch lds)
+__global__ void add_cols_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int cols, int ldd, int lds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  dst[(size_t)r * ldd + c] += src[(size_t)r * lds + c];
+}
+
 __global__ void scale_kernel(float* __restrict__ x, size_t n, float s) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= s;
 }
@@ -105,6 +113,11 @@ extern "C" int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float*
 }
 extern "C" int tsd_scale_f32(void* stream, float* x, int64_t n, float s) {
   scale_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, s);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_add_cols_f32(void* stream, float* dst, const float* src, int rows, int cols, int ldd, int lds) {
+  add_cols_kernel<<<ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, rows, cols, ldd, lds);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -368,8 +368,18 @@ class UNetEngine:
             kind, key = rec.kind, rec.key
             if kind == "tail":
                 hh, ww = rec.h, rec.w
-                da = ops.tail_conv_bwd(deps.contiguous().float(), rec.a, P["tail.2.weight"], G["tail.2.weight"],
-                                       G["tail.2.bias"], n, hh, ww)
+                # tail conv backward: data gradient on CUDA cores (N = 3), weight gradient on the tensor cores through
+                # the generic 3x3 wgrad path with d(eps) padded to 64 channels
+                deps_c = deps.contiguous().float()
+                da = ops.tail_conv_dgrad(deps_c, rec.a, P["tail.2.weight"], n, hh, ww)
+                co_img = P["tail.2.weight"].shape[0]
+                dyp = ops.nchw_to_nhwc_pad(deps_c, 64)
+                tmpw = torch.zeros(64, 9 * rec.a.shape[1], device=dev, dtype=F32)
+                ops.conv3x3_wgrad(dyp, rec.a, n, hh, ww, tmpw)
+                ops.unpack_conv3x3_grad(tmpw[:co_img], G["tail.2.weight"])
+                tmpb = torch.zeros(64, device=dev, dtype=F32)
+                ops.bias_grad(dyp, n, hh * ww, tmpb)
+                ops.add_cols(G["tail.2.bias"], tmpb, 1, co_img, co_img, 64)
                 dcur, _ = ops.gn_bwd(da, rec.xin, n, hh * ww, rec.st, P["tail.0.weight"], P["tail.0.bias"], True,
                                      G["tail.0.weight"], G["tail.0.bias"])
             elif kind == "skip_pop":
@@ -402,7 +412,13 @@ class UNetEngine:
                 du = ops.conv3x3(dcur, n, 2 * hh, 2 * ww, D[key + ".conv"], rec.b[1])
                 dcur = ops.upsample2_bwd(du, n, hh, ww)
             elif kind == "head":
-                ops.head_conv_wgrad(dcur, x, G[key + ".weight"], G[key + ".bias"])
+                # head conv weight gradient on the tensor cores: dW[co][c*9+tap] = dY^T * im2col(x)
+                gw = G[key + ".weight"]
+                patch = ops.im2col_head(x, 128)
+                tmpw = torch.zeros(gw.shape[0], 128, device=dev, dtype=F32)
+                ops.gemm_wgrad(dcur, patch, tmpw)
+                ops.add_cols(gw, tmpw, gw.shape[0], gw.shape[1] * 9, gw.shape[1] * 9, 128)
+                ops.bias_grad(dcur, n, dcur.shape[0] // n, G[key + ".bias"])
                 dcur = None
         assert not skip_grads
         # conditioning backward (time / label MLPs, embedding)

@@ -235,6 +235,20 @@ def head_conv_wgrad(dy, x, dw, db):
     call("tsd_head_conv_wgrad", _chk(dy, BF16), x, _chk(dw, F32), db, n, ci, H, W, dw.shape[0])
 
 
+def im2col_head(x, KP=128):
+    n, ci, H, W = x.shape
+    patch = torch.empty(n * H * W, KP, device=x.device, dtype=BF16)
+    call("tsd_im2col_head", _chk(x, F32), patch, n, ci, H, W, KP)
+    return patch
+
+
+def nchw_to_nhwc_pad(src, CP=64):
+    n, co, H, W = src.shape
+    out = torch.empty(n * H * W, CP, device=src.device, dtype=BF16)
+    call("tsd_nchw_to_nhwc_pad", _chk(src, F32), out, n, co, H * W, CP)
+    return out
+
+
 def tail_conv_fwd(a, w, bias, n, H, W, out=None):
     co = w.shape[0]
     if out is None:
@@ -246,6 +260,12 @@ def tail_conv_fwd(a, w, bias, n, H, W, out=None):
 def tail_conv_bwd(dy, a, w, dw, db, n, H, W):
     da = torch.empty_like(a)
     call("tsd_tail_conv_bwd", _chk(dy, F32), a, w, da, dw, db, n, H, W, a.shape[1], w.shape[0])
+    return da
+
+
+def tail_conv_dgrad(dy, a, w, n, H, W):
+    da = torch.empty_like(a)
+    call("tsd_tail_conv_dgrad", _chk(dy, F32), w, da, n, H, W, a.shape[1], w.shape[0])
     return da
 
 
@@ -322,6 +342,10 @@ def pack_conv3x3_dgrad(w):
 def unpack_conv3x3_grad(src_packed, dst_oihw):
     co, ci = dst_oihw.shape[:2]
     call("tsd_unpack_conv3x3_grad", _chk(src_packed, F32), _chk(dst_oihw, F32), co, ci)
+
+
+def add_cols(dst, src, rows, cols, ldd, lds):
+    call("tsd_add_cols_f32", _chk(dst, F32), _chk(src, F32), rows, cols, ldd, lds)
 
 
 def sumsq(g, out):

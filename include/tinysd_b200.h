@@ -143,9 +143,15 @@ int tsd_head_conv_fwd(void* stream, const float* x, const float* w, const float*
                       int H, int W, int co);
 int tsd_head_conv_wgrad(void* stream, const void* dy, const float* x, float* dw, float* db, int n_img, int ci, int H,
                         int W, int co);
+/* operands that put the two skinny weight gradients on the tensor cores: patch[p][c*9+tap] (bf16, zero-padded to KP
+ * columns) of the fp32 NCHW image for tsd_gemm_wgrad, and d(eps) as bf16 NHWC padded to CP channels for tsd_conv3x3_wgrad */
+int tsd_im2col_head(void* stream, const float* x, void* patch, int n_img, int ci, int H, int W, int KP);
+int tsd_nchw_to_nhwc_pad(void* stream, const float* src, void* dst, int n_img, int co, int HW, int CP);
 /* tail conv 128 -> co in {3,4} on the GroupNorm+SiLU'ed features (diffusion.py:260); out fp32 NCHW */
 int tsd_tail_conv_fwd(void* stream, const void* a, const float* w, const float* bias, float* out, int n_img, int H,
                       int W, int c_in, int co);
+int tsd_tail_conv_dgrad(void* stream, const float* dy, const float* w, void* da, int n_img, int H, int W, int c_in,
+                        int co);
 int tsd_tail_conv_bwd(void* stream, const float* dy, const void* a, const float* w, void* da, float* dw, float* db,
                       int n_img, int H, int W, int c_in, int co);
 /* x_t = sqrt_ab[t_n] x0 + sqrt_1mab[t_n] noise (utils.py:115-116); noise_in NULL => Philox N(0,1), written to
@@ -190,6 +196,8 @@ int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out);
 int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float wd, int step, float max_norm, const float* sumsq, int write_clipped_grad);
 int tsd_scale_f32(void* stream, float* x, int64_t n, float s);
+/* dst[r][c] += src[r][c], c < cols (row pitches ldd / lds): folds padded tensor-core gradients into parameter grads */
+int tsd_add_cols_f32(void* stream, float* dst, const float* src, int rows, int cols, int ldd, int lds);
 /* number of kernel launches issued by this library so far (host-side counter, for bench.py's gpu_launches) */
 unsigned long long tsd_launch_count(void);
 
