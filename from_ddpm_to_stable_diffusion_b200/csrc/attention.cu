@@ -826,6 +826,7 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dkv2_kernel(const bf16* _
       dv[mt][j][0] = dv[mt][j][1] = dv[mt][j][2] = dv[mt][j][3] = 0.f;
     }
   }
+  const bool partial_keys = k0 + 16 * MT > L;  // warp-uniform: only the last key block needs masking
   const int nstages = (L + STAGE_Q - 1) / STAGE_Q;
   auto load_stats = [&](int buf, int stage) {
     for (int i = threadIdx.x; i < STAGE_Q; i += blockDim.x) {
@@ -891,7 +892,7 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dkv2_kernel(const bf16* _
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float pe = ex2(fmaf(sacc[mt][j][e], scale_log2, -((e & 1) ? ls.y : ls.x)));
-            if (!key_ok[mt][e >> 1]) pe = 0.f;
+            if (partial_keys && !key_ok[mt][e >> 1]) pe = 0.f;
             p[e] = pe;
             ds[e] = pe * (pacc[mt][j][e] - ((e & 1) ? dl.y : dl.x));
           }
@@ -1030,10 +1031,12 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dq2_kernel(const bf16* __
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          float ds[4];
+          float ds[4], pe4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pe4[e] = ex2(fmaf(sacc[mt][j][e], scale_log2, nlse[mt][e >> 1]));
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float pe = ex2(fmaf(sacc[mt][j][e], scale_log2, nlse[mt][e >> 1]));
+            float pe = pe4[e];
             if (partial && (key0 + 8 * j + 2 * t + (e & 1)) >= L) pe = 0.f;
             ds[e] = pe * (pacc[mt][j][e] - dl[mt][e >> 1]);
           }
