@@ -79,6 +79,17 @@ __global__ void add_cols_kernel(float* __restrict__ dst, const float* __restrict
   dst[(size_t)r * ldd + c] += src[(size_t)r * lds + c];
 }
 
+// shadow = decay * shadow + (1 - decay) * p   (EMA.update, utils.py:54-58)
+__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p, size_t n4, float decay) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 e = reinterpret_cast<float4*>(ema)[i];
+    const float4 v = reinterpret_cast<const float4*>(p)[i];
+    const float w = 1.f - decay;
+    e.x = w * v.x + decay * e.x; e.y = w * v.y + decay * e.y; e.z = w * v.z + decay * e.z; e.w = w * v.w + decay * e.w;
+    reinterpret_cast<float4*>(ema)[i] = e;
+  }
+}
+
 __global__ void scale_kernel(float* __restrict__ x, size_t n, float s) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= s;
 }
@@ -118,6 +129,12 @@ extern "C" int tsd_scale_f32(void* stream, float* x, int64_t n, float s) {
 }
 extern "C" int tsd_add_cols_f32(void* stream, float* dst, const float* src, int rows, int cols, int ldd, int lds) {
   add_cols_kernel<<<ceil_div(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, rows, cols, ldd, lds);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_ema_update(void* stream, float* ema, const float* p, int64_t n, float decay) {
+  TSD_CHECK(n % 4 == 0, "ema_update: flat buffers are padded to multiples of 4 elements");
+  ema_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(ema, p, n / 4, decay);
   TSD_LAUNCH_CHECK();
   return 0;
 }

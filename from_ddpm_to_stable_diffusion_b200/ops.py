@@ -348,6 +348,10 @@ def add_cols(dst, src, rows, cols, ldd, lds):
     call("tsd_add_cols_f32", _chk(dst, F32), _chk(src, F32), rows, cols, ldd, lds)
 
 
+def ema_update(ema, p, decay):
+    call("tsd_ema_update", _chk(ema, F32), _chk(p, F32), i64(p.numel()), f32(decay))
+
+
 def sumsq(g, out):
     call("tsd_sumsq_f32", _chk(g, F32), i64(g.numel()), out)
 

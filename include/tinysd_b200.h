@@ -196,6 +196,8 @@ int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out);
 int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float wd, int step, float max_norm, const float* sumsq, int write_clipped_grad);
 int tsd_scale_f32(void* stream, float* x, int64_t n, float s);
+/* shadow = decay*shadow + (1-decay)*p over the flat parameter buffer (EMA.update, utils.py:54-58) */
+int tsd_ema_update(void* stream, float* ema, const float* p, int64_t n, float decay);
 /* dst[r][c] += src[r][c], c < cols (row pitches ldd / lds): folds padded tensor-core gradients into parameter grads */
 int tsd_add_cols_f32(void* stream, float* dst, const float* src, int rows, int cols, int ldd, int lds);
 /* number of kernel launches issued by this library so far (host-side counter, for bench.py's gpu_launches) */

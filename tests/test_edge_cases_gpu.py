@@ -142,3 +142,33 @@ def test_checkpoint_round_trip(cuda):
         m2.tail[2].bias.add_(1.0)
         c = m2(x, t, y)
     assert ((c - b) - 1.0).abs().max().item() < 1e-5
+
+
+def test_optimizer_is_a_torch_optimizer_with_scheduler_and_ema(cuda):
+    """FusedClipAdamW plugs into torch LR schedulers (the reference drives AdamW with CosineWarmupScheduler,
+    02_train_direct.py:53-56,83) and keeps the EMA shadow of utils.py:42-72."""
+    from from_ddpm_to_stable_diffusion_b200 import TrainerDDPM
+    from from_ddpm_to_stable_diffusion_b200.optim import FusedClipAdamW
+    m, _ = _model(cuda)
+    m.train()
+    opt = FusedClipAdamW(m, lr=1e-3, weight_decay=1e-5, max_norm=1.0, ema_decay=0.9)
+    assert isinstance(opt, torch.optim.Optimizer)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 0.5 ** e)
+    tr = TrainerDDPM(m, 0.0015, 0.0195, 1000).to(cuda)
+    x = torch.randn(2, 3, 32, 32, device=cuda)
+    y = torch.tensor([1, 2], device=cuda)
+    w0 = m.tail[2].weight.detach().clone()
+    losses = []
+    for it in range(3):
+        opt.zero_grad()
+        loss = tr(x, y).sum() / 4
+        loss.backward()
+        opt.step()
+        sched.step()
+        losses.append(loss.item())
+    assert abs(opt.param_groups[0]["lr"] - 1e-3 * 0.125) < 1e-12
+    w1 = m.tail[2].weight.detach()
+    assert (w1 - w0).abs().max().item() > 0  # parameters moved ...
+    ema = opt.ema_state_dict()["tail.2.weight"]
+    assert (ema - w0).abs().max().item() > 0 and (ema - w1).abs().max().item() > 0  # ... and the shadow lags behind
+    assert all(torch.isfinite(torch.tensor(losses)))
