@@ -33,20 +33,31 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
   const int cv = (threadIdx.x % vec_per_pix) * 8;
   const int my_slot = threadIdx.x / vec_per_pix;
   float ls[4] = {0.f, 0.f, 0.f, 0.f}, lq[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int pix = p_begin + my_slot; pix < p_end; pix += slots) {
-    const bf16* src = cv < c0 ? x0 + ((size_t)n * hw + pix) * c0 + cv : x1 + ((size_t)n * hw + pix) * c1 + (cv - c0);
-    const uint4 u = *reinterpret_cast<const uint4*>(src);
-    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-    const float e[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-    if (cpg >= 8) {
+  const bool from0 = cv < c0;
+  const bf16* src_base = from0 ? x0 + (size_t)n * hw * c0 + cv : x1 + (size_t)n * hw * c1 + (cv - c0);
+  const int src_ld = from0 ? c0 : c1;
+  constexpr int UNROLL = 4;  // independent 16-byte loads in flight per thread
+  for (int pix0 = p_begin + my_slot; pix0 < p_end; pix0 += slots * UNROLL) {
+    uint4 u[UNROLL];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { ls[0] += e[j]; lq[0] += e[j] * e[j]; }
-    } else if (cpg == 4) {
+    for (int k = 0; k < UNROLL; ++k) {
+      const int pix = pix0 + k * slots;
+      u[k] = pix < p_end ? *reinterpret_cast<const uint4*>(src_base + (size_t)pix * src_ld) : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { ls[j >> 2] += e[j]; lq[j >> 2] += e[j] * e[j]; }
-    } else {
+    for (int k = 0; k < UNROLL; ++k) {
+      const float2 a = unpack_bf16(u[k].x), b = unpack_bf16(u[k].y), c = unpack_bf16(u[k].z), d = unpack_bf16(u[k].w);
+      const float e[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+      if (cpg >= 8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { ls[j >> 1] += e[j]; lq[j >> 1] += e[j] * e[j]; }
+        for (int j = 0; j < 8; ++j) { ls[0] += e[j]; lq[0] += e[j] * e[j]; }
+      } else if (cpg == 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ls[j >> 2] += e[j]; lq[j >> 2] += e[j] * e[j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ls[j >> 1] += e[j]; lq[j >> 1] += e[j] * e[j]; }
+      }
     }
   }
   __shared__ float s_ps[256][4], s_pq[256][4];
@@ -88,14 +99,18 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, float* __rest
   stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
-// Keep/scale factors for the 8 consecutive elements starting at flat index ebase (ebase % 8 == 0):
-// two Philox calls, one 32-bit word per element.  The backward kernels regenerate the same mask.
+// Keep/scale factors for the 8 consecutive elements starting at flat index ebase (ebase % 8 == 0): one Philox call,
+// one 16-bit uniform per element (keep probability quantised to 1/65536).  The backward kernels regenerate the mask.
 __device__ __forceinline__ void dropout_scales8(const Philox& rng, uint64_t ebase, float p, float inv_keep,
                                                 float* sc) {
-  const uint4 r0 = rng(ebase >> 2, 0x5eedULL), r1 = rng((ebase >> 2) + 1, 0x5eedULL);
-  const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  const uint4 r = rng(ebase >> 3, 0x5eedULL);
+  const uint32_t thr = (uint32_t)(p * 65536.f);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sc[j] = (w[j] * 2.3283064365386963e-10f) >= p ? inv_keep : 0.f;
+  for (int j = 0; j < 4; ++j) {
+    sc[2 * j] = (w[j] & 0xFFFFu) >= thr ? inv_keep : 0.f;
+    sc[2 * j + 1] = (w[j] >> 16) >= thr ? inv_keep : 0.f;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -194,15 +209,19 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_sums_kernel(const bf16* __restr
   const int slots = blockDim.x / vec_per_pix;
   const int cv = (threadIdx.x % vec_per_pix) * 8;
   const int my_slot = threadIdx.x / vec_per_pix;
-  float fa[8], fb[8], rs[8], ms[8];
+  // cpg >= 4 here (C >= 128): an 8-channel vector touches at most two groups -> per-group constants in 2-entry arrays
+  float fa[8], fb[8], rs[2], ms[2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (cv + j) / cpg;
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int g = (cv + 4 * h2) / cpg;
     const float mean = stats[((size_t)n * GROUPS + g) * 2], rstd = stats[((size_t)n * GROUPS + g) * 2 + 1];
-    rs[j] = rstd;
-    ms[j] = -mean * rstd;
-    fa[j] = rstd * gamma[cv + j];
-    fb[j] = beta[cv + j] - mean * fa[j];
+    rs[h2] = rstd;
+    ms[h2] = -mean * rstd;
+#pragma unroll
+    for (int j = 4 * h2; j < 4 * h2 + 4; ++j) {
+      fa[j] = rstd * gamma[cv + j];
+      fb[j] = beta[cv + j] - mean * fa[j];
+    }
   }
   float accA[8], accB[8];
 #pragma unroll
@@ -241,7 +260,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_sums_kernel(const bf16* __restr
       for (int j = 0; j < 8; ++j) {
         float dz = d[j];
         if (act_silu) dz *= silu_grad_f(fmaf(e[j], fa[j], fb[j]));
-        accA[j] = fmaf(dz, fmaf(e[j], rs[j], ms[j]), accA[j]);
+        accA[j] = fmaf(dz, fmaf(e[j], rs[j >> 2], ms[j >> 2]), accA[j]);
         accB[j] += dz;
       }
     }
@@ -288,18 +307,20 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
   const int cv = (threadIdx.x % vec_per_pix) * 8;
   const int my_slot = threadIdx.x / vec_per_pix;
   // dx = g1*dz - (k1 + xhat*k2), z = x*fa + fb, xhat = x*rs + ms
-  float fa[8], fb[8], rs[8], ms[8], k1[8], k2[8];
+  float fa[8], fb[8], rs[2], ms[2], k1[2], k2[2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (cv + j) / cpg;
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const int g = (cv + 4 * h2) / cpg;
     const float mean = stats[((size_t)n * GROUPS + g) * 2], rstd = stats[((size_t)n * GROUPS + g) * 2 + 1];
-    const float gm = gamma[cv + j];
-    rs[j] = rstd;
-    ms[j] = -mean * rstd;
-    fa[j] = rstd * gm;
-    fb[j] = beta[cv + j] - mean * fa[j];
-    k1[j] = rstd * s_m1[g];
-    k2[j] = rstd * s_m2[g];
+    rs[h2] = rstd;
+    ms[h2] = -mean * rstd;
+    k1[h2] = rstd * s_m1[g];
+    k2[h2] = rstd * s_m2[g];
+#pragma unroll
+    for (int j = 4 * h2; j < 4 * h2 + 4; ++j) {
+      fa[j] = rstd * gamma[cv + j];
+      fb[j] = beta[cv + j] - mean * fa[j];
+    }
   }
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(hw, p_begin + pix_per_cta);
@@ -341,8 +362,8 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
       for (int j = 0; j < 8; ++j) {
         float dz = d[j];
         if (act_silu) dz *= silu_grad_f(fmaf(e[j], fa[j], fb[j]));
-        const float xhat = fmaf(e[j], rs[j], ms[j]);
-        e[j] = fmaf(fa[j], dz, r[j]) - fmaf(xhat, k2[j], k1[j]);
+        const float xhat = fmaf(e[j], rs[j >> 2], ms[j >> 2]);
+        e[j] = fmaf(fa[j], dz, r[j]) - fmaf(xhat, k2[j >> 2], k1[j >> 2]);
       }
       *reinterpret_cast<uint4*>(dst_base + (size_t)pix * src_ld) =
           make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
@@ -367,35 +388,52 @@ __global__ void gn_bwd_params_kernel(const float* __restrict__ ab, int n_img, in
 // ------------------------------------------------------------------------------------------
 // LayerNorm over C (128 / 256 / 512): one warp per token row.
 // ------------------------------------------------------------------------------------------
-template <int VEC>  // VEC = C / 256 uint4 loads per lane ... we use C/32 elements per lane = 8*VEC... see below
+template <int VEC>  // C = 128 * VEC: each lane handles VEC chunks of 4 channels (8 bytes)
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, int M, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float eps, bf16* __restrict__ out) {
-  // C = 64 * VEC * ... : each lane handles VEC chunks of 4 channels (8 bytes): C = 32 * 4 * VEC
   constexpr int C = 128 * VEC;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int RPW = 4;  // rows per warp per pass: RPW independent row loads in flight
   const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float v[4 * VEC];
-  float s = 0.f;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  float4 g[VEC], bt[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const uint2 u = *reinterpret_cast<const uint2*>(x + (size_t)row * C + (i * 32 + lane) * 4);
-    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
-    v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
-    s += a.x + a.y + b.x + b.y;
+    g[i] = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+    bt[i] = *reinterpret_cast<const float4*>(beta + (i * 32 + lane) * 4);
   }
-  const float mean = warp_sum(s) * (1.f / C);
-  float q = 0.f;
+  for (int row0 = warp_global * RPW; row0 < M; row0 += nwarps * RPW) {
+    uint2 u[RPW][VEC];
 #pragma unroll
-  for (int i = 0; i < 4 * VEC; ++i) { const float d = v[i] - mean; q += d * d; }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+    for (int r = 0; r < RPW; ++r)
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
-    const float o0 = (v[4 * i] - mean) * rstd * g.x + b.x, o1 = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
-    const float o2 = (v[4 * i + 2] - mean) * rstd * g.z + b.z, o3 = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
-    *reinterpret_cast<uint2*>(out + (size_t)row * C + c) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+      for (int i = 0; i < VEC; ++i)
+        u[r][i] = (row0 + r < M) ? *reinterpret_cast<const uint2*>(x + (size_t)(row0 + r) * C + (i * 32 + lane) * 4)
+                                 : make_uint2(0, 0);
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      if (row0 + r >= M) break;
+      float v[4 * VEC];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float2 a = unpack_bf16(u[r][i].x), b = unpack_bf16(u[r][i].y);
+        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
+        s += a.x + a.y + b.x + b.y;
+      }
+      const float mean = warp_sum(s) * (1.f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4 * VEC; ++i) { const float d = v[i] - mean; q += d * d; }
+      const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float o0 = (v[4 * i] - mean) * rstd * g[i].x + bt[i].x, o1 = (v[4 * i + 1] - mean) * rstd * g[i].y + bt[i].y;
+        const float o2 = (v[4 * i + 2] - mean) * rstd * g[i].z + bt[i].z, o3 = (v[4 * i + 3] - mean) * rstd * g[i].w + bt[i].w;
+        *reinterpret_cast<uint2*>(out + (size_t)(row0 + r) * C + (i * 32 + lane) * 4) =
+            make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+      }
+    }
   }
 }
 
@@ -532,7 +570,7 @@ extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const vo
                           float drop_p, uint64_t seed, float* ab, const void* radd, void* dx0, void* dx1,
                           float* dgamma, float* dbeta) {
   const int C = c0 + c1;
-  TSD_CHECK(C % 64 == 0 && c0 % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "gn_bwd: unsupported channels c0=%d c1=%d", c0, c1);
+  TSD_CHECK(C % 128 == 0 && c0 % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "gn_bwd: unsupported channels c0=%d c1=%d", c0, c1);
   cudaStream_t st = (cudaStream_t)stream;
   TSD_CUDA(cudaMemsetAsync(ab, 0, (size_t)n_img * C * 2 * sizeof(float), st));
   int ppc;
@@ -554,7 +592,8 @@ extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const vo
 extern "C" int tsd_ln_fwd(void* stream, const void* x, int M, int C, const float* gamma, const float* beta, float eps,
                           void* out) {
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = ceil_div(M, 8);
+  int grid = ceil_div(M, 8 * 4);  // 8 warps x 4 rows per pass
+  if (grid > 8 * num_sms()) grid = 8 * num_sms();
   if (C == 128) ln_fwd_kernel<1><<<grid, 256, 0, st>>>((const bf16*)x, M, gamma, beta, eps, (bf16*)out);
   else if (C == 256) ln_fwd_kernel<2><<<grid, 256, 0, st>>>((const bf16*)x, M, gamma, beta, eps, (bf16*)out);
   else if (C == 512) ln_fwd_kernel<4><<<grid, 256, 0, st>>>((const bf16*)x, M, gamma, beta, eps, (bf16*)out);
