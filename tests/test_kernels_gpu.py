@@ -1,0 +1,205 @@
+"""Per-kernel parity on the GPU against plain PyTorch fp32 references of the same op (same bf16 inputs)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from from_ddpm_to_stable_diffusion_b200 import ops
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _rel(got, ref):
+    return ((got.float() - ref.float()).abs().max() / (ref.float().abs().max() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("B,L,C", [(2, 4096, 128), (3, 1024, 128), (2, 1024, 256), (4, 256, 256), (5, 64, 256),
+                                   (3, 16, 128), (6, 4, 256), (2, 320, 128)])
+def test_attention_fwd_bwd_vs_sdpa(cuda, B, L, C):
+    """softmax(q k^T / sqrt(dh)) v with 8 heads (diffusion.py:46-58), all sequence lengths of both configs + ragged."""
+    H = 8
+    dh = C // H
+    g = torch.Generator(device="cuda").manual_seed(L + C)
+    qkv = (torch.randn(B * L, 3 * C, device=cuda, generator=g) * 1.3).to(BF)
+    dout = torch.randn(B * L, C, device=cuda, generator=g).to(BF)
+    out, lse = ops.attn_fwd(qkv, B, L, C, H, need_lse=True)
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, B, L, C, H)
+    x = qkv.float().view(B, L, 3, H, dh).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+    ref = F.scaled_dot_product_attention(x[0], x[1], x[2])
+    ref.backward(dout.float().view(B, L, H, dh).permute(0, 2, 1, 3))
+    ref_o = ref.permute(0, 2, 1, 3).reshape(B * L, C)
+    ref_d = x.grad.permute(1, 3, 0, 2, 4).reshape(B * L, 3 * C)
+    torch.cuda.synchronize()
+    assert _rel(out, ref_o) < 8e-3
+    assert _rel(dqkv, ref_d) < 1.2e-2
+    # log2-domain logsumexp saved for the backward pass
+    s = (x[0] @ x[1].transpose(-1, -2)) / math.sqrt(dh)
+    ref_lse2 = torch.logsumexp(s, dim=-1) / math.log(2.0)
+    assert (lse - ref_lse2.detach()).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("n,hw,c0,c1,silu,eps", [(3, 4096, 128, 0, True, 1e-5), (2, 1024, 128, 128, True, 1e-5),
+                                                 (4, 64, 256, 256, True, 1e-5), (2, 256, 256, 0, False, 1e-6),
+                                                 (5, 16, 256, 0, True, 1e-5), (2, 4, 256, 256, True, 1e-5)])
+def test_groupnorm_fwd_bwd(cuda, n, hw, c0, c1, silu, eps):
+    """GroupNorm(32) (+SiLU) over a (concatenated) channels-last tensor, forward and backward (diffusion.py:90-96,122)."""
+    C = c0 + c1
+    g = torch.Generator(device="cuda").manual_seed(hw + C)
+    x = (torch.randn(n * hw, C, device=cuda, generator=g) * 2 + 0.5).to(BF)
+    x0 = x[:, :c0].contiguous()
+    x1 = x[:, c0:].contiguous() if c1 else None
+    gamma = torch.rand(C, device=cuda, generator=g) + 0.5
+    beta = torch.randn(C, device=cuda, generator=g) * 0.2
+    dy = torch.randn(n * hw, C, device=cuda, generator=g).to(BF)
+    radd = torch.randn(n * hw, C, device=cuda, generator=g).to(BF)
+    scratch = torch.zeros((8 * 160 + n) * 64 + 64, device=cuda)
+    stats = ops.gn_stats(x0, n, hw, eps, scratch, x1=x1)
+    out = ops.gn_apply(x0, n, hw, stats, gamma, beta, silu, x1=x1)
+    dg, db = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+    dx0, dx1 = ops.gn_bwd(dy, x0, n, hw, stats, gamma, beta, silu, dg, db, x1=x1, radd=radd)
+    xr = x.float().view(n, hw, C).permute(0, 2, 1).contiguous().requires_grad_(True)  # [n, C, hw]
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.group_norm(xr, 32, gr, br, eps=eps)
+    if silu:
+        y = F.silu(y)
+    y.backward(dy.float().view(n, hw, C).permute(0, 2, 1))
+    ref_out = y.permute(0, 2, 1).reshape(n * hw, C)
+    ref_dx = xr.grad.permute(0, 2, 1).reshape(n * hw, C) + radd.float()
+    torch.cuda.synchronize()
+    assert _rel(out, ref_out) < 1e-2
+    got_dx = dx0 if dx1 is None else torch.cat([dx0, dx1], 1)
+    assert _rel(got_dx, ref_dx) < 1.5e-2
+    assert _rel(dg, gr.grad) < 1e-2 and _rel(db, br.grad) < 1e-2
+    # statistics themselves
+    m_ref = xr.detach().view(n, 32, -1).mean(-1)
+    assert (stats[..., 0] - m_ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("M,C", [(4096, 128), (1000, 256), (77, 512)])
+def test_layernorm_fwd_bwd(cuda, M, C):
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = (torch.randn(M, C, device=cuda, generator=g) * 3 + 1).to(BF)
+    dy = torch.randn(M, C, device=cuda, generator=g).to(BF)
+    radd = torch.randn(M, C, device=cuda, generator=g).to(BF)
+    gamma = torch.rand(C, device=cuda, generator=g) + 0.5
+    beta = torch.randn(C, device=cuda, generator=g) * 0.2
+    out = ops.ln_fwd(x, gamma, beta)
+    dg, db = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+    dx = ops.ln_bwd(dy, x, gamma, dg, db, radd=radd)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.layer_norm(xr, (C,), gr, br, eps=1e-5)
+    y.backward(dy.float())
+    torch.cuda.synchronize()
+    assert _rel(out, y) < 1e-2
+    assert _rel(dx, xr.grad + radd.float()) < 1.5e-2
+    assert _rel(dg, gr.grad) < 1e-2 and _rel(db, br.grad) < 1e-2
+
+
+def test_geglu_and_elementwise(cuda):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    M, H = 777 * 8, 512
+    h8 = torch.randn(M, 2 * H, device=cuda, generator=g).to(BF)
+    dout = torch.randn(M, H, device=cuda, generator=g).to(BF)
+    out = ops.geglu_fwd(h8)
+    dh8 = ops.geglu_bwd(h8, dout)
+    hr = h8.float().requires_grad_(True)
+    a, gate = hr.chunk(2, dim=-1)
+    y = a * F.gelu(gate)  # exact erf GELU (diffusion.py:152)
+    y.backward(dout.float())
+    torch.cuda.synchronize()
+    assert _rel(out, y) < 1e-2 and _rel(dh8, hr.grad) < 1e-2
+    # nearest upsample and its adjoint, zero stuffing, column sums
+    n, Hh, Ww, C = 3, 8, 8, 128
+    x = torch.randn(n * Hh * Ww, C, device=cuda, generator=g).to(BF)
+    up = ops.upsample2_fwd(x, n, Hh, Ww)
+    ref = F.interpolate(x.float().view(n, Hh, Ww, C).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    assert torch.equal(up.float().view(n, 2 * Hh, 2 * Ww, C).permute(0, 3, 1, 2), ref)
+    back = ops.upsample2_bwd(up, n, Hh, Ww)
+    assert _rel(back, 4 * x.float()) < 1e-2
+    zs = ops.zero_stuff2(x, n, Hh, Ww).float().view(n, 2 * Hh, 2 * Ww, C)
+    assert torch.equal(zs[:, ::2, ::2], x.float().view(n, Hh, Ww, C)) and zs[:, 1::2].abs().max() == 0
+    cs = ops.colsum(x, n, Hh * Ww)
+    assert _rel(cs, x.float().view(n, Hh * Ww, C).sum(1)) < 1e-3
+    assert _rel(ops.add(x, x), 2 * x.float()) < 1e-2
+
+
+def test_conditioning_kernels(cuda):
+    """Sinusoidal embedding (cos first, diffusion.py:28), embedding lookup, small fp32 linears and their gradients."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    t = torch.tensor([0, 1, 17, 500, 999], device=cuda)
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, 128) / 128).to(cuda)
+    emb = ops.timestep_embedding(t, freqs)
+    args = t[:, None].float() * freqs[None]
+    assert (emb - torch.cat([torch.cos(args), torch.sin(args)], -1)).abs().max().item() < 2e-4
+    M, K, N = 37, 512, 256
+    x = torch.randn(M, K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) * 0.05
+    b = torch.randn(N, device=cuda, generator=g)
+    for silu in (False, True):
+        out = ops.small_linear(x, w, b, silu_in=silu)
+        xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        y = F.linear(F.silu(xr) if silu else xr, wr, br)
+        dy = torch.randn(M, N, device=cuda, generator=g)
+        y.backward(dy)
+        dx, dw, db = torch.zeros_like(x), torch.zeros_like(w), torch.zeros_like(b)
+        ops.small_linear_bwd(dy, x, w, dx, dw, db, silu_in=silu)
+        torch.cuda.synchronize()
+        assert _rel(out, y) < 1e-5 and _rel(dx, xr.grad) < 1e-4 and _rel(dw, wr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+    table = torch.randn(11, 256, device=cuda, generator=g)
+    idx = torch.tensor([0, 3, 3, 10, 0], device=cuda)
+    assert torch.equal(ops.embedding_fwd(idx, table), table[idx])
+    dt = torch.zeros_like(table)
+    dyv = torch.randn(5, 256, device=cuda, generator=g)
+    ops.embedding_bwd(idx, dyv, dt, padding_idx=0)
+    torch.cuda.synchronize()
+    assert dt[0].abs().max().item() == 0 and torch.allclose(dt[3], dyv[1] + dyv[2], atol=1e-6) and torch.allclose(dt[10], dyv[3])
+
+
+def test_q_sample_bit_exact_and_philox_moments(cuda):
+    """x_t = sqrt(ab_t) x0 + sqrt(1-ab_t) noise with the reference's fp32 rounding (utils.py:115-116) is BIT-exact when
+    the noise is injected; the on-device Philox noise has N(0,1) moments and is reproducible per (seed, offset)."""
+    from from_ddpm_to_stable_diffusion_b200 import TrainerDDPM, extract
+    tr = TrainerDDPM(torch.nn.Identity(), 0.0015, 0.0195, 1000)
+    sa, sb = (v.to(cuda) for v in tr._f32_tables(torch.device("cpu")))
+    g = torch.Generator().manual_seed(2)
+    x0 = torch.randn(6, 3, 64, 64, generator=g)
+    noise = torch.randn(6, 3, 64, 64, generator=g)
+    t = torch.tensor([0, 1, 2, 500, 998, 999])
+    ref = extract(tr.sqrt_alphas_bar, t, x0.shape) * x0 + extract(tr.sqrt_one_minus_alphas_bar, t, x0.shape) * noise
+    x_t, nz = ops.q_sample(x0.to(cuda), t.to(cuda), sa, sb, noise=noise.to(cuda))
+    assert torch.equal(x_t.cpu(), ref) and torch.equal(nz.cpu(), noise)
+    x_t2, z = ops.q_sample(torch.zeros(64, 3, 64, 64, device=cuda), torch.zeros(64, dtype=torch.long, device=cuda), sa, sb,
+                           seed=99, offset=5)
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1.0) < 5e-3
+    assert abs((z ** 3).mean().item()) < 2e-2 and abs((z ** 4).mean().item() - 3.0) < 5e-2
+    _, z2 = ops.q_sample(torch.zeros(64, 3, 64, 64, device=cuda), torch.zeros(64, dtype=torch.long, device=cuda), sa, sb,
+                         seed=99, offset=5)
+    _, z3 = ops.q_sample(torch.zeros(64, 3, 64, 64, device=cuda), torch.zeros(64, dtype=torch.long, device=cuda), sa, sb,
+                         seed=99, offset=6)
+    assert torch.equal(z, z2) and not torch.equal(z, z3)
+
+
+def test_sampler_update_matches_reference_arithmetic(cuda):
+    """CFG combine + posterior mean + sigma z in the reference's fp32 operation order (utils.py:153-154,166): bit-exact."""
+    from from_ddpm_to_stable_diffusion_b200 import SamplerDDPM, extract
+    sm = SamplerDDPM(torch.nn.Identity(), 0.0015, 0.0195, 1000, w=1.8)
+    c1, c2, sigma = (v.to(cuda) for v in sm._f32_tables(torch.device("cpu")))
+    g = torch.Generator().manual_seed(4)
+    B = 3
+    x = torch.randn(B, 3, 32, 32, generator=g) * 5
+    ec, eu, z = (torch.randn(B, 3, 32, 32, generator=g) for _ in range(3))
+    var = torch.cat([sm.posterior_var[1:2], sm.betas[1:]])
+    for ts in (999, 1, 0):
+        t = torch.full((B,), ts, dtype=torch.long)
+        eps = (1. + sm.w) * ec - sm.w * eu
+        mean = extract(sm.coeff1, t, x.shape) * x - extract(sm.coeff2, t, x.shape) * eps
+        ref = mean + torch.sqrt(extract(var, t, x.shape)) * (z if ts > 0 else 0)
+        x2 = torch.cat([x, x]).to(cuda)
+        step = torch.full((1,), ts, dtype=torch.int32, device=cuda)
+        flag = torch.zeros(1, dtype=torch.int32, device=cuda)
+        ops.sampler_update(x2, torch.cat([ec, eu]).to(cuda), step, c1, c2, sigma, sm.w, x2, flag, noise=z.to(cuda),
+                           clip_last=False, dup=True)
+        assert torch.equal(x2[:B].cpu(), ref) and torch.equal(x2[B:], x2[:B]) and flag.item() == 0
