@@ -28,31 +28,53 @@ __global__ void __launch_bounds__(256) head_conv_fwd_kernel(const float* __restr
   }
   for (int i = threadIdx.x; i < co; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
+  // thread = (4 consecutive pixels of a row, 8 output channels): every weight vector read from shared memory is
+  // used for 4 pixels and every input value for up to 3 taps (the smem weight reads bound the 1-pixel version)
+  constexpr int PX = 4;
   const int groups = co / 8;
-  const int total = n_img * H * W * groups;  // < 2^31 for any batch that fits the GPU
+  const int wq = W / PX;
+  const int total = n_img * H * wq * groups;  // < 2^31 for any batch that fits the GPU
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int gsel = i % groups;
     int p = i / groups;
-    const int xx = p % W; p /= W;
+    const int x0 = (p % wq) * PX; p /= wq;
     const int yy = p % H;
     const int n = p / H;
-    float acc[8];
+    float acc[PX][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[gsel * 8 + j];
+    for (int q = 0; q < PX; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = sb[gsel * 8 + j];
     for (int c = 0; c < ci; ++c) {
       const float* xp = x + ((size_t)n * ci + c) * H * W;
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
-        if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
-        const float v = __ldg(xp + (size_t)y2 * W + x2);
-        const float* wr = sw + (c * 9 + tap) * co + gsel * 8;
+      for (int dy = 0; dy < 3; ++dy) {
+        const int y2 = yy + dy - 1;
+        if (y2 < 0 || y2 >= H) continue;
+        float v[PX + 2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += v * wr[j];
+        for (int k = 0; k < PX + 2; ++k) {
+          const int x2 = x0 + k - 1;
+          v[k] = (x2 >= 0 && x2 < W) ? __ldg(xp + (size_t)y2 * W + x2) : 0.f;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float* wr = sw + (c * 9 + dy * 3 + dx) * co + gsel * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int q = 0; q < PX; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(v[q + dx], wv[j], acc[q][j]);
+        }
       }
     }
-    *reinterpret_cast<uint4*>(out + (size_t)i * 8) =
-        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
+    const size_t pix = ((size_t)n * H + yy) * W + x0;
+#pragma unroll
+    for (int q = 0; q < PX; ++q)
+      *reinterpret_cast<uint4*>(out + ((pix + q) * groups + gsel) * 8) =
+          make_uint4(pack_bf16(acc[q][0], acc[q][1]), pack_bf16(acc[q][2], acc[q][3]), pack_bf16(acc[q][4], acc[q][5]),
+                     pack_bf16(acc[q][6], acc[q][7]));
   }
 }
 
@@ -490,9 +512,9 @@ inline int ew_grid(size_t items) {
 
 extern "C" int tsd_head_conv_fwd(void* stream, const float* x, const float* w, const float* bias, void* out, int n_img,
                                  int ci, int H, int W, int co) {
-  TSD_CHECK(ci <= MAX_CI && co % 8 == 0, "head_conv_fwd: unsupported channels ci=%d co=%d", ci, co);
+  TSD_CHECK(ci <= MAX_CI && co % 8 == 0 && W % 4 == 0, "head_conv_fwd: unsupported shape ci=%d co=%d W=%d", ci, co, W);
   const size_t smem = (size_t)(ci * 9 * co + co) * sizeof(float);
-  head_conv_fwd_kernel<<<ew_grid((size_t)n_img * H * W * (co / 8)), 256, smem, (cudaStream_t)stream>>>(x, w, bias, (bf16*)out, n_img, ci, H, W, co);
+  head_conv_fwd_kernel<<<ew_grid((size_t)n_img * H * (W / 4) * (co / 8)), 256, smem, (cudaStream_t)stream>>>(x, w, bias, (bf16*)out, n_img, ci, H, W, co);
   TSD_LAUNCH_CHECK();
   return 0;
 }
