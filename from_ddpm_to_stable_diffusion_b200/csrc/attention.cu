@@ -1122,7 +1122,7 @@ static int g_attn_variant = -1;  // experiment knob: TSD_ATTN_FWD = mt*10 + nsub
 extern "C" int tsd_attn_fwd(void* stream, const void* qkv, void* out, float* lse2, int B, int L, int C, int heads) {
   TSD_CHECK(C % heads == 0, "attn_fwd: C %% heads != 0");
   const int dh = C / heads;
-  TSD_CHECK(dh == 16 || dh == 32, "attn_fwd: head_dim %d not in {16, 32}", dh);
+  TSD_CHECK(dh == 16 || dh == 32 || dh == 64, "attn_fwd: head_dim %d not in {16, 32, 64}", dh);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)dh);
   if (g_attn_variant < 0) {
     const char* e = getenv("TSD_ATTN_FWD");
@@ -1161,6 +1161,10 @@ extern "C" int tsd_attn_fwd(void* stream, const void* qkv, void* out, float* lse
     if (s.mt == 1 && nsub == 2) return launch_fwd<16, 1, 2>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
     return launch_fwd<16, 1, 1>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
   }
+  if (dh == 64) {  // the wider [1,2,4,4] configuration (diffusion.py:203): 512 channels / 8 heads
+    if (nsub == 4) return launch_fwd<64, 1, 2>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+    return launch_fwd<64, 1, 1>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
+  }
   if (nsub == 4) return launch_fwd<32, 1, 4>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
   return launch_fwd<32, 1, 1>(st, grid, block, qkv, out, lse2, L, C, scale_log2);
 }
@@ -1168,20 +1172,27 @@ extern "C" int tsd_attn_fwd(void* stream, const void* qkv, void* out, float* lse
 template <int NSUB>
 static int launch_bwd(cudaStream_t st, dim3 grid, dim3 block, int dh, const void* qkv, const void* dout, const float* lse2,
                       const float* delta, void* dqkv, int L, int C, float scale, float scale_log2) {
-  const int smem_dq16 = 4 * KV_TILE * NSUB * 48, smem_dq32 = 4 * KV_TILE * NSUB * 80;
+  const int smem_dq16 = 4 * KV_TILE * NSUB * 48, smem_dq32 = 4 * KV_TILE * NSUB * 80, smem_dq64 = 4 * KV_TILE * NSUB * 144;
   const int smem_kv16 = smem_dq16 + 4 * KV_TILE * NSUB * 4, smem_kv32 = smem_dq32 + 4 * KV_TILE * NSUB * 4;
+  const int smem_kv64 = smem_dq64 + 4 * KV_TILE * NSUB * 4;
   static bool configured = false;
   if (!configured) {
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<16, NSUB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq16));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<32, NSUB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq32));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<16, NSUB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv16));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<32, NSUB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv32));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<64, NSUB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq64));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<64, NSUB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv64));
     configured = true;
   }
   if (dh == 16) {
     attn_bwd_dq_kernel<16, NSUB, 3><<<grid, block, smem_dq16, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
     TSD_LAUNCH_CHECK();
     attn_bwd_dkv_kernel<16, NSUB, 3><<<grid, block, smem_kv16, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+  } else if (dh == 64) {
+    attn_bwd_dq_kernel<64, NSUB, 1><<<grid, block, smem_dq64, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
+    TSD_LAUNCH_CHECK();
+    attn_bwd_dkv_kernel<64, NSUB, 1><<<grid, block, smem_kv64, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
   } else {
     attn_bwd_dq_kernel<32, NSUB, 2><<<grid, block, smem_dq32, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
     TSD_LAUNCH_CHECK();
@@ -1196,7 +1207,7 @@ extern "C" int tsd_attn_bwd(void* stream, const void* qkv, const void* out, cons
                             float* delta, void* dqkv, int B, int L, int C, int heads) {
   TSD_CHECK(C % heads == 0, "attn_bwd: C %% heads != 0");
   const int dh = C / heads;
-  TSD_CHECK(dh == 16 || dh == 32, "attn_bwd: head_dim %d not in {16, 32}", dh);
+  TSD_CHECK(dh == 16 || dh == 32 || dh == 64, "attn_bwd: head_dim %d not in {16, 32, 64}", dh);
   const float scale = 1.f / sqrtf((float)dh);
   const float scale_log2 = 1.4426950408889634f * scale;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1204,7 +1215,8 @@ extern "C" int tsd_attn_bwd(void* stream, const void* qkv, const void* out, cons
   int pg = (int)((total + 255) / 256);
   if (pg > num_sms() * 16) pg = num_sms() * 16;
   if (dh == 16) attn_bwd_prep_kernel<16><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
-  else attn_bwd_prep_kernel<32><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
+  else if (dh == 32) attn_bwd_prep_kernel<32><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
+  else attn_bwd_prep_kernel<64><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
   TSD_LAUNCH_CHECK();
   static int bwd_variant = -1;
   if (bwd_variant < 0) { const char* e = getenv("TSD_ATTN_BWD"); bwd_variant = e ? atoi(e) : 44; }
@@ -1232,8 +1244,8 @@ extern "C" int tsd_attn_bwd(void* stream, const void* qkv, const void* out, cons
   }
   const LaunchShape s = pick_shape(L, false);
   dim3 grid(s.grid_x, heads, B), block(s.warps * 32);
-  const int rc = L >= 256 ? launch_bwd<4>(st, grid, block, dh, qkv, dout, lse2, delta, dqkv, L, C, scale, scale_log2)
-                          : launch_bwd<1>(st, grid, block, dh, qkv, dout, lse2, delta, dqkv, L, C, scale, scale_log2);
+  const int rc = (L >= 256 && dh != 64) ? launch_bwd<4>(st, grid, block, dh, qkv, dout, lse2, delta, dqkv, L, C, scale, scale_log2)
+                                        : launch_bwd<1>(st, grid, block, dh, qkv, dout, lse2, delta, dqkv, L, C, scale, scale_log2);
   if (rc) return rc;
   TSD_LAUNCH_CHECK();
   return 0;

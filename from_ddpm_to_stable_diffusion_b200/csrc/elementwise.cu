@@ -120,13 +120,15 @@ __global__ void zero_stuff2_kernel(const bf16* __restrict__ in, bf16* __restrict
 
 // Per-sample column sums: out[n][c] (+)= sum over the rows of sample n of x[row][c].
 // grid = (chunks, n_img); used for bias gradients (sum over n afterwards) and the time-bias gradient.
-__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int rows_per_sample, int C,
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int rows_per_sample, int C, int CW,
                                                      int rows_per_cta, float* __restrict__ out) {
-  extern __shared__ float s_acc[];  // [C]
-  for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
+  // blockIdx.z selects a chunk of CW <= 2048 channels (row pitch stays C)
+  extern __shared__ float s_acc[];  // [CW]
+  for (int i = threadIdx.x; i < CW; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int n = blockIdx.y;
-  const int vec = C / 8;
+  const int cbase = blockIdx.z * CW;
+  const int vec = CW / 8;
   const int slots = blockDim.x / vec;
   const int cv = (threadIdx.x % vec) * 8;
   const int slot = threadIdx.x / vec;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   if (slot < slots) {
     for (int r = r0 + slot; r < r1; r += slots) {
       float e[8];
-      load8(x + ((size_t)n * rows_per_sample + r) * C + cv, e);
+      load8(x + ((size_t)n * rows_per_sample + r) * C + cbase + cv, e);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += e[j];
     }
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
     for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[cv + j], acc[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[(size_t)n * C + i], s_acc[i]);
+  for (int i = threadIdx.x; i < CW; i += blockDim.x) atomicAdd(&out[(size_t)n * C + cbase + i], s_acc[i]);
 }
 
 // out[c] += sum_n in[n][c]
@@ -254,13 +256,15 @@ extern "C" int tsd_zero_stuff2(void* stream, const void* in, void* out, int n_im
   return 0;
 }
 extern "C" int tsd_colsum(void* stream, const void* x, int n_samples, int rows_per_sample, int C, float* out) {
-  TSD_CHECK(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "colsum: unsupported C=%d", C);
-  int want = ceil_div(4 * num_sms(), n_samples);
+  int CW = C;
+  while (CW > 2048) CW /= 2;
+  TSD_CHECK(C % 8 == 0 && C % CW == 0 && 256 % (CW / 8) == 0, "colsum: unsupported C=%d", C);
+  int want = ceil_div(4 * num_sms(), n_samples * (C / CW));
   int rpc = ceil_div(rows_per_sample, want < 1 ? 1 : want);
   if (rpc < 16) rpc = 16;
   if (rpc > rows_per_sample) rpc = rows_per_sample;
-  colsum_kernel<<<dim3(ceil_div(rows_per_sample, rpc), n_samples), 256, C * sizeof(float), (cudaStream_t)stream>>>(
-      (const bf16*)x, rows_per_sample, C, rpc, out);
+  colsum_kernel<<<dim3(ceil_div(rows_per_sample, rpc), n_samples, C / CW), 256, CW * sizeof(float), (cudaStream_t)stream>>>(
+      (const bf16*)x, rows_per_sample, C, CW, rpc, out);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -172,3 +172,36 @@ def test_optimizer_is_a_torch_optimizer_with_scheduler_and_ema(cuda):
     ema = opt.ema_state_dict()["tail.2.weight"]
     assert (ema - w0).abs().max().item() > 0 and (ema - w1).abs().max().item() > 0  # ... and the shadow lags behind
     assert all(torch.isfinite(torch.tensor(losses)))
+
+
+def test_wider_config_1244(cuda):
+    """channel_multy [1,2,4,4] -- the widths the reference's code comment documents (diffusion.py:203): 512-channel
+    stages, head_dim 64 attention, 1024-channel concatenations.  Forward and parameter gradients vs the oracle."""
+    from from_ddpm_to_stable_diffusion_b200 import Diffusion, TrainerDDPM
+    multy = [1, 2, 4, 4]
+    sd = R.init_state_dict(3, 3, multy, 128, 3)
+    m = Diffusion(3, multy, 128, num_class=3, dropout=0.0)
+    m.load_state_dict(sd)
+    m = m.to(cuda).train()
+    B = 2
+    g = torch.Generator().manual_seed(12)
+    x0 = torch.randn(B, 3, 32, 32, generator=g)
+    t = torch.tensor([30, 700])
+    y = torch.tensor([2, 0])
+    noise = torch.randn(B, 3, 32, 32, generator=g)
+    sched = R.make_schedule(0.0015, 0.0195, 1000)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss_ref = R.trainer_loss(sdg, sched, x0, y, t, noise, multy).sum() / B ** 2
+    loss_ref.backward()
+    tr = TrainerDDPM(m, 0.0015, 0.0195, 1000).to(cuda)
+    loss = tr(x0.to(cuda), y.to(cuda), t=t.to(cuda), noise=noise.to(cuda)).sum() / B ** 2
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 1e-2
+    low = []
+    for k, p in m.named_parameters():
+        gr, gg = sdg[k].grad, p.grad.float().cpu()
+        if gr.norm() > 1e-6:
+            c = (gr.flatten() @ gg.flatten() / (gr.norm() * gg.norm())).item()
+            if c < 0.985:
+                low.append((k, c))
+    assert not low, low[:8]
