@@ -11,6 +11,7 @@
 // Layout: qkv bf16 [B*L][3C]; out bf16 [B*L][C]; lse2 fp32 [B][heads][L] (log2-domain logsumexp).
 #include "../../include/tinysd_b200.h"
 #include "common.cuh"
+#include "attention_tc.cuh"
 #include <cstdlib>
 
 using namespace tsd;
@@ -1124,6 +1125,17 @@ extern "C" int tsd_attn_fwd(void* stream, const void* qkv, void* out, float* lse
   const int dh = C / heads;
   TSD_CHECK(dh == 16 || dh == 32 || dh == 64, "attn_fwd: head_dim %d not in {16, 32, 64}", dh);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)dh);
+  {  // tcgen05 / TMEM path (attention_tc.cu): TSD_ATTN_TC=0 falls back to the mma.sync kernels below
+    static int use_tc = -1, tc_poly = 3;
+    if (use_tc < 0) {
+      const char* e = getenv("TSD_ATTN_TC");
+      use_tc = e ? atoi(e) : 1;
+      const char* pe = getenv("TSD_ATTN_TC_POLY");
+      if (pe) tc_poly = atoi(pe);
+    }
+    if (use_tc && attn_tc_supported(L, C, heads))
+      return launch_attn_fwd_tc((cudaStream_t)stream, qkv, out, lse2, B, L, C, heads, tc_poly);
+  }
   if (g_attn_variant < 0) {
     const char* e = getenv("TSD_ATTN_FWD");
     g_attn_variant = e ? atoi(e) : 112;

@@ -1,0 +1,13 @@
+// tcgen05 / TMEM attention kernels (attention_tc.cu); dispatched from tsd_attn_fwd / tsd_attn_bwd (attention.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tsd {
+
+// head_dim 16 and L a multiple of 256 (two 128-row query tiles per CTA)
+bool attn_tc_supported(int L, int C, int heads);
+// poly: every poly-th pair of exponentials is evaluated on the FMA pipe (0 = none; 2, 3, 4)
+int launch_attn_fwd_tc(cudaStream_t st, const void* qkv, void* out, float* lse2, int B, int L, int C, int heads,
+                       int poly);
+
+}  // namespace tsd

@@ -68,6 +68,28 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
   return 0;
 }
 
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                    uint64_t row_stride_elems, uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
+  auto enc = get_encode();
+  TSD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  TSD_CHECK(swizzle_bytes == 32 || swizzle_bytes == 64 || swizzle_bytes == 128, "tensor map: swizzle must be 32/64/128 B");
+  TSD_CHECK((int)(box_cols * elem_bytes) == swizzle_bytes, "2-D tensor map: inner box must span the swizzle width");
+  TSD_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
+  TSD_CHECK((row_stride_elems * elem_bytes) % 16 == 0, "tensor map row stride must be a multiple of 16 B");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {row_stride_elems * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TSD_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d, sw%d) failed: %d (rows=%llu cols=%llu box=%ux%u)", swizzle_bytes,
+            (int)r, (unsigned long long)rows, (unsigned long long)cols, box_cols, box_rows);
+  return 0;
+}
+
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C,
                    uint32_t box_c, uint32_t bw, uint32_t bh, uint32_t bn, uint32_t s) {
   auto enc = get_encode();

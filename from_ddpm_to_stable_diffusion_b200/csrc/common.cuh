@@ -41,6 +41,9 @@ int num_sms();
 // 2-D: tensor [rows][cols] with cols contiguous; box = box_cols x box_rows.
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
                  uint64_t row_stride_elems, uint32_t box_cols, uint32_t box_rows);
+// Same with a 32 / 64 / 128-byte swizzle; the inner box spans exactly the swizzle width.
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                    uint64_t row_stride_elems, uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 // 4-D NHWC activation [N][H][W][C]; box = (box_c, bw, bh, bn) elements *loaded*; traversal stride s
 // along W and H (s = 2 gives the stride-2 convolution gather).
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, uint64_t W,
