@@ -1120,21 +1120,31 @@ static int launch_fwd2(cudaStream_t st, int B, int heads, const void* qkv, void*
 
 static int g_attn_variant = -1;  // experiment knob: TSD_ATTN_FWD = mt*10 + nsub
 
+static int attn_fwd_impl(void* stream, const void* qkv, void* out, float* lse2, float* ws, int B, int L, int C, int heads);
 extern "C" int tsd_attn_fwd(void* stream, const void* qkv, void* out, float* lse2, int B, int L, int C, int heads) {
+  return attn_fwd_impl(stream, qkv, out, lse2, nullptr, B, L, C, heads);
+}
+extern "C" int tsd_attn_fwd_ws(void* stream, const void* qkv, void* out, float* lse2, float* ws, int B, int L, int C,
+                               int heads) {
+  return attn_fwd_impl(stream, qkv, out, lse2, ws, B, L, C, heads);
+}
+static int attn_fwd_impl(void* stream, const void* qkv, void* out, float* lse2, float* ws, int B, int L, int C, int heads) {
   TSD_CHECK(C % heads == 0, "attn_fwd: C %% heads != 0");
   const int dh = C / heads;
   TSD_CHECK(dh == 16 || dh == 32 || dh == 64, "attn_fwd: head_dim %d not in {16, 32, 64}", dh);
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)dh);
   {  // tcgen05 / TMEM path (attention_tc.cu): TSD_ATTN_TC=0 falls back to the mma.sync kernels below
-    static int use_tc = -1, tc_poly = 3;
+    static int use_tc = -1, tc_poly = 4, tc_bound = 1;
     if (use_tc < 0) {
       const char* e = getenv("TSD_ATTN_TC");
       use_tc = e ? atoi(e) : 1;
       const char* pe = getenv("TSD_ATTN_TC_POLY");
       if (pe) tc_poly = atoi(pe);
+      const char* be = getenv("TSD_ATTN_TC_BOUND");
+      if (be) tc_bound = atoi(be);
     }
     if (use_tc && attn_tc_supported(L, C, heads))
-      return launch_attn_fwd_tc((cudaStream_t)stream, qkv, out, lse2, B, L, C, heads, tc_poly);
+      return launch_attn_fwd_tc((cudaStream_t)stream, qkv, out, lse2, tc_bound ? ws : nullptr, B, L, C, heads, tc_poly);
   }
   if (g_attn_variant < 0) {
     const char* e = getenv("TSD_ATTN_FWD");

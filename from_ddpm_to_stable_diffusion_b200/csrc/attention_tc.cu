@@ -19,6 +19,8 @@
 // score tile is ready before the current one is finished.
 #include "attention_tc.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
+#include <type_traits>
 
 namespace tsd {
 namespace {
@@ -33,8 +35,9 @@ constexpr int Q_BYTES = NWG * QT * ROWB;
 constexpr int KV_BYTES = KB * ROWB;
 constexpr int STAGE_BYTES = 2 * KV_BYTES;
 constexpr int TC_THREADS = NWG * 128 + 64;  // warps 0-7 softmax (warp % 4 = TMEM sub-partition), 8 = TMA, 9 = MMA
-constexpr int WG_COLS = 128;  // TMEM columns per warpgroup: S [0,64) (P overwrites [0,32)), O [64,80)
-constexpr int O_COL = 64;
+constexpr int WG_COLS = 128;  // TMEM columns per warpgroup: S [0,64), P [64,96), O [96,112)
+constexpr int S_COL = 0, P_COL = 64, O_COL = 96;
+constexpr float BOUND_LIMIT = 50.f;  // log2 units: |s*c| <= 50 for every key, so 2^(s*c - bound) >= 2^-100
 constexpr int TMEM_COLS = NWG * WG_COLS;  // 256: two CTAs per SM
 constexpr uint32_t SW32 = 6;
 constexpr int SMEM_BYTES = 1024 + Q_BYTES + NST * STAGE_BYTES + 256;
@@ -69,10 +72,14 @@ __device__ __forceinline__ uint64_t fadd2_(uint64_t a, uint64_t b) {
   return d;
 }
 // 2^x for a packed pair, x <= 8: cubic on [-0.5, 0.5] after a Cody-Waite split, |rel err| < 2e-4 (bf16 P needs 4e-3)
+template <bool CLAMP>
 __device__ __forceinline__ void exp2_poly2_(uint64_t x, float& o0, float& o1) {
-  float x0, x1;
-  upk2(x, x0, x1);
-  const uint64_t xc = pk2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  uint64_t xc = x;
+  if (CLAMP) {  // the exponent insertion below needs x >= -126 (guaranteed without a clamp in bound mode)
+    float x0, x1;
+    upk2(x, x0, x1);
+    xc = pk2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  }
   const uint64_t r = fadd2_(xc, pk2(12582912.f, 12582912.f));
   const uint64_t fl = fadd2_(r, pk2(-12582912.f, -12582912.f));
   const uint64_t f = ffma2_(fl, pk2(-1.f, -1.f), xc);
@@ -86,22 +93,51 @@ __device__ __forceinline__ void exp2_poly2_(uint64_t x, float& o0, float& o1) {
   o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
 }
 
+// max_k |k|^2 per (sample, head): one thread per (key row, head), 16 bf16 each.  knmax2 must be zeroed.
+__global__ void __launch_bounds__(512) attn_knorm_kernel(const bf16* __restrict__ qkv, float* __restrict__ knmax2,
+                                                         int L, int C, int H) {
+  __shared__ int s_max[32];
+  if (threadIdx.x < 32) s_max[threadIdx.x] = 0;
+  __syncthreads();
+  const int rows_per_block = blockDim.x / H;
+  const int r = threadIdx.x / H, hd = threadIdx.x - r * H;
+  const int row = blockIdx.x * rows_per_block + r;
+  const int b = blockIdx.y;
+  if (r < rows_per_block && row < L) {
+    const uint4* p = reinterpret_cast<const uint4*>(qkv + ((size_t)b * L + row) * 3 * C + C + hd * DH);
+    const uint4 a = p[0], c = p[1];
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = unpack_bf16(w[i]);
+      s = fmaf(f.x, f.x, s);
+      s = fmaf(f.y, f.y, s);
+    }
+    atomicMax(&s_max[hd], __float_as_int(s));  // non-negative floats order like ints
+  }
+  __syncthreads();
+  if (threadIdx.x < H) atomicMax(reinterpret_cast<int*>(knmax2) + b * H + threadIdx.x, s_max[threadIdx.x]);
+}
+
 template <int POLY>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse2,
-                   int L, int C, float scale_log2) {
+                   const float* __restrict__ knmax2, int L, int C, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
   const uint32_t sKV = smem_base + Q_BYTES;
   const uint32_t bar_base = sKV + NST * STAGE_BYTES;
-  // barriers (8 B each): q_full, kv_full[NST], kv_empty[NST], s_full[NWG], p_full[NWG]
+  // barriers (8 B each): q_full, kv_full[NST], kv_empty[NST], s_full[NWG], s_free[NWG], p_full[NWG], pv_done[NWG]
   const uint32_t q_full = bar_base;
   auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (1 + NST + s); };
   auto s_full = [&](int g) { return bar_base + 8u * (1 + 2 * NST + g); };
-  auto p_full = [&](int g) { return bar_base + 8u * (1 + 2 * NST + NWG + g); };
-  const uint32_t tmem_slot = bar_base + 8u * (1 + 2 * NST + 2 * NWG);
+  auto s_free = [&](int g) { return bar_base + 8u * (1 + 2 * NST + NWG + g); };
+  auto p_full = [&](int g) { return bar_base + 8u * (1 + 2 * NST + 2 * NWG + g); };
+  auto pv_done = [&](int g) { return bar_base + 8u * (1 + 2 * NST + 3 * NWG + g); };
+  const uint32_t tmem_slot = bar_base + 8u * (1 + 2 * NST + 4 * NWG);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -119,7 +155,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     }
     for (int g = 0; g < NWG; ++g) {
       mbar_init(s_full(g), 1);
+      mbar_init(s_free(g), QT);
       mbar_init(p_full(g), QT);
+      mbar_init(pv_done(g), 1);
     }
     fence_mbar_init();
   }
@@ -129,70 +167,57 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 8) {
+  if (warp >= 8) {
     if (lane == 0) {
-      // =========================================================== TMA producer
-      const int row_base = b * L;
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-#pragma unroll
-      for (int i = 0; i < NWG * QT / 64; ++i)
-        tma_load_2d(sQ + i * 64 * ROWB, &tmQKV, q_full, h * DH, row_base + q0 + i * 64);
-      for (int j = 0; j < nkb; ++j) {
-        const int s = j % NST;
-        mbar_wait(kv_empty(s), ((j / NST) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full(s), STAGE_BYTES);
-        tma_load_2d(sKV + s * STAGE_BYTES, &tmQKV, kv_full(s), C + h * DH, row_base + j * KB);
-        tma_load_2d(sKV + s * STAGE_BYTES + KV_BYTES, &tmQKV, kv_full(s), 2 * C + h * DH, row_base + j * KB);
-      }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      // =========================================================== MMA issuer (serves whichever warpgroup is ready)
+      // =========================================================== MMA issuer of warpgroup g (g == 0 also feeds TMA)
+      // The softmax warps raise their events in program order (s_free(j), p_full(j), s_free(j+1), ...), so the issuer
+      // simply blocks on them in that order: no polling, and one issuer per warpgroup keeps the two independent.
+      const int g = warp - 8;
       constexpr uint32_t idescS = umma_idesc_bf16(QT, KB, 0, 0);
       constexpr uint32_t idescPV = umma_idesc_bf16(QT, DH, 0, 1);
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      auto issue_S = [&](int j, int g) {
+      constexpr int AHEAD = NST - 2;  // K/V blocks in flight beyond the one being consumed
+      const int row_base = b * L;
+      auto load_kv = [&](int jn) {
+        const int s = jn % NST;
+        mbar_wait(kv_empty(s), ((jn / NST) & 1) ^ 1);
+        mbar_arrive_expect_tx(kv_full(s), STAGE_BYTES);
+        tma_load_2d(sKV + s * STAGE_BYTES, &tmQKV, kv_full(s), C + h * DH, row_base + jn * KB);
+        tma_load_2d(sKV + s * STAGE_BYTES + KV_BYTES, &tmQKV, kv_full(s), 2 * C + h * DH, row_base + jn * KB);
+      };
+      if (g == 0) {
+        mbar_arrive_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+        for (int i = 0; i < NWG * QT / 64; ++i)
+          tma_load_2d(sQ + i * 64 * ROWB, &tmQKV, q_full, h * DH, row_base + q0 + i * 64);
+        for (int jn = 0; jn < AHEAD && jn < nkb; ++jn) load_kv(jn);
+      }
+      const uint64_t descQ = umma_smem_desc_sw(sQ + g * QT * ROWB, 0, 8 * ROWB, SW32);
+      const uint32_t tW = tmem_base + g * WG_COLS;
+      auto issue_S = [&](int j) {
         const int s = j % NST;
         mbar_wait(kv_full(s), (j / NST) & 1);
         tc_fence_after();
-        const uint64_t da = umma_smem_desc_sw(sQ + g * QT * ROWB, 0, 8 * ROWB, SW32);
-        const uint64_t db = umma_smem_desc_sw(sKV + s * STAGE_BYTES, 0, 8 * ROWB, SW32);
-        umma_bf16(tmem_base + g * WG_COLS, da, db, idescS, 0u);
+        umma_bf16(tW + S_COL, descQ, umma_smem_desc_sw(sKV + s * STAGE_BYTES, 0, 8 * ROWB, SW32), idescS, 0u);
         umma_commit(s_full(g));
       };
-      for (int g = 0; g < NWG; ++g) issue_S(0, g);
-      int jg[NWG];
-      for (int g = 0; g < NWG; ++g) jg[g] = 0;
-      int remaining = NWG * nkb;
-      uint32_t spins = 0;
-      while (remaining > 0) {
-#pragma unroll
-        for (int g = 0; g < NWG; ++g) {
-          const int j = jg[g];
-          if (j >= nkb || !mbar_try_wait(p_full(g), j & 1)) continue;
-          spins = 0;
-          tc_fence_after();
-          const int s = j % NST;
-          const uint32_t sV = sKV + s * STAGE_BYTES + KV_BYTES;
-          const uint32_t tP = tmem_base + g * WG_COLS;
-#pragma unroll
-          for (int k = 0; k < KB / 16; ++k) {
-            const uint64_t db = umma_smem_desc_sw(sV + k * 16 * ROWB, 0, 8 * ROWB, SW32);
-            umma_bf16_ts(tP + O_COL, tP + k * 8, db, idescPV, (j > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(kv_empty(s));
-          // S_{j+1} overwrites P_j: the tensor pipe executes in issue order.  Its commit also covers P_j V_j,
-          // so "S_{j+1} ready" tells the softmax warps that O is up to date; the last commit stands in for it.
-          if (j + 1 < nkb) issue_S(j + 1, g);
-          else umma_commit(s_full(g));
-          jg[g] = j + 1;
-          --remaining;
+      mbar_wait(q_full, 0);
+      issue_S(0);
+      for (int j = 0; j < nkb; ++j) {
+        if (j + 1 < nkb) {
+          mbar_wait(s_free(g), j & 1);  // S_j sits in the softmax warps' registers
+          issue_S(j + 1);
         }
-        if (++spins > TSD_SPIN_LIMIT) {
-          printf("tsd: attention MMA issuer timeout (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
-          __trap();
-        }
+        mbar_wait(p_full(g), j & 1);
+        tc_fence_after();
+        const int s = j % NST;
+        const uint32_t sV = sKV + s * STAGE_BYTES + KV_BYTES;
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k)
+          umma_bf16_ts(tW + O_COL, tW + P_COL + k * 8, umma_smem_desc_sw(sV + k * 16 * ROWB, 0, 8 * ROWB, SW32), idescPV,
+                       (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(pv_done(g));
+        umma_commit(kv_empty(s));
+        if (g == 0 && j + AHEAD < nkb) load_kv(j + AHEAD);  // its stage was released by block j - 2
       }
     }
   } else {
@@ -200,17 +225,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     const int g = warp >> 2;
     const int sub = warp & 3;  // TMEM sub-partition of this warp
     const int row = sub * 32 + lane;
-    const uint32_t tS = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + g * WG_COLS;
-    const uint32_t tO = tS + O_COL;
+    const uint32_t tW = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + g * WG_COLS;
+    const uint32_t tS = tW + S_COL, tP = tW + P_COL, tO = tW + O_COL;
     const uint64_t c2 = pk2(scale_log2, scale_log2);
+    // Cauchy-Schwarz bound on this row's scores: |q||k|max.  When it is small enough that 2^(s*c - bound) cannot
+    // underflow for any key, it serves as the softmax reference from the start: no maximum pass, no rescale.
     float m_ref = -INFINITY;
+    bool bound_mode = false;
+    if (knmax2 != nullptr) {
+      mbar_wait(q_full, 0);
+      const uint4* qrow = reinterpret_cast<const uint4*>(smem_raw + (sQ - smem_u32(smem_raw)) + (g * QT + row) * ROWB);
+      const uint4 a = qrow[0], c = qrow[1];
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+      float qn2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = unpack_bf16(w[i]);
+        qn2 = fmaf(f.x, f.x, qn2);
+        qn2 = fmaf(f.y, f.y, qn2);
+      }
+      const float bound = sqrtf(qn2 * __ldg(knmax2 + b * H + h)) * scale_log2 * 1.001f + 1e-3f;
+      bound_mode = __all_sync(0xffffffffu, bound <= BOUND_LIMIT);
+      if (bound_mode) m_ref = bound;
+    }
     uint64_t l2 = pk2(0.f, 0.f);
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(s_full(g), j & 1);
       tc_fence_after();
-      // ---- pass 1: block maximum
-      float mx0, mx1;
-      {
+      float alpha = 1.f;
+      bool rescale = false;
+      if (!bound_mode) {
+        // ---- exact mode: block maximum first, lazy refresh of the reference
+        float mx0, mx1;
         uint32_t sv[32];
         tmem_ld32(tS, sv);
         tmem_ld_wait();
@@ -228,16 +274,55 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           mx0 = max3f(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
           mx1 = max3f(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
         }
+        const float bm = fmaxf(mx0, mx1) * scale_log2;
+        const bool need = bm > m_ref + RESCALE_THRESHOLD;  // first block: m_ref = -inf
+        rescale = __any_sync(0xffffffffu, need);
+        if (need) {
+          alpha = ex2f(m_ref - bm);  // 0 on the first block
+          m_ref = bm;
+          float la, lb;
+          upk2(l2, la, lb);
+          l2 = pk2(la * alpha, lb * alpha);
+        }
       }
-      const float bm = fmaxf(mx0, mx1) * scale_log2;
-      const bool need = bm > m_ref + RESCALE_THRESHOLD;  // first block: m_ref = -inf
-      if (__any_sync(0xffffffffu, need)) {
-        const float alpha = need ? ex2f(m_ref - bm) : 1.f;  // 0 on the first block
-        if (need) m_ref = bm;
-        float la, lb;
-        upk2(l2, la, lb);
-        l2 = pk2(la * alpha, lb * alpha);
-        if (j > 0) {  // O already holds P_{j-1} V_{j-1}: the commit behind s_full covered it
+      // ---- P = 2^(s*c - m_ref) as bf16 pairs; the S buffer is handed back as soon as it sits in registers
+      const uint64_t nm2 = pk2(-m_ref, -m_ref);
+      uint32_t pk[KB / 2];
+      auto exp_pass = [&](auto clamp_tag) {
+        constexpr bool CLAMP = decltype(clamp_tag)::value;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sv[32];
+          tmem_ld32(tS + half * 32, sv);
+          tmem_ld_wait();
+          if (half == 1) {
+            tc_fence_before();
+            mbar_arrive(s_free(g));
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint64_t x = ffma2_(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nm2);
+            float p0, p1;
+            if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
+              exp2_poly2_<CLAMP>(x, p0, p1);
+            } else {
+              float a0, a1;
+              upk2(x, a0, a1);
+              p0 = ex2f(a0);
+              p1 = ex2f(a1);
+            }
+            l2 = fadd2_(l2, pk2(p0, p1));
+            pk[half * 16 + i] = pack_bf16(p0, p1);
+          }
+        }
+      };
+      if (bound_mode) exp_pass(std::false_type{});  // x >= -2 * BOUND_LIMIT: no clamp needed
+      else exp_pass(std::true_type{});
+      // ---- the P region (and O) are free once P_{j-1} V_{j-1} has completed
+      if (j > 0) {
+        mbar_wait(pv_done(g), (j - 1) & 1);
+        tc_fence_after();
+        if (rescale) {
           uint32_t o[16];
           tmem_ld16(tO, o);
           tmem_ld_wait();
@@ -246,37 +331,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           tmem_st16(tO, o);
         }
       }
-      // ---- pass 2: P = 2^(s*c - m_ref) as bf16 pairs, written over S columns [0, 32)
-      const uint64_t nm2 = pk2(-m_ref, -m_ref);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32];
-        tmem_ld32(tS + half * 32, sv);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const uint64_t x = ffma2_(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nm2);
-          float p0, p1;
-          if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
-            exp2_poly2_(x, p0, p1);
-          } else {
-            float a0, a1;
-            upk2(x, a0, a1);
-            p0 = ex2f(a0);
-            p1 = ex2f(a1);
-          }
-          l2 = fadd2_(l2, pk2(p0, p1));
-          pk[i] = pack_bf16(p0, p1);
-        }
-        tmem_st16(tS + half * 16, pk);
-      }
+      tmem_st32(tP, pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full(g));
     }
     // ---- epilogue: O / l -> bf16, lse
-    mbar_wait(s_full(g), nkb & 1);
+    mbar_wait(pv_done(g), (nkb - 1) & 1);
     tc_fence_after();
     uint32_t o[16];
     tmem_ld16(tO, o);
@@ -306,8 +367,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 }
 
 template <int POLY>
-int launch_fwd_t(cudaStream_t st, const CUtensorMap& tm, void* out, float* lse2, int B, int L, int C, int heads,
-                 float scale_log2) {
+int launch_fwd_t(cudaStream_t st, const CUtensorMap& tm, void* out, float* lse2, const float* knmax2, int B, int L,
+                 int C, int heads, float scale_log2) {
   auto kern = attn_fwd_tc_kernel<POLY>;
   static bool configured = false;
   if (!configured) {
@@ -315,7 +376,7 @@ int launch_fwd_t(cudaStream_t st, const CUtensorMap& tm, void* out, float* lse2,
     configured = true;
   }
   dim3 grid(L / (NWG * QT), heads, B);
-  kern<<<grid, TC_THREADS, SMEM_BYTES, st>>>(tm, (bf16*)out, lse2, L, C, scale_log2);
+  kern<<<grid, TC_THREADS, SMEM_BYTES, st>>>(tm, (bf16*)out, lse2, knmax2, L, C, scale_log2);
   TSD_LAUNCH_CHECK();
   return 0;
 }
@@ -323,20 +384,26 @@ int launch_fwd_t(cudaStream_t st, const CUtensorMap& tm, void* out, float* lse2,
 }  // namespace
 
 bool attn_tc_supported(int L, int C, int heads) {
-  return C % heads == 0 && C / heads == DH && L % (NWG * QT) == 0 && L >= NWG * QT;
+  return C % heads == 0 && C / heads == DH && heads <= 32 && L % (NWG * QT) == 0 && L >= NWG * QT;
 }
 
-int launch_attn_fwd_tc(cudaStream_t st, const void* qkv, void* out, float* lse2, int B, int L, int C, int heads,
-                       int poly) {
+int launch_attn_fwd_tc(cudaStream_t st, const void* qkv, void* out, float* lse2, float* ws, int B, int L, int C,
+                       int heads, int poly) {
   TSD_CHECK(attn_tc_supported(L, C, heads), "attn_fwd_tc: unsupported shape L=%d C=%d heads=%d", L, C, heads);
   CUtensorMap tm;
   if (make_tmap_2d_sw(&tm, qkv, 2, (uint64_t)B * L, 3 * (uint64_t)C, 3 * (uint64_t)C, DH, 64, 32)) return 1;
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
+  if (ws) {  // max |k|^2 per (sample, head) for the score bound
+    TSD_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * B * heads, st));
+    const int rows_per_block = 512 / heads;
+    attn_knorm_kernel<<<dim3(ceil_div(L, rows_per_block), B), 512, 0, st>>>((const bf16*)qkv, ws, L, C, heads);
+    TSD_LAUNCH_CHECK();
+  }
   switch (poly) {
-    case 0: return launch_fwd_t<0>(st, tm, out, lse2, B, L, C, heads, scale_log2);
-    case 2: return launch_fwd_t<2>(st, tm, out, lse2, B, L, C, heads, scale_log2);
-    case 4: return launch_fwd_t<4>(st, tm, out, lse2, B, L, C, heads, scale_log2);
-    default: return launch_fwd_t<3>(st, tm, out, lse2, B, L, C, heads, scale_log2);
+    case 0: return launch_fwd_t<0>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    case 2: return launch_fwd_t<2>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    case 4: return launch_fwd_t<4>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    default: return launch_fwd_t<3>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
   }
 }
 

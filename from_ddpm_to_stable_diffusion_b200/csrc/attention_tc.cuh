@@ -7,7 +7,8 @@ namespace tsd {
 // head_dim 16 and L a multiple of 256 (two 128-row query tiles per CTA)
 bool attn_tc_supported(int L, int C, int heads);
 // poly: every poly-th pair of exponentials is evaluated on the FMA pipe (0 = none; 2, 3, 4)
-int launch_attn_fwd_tc(cudaStream_t st, const void* qkv, void* out, float* lse2, int B, int L, int C, int heads,
-                       int poly);
+// ws: optional scratch of B * heads floats (max |k|^2 per sample and head); enables the bound mode (no max pass)
+int launch_attn_fwd_tc(cudaStream_t st, const void* qkv, void* out, float* lse2, float* ws, int B, int L, int C,
+                       int heads, int poly);
 
 }  // namespace tsd

@@ -114,7 +114,8 @@ def ln_bwd(dy, x, gamma, dgamma, dbeta, eps=1e-5, radd=None):
 def attn_fwd(qkv, B, L, C, heads=8, need_lse=False):
     out = empty_bf16(B * L, C, like=qkv)
     lse = torch.empty(B, heads, L, device=qkv.device, dtype=F32) if need_lse else None
-    call("tsd_attn_fwd", _chk(qkv, BF16), out, lse, B, L, C, heads)
+    ws = torch.empty(B * heads, device=qkv.device, dtype=F32)  # max |k|^2 per (sample, head): score bound
+    call("tsd_attn_fwd_ws", _chk(qkv, BF16), out, lse, ws, B, L, C, heads)
     return out, lse
 
 

@@ -44,5 +44,5 @@ def timeit(fn, n=10):
 
 tf = timeit(lambda: ops.attn_fwd(qkv, B, L, C, H, need_lse=True))
 nexp = B * H * L * L
-print(f"B={B} L={L} C={C} TC={os.environ.get('TSD_ATTN_TC','1')} POLY={os.environ.get('TSD_ATTN_TC_POLY','3')}: "
+print(f"B={B} L={L} C={C} TC={os.environ.get('TSD_ATTN_TC','1')} POLY={os.environ.get("TSD_ATTN_TC_POLY","4")}: "
       f"fwd {tf:.3f} ms  {nexp/tf/1e9:.2f} Texp/s  {4*B*L*L*C/tf/1e9:.0f} TF/s")
