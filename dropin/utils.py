@@ -1,8 +1,8 @@
 """Drop-in replacement for the DDPM part of 06_tiny_stable_diffusion/utils.py:
 `from utils import SamplerDDPM, TrainerDDPM, ...` (02_train_direct.py:7) resolves to the B200-native
-classes.  The reference's data / LR glue (animal_faces_loader, denormalize, EMA, CosineWarmupScheduler,
-utils.py:10-93) is out of scope for this path and is re-exported unchanged from the reference's own file
-when it has been kept beside this one as `utils_reference.py`."""
+classes.  `denormalize`, `EMA` and `CosineWarmupScheduler` (utils.py:14-18, 42-93) resolve to the B200-native versions too;
+only `animal_faces_loader` (CPU DataLoader, utils.py:21-29) is re-exported from the reference's own file when it has been
+kept beside this one as `utils_reference.py`."""
 import os
 import sys
 
@@ -10,10 +10,12 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-try:  # the maintainer's renamed copy of the original utils.py, if present
-    from utils_reference import (CosineWarmupScheduler, EMA, animal_faces_loader, denormalize, means, stds)  # noqa: F401
+try:  # the data loader stays the reference's (CPU workers, PIL resize): the maintainer's renamed copy of utils.py
+    from utils_reference import animal_faces_loader  # noqa: F401
 except ImportError:  # pragma: no cover
     pass
 
 from from_ddpm_to_stable_diffusion_b200.utils import SamplerDDPM, TrainerDDPM, extract  # noqa: E402,F401
 from from_ddpm_to_stable_diffusion_b200.optim import FusedClipAdamW  # noqa: E402,F401
+from from_ddpm_to_stable_diffusion_b200.training import (CosineWarmupScheduler, EMA, denormalize, generate_grid,  # noqa: E402,F401
+                                                          image_grid_u8, means, normalize_u8, stds, train_step)

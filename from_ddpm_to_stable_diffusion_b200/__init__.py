@@ -3,7 +3,8 @@
 Mirrors the reference's Python surface (06_tiny_stable_diffusion/diffusion.py, utils.py):
 ``Diffusion``, ``TrainerDDPM``, ``SamplerDDPM``, ``extract``.
 """
-__all__ = ["Diffusion", "TrainerDDPM", "SamplerDDPM", "extract"]
+__all__ = ["Diffusion", "TrainerDDPM", "SamplerDDPM", "extract", "EMA", "CosineWarmupScheduler", "denormalize",
+           "normalize_u8", "image_grid_u8", "train_step", "generate_grid", "means", "stds"]
 
 
 def __getattr__(name):
@@ -13,4 +14,8 @@ def __getattr__(name):
     if name in ("TrainerDDPM", "SamplerDDPM", "extract"):
         from . import utils
         return getattr(utils, name)
+    if name in ("EMA", "CosineWarmupScheduler", "denormalize", "normalize_u8", "image_grid_u8", "train_step",
+                "generate_grid", "means", "stds"):
+        from . import training
+        return getattr(training, name)
     raise AttributeError(name)

@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(256, MINB) attn_bwd_dkv_kernel(const bf16* __r
 // QT = 64/MT queries, so every ldmatrix of Q / dO feeds MT m-tiles (half the shared-memory traffic per MMA,
 // which is what bounds the one-m-tile kernel above: ncu shows its smem pipe at 63 %).
 // ------------------------------------------------------------------------------------------
-template <int DH, int MT, int NSUB, int NTHR, int MINB>
+template <int DH, int MT, int NSUB, int NTHR, int MINB, int POLY = 0>
 __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dkv2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                    const float* __restrict__ lse2, const float* __restrict__ delta,
                                                                    bf16* __restrict__ dqkv, int L, int C, float scale,
@@ -890,12 +890,18 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dkv2_kernel(const bf16* _
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           float p[4], ds[4];
+          if (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == POLY - 1) {  // this n-tile's exponentials on the FMA pipe
+            const uint64_t c2 = pack2(scale_log2, scale_log2), nl = pack2(-ls.x, -ls.y);
+            exp2_poly2(ffma2(pack2(sacc[mt][j][0], sacc[mt][j][1]), c2, nl), p[0], p[1]);
+            exp2_poly2(ffma2(pack2(sacc[mt][j][2], sacc[mt][j][3]), c2, nl), p[2], p[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) p[e] = ex2(fmaf(sacc[mt][j][e], scale_log2, -((e & 1) ? ls.y : ls.x)));
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float pe = ex2(fmaf(sacc[mt][j][e], scale_log2, -((e & 1) ? ls.y : ls.x)));
-            if (partial_keys && !key_ok[mt][e >> 1]) pe = 0.f;
-            p[e] = pe;
-            ds[e] = pe * (pacc[mt][j][e] - ((e & 1) ? dl.y : dl.x));
+            if (partial_keys && !key_ok[mt][e >> 1]) p[e] = 0.f;
+            ds[e] = p[e] * (pacc[mt][j][e] - ((e & 1) ? dl.y : dl.x));
           }
           pf[mt][j >> 1][(j & 1) * 2] = pack_bf16(p[0], p[1]);
           pf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
@@ -940,7 +946,7 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dkv2_kernel(const bf16* _
 }
 
 // Same idea for dQ: each warp owns MT*16 query rows and walks the key stage in sub-tiles of 64/MT keys.
-template <int DH, int MT, int NSUB, int NTHR, int MINB>
+template <int DH, int MT, int NSUB, int NTHR, int MINB, int POLY = 0>
 __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dq2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                   const float* __restrict__ lse2, const float* __restrict__ delta,
                                                                   bf16* __restrict__ dqkv, int L, int C, float scale,
@@ -1033,8 +1039,14 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dq2_kernel(const bf16* __
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           float ds[4], pe4[4];
+          if (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+            const uint64_t c2 = pack2(scale_log2, scale_log2);
+            exp2_poly2(ffma2(pack2(sacc[mt][j][0], sacc[mt][j][1]), c2, pack2(nlse[mt][0], nlse[mt][0])), pe4[0], pe4[1]);
+            exp2_poly2(ffma2(pack2(sacc[mt][j][2], sacc[mt][j][3]), c2, pack2(nlse[mt][1], nlse[mt][1])), pe4[2], pe4[3]);
+          } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) pe4[e] = ex2(fmaf(sacc[mt][j][e], scale_log2, nlse[mt][e >> 1]));
+            for (int e = 0; e < 4; ++e) pe4[e] = ex2(fmaf(sacc[mt][j][e], scale_log2, nlse[mt][e >> 1]));
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float pe = pe4[e];
@@ -1256,10 +1268,14 @@ extern "C" int tsd_attn_bwd(void* stream, const void* qkv, const void* out, cons
     if (vq == 1) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 1>), 2, 256, smem_q);
     else if (vq == 2) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 128, 3>), 2, 128, smem_q);
     else if (vq == 3) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 1, 4, 256, 3>), 1, 256, smem_q);
+    else if (vq == 5) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 2, 4>), 2, 256, smem_q);
+    else if (vq == 6) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 2, 2>), 2, 256, smem_q);
     else TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 2>), 2, 256, smem_q);
     if (vk == 1) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 1>), 2, 256, smem_k);
     else if (vk == 2) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 128, 3>), 2, 128, smem_k);
     else if (vk == 3) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 1, 4, 256, 3>), 1, 256, smem_k);
+    else if (vk == 5) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 2, 4>), 2, 256, smem_k);
+    else if (vk == 6) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 2, 2>), 2, 256, smem_k);
     else TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 2>), 2, 256, smem_k);
 #undef TSD_BWD_LAUNCH
     return 0;

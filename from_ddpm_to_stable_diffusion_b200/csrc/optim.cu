@@ -80,12 +80,15 @@ __global__ void add_cols_kernel(float* __restrict__ dst, const float* __restrict
 }
 
 // shadow = decay * shadow + (1 - decay) * p   (EMA.update, utils.py:54-58)
-__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p, size_t n4, float decay) {
+__global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p, size_t n4, float decay, float w) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 e = reinterpret_cast<float4*>(ema)[i];
     const float4 v = reinterpret_cast<const float4*>(p)[i];
-    const float w = 1.f - decay;
-    e.x = w * v.x + decay * e.x; e.y = w * v.y + decay * e.y; e.z = w * v.z + decay * e.z; e.w = w * v.w + decay * e.w;
+    // (1 - decay) * p + decay * shadow with each product and the sum rounded separately, as torch evaluates it
+    e.x = __fadd_rn(__fmul_rn(w, v.x), __fmul_rn(decay, e.x));
+    e.y = __fadd_rn(__fmul_rn(w, v.y), __fmul_rn(decay, e.y));
+    e.z = __fadd_rn(__fmul_rn(w, v.z), __fmul_rn(decay, e.z));
+    e.w = __fadd_rn(__fmul_rn(w, v.w), __fmul_rn(decay, e.w));
     reinterpret_cast<float4*>(ema)[i] = e;
   }
 }
@@ -132,9 +135,9 @@ extern "C" int tsd_add_cols_f32(void* stream, float* dst, const float* src, int 
   TSD_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int tsd_ema_update(void* stream, float* ema, const float* p, int64_t n, float decay) {
+extern "C" int tsd_ema_update(void* stream, float* ema, const float* p, int64_t n, float decay, float one_minus_decay) {
   TSD_CHECK(n % 4 == 0, "ema_update: flat buffers are padded to multiples of 4 elements");
-  ema_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(ema, p, n / 4, decay);
+  ema_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(ema, p, n / 4, decay, one_minus_decay);
   TSD_LAUNCH_CHECK();
   return 0;
 }

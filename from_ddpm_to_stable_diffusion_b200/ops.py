@@ -350,7 +350,7 @@ def add_cols(dst, src, rows, cols, ldd, lds):
 
 
 def ema_update(ema, p, decay):
-    call("tsd_ema_update", _chk(ema, F32), _chk(p, F32), i64(p.numel()), f32(decay))
+    call("tsd_ema_update", _chk(ema, F32), _chk(p, F32), i64(p.numel()), f32(decay), f32(1.0 - decay))
 
 
 def sumsq(g, out):
@@ -360,3 +360,32 @@ def sumsq(g, out):
 def adamw_clip(p, g, m, v, lr, beta1, beta2, eps, wd, step, max_norm, sumsq_buf, write_clipped_grad=True):
     call("tsd_adamw_clip", p, g, m, v, i64(p.numel()), f32(lr), f32(beta1), f32(beta2), f32(eps), f32(wd), int(step),
          f32(max_norm), sumsq_buf, int(write_clipped_grad))
+
+
+# ------------------------------------------------------------------ image input / output (csrc/imageio.cu)
+def _host_floats(vals):
+    import ctypes
+    return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def u8_to_f32_norm(img_u8_nhwc, mean, std):
+    """uint8 [N,H,W,C] -> fp32 [N,C,H,W] = ((x / 255) - mean) / std  (ToTensor + Normalize, utils.py:21-25)."""
+    if img_u8_nhwc.dtype != torch.uint8 or not img_u8_nhwc.is_cuda or not img_u8_nhwc.is_contiguous():
+        raise RuntimeError("u8_to_f32_norm: expected a contiguous CUDA uint8 tensor [N,H,W,C]")
+    N, H, W, C = img_u8_nhwc.shape
+    out = torch.empty(N, C, H, W, device=img_u8_nhwc.device, dtype=F32)
+    call("tsd_u8_to_f32_norm", img_u8_nhwc, out, N, C, H, W, _host_floats(mean), _host_floats(std))
+    return out
+
+
+def denorm_grid_u8(x, nrow, padding, mean, std):
+    """fp32 [N,C,H,W] -> uint8 [GH,GW,C|3]: denormalize + make_grid + save_image's uint8 conversion."""
+    N, C, H, W = x.shape
+    if N == 1:
+        padding = 0  # torchvision.utils.make_grid returns a single image unframed
+    xmaps = min(nrow, N)
+    ymaps = (N + xmaps - 1) // xmaps
+    GH, GW = (H + padding) * ymaps + padding, (W + padding) * xmaps + padding
+    out = torch.empty(GH, GW, 3 if C == 1 else C, device=x.device, dtype=torch.uint8)
+    call("tsd_denorm_grid_u8", _chk(x, F32), out, N, C, H, W, int(nrow), int(padding), _host_floats(mean), _host_floats(std))
+    return out

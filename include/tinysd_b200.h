@@ -199,10 +199,23 @@ int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out);
 int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float wd, int step, float max_norm, const float* sumsq, int write_clipped_grad);
 int tsd_scale_f32(void* stream, float* x, int64_t n, float s);
-/* shadow = decay*shadow + (1-decay)*p over the flat parameter buffer (EMA.update, utils.py:54-58) */
-int tsd_ema_update(void* stream, float* ema, const float* p, int64_t n, float decay);
+/* shadow = (1-decay)*p + decay*shadow over a flat fp32 buffer (EMA.update, utils.py:54-58); one_minus_decay is the
+ * host's float(1.0 - decay) and every step is separately rounded, so the result equals the torch expression bit for bit */
+int tsd_ema_update(void* stream, float* ema, const float* p, int64_t n, float decay, float one_minus_decay);
 /* dst[r][c] += src[r][c], c < cols (row pitches ldd / lds): folds padded tensor-core gradients into parameter grads */
 int tsd_add_cols_f32(void* stream, float* dst, const float* src, int rows, int cols, int ldd, int lds);
+/* ------------------------------------------------------------------------------------------
+ * Image input / output either side of the denoiser (utils.py:10-29; 02_train_direct.py:24-27).
+ * in_hwc uint8 [N][H][W][C] -> out_chw fp32 [N][C][H][W] = ((in / 255) - mean[c]) / std[c]   (ToTensor + Normalize);
+ * mean / std are HOST arrays of C floats.  Bit-exact with the torch expressions.
+ * ------------------------------------------------------------------------------------------ */
+int tsd_u8_to_f32_norm(void* stream, const void* in_hwc, float* out_chw, int N, int C, int H, int W, const float* mean,
+                       const float* stdv);
+/* x fp32 [N][C][H][W] -> out_hwc uint8 [(H+pad)*ceil(N/min(nrow,N))+pad][(W+pad)*min(nrow,N)+pad][C or 3]:
+ * denormalize (x*std+mean), torchvision make_grid(nrow, padding, pad_value 0) and save_image's uint8 conversion
+ * (N == 1: the image itself, no padding frame, as make_grid returns it) */
+int tsd_denorm_grid_u8(void* stream, const float* x, void* out_hwc, int N, int C, int H, int W, int nrow, int padding,
+                       const float* mean, const float* stdv);
 /* number of kernel launches issued by this library so far (host-side counter, for bench.py's gpu_launches) */
 unsigned long long tsd_launch_count(void);
 

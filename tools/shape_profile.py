@@ -37,10 +37,10 @@ def flops(name, k):
     if name == "tsd_conv3x3_wgrad":
         c0, c1, n, H, W, s, cout = k[:7]
         return 2.0 * n * (H // s) * (W // s) * cout * 9 * (c0 + c1)
-    if name in ("tsd_attn_fwd", "tsd_attn_bwd"):
+    if name in ("tsd_attn_fwd", "tsd_attn_fwd_ws", "tsd_attn_bwd"):
         Bn, L, C, heads = k[:4]
         f = 4.0 * Bn * L * L * C
-        return f if name == "tsd_attn_fwd" else 3.5 * f
+        return f if name.startswith("tsd_attn_fwd") else 3.5 * f
     return 0.0
 
 
