@@ -173,9 +173,15 @@ class UNetEngine:
         return vv, cb
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x, t, labels, save, tb_override=None, cb_override=None, eps_out=None, taps=None, sample_tail=None):
+    def forward(self, x, t, labels, save, tb_override=None, cb_override=None, eps_out=None, taps=None, sample_tail=None,
+                shared_prefix=False):
         """Returns (eps fp32 NCHW, tape).  tb_override / cb_override: precomputed per-block conditioning
-        (sampling: one shared time row for the whole batch, constant label vectors)."""
+        (sampling: one shared time row for the whole batch, constant label vectors).
+
+        shared_prefix (sampling with classifier-free guidance): rows [0, n/2) and [n/2, n) hold the same x_t and differ
+        only in the label, and the label first enters through the cross-attention vector of the first attention block
+        (diffusion.py:141-148).  Everything before it -- head conv, first ResBlock, and that block's GroupNorm,
+        conv_1, LayerNorm, in_proj and the L = H*W self-attention -- is computed once on n/2 rows and duplicated."""
         m = self.model
         P = self.params()
         W = self.packed(P)
@@ -186,6 +192,15 @@ class UNetEngine:
         training = m.training
         tape = []
         x = x.contiguous().float()
+        n_full = n
+        first_attn = None
+        if shared_prefix:
+            assert not save and tb_override is not None and cb_override is not None and n % 2 == 0
+            first_attn = next((f"encoders.{i}.{j}" for i, st in enumerate(m._enc) for j, b in enumerate(st)
+                               if b[0] == "attn"), None)
+            if first_attn is not None:
+                n = n_full // 2  # rows computed until the label enters
+        skips = []
 
         if tb_override is None:
             temb, ctx, crec = self.conditioning(P, t.contiguous(), labels.contiguous(), save)
@@ -224,6 +239,7 @@ class UNetEngine:
             return out
 
         def run_attn(key, b, x0, h, w):
+            nonlocal n
             C = b[1]
             L = h * w
             if cb_override is None:
@@ -236,6 +252,10 @@ class UNetEngine:
             l1 = ops.ln_fwd(t0, P[key + ".atten_1.0.weight"], P[key + ".atten_1.0.bias"])
             qkv = ops.gemm(l1, W[key + ".atten_1.1.in_proj"], 3 * C)
             o, lse = ops.attn_fwd(qkv, n, L, C, m.N_HEAD, need_lse=save)
+            if key == first_attn:  # the cross-attention vector is the first label-dependent term: widen to all rows
+                n = n_full
+                o, t0, x0 = torch.cat([o, o]), torch.cat([t0, t0]), torch.cat([x0, x0])
+                skips[:] = [torch.cat([sk, sk]) for sk in skips]
             t2 = ops.gemm(o, W[key + ".atten_1.1.out_proj"], C, bias=P[key + ".atten_1.1.out_proj.bias"],
                           row_bias=cb, rows_per_sample=L, residual=t0)
             l3 = ops.ln_fwd(t2, P[key + ".norm_3.weight"], P[key + ".norm_3.bias"])
@@ -256,7 +276,7 @@ class UNetEngine:
             """returns (out, h, w)"""
             if b[0] == "conv":
                 if b[1] % 64 != 0:  # head conv on the fp32 NCHW image
-                    out = ops.head_conv_fwd(x, P[key + ".weight"], P[key + ".bias"])
+                    out = ops.head_conv_fwd(x if n == n_full else x[:n], P[key + ".weight"], P[key + ".bias"])
                     if save:
                         tape.append(_Rec("head", key, b=b))
                     return out, h, w
@@ -276,7 +296,6 @@ class UNetEngine:
 
         h, w = H, Wd
         cur = None
-        skips = []
         for i, st in enumerate(m._enc):
             for j, b in enumerate(st):
                 cur, h, w = run_block(f"encoders.{i}.{j}", b, cur, None, h, w)

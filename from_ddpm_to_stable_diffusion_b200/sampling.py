@@ -2,7 +2,9 @@
 
 Reference: SamplerDDPM.forward / p_mean_variance, 06_tiny_stable_diffusion/utils.py:147-171.  What
 changes versus the reference's loop, not its arithmetic:
-  * the two forwards of a step (label and label 0, utils.py:151-152) run as one 2B-row batch;
+  * the two forwards of a step (label and label 0, utils.py:151-152) run as one 2B-row batch, and the part of the
+    network that comes before the first label-dependent term (head conv, first ResBlock, the first attention
+    block up to and including its 64x64 self-attention) is evaluated once for both (engine.forward shared_prefix);
   * everything that does not depend on x_t is hoisted out of the loop: the time MLP and every
     ResBlock's linear_time for all T steps ([T, sum Cout] table), the label MLP and the ten
     cross-attention vectors (constant over the loop);
@@ -33,6 +35,8 @@ class SamplingPlan:
         self.tb_table = None
         self.cond_sig = None
         self.fused_tail = getattr(sampler, "fused_tail", True)
+        # the two forwards of a step see the same x_t: their label-independent prefix is computed once
+        self.shared_prefix = getattr(sampler, "shared_prefix", True)
 
     def matches(self, x_T, model):
         return tuple(x_T.shape) == self.shape and x_T.device == self.device and model is self.sampler.model
@@ -81,10 +85,10 @@ class SamplingPlan:
             tail = dict(step_ptr=self.step, c1=self.c1, c2=self.c2, sigma=self.sigma, wcfg=float(self.sampler.w),
                         nan_flag=self.nan_flag, noise=noise, seed=self.sampler.seed, clip_last=True)
             model._engine.forward(self.x2, None, None, save=False, tb_override=self.tb_override,
-                                  cb_override=self.cb_override, sample_tail=tail)
+                                  cb_override=self.cb_override, sample_tail=tail, shared_prefix=self.shared_prefix)
         else:
             model._engine.forward(self.x2, None, None, save=False, tb_override=self.tb_override,
-                                  cb_override=self.cb_override, eps_out=self.eps)
+                                  cb_override=self.cb_override, eps_out=self.eps, shared_prefix=self.shared_prefix)
             ops.sampler_update(self.x2, self.eps, self.step, self.c1, self.c2, self.sigma, float(self.sampler.w), self.x2,
                                self.nan_flag, noise=noise, seed=self.sampler.seed, clip_last=True, dup=True)
         ops.step_add(self.step, -1)

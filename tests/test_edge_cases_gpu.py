@@ -205,3 +205,24 @@ def test_wider_config_1244(cuda):
             if c < 0.985:
                 low.append((k, c))
     assert not low, low[:8]
+
+
+def test_sampling_shared_prefix_is_exact(cuda):
+    """Classifier-free guidance runs the label and the label-0 forward on the same x_t (utils.py:151-152): the part of
+    the UNet before the first label-dependent term is computed once.  Same kernels on the same rows => same bits."""
+    from from_ddpm_to_stable_diffusion_b200 import Diffusion, SamplerDDPM
+    multy = [1, 2, 2, 2]
+    sd = R.init_state_dict(0, 3, multy, 128, 3)
+    m = Diffusion(3, multy, 128, num_class=3, dropout=0.0)
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    g = torch.Generator().manual_seed(1)
+    xT = torch.randn(4, 3, 32, 32, generator=g).to(cuda)
+    y = torch.tensor([1, 2, 3, 1]).to(cuda)
+    outs = []
+    for shared in (True, False):
+        s = SamplerDDPM(m, 0.0015, 0.0195, 1000, w=1.8).to(cuda)
+        s.shared_prefix = shared
+        outs.append(s(xT, y, steps=range(999, 989, -1)))  # 10 reverse steps through the CUDA graph
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
