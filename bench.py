@@ -275,7 +275,10 @@ def run_ours(args):
         s_ms = timed(lambda: sampler(xT, ys, steps=range(CFG["T"] - 1, CFG["T"] - 1 - k, -1)), 1) / k
         sampling = {"images_per_s": Bs * world / (s_ms / 1e3 * CFG["T"]), "ms_per_reverse_step": s_ms,
                     "batch_per_gpu": Bs, "T": CFG["T"], "w": CFG["w"], "timed_reverse_steps": k,
-                    "tflops": 2 * FWD_GF_PER_SAMPLE * Bs / (s_ms / 1e3) / 1e3}
+                    # executed work: the label-independent prefix (11.57 GF: head conv, first ResBlock, first attention
+                    # block up to its self-attention) runs once for the conditional / unconditional pair
+                    "gflop_per_image_step_executed": 2 * FWD_GF_PER_SAMPLE - 11.57,
+                    "tflops": (2 * FWD_GF_PER_SAMPLE - 11.57) * Bs / (s_ms / 1e3) / 1e3}
         model.train()
 
     cpu = None
