@@ -97,6 +97,16 @@ __device__ __forceinline__ float silu_grad_f(float x) {
 __device__ __forceinline__ float gelu_f(float x) {  // exact erf form (F.gelu default)
   return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752440f));
 }
+// value * gelu(gate) with ONE MUFU op: erf(u) ~= tanh(u (a + b u^2)), u = g / sqrt(2), (a, b) fitted for the minimax
+// error of gelu itself (2.7e-4 absolute; tanh.approx adds <= 2.5e-4 |g|) -- an order of magnitude below the bf16
+// rounding of the product.  Used where the activation sits in a GEMM epilogue and instruction issue is the bound
+// (inference GEGLU, diffusion.py:151-152); the stand-alone training kernels keep the erf form above.
+__device__ __forceinline__ float geglu_fast_f(float x, float g) {
+  const float t = g * g;
+  const float z = g * fmaf(0.0347008941f, t, 0.8001570768f);  // a / sqrt(2), b / (2 sqrt(2))
+  const float hg = 0.5f * x * g;
+  return fmaf(hg, tanh_fast(z), hg);
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float cdf = 0.5f * (1.f + erf_fast(x * 0.70710678118654752440f));
   float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);

@@ -277,12 +277,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
               float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
               if (p.bias) {
-                x0 += __ldg(p.bias + n0 + ch * 32 + j);
-                x1 += __ldg(p.bias + n0 + ch * 32 + j + 1);
-                g0 += __ldg(p.bias + n0 + 64 + ch * 32 + j);
-                g1 += __ldg(p.bias + n0 + 64 + ch * 32 + j + 1);
+                const float2 bx = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + ch * 32 + j));
+                const float2 bg = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + 64 + ch * 32 + j));
+                x0 += bx.x; x1 += bx.y; g0 += bg.x; g1 += bg.y;
               }
-              o[e] = pack_bf16(x0 * gelu_f(g0), x1 * gelu_f(g1));
+              o[e] = pack_bf16(geglu_fast_f(x0, g0), geglu_fast_f(x1, g1));
             }
             const int cj = ch * 4 + q;
             *reinterpret_cast<uint4*>(dst + ((cj ^ r7) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
