@@ -40,6 +40,47 @@ def test_attention_fwd_bwd_vs_sdpa(cuda, B, L, C):
     assert (lse - ref_lse2.detach()).abs().max().item() < 2e-2
 
 
+def _sdpa_ref(qkv, B, L, C, H):
+    dh = C // H
+    x = qkv.float().view(B, L, 3, H, dh).permute(2, 0, 3, 1, 4).contiguous()
+    o = F.scaled_dot_product_attention(x[0], x[1], x[2]).permute(0, 2, 1, 3).reshape(B * L, C)
+    s = (x[0] @ x[1].transpose(-1, -2)) / math.sqrt(dh)
+    return o, torch.logsumexp(s, dim=-1) / math.log(2.0)
+
+
+@pytest.mark.parametrize("mode", ["bound", "exact_large_norms", "exact_growing_scores", "no_workspace"])
+def test_attention_tc_forward_modes(cuda, mode):
+    """The tcgen05 forward (head_dim 16, L % 256 == 0) has two softmax-reference modes: the |q| max|k| score bound
+    (no maximum pass) and, when that bound is too loose or no workspace is given, a lazily refreshed running maximum
+    with an O rescale in TMEM.  All must agree with SDPA; the last two force the rescale path."""
+    from from_ddpm_to_stable_diffusion_b200 import _lib
+    B, L, C, H = 3, 1024, 128, 8
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn(B * L, 3 * C, device=cuda, generator=g)
+    if mode == "exact_large_norms":
+        qkv[:, :2 * C] *= 5.0        # |q||k|c far above the bound limit: scores spread over +-100 log2 units
+    elif mode == "exact_growing_scores":
+        # keys whose scores grow along the sequence: the running reference must be refreshed (and O rescaled) many times
+        ramp = torch.linspace(0.0, 12.0, L, device=cuda).repeat(B)
+        qkv[:, :C] = 2.0             # q = 2 on every channel
+        qkv[:, C:2 * C] = ramp[:, None] / 4.0 + 0.05 * qkv[:, C:2 * C]
+    qkv = qkv.to(BF)
+    ref_o, ref_lse = _sdpa_ref(qkv, B, L, C, H)
+    if mode == "no_workspace":
+        out = torch.empty(B * L, C, device=cuda, dtype=BF)
+        lse = torch.empty(B, H, L, device=cuda, dtype=torch.float32)
+        _lib.call("tsd_attn_fwd", qkv, out, lse, B, L, C, H)   # the original entry point: no score bound available
+    else:
+        out, lse = ops.attn_fwd(qkv, B, L, C, H, need_lse=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert _rel(out, ref_o) < 1e-2
+    assert (lse - ref_lse).abs().max().item() < 2e-2 + 2e-3 * ref_lse.abs().max().item()
+    # and without lse (the sampling path)
+    out2, _ = ops.attn_fwd(qkv, B, L, C, H, need_lse=False)
+    assert torch.equal(out2, out) or mode == "no_workspace"
+
+
 @pytest.mark.parametrize("n,hw,c0,c1,silu,eps", [(3, 4096, 128, 0, True, 1e-5), (2, 1024, 128, 128, True, 1e-5),
                                                  (4, 64, 256, 256, True, 1e-5), (2, 256, 256, 0, False, 1e-6),
                                                  (5, 16, 256, 0, True, 1e-5), (2, 4, 256, 256, True, 1e-5)])
