@@ -125,12 +125,16 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 struct Philox {
   uint32_t key0, key1;
   __device__ __forceinline__ Philox(uint64_t seed) : key0((uint32_t)seed), key1((uint32_t)(seed >> 32)) {}
-  __device__ __forceinline__ uint4 operator()(uint64_t ctr_lo, uint64_t ctr_hi) const {
+  __device__ __forceinline__ uint4 operator()(uint64_t ctr_lo, uint64_t ctr_hi) const { return rounds<10>(ctr_lo, ctr_hi); }
+  // Philox4x32-R: R = 10 is the standard generator (Gaussian noise); R = 7 is the smallest variant that passes
+  // BigCrush (Salmon et al., SC'11) and is used for dropout masks, where the generator is the ALU cost of the kernel.
+  template <int R>
+  __device__ __forceinline__ uint4 rounds(uint64_t ctr_lo, uint64_t ctr_hi) const {
     uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi,
              c3 = (uint32_t)(ctr_hi >> 32);
     uint32_t k0 = key0, k1 = key1;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < R; ++i) {
       uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
       uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
       uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;

@@ -64,8 +64,18 @@ __global__ void __launch_bounds__(64) small_linear_dgrad_kernel(const float* __r
   float acc[ROWS];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float wv = w[(size_t)n * K + k];  // coalesced over k
+  int n = 0;
+  for (; n + 8 <= N; n += 8) {  // eight weight rows in flight
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(n + u) * K + k);  // coalesced over k
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(wv[u], sdy[r * N + n + u], acc[r]);
+  }
+  for (; n < N; ++n) {
+    const float wv = w[(size_t)n * K + k];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) acc[r] += wv * sdy[r * N + n];
   }
@@ -103,12 +113,17 @@ __global__ void __launch_bounds__(64) small_linear_wgrad_kernel(const float* __r
     }
     __syncthreads();
     if (k < K) {
-      const int mend = min(32, M - m0);
-      for (int mm = 0; mm < mend; ++mm) {
-        float v = x[(size_t)(m0 + mm) * K + k];
+      // all 32 activations of the chunk are requested before the first is used (the loop was bound by the latency of
+      // one dependent global load per row)
+      float xv[32];
+#pragma unroll
+      for (int mm = 0; mm < 32; ++mm) xv[mm] = (m0 + mm < M) ? __ldg(x + (size_t)(m0 + mm) * K + k) : 0.f;
+#pragma unroll
+      for (int mm = 0; mm < 32; ++mm) {
+        float v = xv[mm];
         if (silu_in) v = v / (1.f + expf(-v));
 #pragma unroll
-        for (int j = 0; j < NT; ++j) acc[j] += sdy[mm][j] * v;
+        for (int j = 0; j < NT; ++j) acc[j] = fmaf(sdy[mm][j], v, acc[j]);
       }
     }
     if (db && blockIdx.x == 0 && threadIdx.x < NT) {

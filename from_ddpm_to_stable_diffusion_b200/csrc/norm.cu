@@ -103,7 +103,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, float* __rest
 // one 16-bit uniform per element (keep probability quantised to 1/65536).  The backward kernels regenerate the mask.
 __device__ __forceinline__ void dropout_scales8(const Philox& rng, uint64_t ebase, float p, float inv_keep,
                                                 float* sc) {
-  const uint4 r = rng(ebase >> 3, 0x5eedULL);
+  const uint4 r = rng.rounds<7>(ebase >> 3, 0x5eedULL);
   const uint32_t thr = (uint32_t)(p * 65536.f);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
