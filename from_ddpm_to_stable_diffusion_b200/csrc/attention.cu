@@ -1086,6 +1086,285 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dq2_kernel(const bf16* __
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// One-pass backward (head_dim 16, L % 256 == 0): the key-outer dK/dV kernel above also produces dQ, so S, dP and the
+// exponentials are evaluated once instead of twice.
+//   * per 32-query sub-tile a warp holds dS^T (its 32 keys x 32 queries) as MMA fragments; one stmatrix.trans /
+//     ldmatrix round trip through a private shared-memory scratch turns them into the B operand of
+//     dQ^T[16 x 32 q] += K^T[16 x 32 keys] dS^T   (8 more HMMA; K^T fragments are loaded once per warp);
+//   * the eight warps' partial dQ^T tiles (each over 32 of the CTA's 256 keys) go to per-warp slots; after the
+//     sub-tile's CTA barrier every thread sums two of the 512 outputs over the eight slots and writes them, scaled, to
+//     a [32 q][16] fp32 staging tile; one thread adds that tile to the fp32 dQ workspace [B][H][L][16] with a bulk
+//     reduce (cp.reduce.async.bulk ... add.f32: 2 KB per 8192 scores of L2 reduction traffic).  Slots and staging are
+//     double buffered, so there is exactly one barrier per sub-tile;
+//   * a small kernel converts the workspace to the bf16 dq columns of dqkv.
+// dQ partials of different key blocks are summed by the L2 in arrival order: like the split-K weight gradients, dQ is
+// reproducible only up to fp32 summation order.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stsm_t4(uint32_t addr, const uint32_t* r) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1,%2,%3,%4};"
+               ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int FB_MT = 2, FB_NSUB = 4, FB_NTHR = 256;
+constexpr int FB_QT = KV_TILE / FB_MT;               // 32 queries per sub-tile
+constexpr int FB_RS = 16 * 2 + 16;                   // padded Q / dO row
+constexpr int FB_STAGE_Q = KV_TILE * FB_NSUB;        // 256 queries per stage
+constexpr int FB_STAGE_BYTES = FB_STAGE_Q * FB_RS;   // 12 KB
+constexpr int FB_SCR_PITCH = 80;                     // [32 q][32 keys] bf16 + 16 B pad: conflict-free ldmatrix
+constexpr int FB_SCR_BYTES = FB_QT * FB_SCR_PITCH;   // 2560 B per warp
+constexpr int FB_SLOT_FLOATS = 16 * FB_QT;           // 512 floats = dQ^T tile of one warp
+constexpr int FB_OFF_STATS = 4 * FB_STAGE_BYTES;
+constexpr int FB_OFF_SCR = FB_OFF_STATS + 4 * FB_STAGE_Q * 4;
+constexpr int FB_OFF_SLOTS = FB_OFF_SCR + 8 * FB_SCR_BYTES;
+constexpr int FB_OFF_STAGING = FB_OFF_SLOTS + 2 * 8 * FB_SLOT_FLOATS * 4;
+constexpr int FB_SMEM = FB_OFF_STAGING + 2 * FB_SLOT_FLOATS * 4;
+
+__global__ void __launch_bounds__(FB_NTHR, 2)
+attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse2,
+                      const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ dq_ws, int L, int C,
+                      float scale, float scale_log2) {
+  constexpr int DH = 16, MT = FB_MT, RS = FB_RS, ND = 2, QT = FB_QT, NJ = QT / 8, STAGE_Q = FB_STAGE_Q,
+                STAGE_BYTES = FB_STAGE_BYTES;
+  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  const uint32_t smem0 = smem_u32_(smem_dyn);
+  float* sLse = reinterpret_cast<float*>(smem_dyn + FB_OFF_STATS);
+  float* sDl = sLse + 2 * STAGE_Q;
+  float* sSlots = reinterpret_cast<float*>(smem_dyn + FB_OFF_SLOTS);
+  float* sStaging = reinterpret_cast<float*>(smem_dyn + FB_OFF_STAGING);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const size_t ld = 3 * (size_t)C;
+  const bf16* qbase = qkv + (size_t)b * L * ld + h * DH;
+  const bf16* kbase = qbase + C;
+  const bf16* vbase = qbase + 2 * C;
+  const bf16* dobase = dout + (size_t)b * L * C + h * DH;
+  const size_t sbase = ((size_t)b * H + h) * L;
+  float* dq_head = dq_ws + sbase * DH;  // [L][16] fp32 of this (sample, head)
+  const int k0 = (blockIdx.x * 8 + warp) * 16 * MT;
+  const uint32_t scr = smem0 + FB_OFF_SCR + warp * FB_SCR_BYTES;
+
+  uint32_t kf[MT][4], vf[MT][4], kT[MT][4];
+  float dk[MT][ND][4], dv[MT][ND][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    load_a_frag(kf[mt], kbase, ld, k0 + 16 * mt, L, 0, lane);
+    load_a_frag(vf[mt], vbase, ld, k0 + 16 * mt, L, 0, lane);
+    // A fragment of K^T (rows = head dim, cols = the 16 keys of this m-tile): a0 = K^T[g][2t,2t+1], a1 = rows g+8,
+    // a2 / a3 = keys +8
+    const bf16* kr = kbase + (size_t)(k0 + 16 * mt) * ld;
+    auto pair = [&](int key, int d) {
+      const uint32_t lo = *reinterpret_cast<const uint16_t*>(kr + (size_t)key * ld + d);
+      const uint32_t hi = *reinterpret_cast<const uint16_t*>(kr + (size_t)(key + 1) * ld + d);
+      return lo | (hi << 16);
+    };
+    kT[mt][0] = pair(2 * t, g);
+    kT[mt][1] = pair(2 * t, g + 8);
+    kT[mt][2] = pair(2 * t + 8, g);
+    kT[mt][3] = pair(2 * t + 8, g + 8);
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      dk[mt][j][0] = dk[mt][j][1] = dk[mt][j][2] = dk[mt][j][3] = 0.f;
+      dv[mt][j][0] = dv[mt][j][1] = dv[mt][j][2] = dv[mt][j][3] = 0.f;
+    }
+  }
+  // where this thread's two reduced outputs (slot elements tid and tid + 256, layout [n-tile][lane][4]) land in the
+  // [32 q][16] staging tile
+  int stg_off[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int e = threadIdx.x + 256 * i;
+    const int nt = e >> 7, ln = (e >> 2) & 31, c = e & 3;
+    const int d = (ln >> 2) + 8 * (c >> 1), q = 8 * nt + 2 * (ln & 3) + (c & 1);
+    stg_off[i] = q * 16 + d;
+  }
+  const int nstages = L / STAGE_Q;
+  const int nsub_total = nstages * (STAGE_Q / QT);
+  auto load_stats = [&](int buf, int stage) {
+    for (int i = threadIdx.x; i < STAGE_Q; i += blockDim.x) {
+      const int q = stage * STAGE_Q + i;
+      sLse[buf * STAGE_Q + i] = lse2[sbase + q];
+      sDl[buf * STAGE_Q + i] = delta[sbase + q];
+    }
+  };
+  // reduce the eight slots of sub-tile `it`, write the staging tile; then (one thread) add staging tile it-1 to global
+  auto reduce_and_flush = [&](int it) {
+    if (it >= 0 && it < nsub_total) {
+      const float* sl = sSlots + (it & 1) * 8 * FB_SLOT_FLOATS;
+      float* stg = sStaging + (it & 1) * FB_SLOT_FLOATS;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int e = threadIdx.x + 256 * i;
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += sl[w * FB_SLOT_FLOATS + e];
+        stg[stg_off[i]] = a * scale;
+      }
+      fence_async_smem();
+    }
+    if (threadIdx.x == 0 && it >= 1 && it - 1 < nsub_total) {
+      const int pit = it - 1;
+      bulk_reduce_add_f32(dq_head + (size_t)pit * QT * DH, smem0 + FB_OFF_STAGING + (pit & 1) * FB_SLOT_FLOATS * 4,
+                          FB_SLOT_FLOATS * 4);
+      bulk_commit();
+    }
+  };
+
+  load_rows_async<DH>(smem0, qbase, ld, 0, L, STAGE_Q);
+  load_rows_async<DH>(smem0 + STAGE_BYTES, dobase, C, 0, L, STAGE_Q);
+  cp_async_commit();
+  load_stats(0, 0);
+  int it = 0;  // global sub-tile counter
+  for (int st = 0; st < nstages; ++st) {
+    const int buf = st & 1;
+    if (st + 1 < nstages) {
+      const uint32_t nb = smem0 + (buf ^ 1) * 2 * STAGE_BYTES;
+      load_rows_async<DH>(nb, qbase, ld, (st + 1) * STAGE_Q, L, STAGE_Q);
+      load_rows_async<DH>(nb + STAGE_BYTES, dobase, C, (st + 1) * STAGE_Q, L, STAGE_Q);
+      cp_async_commit();
+      load_stats(buf ^ 1, st + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int sub = 0; sub < STAGE_Q / QT; ++sub, ++it) {
+      const uint32_t qS = smem0 + buf * 2 * STAGE_BYTES + sub * QT * RS, dS_ = qS + STAGE_BYTES;
+      const float* lseS = sLse + buf * STAGE_Q + sub * QT;
+      const float* dlS = sDl + buf * STAGE_Q + sub * QT;
+      float sacc[MT][NJ][4], pacc[MT][NJ][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          sacc[mt][j][0] = sacc[mt][j][1] = sacc[mt][j][2] = sacc[mt][j][3] = 0.f;
+          pacc[mt][j][0] = pacc[mt][j][1] = pacc[mt][j][2] = pacc[mt][j][3] = 0.f;
+        }
+#pragma unroll
+      for (int jp = 0; jp < NJ / 2; ++jp) {
+        uint32_t r[4], r2[4];
+        ldsm_nt(r, qS, RS, 16 * jp, 0, lane);
+        ldsm_nt(r2, dS_, RS, 16 * jp, 0, lane);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          mma_bf16(sacc[mt][2 * jp], kf[mt], r[0], r[1]);
+          mma_bf16(sacc[mt][2 * jp + 1], kf[mt], r[2], r[3]);
+          mma_bf16(pacc[mt][2 * jp], vf[mt], r2[0], r2[1]);
+          mma_bf16(pacc[mt][2 * jp + 1], vf[mt], r2[2], r2[3]);
+        }
+      }
+      uint32_t pf[MT][NJ / 2][4], dsf[MT][NJ / 2][4];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float2 ls = *reinterpret_cast<const float2*>(lseS + 8 * j + 2 * t);
+        const float2 dl = *reinterpret_cast<const float2*>(dlS + 8 * j + 2 * t);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          float p[4], ds[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            p[e] = ex2(fmaf(sacc[mt][j][e], scale_log2, -((e & 1) ? ls.y : ls.x)));
+            ds[e] = p[e] * (pacc[mt][j][e] - ((e & 1) ? dl.y : dl.x));
+          }
+          pf[mt][j >> 1][(j & 1) * 2] = pack_bf16(p[0], p[1]);
+          pf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
+          dsf[mt][j >> 1][(j & 1) * 2] = pack_bf16(ds[0], ds[1]);
+          dsf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+        }
+      }
+      // dS^T fragments -> scratch as [query][key] (transposing store), for the dQ product below
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int kk = 0; kk < NJ / 2; ++kk) {
+          const int mtx = lane >> 3, i = lane & 7;  // matrix 0/1: queries 16kk + i, keys +0 / +8; 2/3: queries + 8
+          stsm_t4(scr + (16 * kk + 8 * (mtx >> 1) + i) * FB_SCR_PITCH + (16 * mt + 8 * (mtx & 1)) * 2, dsf[mt][kk]);
+        }
+#pragma unroll
+      for (int kk = 0; kk < NJ / 2; ++kk)
+#pragma unroll
+        for (int jp = 0; jp < ND / 2; ++jp) {
+          uint32_t r[4], r2[4];
+          ldsm_t(r, dS_, RS, 16 * kk, 16 * jp, lane);
+          ldsm_t(r2, qS, RS, 16 * kk, 16 * jp, lane);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_bf16(dv[mt][2 * jp], pf[mt][kk], r[0], r[1]);
+            mma_bf16(dv[mt][2 * jp + 1], pf[mt][kk], r[2], r[3]);
+            mma_bf16(dk[mt][2 * jp], dsf[mt][kk], r2[0], r2[1]);
+            mma_bf16(dk[mt][2 * jp + 1], dsf[mt][kk], r2[2], r2[3]);
+          }
+        }
+      // dQ^T[16 x 32 q] = K^T[16 x 32 keys] dS^T: B fragments come back from the scratch ([n = query][k = key])
+      __syncwarp();
+      float dqT[NJ][4];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) dqT[j][0] = dqT[j][1] = dqT[j][2] = dqT[j][3] = 0.f;
+#pragma unroll
+      for (int qh = 0; qh < QT / 16; ++qh)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          uint32_t r[4];
+          ldsm_nt(r, scr, FB_SCR_PITCH, 16 * qh, 16 * mt, lane);
+          mma_bf16(dqT[2 * qh], kT[mt], r[0], r[1]);
+          mma_bf16(dqT[2 * qh + 1], kT[mt], r[2], r[3]);
+        }
+      __syncwarp();  // the scratch is rewritten in the next sub-tile
+      float4* slot = reinterpret_cast<float4*>(sSlots + ((it & 1) * 8 + warp) * FB_SLOT_FLOATS);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) slot[j * 32 + lane] = make_float4(dqT[j][0], dqT[j][1], dqT[j][2], dqT[j][3]);
+      // the staging tile reduce_and_flush(it) is about to rewrite was handed to the bulk reduce one sub-tile ago
+      if (threadIdx.x == 0) bulk_wait_read<0>();
+      __syncthreads();
+      reduce_and_flush(it);
+    }
+  }
+  __syncthreads();
+  reduce_and_flush(nsub_total);  // flushes the last staging tile
+  if (threadIdx.x == 0) bulk_wait_all<0>();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int r0 = k0 + 16 * mt + g, r1 = r0 + 8;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      const int col = h * DH + 8 * j + 2 * t;
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r0) * ld + C + col) = pack_bf16(dk[mt][j][0] * scale, dk[mt][j][1] * scale);
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r0) * ld + 2 * C + col) = pack_bf16(dv[mt][j][0], dv[mt][j][1]);
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r1) * ld + C + col) = pack_bf16(dk[mt][j][2] * scale, dk[mt][j][3] * scale);
+      *reinterpret_cast<uint32_t*>(dqkv + ((size_t)b * L + r1) * ld + 2 * C + col) = pack_bf16(dv[mt][j][2], dv[mt][j][3]);
+    }
+  }
+}
+
+// dq workspace fp32 [B][H][L][16] -> bf16 dq columns of dqkv [B*L][3C]; one thread per (row, head)
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ ws, bf16* __restrict__ dqkv, int B,
+                                                              int L, int C) {
+  const int H = C / 16;
+  const size_t total = (size_t)B * L * H;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i % H);
+    const size_t row = i / H;  // b * L + l: consecutive threads write consecutive 32-byte head slices of one row
+    const size_t bb = row / L, l = row - bb * L;
+    const float4* src = reinterpret_cast<const float4*>(ws + (((bb * H + h) * L) + l) * 16);
+    const float4 a = src[0], b4 = src[1], c = src[2], d = src[3];
+    uint4* dst = reinterpret_cast<uint4*>(dqkv + row * 3 * C + h * 16);
+    dst[0] = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b4.x, b4.y), pack_bf16(b4.z, b4.w));
+    dst[1] = make_uint4(pack_bf16(c.x, c.y), pack_bf16(c.z, c.w), pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
+  }
+}
+
 struct LaunchShape { int warps, mt, grid_x; };
 LaunchShape pick_shape(int L, bool allow_mt2) {
   LaunchShape s;
@@ -1237,8 +1516,18 @@ static int launch_bwd(cudaStream_t st, dim3 grid, dim3 block, int dh, const void
 }
 
 // dqkv [B*L][3C] receives (dq, dk, dv); delta is scratch fp32 [B][heads][L].
+static int attn_bwd_impl(void* stream, const void* qkv, const void* out, const void* dout, const float* lse2, float* delta,
+                         void* dqkv, float* ws, int B, int L, int C, int heads);
 extern "C" int tsd_attn_bwd(void* stream, const void* qkv, const void* out, const void* dout, const float* lse2,
                             float* delta, void* dqkv, int B, int L, int C, int heads) {
+  return attn_bwd_impl(stream, qkv, out, dout, lse2, delta, dqkv, nullptr, B, L, C, heads);
+}
+extern "C" int tsd_attn_bwd_ws(void* stream, const void* qkv, const void* out, const void* dout, const float* lse2,
+                               float* delta, void* dqkv, float* ws, int B, int L, int C, int heads) {
+  return attn_bwd_impl(stream, qkv, out, dout, lse2, delta, dqkv, ws, B, L, C, heads);
+}
+static int attn_bwd_impl(void* stream, const void* qkv, const void* out, const void* dout, const float* lse2, float* delta,
+                         void* dqkv, float* ws, int B, int L, int C, int heads) {
   TSD_CHECK(C % heads == 0, "attn_bwd: C %% heads != 0");
   const int dh = C / heads;
   TSD_CHECK(dh == 16 || dh == 32 || dh == 64, "attn_bwd: head_dim %d not in {16, 32, 64}", dh);
@@ -1252,8 +1541,30 @@ extern "C" int tsd_attn_bwd(void* stream, const void* qkv, const void* out, cons
   else if (dh == 32) attn_bwd_prep_kernel<32><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
   else attn_bwd_prep_kernel<64><<<pg, 256, 0, st>>>((const bf16*)out, (const bf16*)dout, delta, B, L, C);
   TSD_LAUNCH_CHECK();
-  static int bwd_variant = -1;
-  if (bwd_variant < 0) { const char* e = getenv("TSD_ATTN_BWD"); bwd_variant = e ? atoi(e) : 44; }
+  static int bwd_variant = -1, bwd_fused = 1;
+  if (bwd_variant < 0) {
+    const char* e = getenv("TSD_ATTN_BWD");
+    bwd_variant = e ? atoi(e) : 44;
+    const char* f = getenv("TSD_ATTN_BWD_FUSED");
+    if (f) bwd_fused = atoi(f);
+  }
+  if (bwd_fused && ws != nullptr && dh == 16 && L % 256 == 0) {
+    // one-pass backward: dK/dV in registers, dQ through the fp32 workspace [B][heads][L][16]
+    static bool cfgd = false;
+    if (!cfgd) {
+      TSD_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
+      cfgd = true;
+    }
+    TSD_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)B * L * C, st));
+    attn_bwd_fused_kernel<<<dim3(L / 256, heads, B), FB_NTHR, FB_SMEM, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta,
+                                                                           (bf16*)dqkv, ws, L, C, scale, scale_log2);
+    TSD_LAUNCH_CHECK();
+    int cg = (int)((total + 255) / 256);
+    if (cg > num_sms() * 16) cg = num_sms() * 16;
+    attn_dq_convert_kernel<<<cg, 256, 0, st>>>(ws, (bf16*)dqkv, B, L, C);
+    TSD_LAUNCH_CHECK();
+    return 0;
+  }
   if (bwd_variant > 0 && dh == 16 && L % 256 == 0) {
     const int vq = bwd_variant / 10, vk = bwd_variant % 10;
     const int smem_q = 4 * KV_TILE * 4 * 48, smem_k = smem_q + 4 * KV_TILE * 4 * 4;

@@ -106,6 +106,11 @@ int tsd_attn_fwd_ws(void* stream, const void* qkv, void* out, float* lse2, float
 /* dqkv [B*L][3C] receives (dq | dk | dv); delta: fp32 scratch [B][heads][L] */
 int tsd_attn_bwd(void* stream, const void* qkv, const void* out, const void* dout, const float* lse2, float* delta,
                  void* dqkv, int B, int L, int C, int heads);
+/* Same, with a caller-provided fp32 scratch of B*L*C floats: enables the one-pass backward for head_dim 16 and
+ * L % 256 == 0 (dK/dV and dQ from one evaluation of the scores; dQ partials are summed in the scratch by bulk
+ * reduce-adds, so dQ is reproducible up to fp32 summation order).  ws == NULL behaves like tsd_attn_bwd. */
+int tsd_attn_bwd_ws(void* stream, const void* qkv, const void* out, const void* dout, const float* lse2, float* delta,
+                    void* dqkv, float* ws, int B, int L, int C, int heads);
 
 /* ------------------------------------------------------------------------------------------
  * Elementwise / small reductions on bf16 channels-last tensors.
