@@ -1116,6 +1116,24 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void fb_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fb_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fb_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();  // a protocol bug becomes a launch error, not a hung box
+  }
+}
+
 constexpr int FB_MT = 2, FB_NSUB = 4, FB_NTHR = 256;
 constexpr int FB_QT = KV_TILE / FB_MT;               // 32 queries per sub-tile
 constexpr int FB_RS = 16 * 2 + 16;                   // padded Q / dO row
@@ -1128,7 +1146,8 @@ constexpr int FB_OFF_STATS = 4 * FB_STAGE_BYTES;
 constexpr int FB_OFF_SCR = FB_OFF_STATS + 4 * FB_STAGE_Q * 4;
 constexpr int FB_OFF_SLOTS = FB_OFF_SCR + 8 * FB_SCR_BYTES;
 constexpr int FB_OFF_STAGING = FB_OFF_SLOTS + 2 * 8 * FB_SLOT_FLOATS * 4;
-constexpr int FB_SMEM = FB_OFF_STAGING + 2 * FB_SLOT_FLOATS * 4;
+constexpr int FB_OFF_BARS = FB_OFF_STAGING + 3 * FB_SLOT_FLOATS * 4;  // three staging tiles, then 4 mbarriers
+constexpr int FB_SMEM = FB_OFF_BARS + 64;
 
 __global__ void __launch_bounds__(FB_NTHR, 2)
 attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse2,
@@ -1198,27 +1217,38 @@ attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dou
       sDl[buf * STAGE_Q + i] = delta[sbase + q];
     }
   };
-  // reduce the eight slots of sub-tile `it`, write the staging tile; then (one thread) add staging tile it-1 to global
-  auto reduce_and_flush = [&](int it) {
-    if (it >= 0 && it < nsub_total) {
-      const float* sl = sSlots + (it & 1) * 8 * FB_SLOT_FLOATS;
-      float* stg = sStaging + (it & 1) * FB_SLOT_FLOATS;
+  // Split-phase hand-off (mbarriers, 256 arrivals each), so the warps need not run in lockstep:
+  //   slot_bar[k & 1]: every thread has written its warp's dQ^T slot of sub-tile k;
+  //   stg_bar[k & 1] : every thread has reduced sub-tile k into staging tile k % 3 (its slots are free again).
+  // Sub-tile k is reduced while sub-tile k + 1 is in flight and its staging tile is handed to the bulk reduce one
+  // sub-tile later still; three staging tiles make the read-completion wait of that copy fall two sub-tiles back.
+  const uint32_t bars = smem0 + FB_OFF_BARS;
+  auto slot_bar = [&](int k) { return bars + 8u * (k & 1); };
+  auto stg_bar = [&](int k) { return bars + 16u + 8u * (k & 1); };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) fb_mbar_init(bars + 8u * i, FB_NTHR);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto reduce_subtile = [&](int k) {  // after slot_bar(k) completed
+    fb_mbar_wait(slot_bar(k), (k >> 1) & 1);
+    const float* sl = sSlots + (k & 1) * 8 * FB_SLOT_FLOATS;
+    float* stg = sStaging + (k % 3) * FB_SLOT_FLOATS;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int e = threadIdx.x + 256 * i;
-        float a = 0.f;
+    for (int i = 0; i < 2; ++i) {
+      const int e = threadIdx.x + 256 * i;
+      float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) a += sl[w * FB_SLOT_FLOATS + e];
-        stg[stg_off[i]] = a * scale;
-      }
-      fence_async_smem();
+      for (int w = 0; w < 8; ++w) a += sl[w * FB_SLOT_FLOATS + e];
+      stg[stg_off[i]] = a * scale;
     }
-    if (threadIdx.x == 0 && it >= 1 && it - 1 < nsub_total) {
-      const int pit = it - 1;
-      bulk_reduce_add_f32(dq_head + (size_t)pit * QT * DH, smem0 + FB_OFF_STAGING + (pit & 1) * FB_SLOT_FLOATS * 4,
-                          FB_SLOT_FLOATS * 4);
-      bulk_commit();
-    }
+    fence_async_smem();
+    fb_mbar_arrive(stg_bar(k));
+  };
+  auto flush_subtile = [&](int k) {  // thread 0, after stg_bar(k) completed
+    bulk_reduce_add_f32(dq_head + (size_t)k * QT * DH, smem0 + FB_OFF_STAGING + (k % 3) * FB_SLOT_FLOATS * 4,
+                        FB_SLOT_FLOATS * 4);
+    bulk_commit();
   };
 
   load_rows_async<DH>(smem0, qbase, ld, 0, L, STAGE_Q);
@@ -1322,18 +1352,30 @@ attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dou
           mma_bf16(dqT[2 * qh + 1], kT[mt], r[2], r[3]);
         }
       __syncwarp();  // the scratch is rewritten in the next sub-tile
+      if (it >= 2) {
+        fb_mbar_wait(stg_bar(it), ((it - 2) >> 1) & 1);  // sub-tile it-2 fully reduced: its slots are free, its staging final
+        if (threadIdx.x == 0) {
+          flush_subtile(it - 2);
+          bulk_wait_read<1>();  // everything but the copy just issued has been read out of its staging tile
+        }
+      }
       float4* slot = reinterpret_cast<float4*>(sSlots + ((it & 1) * 8 + warp) * FB_SLOT_FLOATS);
 #pragma unroll
       for (int j = 0; j < NJ; ++j) slot[j * 32 + lane] = make_float4(dqT[j][0], dqT[j][1], dqT[j][2], dqT[j][3]);
-      // the staging tile reduce_and_flush(it) is about to rewrite was handed to the bulk reduce one sub-tile ago
-      if (threadIdx.x == 0) bulk_wait_read<0>();
-      __syncthreads();
-      reduce_and_flush(it);
+      fb_mbar_arrive(slot_bar(it));
+      if (it >= 1) reduce_subtile(it - 1);
     }
+    __syncthreads();  // stage boundary: the Q / dO buffers are about to be refilled
   }
-  __syncthreads();
-  reduce_and_flush(nsub_total);  // flushes the last staging tile
-  if (threadIdx.x == 0) bulk_wait_all<0>();
+  reduce_subtile(nsub_total - 1);
+  if (threadIdx.x == 0) {
+    for (int k = nsub_total - 2; k < nsub_total; ++k) {
+      if (k < 0) continue;
+      fb_mbar_wait(stg_bar(k), (k >> 1) & 1);
+      flush_subtile(k);
+    }
+    bulk_wait_all<0>();
+  }
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
     const int r0 = k0 + 16 * mt + g, r1 = r0 + 8;

@@ -47,4 +47,4 @@ for B, L, C in cases:
     tb = timeit(lambda: ops.attn_bwd(qkv, out, dout, lse, B, L, C, H))
     nexp = B * H * L * L
     print(f"B={B} L={L} C={C} dh={dh}: fwd {tf:.3f} ms ({nexp/tf/1e9:.2f} Texp/s, {4*B*L*L*C/tf/1e9:.0f} TF/s) "
-          f"bwd {tb:.3f} ms ({2*nexp/tb/1e9:.2f} Texp/s)  err_o {eo:.2e} err_dqkv {ed:.2e}")
+          f"bwd {tb:.3f} ms ({nexp/tb/1e9:.2f} Texp/s per pass-equivalent)  err_o {eo:.2e} err_dqkv {ed:.2e}")

@@ -37,7 +37,7 @@ def flops(name, k):
     if name == "tsd_conv3x3_wgrad":
         c0, c1, n, H, W, s, cout = k[:7]
         return 2.0 * n * (H // s) * (W // s) * cout * 9 * (c0 + c1)
-    if name in ("tsd_attn_fwd", "tsd_attn_fwd_ws", "tsd_attn_bwd"):
+    if name in ("tsd_attn_fwd", "tsd_attn_fwd_ws", "tsd_attn_bwd", "tsd_attn_bwd_ws"):
         Bn, L, C, heads = k[:4]
         f = 4.0 * Bn * L * L * C
         return f if name.startswith("tsd_attn_fwd") else 3.5 * f
