@@ -40,6 +40,33 @@ def test_attention_fwd_bwd_vs_sdpa(cuda, B, L, C):
     assert (lse - ref_lse2.detach()).abs().max().item() < 2e-2
 
 
+def test_attention_backward_one_pass_vs_two_pass(cuda):
+    """head_dim 16, L % 256 == 0: tsd_attn_bwd_ws (one pass: dK/dV in registers, dQ through the fp32 workspace by bulk
+    reduce-add) against tsd_attn_bwd (two deterministic passes) and SDPA.  dK / dV come from the same arithmetic in both
+    (bit-identical); dQ is summed in a different order (fp32) and rounded once to bf16."""
+    from from_ddpm_to_stable_diffusion_b200 import _lib
+    B, L, C, H = 3, 1024, 128, 8
+    dh = C // H
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = (torch.randn(B * L, 3 * C, device=cuda, generator=g) * 1.3).to(BF)
+    dout = torch.randn(B * L, C, device=cuda, generator=g).to(BF)
+    out, lse = ops.attn_fwd(qkv, B, L, C, H, need_lse=True)
+    d1 = ops.attn_bwd(qkv, out, dout, lse, B, L, C, H)                       # one pass
+    d2 = torch.empty_like(qkv)
+    delta = torch.empty(B, H, L, device=cuda, dtype=torch.float32)
+    _lib.call("tsd_attn_bwd", qkv, out, dout, lse, delta, d2, B, L, C, H)     # two passes (no workspace)
+    torch.cuda.synchronize()
+    assert torch.equal(d1[:, C:], d2[:, C:])                                 # dK, dV
+    assert _rel(d1[:, :C], d2[:, :C]) < 8e-3                                 # dQ: one bf16 ulp of the largest entry
+    x = qkv.float().view(B, L, 3, H, dh).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+    ref = F.scaled_dot_product_attention(x[0], x[1], x[2])
+    ref.backward(dout.float().view(B, L, H, dh).permute(0, 2, 1, 3))
+    ref_d = x.grad.permute(1, 3, 0, 2, 4).reshape(B * L, 3 * C)
+    assert _rel(d1, ref_d) < 1.2e-2 and _rel(d2, ref_d) < 1.2e-2
+    d3 = ops.attn_bwd(qkv, out, dout, lse, B, L, C, H)                       # run-to-run: dK / dV exact, dQ to fp32 order
+    assert torch.equal(d1[:, C:], d3[:, C:]) and _rel(d1[:, :C], d3[:, :C]) < 8e-3
+
+
 def _sdpa_ref(qkv, B, L, C, H):
     dh = C // H
     x = qkv.float().view(B, L, 3, H, dh).permute(2, 0, 3, 1, 4).contiguous()
