@@ -252,7 +252,10 @@ def run_ours(args):
     att_exps = float(B) * Hh * L * L  # per pass; the one-pass backward evaluates them once
     ach = (nf * att_flops + nb * 2.5 * att_flops) / ((tfw + tb) * 1e-3) / 1e12
     roof = {"kernel": "attn_fwd_tc_kernel (tcgen05/TMEM) + attn_bwd_fused_kernel (one-pass, mma.sync), L=4096, head_dim 16, %d launches/step" % (nf + nb),
-            "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "traffic": None,
+            "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
+            # DRAM bytes per launch (read + write) of the backward kernel at this shape, from ncu
+            # (profiles/r01_attn_dram_traffic_b256.csv); the forward kernel moves 1.088e9 (qkv once, out + lse once)
+            "traffic": 2.713e9 if B == 256 else None,
             "peak_source": how + " (bf16_tflops_sustained)", "share_of_step": (tfw + tb) / tot_ms,
             "avg_launch_ms": {"fwd": tfw / max(nf, 1), "bwd": tb / max(nb, 1)},
             "exp_bound": {"achieved_texp_s": (nf + nb) * att_exps / ((tfw + tb) * 1e-3) / 1e12, "mufu_peak_texp_s": 4.64,
