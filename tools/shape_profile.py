@@ -13,9 +13,10 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 mode = sys.argv[2] if len(sys.argv) > 2 else "train"
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-model = Diffusion(3, [1, 2, 2, 2], 128, num_class=3, dropout=0.1).to(dev).train()
-x = torch.randn(B, 3, 64, 64, device=dev)
-y = torch.randint(1, 4, (B,), device=dev)
+latent = mode == "latent"  # BASELINE configs[4]: 4x16x16 latents, 10 classes, sampling
+model = Diffusion(4 if latent else 3, [1, 2, 2, 2], 128, num_class=10 if latent else 3, dropout=0.1).to(dev).train()
+x = torch.randn(B, 4, 16, 16, device=dev) if latent else torch.randn(B, 3, 64, 64, device=dev)
+y = torch.randint(1, 11 if latent else 4, (B,), device=dev)
 
 
 def flops(name, k):
