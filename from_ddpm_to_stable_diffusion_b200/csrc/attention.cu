@@ -1,4 +1,5 @@
-// Fused single-pass self-attention (forward + backward) for head_dim 16 / 32.
+// Self-attention on warp-level MMA: forward and two-pass backward for head_dim 16 / 32 / 64 (any L), and the one-pass
+// backward for head_dim 16 with L % 256 == 0.  (The head_dim-16 forward of the large stages is in attention_tc.cu.)
 //
 // Reference: SelfAttention.forward, diffusion.py:46-58 -- softmax(q k^T / sqrt(dh)) v over 8 heads,
 // q, k, v = consecutive C-wide column blocks of the in_proj output, head h = channels [h*dh, (h+1)*dh).
@@ -297,11 +298,6 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 // 2^x for a packed pair, x <= 0 (clamped at -126): cubic on [-0.5, 0.5], |rel err| < 2e-4 (bf16 P needs 4e-3)
 __device__ __forceinline__ void exp2_poly2(uint64_t x, float& o0, float& o1) {
   float x0, x1;
@@ -319,11 +315,6 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x, float& o0, float& o1) {
   o0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
   o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
 }
-__device__ __forceinline__ void ldsm_t2(uint32_t* r, uint32_t base, int RS, int row0, int col0, int lane) {
-  const uint32_t addr = base + (row0 + (lane & 15)) * RS + col0 * 2;
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
-}
-
 template <int DH, int MT, int NSUB, int POLY, int NTHR, int MINB>
 __global__ void __launch_bounds__(NTHR, MINB) attn_fwd2_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                                float* __restrict__ lse2, int L, int C, float scale_log2) {
@@ -782,7 +773,7 @@ __global__ void __launch_bounds__(256, MINB) attn_bwd_dkv_kernel(const bf16* __r
 // QT = 64/MT queries, so every ldmatrix of Q / dO feeds MT m-tiles (half the shared-memory traffic per MMA,
 // which is what bounds the one-m-tile kernel above: ncu shows its smem pipe at 63 %).
 // ------------------------------------------------------------------------------------------
-template <int DH, int MT, int NSUB, int NTHR, int MINB, int POLY = 0>
+template <int DH, int MT, int NSUB, int NTHR, int MINB>
 __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dkv2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                    const float* __restrict__ lse2, const float* __restrict__ delta,
                                                                    bf16* __restrict__ dqkv, int L, int C, float scale,
@@ -890,18 +881,12 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dkv2_kernel(const bf16* _
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           float p[4], ds[4];
-          if (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == POLY - 1) {  // this n-tile's exponentials on the FMA pipe
-            const uint64_t c2 = pack2(scale_log2, scale_log2), nl = pack2(-ls.x, -ls.y);
-            exp2_poly2(ffma2(pack2(sacc[mt][j][0], sacc[mt][j][1]), c2, nl), p[0], p[1]);
-            exp2_poly2(ffma2(pack2(sacc[mt][j][2], sacc[mt][j][3]), c2, nl), p[2], p[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) p[e] = ex2(fmaf(sacc[mt][j][e], scale_log2, -((e & 1) ? ls.y : ls.x)));
-          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            if (partial_keys && !key_ok[mt][e >> 1]) p[e] = 0.f;
-            ds[e] = p[e] * (pacc[mt][j][e] - ((e & 1) ? dl.y : dl.x));
+            float pe = ex2(fmaf(sacc[mt][j][e], scale_log2, -((e & 1) ? ls.y : ls.x)));
+            if (partial_keys && !key_ok[mt][e >> 1]) pe = 0.f;
+            p[e] = pe;
+            ds[e] = pe * (pacc[mt][j][e] - ((e & 1) ? dl.y : dl.x));
           }
           pf[mt][j >> 1][(j & 1) * 2] = pack_bf16(p[0], p[1]);
           pf[mt][j >> 1][(j & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
@@ -946,7 +931,7 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dkv2_kernel(const bf16* _
 }
 
 // Same idea for dQ: each warp owns MT*16 query rows and walks the key stage in sub-tiles of 64/MT keys.
-template <int DH, int MT, int NSUB, int NTHR, int MINB, int POLY = 0>
+template <int DH, int MT, int NSUB, int NTHR, int MINB>
 __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dq2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                   const float* __restrict__ lse2, const float* __restrict__ delta,
                                                                   bf16* __restrict__ dqkv, int L, int C, float scale,
@@ -1039,14 +1024,8 @@ __global__ void __launch_bounds__(NTHR, MINB) attn_bwd_dq2_kernel(const bf16* __
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           float ds[4], pe4[4];
-          if (POLY > 0 && (j % (POLY > 0 ? POLY : 1)) == POLY - 1) {
-            const uint64_t c2 = pack2(scale_log2, scale_log2);
-            exp2_poly2(ffma2(pack2(sacc[mt][j][0], sacc[mt][j][1]), c2, pack2(nlse[mt][0], nlse[mt][0])), pe4[0], pe4[1]);
-            exp2_poly2(ffma2(pack2(sacc[mt][j][2], sacc[mt][j][3]), c2, pack2(nlse[mt][1], nlse[mt][1])), pe4[2], pe4[3]);
-          } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pe4[e] = ex2(fmaf(sacc[mt][j][e], scale_log2, nlse[mt][e >> 1]));
-          }
+          for (int e = 0; e < 4; ++e) pe4[e] = ex2(fmaf(sacc[mt][j][e], scale_log2, nlse[mt][e >> 1]));
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float pe = pe4[e];
@@ -1155,7 +1134,7 @@ attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dou
                       float scale, float scale_log2) {
   constexpr int DH = 16, MT = FB_MT, RS = FB_RS, ND = 2, QT = FB_QT, NJ = QT / 8, STAGE_Q = FB_STAGE_Q,
                 STAGE_BYTES = FB_STAGE_BYTES;
-  extern __shared__ __align__(128) uint8_t smem_dyn[];
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
   const uint32_t smem0 = smem_u32_(smem_dyn);
   float* sLse = reinterpret_cast<float*>(smem_dyn + FB_OFF_STATS);
   float* sDl = sLse + 2 * STAGE_Q;
@@ -1621,14 +1600,10 @@ static int attn_bwd_impl(void* stream, const void* qkv, const void* out, const v
     if (vq == 1) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 1>), 2, 256, smem_q);
     else if (vq == 2) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 128, 3>), 2, 128, smem_q);
     else if (vq == 3) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 1, 4, 256, 3>), 1, 256, smem_q);
-    else if (vq == 5) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 2, 4>), 2, 256, smem_q);
-    else if (vq == 6) TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 2, 2>), 2, 256, smem_q);
     else TSD_BWD_LAUNCH((attn_bwd_dq2_kernel<16, 2, 4, 256, 2>), 2, 256, smem_q);
     if (vk == 1) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 1>), 2, 256, smem_k);
     else if (vk == 2) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 128, 3>), 2, 128, smem_k);
     else if (vk == 3) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 1, 4, 256, 3>), 1, 256, smem_k);
-    else if (vk == 5) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 2, 4>), 2, 256, smem_k);
-    else if (vk == 6) TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 2, 2>), 2, 256, smem_k);
     else TSD_BWD_LAUNCH((attn_bwd_dkv2_kernel<16, 2, 4, 256, 2>), 2, 256, smem_k);
 #undef TSD_BWD_LAUNCH
     return 0;
