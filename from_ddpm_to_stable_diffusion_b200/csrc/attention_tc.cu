@@ -1,4 +1,5 @@
-// tcgen05 / TMEM self-attention for head_dim 16 (the three 64x64 and two 32x32 attention stages, L % 256 == 0).
+// tcgen05 / TMEM self-attention forward for head_dim 16 and 32 with L % 256 == 0 (nine of the ten attention blocks of the
+// 64x64 configuration; the text below describes head_dim 16, head_dim 32 only changes the row width and swizzle).
 //
 // Reference: SelfAttention.forward, diffusion.py:46-58.  Same contract as the mma.sync kernels in attention.cu
 // (qkv bf16 [B*L][3C], out bf16 [B*L][C], lse2 fp32 [B][heads][L] in the log2 domain).
@@ -25,23 +26,26 @@
 namespace tsd {
 namespace {
 
-constexpr int DH = 16;
 constexpr int QT = 128;  // query rows per softmax warpgroup (= TMEM lanes)
 constexpr int NWG = 2;
 constexpr int KB = 64;   // keys per block
 constexpr int NST = 6;   // K/V ring stages
-constexpr int ROWB = DH * 2;
-constexpr int Q_BYTES = NWG * QT * ROWB;
-constexpr int KV_BYTES = KB * ROWB;
-constexpr int STAGE_BYTES = 2 * KV_BYTES;
-constexpr int TC_THREADS = NWG * 128 + 64;  // warps 0-7 softmax (warp % 4 = TMEM sub-partition), 8 = TMA, 9 = MMA
-constexpr int WG_COLS = 128;  // TMEM columns per warpgroup: S [0,64), P [64,96), O [96,112)
+constexpr int TC_THREADS = NWG * 128 + 64;  // warps 0-7 softmax (warp % 4 = TMEM sub-partition), 8 / 9 = MMA issuers
+constexpr int WG_COLS = 128;  // TMEM columns per warpgroup: S [0,64), P [64,96), O [96, 96 + DH)
 constexpr int S_COL = 0, P_COL = 64, O_COL = 96;
 constexpr float BOUND_LIMIT = 50.f;  // log2 units: |s*c| <= 50 for every key, so 2^(s*c - bound) >= 2^-100
 constexpr int TMEM_COLS = NWG * WG_COLS;  // 256: two CTAs per SM
-constexpr uint32_t SW32 = 6;
-constexpr int SMEM_BYTES = 1024 + Q_BYTES + NST * STAGE_BYTES + 256;
 constexpr float RESCALE_THRESHOLD = 8.f;
+// head_dim 16: 32-byte rows, SWIZZLE_32B (descriptor code 6); head_dim 32: 64-byte rows, SWIZZLE_64B (code 4)
+template <int DH>
+struct Geo {
+  static constexpr int ROWB = DH * 2;
+  static constexpr uint32_t SWZ = DH == 16 ? 6u : 4u;
+  static constexpr int Q_BYTES = NWG * QT * ROWB;
+  static constexpr int KV_BYTES = KB * ROWB;
+  static constexpr int STAGE_BYTES = 2 * KV_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + NST * STAGE_BYTES + 256;
+};
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -94,6 +98,7 @@ __device__ __forceinline__ void exp2_poly2_(uint64_t x, float& o0, float& o1) {
 }
 
 // max_k |k|^2 per (sample, head): one thread per (key row, head), 16 bf16 each.  knmax2 must be zeroed.
+template <int DH>
 __global__ void __launch_bounds__(512) attn_knorm_kernel(const bf16* __restrict__ qkv, float* __restrict__ knmax2,
                                                          int L, int C, int H) {
   __shared__ int s_max[32];
@@ -105,14 +110,17 @@ __global__ void __launch_bounds__(512) attn_knorm_kernel(const bf16* __restrict_
   const int b = blockIdx.y;
   if (r < rows_per_block && row < L) {
     const uint4* p = reinterpret_cast<const uint4*>(qkv + ((size_t)b * L + row) * 3 * C + C + hd * DH);
-    const uint4 a = p[0], c = p[1];
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 f = unpack_bf16(w[i]);
-      s = fmaf(f.x, f.x, s);
-      s = fmaf(f.y, f.y, s);
+    for (int v = 0; v < DH / 8; ++v) {
+      const uint4 a = p[v];
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(w[i]);
+        s = fmaf(f.x, f.x, s);
+        s = fmaf(f.y, f.y, s);
+      }
     }
     atomicMax(&s_max[hd], __float_as_int(s));  // non-negative floats order like ints
   }
@@ -120,10 +128,13 @@ __global__ void __launch_bounds__(512) attn_knorm_kernel(const bf16* __restrict_
   if (threadIdx.x < H) atomicMax(reinterpret_cast<int*>(knmax2) + b * H + threadIdx.x, s_max[threadIdx.x]);
 }
 
-template <int POLY>
+template <int DH, int POLY>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse2,
                    const float* __restrict__ knmax2, int L, int C, float scale_log2) {
+  constexpr int ROWB = Geo<DH>::ROWB, Q_BYTES = Geo<DH>::Q_BYTES, KV_BYTES = Geo<DH>::KV_BYTES,
+                STAGE_BYTES = Geo<DH>::STAGE_BYTES;
+  constexpr uint32_t SWZ = Geo<DH>::SWZ;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
@@ -191,13 +202,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           tma_load_2d(sQ + i * 64 * ROWB, &tmQKV, q_full, h * DH, row_base + q0 + i * 64);
         for (int jn = 0; jn < AHEAD && jn < nkb; ++jn) load_kv(jn);
       }
-      const uint64_t descQ = umma_smem_desc_sw(sQ + g * QT * ROWB, 0, 8 * ROWB, SW32);
+      const uint64_t descQ = umma_smem_desc_sw(sQ + g * QT * ROWB, 0, 8 * ROWB, SWZ);
       const uint32_t tW = tmem_base + g * WG_COLS;
       auto issue_S = [&](int j) {
         const int s = j % NST;
         mbar_wait(kv_full(s), (j / NST) & 1);
         tc_fence_after();
-        umma_bf16(tW + S_COL, descQ, umma_smem_desc_sw(sKV + s * STAGE_BYTES, 0, 8 * ROWB, SW32), idescS, 0u);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)  // K-major: a 16-element k-step is 32 bytes further along the swizzled row
+          umma_bf16(tW + S_COL, descQ + (uint64_t)(k * 2), umma_smem_desc_sw(sKV + s * STAGE_BYTES + k * 32, 0, 8 * ROWB, SWZ),
+                    idescS, k > 0 ? 1u : 0u);
         umma_commit(s_full(g));
       };
       mbar_wait(q_full, 0);
@@ -213,7 +227,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         const uint32_t sV = sKV + s * STAGE_BYTES + KV_BYTES;
 #pragma unroll
         for (int k = 0; k < KB / 16; ++k)
-          umma_bf16_ts(tW + O_COL, tW + P_COL + k * 8, umma_smem_desc_sw(sV + k * 16 * ROWB, 0, 8 * ROWB, SW32), idescPV,
+          umma_bf16_ts(tW + O_COL, tW + P_COL + k * 8, umma_smem_desc_sw(sV + k * 16 * ROWB, 0, 8 * ROWB, SWZ), idescPV,
                        (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(pv_done(g));
         umma_commit(kv_empty(s));
@@ -235,14 +249,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     if (knmax2 != nullptr) {
       mbar_wait(q_full, 0);
       const uint4* qrow = reinterpret_cast<const uint4*>(smem_raw + (sQ - smem_u32(smem_raw)) + (g * QT + row) * ROWB);
-      const uint4 a = qrow[0], c = qrow[1];
-      const uint32_t w[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-      float qn2 = 0.f;
+      float qn2 = 0.f;  // the swizzle permutes 16-byte chunks inside the row: irrelevant for a norm
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 f = unpack_bf16(w[i]);
-        qn2 = fmaf(f.x, f.x, qn2);
-        qn2 = fmaf(f.y, f.y, qn2);
+      for (int v = 0; v < DH / 8; ++v) {
+        const uint4 a = qrow[v];
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = unpack_bf16(w[i]);
+          qn2 = fmaf(f.x, f.x, qn2);
+          qn2 = fmaf(f.y, f.y, qn2);
+        }
       }
       const float bound = sqrtf(qn2 * __ldg(knmax2 + b * H + h)) * scale_log2 * 1.001f + 1e-3f;
       bound_mode = __all_sync(0xffffffffu, bound <= BOUND_LIMIT);
@@ -323,12 +340,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         mbar_wait(pv_done(g), (j - 1) & 1);
         tc_fence_after();
         if (rescale) {
-          uint32_t o[16];
-          tmem_ld16(tO, o);
-          tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st16(tO, o);
+          for (int part = 0; part < DH / 16; ++part) {
+            uint32_t o[16];
+            tmem_ld16(tO + part * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tO + part * 16, o);
+          }
         }
       }
       tmem_st32(tP, pk);
@@ -339,21 +359,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     // ---- epilogue: O / l -> bf16, lse
     mbar_wait(pv_done(g), (nkb - 1) & 1);
     tc_fence_after();
-    uint32_t o[16];
-    tmem_ld16(tO, o);
-    tmem_ld_wait();
     float la, lb;
     upk2(l2, la, lb);
     const float l = la + lb;
     const float inv = 1.f / l;
     const size_t grow = (size_t)b * L + q0 + g * QT + row;
-    uint32_t w[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      w[i] = pack_bf16(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
     uint4* dst = reinterpret_cast<uint4*>(out + grow * C + h * DH);
-    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+#pragma unroll
+    for (int part = 0; part < DH / 16; ++part) {
+      uint32_t o[16];
+      tmem_ld16(tO + part * 16, o);
+      tmem_ld_wait();
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        w[i] = pack_bf16(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+      dst[2 * part] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[2 * part + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
     if (lse2) lse2[((size_t)b * H + h) * L + q0 + g * QT + row] = m_ref + log2f(l);
   }
 
@@ -366,45 +389,54 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   }
 }
 
-template <int POLY>
+template <int DH, int POLY>
 int launch_fwd_t(cudaStream_t st, const CUtensorMap& tm, void* out, float* lse2, const float* knmax2, int B, int L,
                  int C, int heads, float scale_log2) {
-  auto kern = attn_fwd_tc_kernel<POLY>;
+  auto kern = attn_fwd_tc_kernel<DH, POLY>;
   static bool configured = false;
   if (!configured) {
-    TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<DH>::SMEM_BYTES));
     configured = true;
   }
   dim3 grid(L / (NWG * QT), heads, B);
-  kern<<<grid, TC_THREADS, SMEM_BYTES, st>>>(tm, (bf16*)out, lse2, knmax2, L, C, scale_log2);
+  kern<<<grid, TC_THREADS, Geo<DH>::SMEM_BYTES, st>>>(tm, (bf16*)out, lse2, knmax2, L, C, scale_log2);
   TSD_LAUNCH_CHECK();
   return 0;
+}
+
+template <int DH>
+int launch_fwd_dh(cudaStream_t st, const void* qkv, void* out, float* lse2, float* ws, int B, int L, int C, int heads,
+                  int poly) {
+  CUtensorMap tm;
+  if (make_tmap_2d_sw(&tm, qkv, 2, (uint64_t)B * L, 3 * (uint64_t)C, 3 * (uint64_t)C, DH, 64, DH * 2)) return 1;
+  const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
+  if (ws) {  // max |k|^2 per (sample, head) for the score bound
+    TSD_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * B * heads, st));
+    const int rows_per_block = 512 / heads;
+    attn_knorm_kernel<DH><<<dim3(ceil_div(L, rows_per_block), B), 512, 0, st>>>((const bf16*)qkv, ws, L, C, heads);
+    TSD_LAUNCH_CHECK();
+  }
+  switch (poly) {
+    case 0: return launch_fwd_t<DH, 0>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    case 2: return launch_fwd_t<DH, 2>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    case 3: return launch_fwd_t<DH, 3>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    default: return launch_fwd_t<DH, 4>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+  }
 }
 
 }  // namespace
 
 bool attn_tc_supported(int L, int C, int heads) {
-  return C % heads == 0 && C / heads == DH && heads <= 32 && L % (NWG * QT) == 0 && L >= NWG * QT;
+  if (C % heads != 0 || heads > 32) return false;
+  const int dh = C / heads;
+  return (dh == 16 || dh == 32) && L % (NWG * QT) == 0 && L >= NWG * QT;
 }
 
 int launch_attn_fwd_tc(cudaStream_t st, const void* qkv, void* out, float* lse2, float* ws, int B, int L, int C,
                        int heads, int poly) {
   TSD_CHECK(attn_tc_supported(L, C, heads), "attn_fwd_tc: unsupported shape L=%d C=%d heads=%d", L, C, heads);
-  CUtensorMap tm;
-  if (make_tmap_2d_sw(&tm, qkv, 2, (uint64_t)B * L, 3 * (uint64_t)C, 3 * (uint64_t)C, DH, 64, 32)) return 1;
-  const float scale_log2 = 1.4426950408889634f / sqrtf((float)DH);
-  if (ws) {  // max |k|^2 per (sample, head) for the score bound
-    TSD_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * B * heads, st));
-    const int rows_per_block = 512 / heads;
-    attn_knorm_kernel<<<dim3(ceil_div(L, rows_per_block), B), 512, 0, st>>>((const bf16*)qkv, ws, L, C, heads);
-    TSD_LAUNCH_CHECK();
-  }
-  switch (poly) {
-    case 0: return launch_fwd_t<0>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
-    case 2: return launch_fwd_t<2>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
-    case 4: return launch_fwd_t<4>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
-    default: return launch_fwd_t<3>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
-  }
+  if (C / heads == 16) return launch_fwd_dh<16>(st, qkv, out, lse2, ws, B, L, C, heads, poly);
+  return launch_fwd_dh<32>(st, qkv, out, lse2, ws, B, L, C, heads, poly);
 }
 
 }  // namespace tsd

@@ -4,7 +4,7 @@
 
 namespace tsd {
 
-// head_dim 16 and L a multiple of 256 (two 128-row query tiles per CTA)
+// head_dim 16 or 32 and L a multiple of 256 (two 128-row query tiles per CTA)
 bool attn_tc_supported(int L, int C, int heads);
 // poly: every poly-th pair of exponentials is evaluated on the FMA pipe (0 = none; 2, 3, 4)
 // ws: optional scratch of B * heads floats (max |k|^2 per sample and head); enables the bound mode (no max pass)

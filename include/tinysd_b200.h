@@ -100,7 +100,7 @@ int tsd_ln_bwd(void* stream, const void* dy, const void* x, int M, int C, const 
  * lse2 fp32 [B][heads][L] = log2-domain logsumexp (NULL when no backward is needed).
  * ------------------------------------------------------------------------------------------ */
 int tsd_attn_fwd(void* stream, const void* qkv, void* out, float* lse2, int B, int L, int C, int heads);
-/* Same, with a caller-provided fp32 scratch of B*heads floats: lets the tcgen05 path (head_dim 16, L % 256 == 0) bound
+/* Same, with a caller-provided fp32 scratch of B*heads floats: lets the tcgen05 path (head_dim 16 / 32, L % 256 == 0) bound
  * every score row by |q| max|k| and skip the running-maximum pass.  ws == NULL behaves like tsd_attn_fwd. */
 int tsd_attn_fwd_ws(void* stream, const void* qkv, void* out, float* lse2, float* ws, int B, int L, int C, int heads);
 /* dqkv [B*L][3C] receives (dq | dk | dv); delta: fp32 scratch [B][heads][L] */

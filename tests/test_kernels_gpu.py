@@ -16,7 +16,7 @@ def _rel(got, ref):
 
 
 @pytest.mark.parametrize("B,L,C", [(2, 4096, 128), (3, 1024, 128), (2, 1024, 256), (4, 256, 256), (5, 64, 256),
-                                   (3, 16, 128), (6, 4, 256), (2, 320, 128)])
+                                   (3, 16, 128), (6, 4, 256), (2, 320, 128), (5, 256, 128), (2, 512, 128)])
 def test_attention_fwd_bwd_vs_sdpa(cuda, B, L, C):
     """softmax(q k^T / sqrt(dh)) v with 8 heads (diffusion.py:46-58), all sequence lengths of both configs + ragged."""
     H = 8
