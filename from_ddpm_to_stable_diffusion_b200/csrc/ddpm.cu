@@ -7,6 +7,7 @@
 //   CFG combine + posterior update + Philox z + NaN flag                              (utils.py:149-167)
 #include "../../include/tinysd_b200.h"
 #include "common.cuh"
+#include <cstdlib>
 
 using namespace tsd;
 
@@ -447,6 +448,154 @@ __global__ void __launch_bounds__(256) tail_conv_sample_kernel(const bf16* __res
   if (bad) atomicOr(nan_flag, 1);
 }
 
+// ------------------------------------------------------------------------------------------ tail conv on tensor cores
+// The same convolution as an implicit GEMM on warp-level MMA (m16n8k16, bf16 in, fp32 accumulate): M = 128 output
+// pixels per CTA (TH = 128 / W rows of one image), N = 8 (CO <= 4 used), K = 9 taps x 128 channels.  The (TH + 2) x
+// (W + 2) halo tile of the bf16 NHWC input is staged once in shared memory (cp.async, zero fill = the padding; 272-byte
+// pixel pitch => conflict-free ldmatrix) and every tap is the same tile read at a shifted address; the weights are
+// converted to bf16 [n][tap * 128 + c] in shared memory by each CTA (14 KB of L2 reads).  SAMPLE = 1 runs the
+// conditional and the unconditional image of the pair through the same staging buffer and applies the classifier-free
+// guidance + posterior update + Philox noise + NaN flag per pixel and channel exactly like tail_conv_sample_kernel.
+// The input is read ~2x (halo rows) instead of 9x per output, and the 3 456 MACs per pixel run on the tensor pipe.
+namespace tcv {
+constexpr int C = 128, PITCH = 272, WK = 9 * C, WPITCH = WK + 8;  // bf16 elements per weight row (+16 B pad)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ldsm4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+}  // namespace tcv
+
+template <int CO, int SAMPLE>
+__global__ void __launch_bounds__(256, 2)
+tail_conv_mma_kernel(const bf16* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                     float* __restrict__ out /* SAMPLE: x (updated in place, both halves); else eps */,
+                     const int* __restrict__ step_ptr, const float* __restrict__ c1, const float* __restrict__ c2,
+                     const float* __restrict__ sigma, float wcfg, const float* __restrict__ noise_in, uint64_t seed,
+                     int* __restrict__ nan_flag, float* __restrict__ eps_out, int B, int H, int W, int clip_last) {
+  using namespace tcv;
+  extern __shared__ __align__(16) uint8_t smem_tc[];
+  const int TH = 128 / W;                 // output rows per CTA
+  const int HWP = W + 2;                  // halo row length in pixels
+  bf16* sW = reinterpret_cast<bf16*>(smem_tc);                         // [8][WPITCH]
+  uint8_t* sA = smem_tc + 8 * WPITCH * 2;                              // [(TH + 2)][W + 2][PITCH bytes]
+  const uint32_t sA_u = smem_addr(sA), sW_u = smem_addr(sW);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int HW = H * W;
+  const int tiles_per_img = HW / 128;
+  const int n = blockIdx.x / tiles_per_img;          // image index inside the first half (SAMPLE) / the batch
+  const int y0 = (blockIdx.x - n * tiles_per_img) * TH;
+  // ---- weights: fp32 OIHW [CO][128][3][3] -> bf16 [n][tap * 128 + c], rows >= CO zero
+  for (int i = threadIdx.x; i < CO * WK; i += blockDim.x) {  // coalesced read of OIHW, scattered 2-byte smem writes
+    const int o = i / WK, r = i - o * WK, c = r / 9, tap = r - c * 9;
+    sW[o * WPITCH + tap * C + c] = __float2bfloat16(__ldg(w + i));
+  }
+  for (int i = threadIdx.x; i < (8 - CO) * WK; i += blockDim.x) sW[(CO + i / WK) * WPITCH + i % WK] = __float2bfloat16(0.f);
+  float acc[SAMPLE ? 2 : 1][4];
+#pragma unroll
+  for (int hf = 0; hf < (SAMPLE ? 2 : 1); ++hf) {
+    acc[hf][0] = acc[hf][1] = acc[hf][2] = acc[hf][3] = 0.f;
+    if (hf == 1) __syncthreads();  // everyone is done reading the first image's tile
+    // ---- stage the halo tile of image n (+ B for the unconditional half)
+    const bf16* img = a + (size_t)(n + hf * B) * HW * C;
+    const int chunks = (TH + 2) * HWP * 16;  // 16-byte chunks
+    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+      const int ck = i & 15, px = i >> 4;
+      const int hy = px / HWP, hx = px - hy * HWP;
+      const int yy = y0 + hy - 1, xx = hx - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      cp16(sA_u + px * PITCH + ck * 16, img + ((size_t)(ok ? yy : 0) * W + (ok ? xx : 0)) * C + ck * 8, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- this warp's 16 pixels: tile pixel p = warp * 16 + row, (ty, tx) = (p / W, p % W)
+    const int prow = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;  // ldmatrix row of this lane
+    const int ty = prow / W, tx = prow - ty * W;
+    const uint32_t a_lane = sA_u + (ty * HWP + tx) * PITCH + (lane >> 4) * 16;
+    const uint32_t b_lane = sW_u + (g * WPITCH + 2 * t) * 2;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap - dy * 3;  // halo coordinates already include the -1 shift
+      const uint32_t a_tap = a_lane + (dy * HWP + dx) * PITCH;
+      const uint32_t b_tap = b_lane + tap * C * 2;
+#pragma unroll
+      for (int kc = 0; kc < C / 16; ++kc) {
+        uint32_t af[4];
+        ldsm4(af, a_tap + kc * 32);
+        uint32_t b0, b1;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b0) : "r"(b_tap + kc * 32));
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(b1) : "r"(b_tap + kc * 32 + 16));
+        mma(acc[hf], af, b0, b1);
+      }
+    }
+  }
+  // ---- epilogue: lane (g, t) holds pixels g, g + 8 of the warp's 16 and channels 2t, 2t + 1
+  int step = 0;
+  float k1 = 0.f, k2 = 0.f, sg = 0.f;
+  if (SAMPLE) {
+    step = *step_ptr;
+    k1 = c1[step]; k2 = c2[step]; sg = sigma[step];
+  }
+  const float w1 = 1.f + wcfg;
+  const Philox rng(seed);
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int p = warp * 16 + g + 8 * r;                 // tile pixel
+    const int rem = y0 * W + p;                          // pixel index inside the image (tile rows are contiguous)
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int o = 2 * t + cc;
+      if (o >= CO) continue;
+      const size_t e = ((size_t)n * CO + o) * HW + rem;
+      const float ec = acc[0][2 * r + cc] + bias[o];
+      if (!SAMPLE) {
+        out[e] = ec;
+      } else {
+        const float eu = acc[SAMPLE ? 1 : 0][2 * r + cc] + bias[o];
+        if (eps_out) {
+          eps_out[e] = ec;
+          eps_out[(size_t)B * CO * HW + e] = eu;
+        }
+        float z = 0.f;
+        if (step > 0) {
+          if (noise_in) {
+            z = noise_in[e];
+          } else {
+            const uint4 rr = rng(e, (uint64_t)step + 1);
+            z = box_muller(rr.x, rr.y).x;
+          }
+        }
+        const float ep = __fsub_rn(__fmul_rn(w1, ec), __fmul_rn(wcfg, eu));
+        const float mean = __fsub_rn(__fmul_rn(k1, out[e]), __fmul_rn(k2, ep));
+        float v = __fadd_rn(mean, __fmul_rn(sg, z));
+        bad |= (v != v);
+        if (clip_last && step == 0) v = fminf(fmaxf(v, -1.f), 1.f);
+        out[e] = v;
+        out[(size_t)B * CO * HW + e] = v;  // the unconditional copy of the 2B batch
+      }
+    }
+  }
+  if (SAMPLE && bad) atomicOr(nan_flag, 1);
+}
+
+static bool tail_mma_ok(int H, int W) {
+  static int enabled = -1;  // TSD_TAIL_MMA=0: the CUDA-core kernels (A/B comparison)
+  if (enabled < 0) { const char* e = getenv("TSD_TAIL_MMA"); enabled = e ? atoi(e) : 1; }
+  return enabled && (W == 16 || W == 32 || W == 64) && (H * W) % 128 == 0 && H % (128 / W) == 0;
+}
+static int tail_mma_smem(int W) { return 8 * tcv::WPITCH * 2 + (128 / W + 2) * (W + 2) * tcv::PITCH; }
+
 // im2col of the fp32 NCHW image for the head-conv weight gradient: patch[p][k], k = c*9 + tap (< ci*9), zero-padded
 // to KP columns, bf16 -> the reduction over all pixels runs on the tensor cores (tsd_gemm_wgrad).
 __global__ void im2col_head_kernel(const float* __restrict__ x, bf16* __restrict__ patch, int n_img, int ci, int H, int W,
@@ -531,6 +680,22 @@ extern "C" int tsd_head_conv_wgrad(void* stream, const void* dy, const float* x,
 extern "C" int tsd_tail_conv_fwd(void* stream, const void* a, const float* w, const float* bias, float* out, int n_img,
                                  int H, int W, int c_in, int co) {
   TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_fwd: unsupported channels c_in=%d co=%d", c_in, co);
+  if (tail_mma_ok(H, W)) {  // tensor-core implicit GEMM
+    const int smem = tail_mma_smem(W);
+    const int grid_tc = n_img * (H * W / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (co == 3) {
+      static bool cfgd = false;
+      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfgd = true; }
+      tail_conv_mma_kernel<3, 0><<<grid_tc, 256, smem, st>>>((const bf16*)a, w, bias, out, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, 0, H, W, 0);
+    } else {
+      static bool cfgd = false;
+      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfgd = true; }
+      tail_conv_mma_kernel<4, 0><<<grid_tc, 256, smem, st>>>((const bf16*)a, w, bias, out, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, 0, H, W, 0);
+    }
+    TSD_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t total = (size_t)n_img * H * W;
   int grid = (int)((total + 255) / 256);  // 8 warps x 32 pixels per CTA pass
   if (grid > num_sms() * 8) grid = num_sms() * 8;
@@ -603,6 +768,22 @@ extern "C" int tsd_tail_conv_sample(void* stream, const void* a, const float* w,
                                     const float* noise_in, uint64_t seed, int* nan_flag, float* eps_out, int B, int H, int W,
                                     int c_in, int co, int clip_last) {
   TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_sample: unsupported channels c_in=%d co=%d", c_in, co);
+  if (tail_mma_ok(H, W)) {  // tensor-core implicit GEMM, both halves of the CFG pair per CTA
+    const int smem = tail_mma_smem(W);
+    const int grid_tc = B * (H * W / 128);
+    cudaStream_t stt = (cudaStream_t)stream;
+    if (co == 3) {
+      static bool cfgd = false;
+      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfgd = true; }
+      tail_conv_mma_kernel<3, 1><<<grid_tc, 256, smem, stt>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
+    } else {
+      static bool cfgd = false;
+      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfgd = true; }
+      tail_conv_mma_kernel<4, 1><<<grid_tc, 256, smem, stt>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
+    }
+    TSD_LAUNCH_CHECK();
+    return 0;
+  }
   const size_t total = (size_t)B * H * W;
   int grid = (int)((total + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
