@@ -13,6 +13,16 @@ namespace {
 
 constexpr int GROUPS = 32;
 
+// two warp reductions interleaved (independent shuffles in flight together)
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ta = __shfl_xor_sync(0xffffffffu, a, o), tb = __shfl_xor_sync(0xffffffffu, b, o);
+    a += ta;
+    b += tb;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // GroupNorm statistics.  grid = (chunks, n_img); each CTA reduces a slab of pixels of one image
 // over all channels of the (optionally concatenated) input and adds per-group partial sums.
@@ -414,18 +424,19 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
     for (int r = 0; r < RPW; ++r) {
       if (row0 + r >= M) break;
       float v[4 * VEC];
-      float s = 0.f;
+      float s = 0.f, q = 0.f;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const float2 a = unpack_bf16(u[r][i].x), b = unpack_bf16(u[r][i].y);
         v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
         s += a.x + a.y + b.x + b.y;
+        q += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
       }
-      const float mean = warp_sum(s) * (1.f / C);
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4 * VEC; ++i) { const float d = v[i] - mean; q += d * d; }
-      const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+      // sum and sum of squares reduced side by side: one dependent shuffle chain per row instead of two (the kernel is
+      // bound by that latency, not by HBM); fp32 E[x^2] - mean^2 over C <= 512 bf16 values, as in the GroupNorm kernels
+      warp_sum2(s, q);
+      const float mean = s * (1.f / C);
+      const float rstd = rsqrtf(fmaxf(q * (1.f / C) - mean * mean, 0.f) + eps);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const float o0 = (v[4 * i] - mean) * rstd * g[i].x + bt[i].x, o1 = (v[4 * i + 1] - mean) * rstd * g[i].y + bt[i].y;
@@ -460,48 +471,62 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   for (int i = 0; i < 4 * VEC; ++i) { adg[i] = 0.f; adb[i] = 0.f; }
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(M, r_begin + rows_per_cta);
-  for (int row = r_begin + warp; row < r_end; row += nwarps) {
-    float v[4 * VEC], d[4 * VEC];
-    float s = 0.f;
+  constexpr int RPW = 2;  // rows per warp per pass: all loads of both rows are issued before the first is used
+  for (int row0 = r_begin + warp * RPW; row0 < r_end; row0 += nwarps * RPW) {
+    uint2 ux[RPW][VEC], ug[RPW][VEC], ur[RPW][VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const size_t off = (size_t)row * C + (i * 32 + lane) * 4;
-      const uint2 u = *reinterpret_cast<const uint2*>(x + off);
-      const uint2 g = *reinterpret_cast<const uint2*>(dy + off);
-      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(g.x), e = unpack_bf16(g.y);
-      v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
-      d[4 * i] = c.x; d[4 * i + 1] = c.y; d[4 * i + 2] = e.x; d[4 * i + 3] = e.y;
-      s += a.x + a.y + b.x + b.y;
-    }
-    const float mean = warp_sum(s) * (1.f / C);
-    float q = 0.f;
+    for (int r = 0; r < RPW; ++r)
 #pragma unroll
-    for (int i = 0; i < 4 * VEC; ++i) { v[i] -= mean; q += v[i] * v[i]; }
-    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
-    float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4 * VEC; ++i) {
-      v[i] *= rstd;  // xhat
-      adg[i] += d[i] * v[i];
-      adb[i] += d[i];
-      d[i] *= gm[i];
-      m1 += d[i];
-      m2 += d[i] * v[i];
-    }
-    m1 = warp_sum(m1) * (1.f / C);
-    m2 = warp_sum(m2) * (1.f / C);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const size_t off = (size_t)row * C + (i * 32 + lane) * 4;
-      float o[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = rstd * (d[4 * i + j] - m1 - v[4 * i + j] * m2);
-      if (radd) {
-        const uint2 r = *reinterpret_cast<const uint2*>(radd + off);
-        const float2 a = unpack_bf16(r.x), b = unpack_bf16(r.y);
-        o[0] += a.x; o[1] += a.y; o[2] += b.x; o[3] += b.y;
+      for (int i = 0; i < VEC; ++i) {
+        const int row = row0 + r < r_end ? row0 + r : row0;  // a duplicate load for the ragged last pass
+        const size_t off = (size_t)row * C + (i * 32 + lane) * 4;
+        ux[r][i] = *reinterpret_cast<const uint2*>(x + off);
+        ug[r][i] = *reinterpret_cast<const uint2*>(dy + off);
+        if (radd) ur[r][i] = *reinterpret_cast<const uint2*>(radd + off);
       }
-      *reinterpret_cast<uint2*>(dx + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int row = row0 + r;
+      if (row >= r_end) break;
+      float v[4 * VEC], d[4 * VEC];
+      float s = 0.f, sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float2 a = unpack_bf16(ux[r][i].x), b = unpack_bf16(ux[r][i].y), c = unpack_bf16(ug[r][i].x),
+                     e = unpack_bf16(ug[r][i].y);
+        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = b.x; v[4 * i + 3] = b.y;
+        d[4 * i] = c.x; d[4 * i + 1] = c.y; d[4 * i + 2] = e.x; d[4 * i + 3] = e.y;
+        s += a.x + a.y + b.x + b.y;
+        sq += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+      }
+      warp_sum2(s, sq);
+      const float mean = s * (1.f / C);
+      const float rstd = rsqrtf(fmaxf(sq * (1.f / C) - mean * mean, 0.f) + eps);
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4 * VEC; ++i) {
+        v[i] = (v[i] - mean) * rstd;  // xhat
+        adg[i] += d[i] * v[i];
+        adb[i] += d[i];
+        d[i] *= gm[i];
+        m1 += d[i];
+        m2 += d[i] * v[i];
+      }
+      warp_sum2(m1, m2);
+      m1 *= (1.f / C);
+      m2 *= (1.f / C);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const size_t off = (size_t)row * C + (i * 32 + lane) * 4;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = rstd * (d[4 * i + j] - m1 - v[4 * i + j] * m2);
+        if (radd) {
+          const float2 a = unpack_bf16(ur[r][i].x), b = unpack_bf16(ur[r][i].y);
+          o[0] += a.x; o[1] += a.y; o[2] += b.x; o[3] += b.y;
+        }
+        *reinterpret_cast<uint2*>(dx + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+      }
     }
   }
 #pragma unroll
