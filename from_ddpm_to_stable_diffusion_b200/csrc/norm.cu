@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_sums_kernel(const bf16* __restr
   const bf16* src_base = from0 ? x0 + (size_t)n * hw * c0 + cv : x1 + (size_t)n * hw * c1 + (cv - c0);
   const int src_ld = from0 ? c0 : c1;
   const bf16* dy_base = dy + (size_t)n * hw * C + cv;
-  constexpr int UNROLL = 2;
+  constexpr int UNROLL = 4;
   for (int pix0 = p_begin + my_slot; pix0 < p_end; pix0 += slots * UNROLL) {
     uint4 u[UNROLL], gq[UNROLL];
 #pragma unroll
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
   bf16* dst_base = from0 ? dx0 + (size_t)n * hw * c0 + cv : dx1 + (size_t)n * hw * c1 + (cv - c0);
   const int src_ld = from0 ? c0 : c1;
   const size_t full_base = (size_t)n * hw * C + cv;
-  constexpr int UNROLL = 2;
+  constexpr int UNROLL = 4;
   for (int pix0 = p_begin + my_slot; pix0 < p_end; pix0 += slots * UNROLL) {
     uint4 u[UNROLL], gq[UNROLL], rq[UNROLL];
 #pragma unroll
