@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
   const bool from0 = cv < c0;
   const bf16* src_base = from0 ? x0 + (size_t)n * hw * c0 + cv : x1 + (size_t)n * hw * c1 + (cv - c0);
   const int src_ld = from0 ? c0 : c1;
-  constexpr int UNROLL = 4;  // independent 16-byte loads in flight per thread
+  constexpr int UNROLL = 8;  // independent 16-byte loads in flight per thread
   for (int pix0 = p_begin + my_slot; pix0 < p_end; pix0 += slots * UNROLL) {
     uint4 u[UNROLL];
 #pragma unroll
