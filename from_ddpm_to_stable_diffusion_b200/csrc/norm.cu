@@ -402,7 +402,7 @@ template <int VEC>  // C = 128 * VEC: each lane handles VEC chunks of 4 channels
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, int M, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float eps, bf16* __restrict__ out) {
   constexpr int C = 128 * VEC;
-  constexpr int RPW = 4;  // rows per warp per pass: RPW independent row loads in flight
+  constexpr int RPW = 8;  // rows per warp per pass: RPW independent row loads in flight
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   for (int i = 0; i < 4 * VEC; ++i) { adg[i] = 0.f; adb[i] = 0.f; }
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(M, r_begin + rows_per_cta);
-  constexpr int RPW = 2;  // rows per warp per pass: all loads of both rows are issued before the first is used
+  constexpr int RPW = VEC == 1 ? 4 : 2;  // rows per warp per pass: all loads of these rows are issued before the first is used
   for (int row0 = r_begin + warp * RPW; row0 < r_end; row0 += nwarps * RPW) {
     uint2 ux[RPW][VEC], ug[RPW][VEC], ur[RPW][VEC];
 #pragma unroll
@@ -617,7 +617,7 @@ extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const vo
 extern "C" int tsd_ln_fwd(void* stream, const void* x, int M, int C, const float* gamma, const float* beta, float eps,
                           void* out) {
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = ceil_div(M, 8 * 4);  // 8 warps x 4 rows per pass
+  int grid = ceil_div(M, 8 * 8);  // 8 warps x 8 rows per pass
   if (grid > 8 * num_sms()) grid = 8 * num_sms();
   if (C == 128) ln_fwd_kernel<1><<<grid, 256, 0, st>>>((const bf16*)x, M, gamma, beta, eps, (bf16*)out);
   else if (C == 256) ln_fwd_kernel<2><<<grid, 256, 0, st>>>((const bf16*)x, M, gamma, beta, eps, (bf16*)out);
