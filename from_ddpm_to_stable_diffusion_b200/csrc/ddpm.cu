@@ -214,6 +214,69 @@ __global__ void __launch_bounds__(256) tail_conv_dgrad_kernel(const float* __res
   }
 }
 
+// Same, register-blocked: thread = (4 consecutive pixels of a row, 8 channels).  Every weight vector read from shared
+// memory serves 4 pixels and every dy value up to 3 taps (the one-pixel version is bound by its shared-memory reads:
+// 4 B per FMA).  W % 4 == 0.
+template <int CO>
+__global__ void __launch_bounds__(256) tail_conv_dgrad4_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                               bf16* __restrict__ da, int n_img, int H, int W) {
+  constexpr int C = 128, PX = 4;
+  __shared__ float sw[CO * 9 * C];  // [co][tap][c]
+  for (int i = threadIdx.x; i < CO * C * 9; i += blockDim.x) {
+    const int o = i / (C * 9), r = i - o * (C * 9), c = r / 9, tap = r - c * 9;
+    sw[(o * 9 + tap) * C + c] = w[i];
+  }
+  __syncthreads();
+  const int wq = W / PX;
+  const int total = n_img * H * wq * (C / 8);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = (i % (C / 8)) * 8;
+    int p = i / (C / 8);
+    const int x0 = (p % wq) * PX; p /= wq;
+    const int yy = p % H;
+    const size_t n = p / H;
+    float acc[PX][8];
+#pragma unroll
+    for (int q = 0; q < PX; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+      const float* dp = dy + (n * CO + o) * (size_t)H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        // forward: out[q] += a[q + off(tap)] * w[tap]  =>  da[p] += dy[p - off(tap)] * w[tap]
+        const int y2 = yy - (ky - 1);
+        if (y2 < 0 || y2 >= H) continue;
+        float v[PX + 2];
+#pragma unroll
+        for (int k = 0; k < PX + 2; ++k) {
+          const int x2 = x0 + k - 1;
+          v[k] = (x2 >= 0 && x2 < W) ? __ldg(dp + (size_t)y2 * W + x2) : 0.f;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float* wr = sw + (o * 9 + ky * 3 + kx) * C + cv;
+          const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int q = 0; q < PX; ++q) {
+            const float d = v[q + 2 - kx];  // dy at x = x0 + q - (kx - 1)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(d, wv[j], acc[q][j]);
+          }
+        }
+      }
+    }
+    bf16* dst = da + (((size_t)n * H + yy) * W + x0) * C + cv;
+#pragma unroll
+    for (int q = 0; q < PX; ++q)
+      *reinterpret_cast<uint4*>(dst + (size_t)q * C) =
+          make_uint4(pack_bf16(acc[q][0], acc[q][1]), pack_bf16(acc[q][2], acc[q][3]), pack_bf16(acc[q][4], acc[q][5]),
+                     pack_bf16(acc[q][6], acc[q][7]));
+  }
+}
+
 // dW[co][c][3][3] += sum_p dy[p][co] * a[p+off][c]; db[co] += sum dy.  thread = input channel c.
 template <int CO>
 __global__ void __launch_bounds__(128) tail_conv_wgrad_kernel(const float* __restrict__ dy, const bf16* __restrict__ a,
@@ -714,11 +777,13 @@ extern "C" int tsd_tail_conv_bwd(void* stream, const float* dy, const void* a, c
   if (ppc < 64) ppc = 64;
   const int g2 = (int)((total + ppc - 1) / ppc);
   if (co == 3) {
-    tail_conv_dgrad_kernel<3><<<g1, 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
+    if (W % 4 == 0) tail_conv_dgrad4_kernel<3><<<ew_grid(total * 4), 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
+    else tail_conv_dgrad_kernel<3><<<g1, 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
     TSD_LAUNCH_CHECK();
     tail_conv_wgrad_kernel<3><<<g2, 128, 0, st>>>(dy, (const bf16*)a, dw, db, n_img, H, W, ppc);
   } else {
-    tail_conv_dgrad_kernel<4><<<g1, 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
+    if (W % 4 == 0) tail_conv_dgrad4_kernel<4><<<ew_grid(total * 4), 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
+    else tail_conv_dgrad_kernel<4><<<g1, 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
     TSD_LAUNCH_CHECK();
     tail_conv_wgrad_kernel<4><<<g2, 128, 0, st>>>(dy, (const bf16*)a, dw, db, n_img, H, W, ppc);
   }
@@ -812,7 +877,10 @@ extern "C" int tsd_tail_conv_dgrad(void* stream, const float* dy, const float* w
   TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_dgrad: unsupported channels c_in=%d co=%d", c_in, co);
   const size_t total = (size_t)n_img * H * W;
   const int g1 = ew_grid(total * 16);
-  if (co == 3) tail_conv_dgrad_kernel<3><<<g1, 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
+  if (W % 4 == 0) {
+    if (co == 3) tail_conv_dgrad4_kernel<3><<<ew_grid(total * 4), 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
+    else tail_conv_dgrad4_kernel<4><<<ew_grid(total * 4), 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
+  } else if (co == 3) tail_conv_dgrad_kernel<3><<<g1, 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
   else tail_conv_dgrad_kernel<4><<<g1, 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
   TSD_LAUNCH_CHECK();
   return 0;
