@@ -139,6 +139,90 @@ __global__ void __launch_bounds__(64) small_linear_wgrad_kernel(const float* __r
   if (db && blockIdx.x == 0 && threadIdx.x < NT && n0 + threadIdx.x < N) db[n0 + threadIdx.x] += accb[0];
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiled fp32 versions of the two kernels above for batch-sized M (>= 32): a CTA of 256 threads owns a 32 x 64 output
+// tile (2 x 4 per thread) and walks the reduction dimension in steps of 32 through shared memory, so every operand
+// element is read from global memory once per tile and from shared memory once per 4-8 FMAs (the row-per-thread
+// kernels read one shared-memory word per FMA and run on 64-128 tiny CTAs).
+//   dgrad: dx[m][k] (+)= f'(x[m][k]) * sum_n dy[m][n] * w[n][k]      tile = 32 m x 64 k, reduce over n
+//   wgrad: dw[n][k] += sum_m dy[m][n] * f(x[m][k]); db[n] += sum_m dy[m][n]   tile = 32 n x 64 k, reduce over m
+// ------------------------------------------------------------------------------------------
+constexpr int TI = 32, TJ = 64, TR = 32;
+
+template <int WGRAD>
+__global__ void __launch_bounds__(256) small_linear_bwd_tiled_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                     const float* __restrict__ w, float* __restrict__ dx,
+                                                                     float* __restrict__ dw, float* __restrict__ db, int M,
+                                                                     int N, int K, int silu_in, int accumulate) {
+  // A(r, i): the dy operand; B(r, j): f(x) (wgrad) or w (dgrad).  sA[r][i], sB[r][j]
+  __shared__ float sA[TR][TI + 1];
+  __shared__ float sB[TR][TJ];
+  const int i0 = blockIdx.y * TI;  // wgrad: n; dgrad: m
+  const int j0 = blockIdx.x * TJ;  // k
+  const int R = WGRAD ? M : N;     // reduction length
+  const int ti = (threadIdx.x >> 4) * 2, tj = (threadIdx.x & 15) * 4;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float accb[2] = {0.f, 0.f};
+  for (int r0 = 0; r0 < R; r0 += TR) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TR * TI; e += blockDim.x) {
+      // wgrad: A(r, i) = dy[m = r][n = i] (i fastest: coalesced); dgrad: A(r, i) = dy[m = i][n = r] (r fastest)
+      const int a = WGRAD ? e / TI : e % TR, bq = WGRAD ? e % TI : e / TR;  // (r, i) local
+      const int r = r0 + a, i = i0 + bq;
+      const int m = WGRAD ? r : i, n = WGRAD ? i : r;
+      sA[a][bq] = (m < M && n < N) ? dy[(size_t)m * N + n] : 0.f;
+    }
+    for (int e = threadIdx.x; e < TR * TJ; e += blockDim.x) {
+      const int a = e / TJ, bq = e - a * TJ;
+      const int r = r0 + a, k = j0 + bq;
+      float v = 0.f;
+      if (k < K && r < R) {
+        if (WGRAD) {
+          v = x[(size_t)r * K + k];
+          if (silu_in) v = v / (1.f + expf(-v));
+        } else {
+          v = w[(size_t)r * K + k];
+        }
+      }
+      sB[a][bq] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int a = 0; a < TR; ++a) {
+      const float a0 = sA[a][ti], a1 = sA[a][ti + 1];
+      const float4 b = *reinterpret_cast<const float4*>(&sB[a][tj]);
+      acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+      if (WGRAD) { accb[0] += a0; accb[1] += a1; }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int i = i0 + ti + u;
+    if (i >= (WGRAD ? N : M)) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int k = j0 + tj + v;
+      if (k >= K) continue;
+      if (WGRAD) {
+        dw[(size_t)i * K + k] += acc[u][v];
+      } else {
+        float val = acc[u][v];
+        if (silu_in) {
+          const float xv = x[(size_t)i * K + k];
+          const float sg = 1.f / (1.f + expf(-xv));
+          val *= sg * (1.f + xv * (1.f - sg));
+        }
+        float* pd = dx + (size_t)i * K + k;
+        *pd = accumulate ? *pd + val : val;
+      }
+    }
+    if (WGRAD && db && blockIdx.x == 0 && (threadIdx.x & 15) == 0) db[i] += accb[u];
+  }
+}
+
 // emb[m][0:half] = cos(t*f_i), emb[m][half:] = sin(t*f_i), f_i = exp(-ln(10000) * i / half)  (diffusion.py:24-28)
 // freqs are passed in (built by the host shell with the reference's own torch expression).
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
@@ -183,14 +267,25 @@ extern "C" int tsd_small_linear_bwd(void* stream, const float* dy, const float* 
                                     float* db, int M, int N, int K, int silu_in, int accumulate_dx) {
   TSD_CHECK(N <= 4096, "small_linear_bwd: N=%d too large", N);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool tiled = M >= 32;  // batch-sized M: the shared-memory tiled kernels
   if (dx) {
-    dim3 grid(ceil_div(K, 64), ceil_div(M, ROWS));
-    small_linear_dgrad_kernel<<<grid, 64, ROWS * N * sizeof(float), st>>>(dy, w, x, dx, M, N, K, silu_in, accumulate_dx);
+    if (tiled) {
+      small_linear_bwd_tiled_kernel<0><<<dim3(ceil_div(K, TJ), ceil_div(M, TI)), 256, 0, st>>>(dy, x, w, dx, nullptr, nullptr, M, N,
+                                                                                              K, silu_in, accumulate_dx);
+    } else {
+      dim3 grid(ceil_div(K, 64), ceil_div(M, ROWS));
+      small_linear_dgrad_kernel<<<grid, 64, ROWS * N * sizeof(float), st>>>(dy, w, x, dx, M, N, K, silu_in, accumulate_dx);
+    }
     TSD_LAUNCH_CHECK();
   }
   if (dw) {
-    dim3 grid(ceil_div(K, 64), ceil_div(N, NT));
-    small_linear_wgrad_kernel<<<grid, 64, 0, st>>>(dy, x, dw, db, M, N, K, silu_in);
+    if (tiled) {
+      small_linear_bwd_tiled_kernel<1><<<dim3(ceil_div(K, TJ), ceil_div(N, TI)), 256, 0, st>>>(dy, x, w, nullptr, dw, db, M, N, K,
+                                                                                              silu_in, 0);
+    } else {
+      dim3 grid(ceil_div(K, 64), ceil_div(N, NT));
+      small_linear_wgrad_kernel<<<grid, 64, 0, st>>>(dy, x, dw, db, M, N, K, silu_in);
+    }
     TSD_LAUNCH_CHECK();
   }
   return 0;
