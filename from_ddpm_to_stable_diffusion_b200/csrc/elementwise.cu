@@ -121,7 +121,7 @@ __global__ void zero_stuff2_kernel(const bf16* __restrict__ in, bf16* __restrict
 // Per-sample column sums: out[n][c] (+)= sum over the rows of sample n of x[row][c].
 // grid = (chunks, n_img); used for bias gradients (sum over n afterwards) and the time-bias gradient.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int rows_per_sample, int C, int CW,
-                                                     int rows_per_cta, float* __restrict__ out) {
+                                                     int rows_per_cta, float* __restrict__ out, float* __restrict__ total) {
   // blockIdx.z selects a chunk of CW <= 2048 channels (row pitch stays C)
   extern __shared__ float s_acc[];  // [CW]
   for (int i = threadIdx.x; i < CW; i += blockDim.x) s_acc[i] = 0.f;
@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
     for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[cv + j], acc[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < CW; i += blockDim.x) atomicAdd(&out[(size_t)n * C + cbase + i], s_acc[i]);
+  for (int i = threadIdx.x; i < CW; i += blockDim.x) {
+    atomicAdd(&out[(size_t)n * C + cbase + i], s_acc[i]);
+    if (total) atomicAdd(&total[cbase + i], s_acc[i]);  // sum over all samples as well (bias gradient): no second kernel
+  }
 }
 
 // out[c] += sum_n in[n][c]
@@ -255,7 +258,8 @@ extern "C" int tsd_zero_stuff2(void* stream, const void* in, void* out, int n_im
   TSD_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int tsd_colsum(void* stream, const void* x, int n_samples, int rows_per_sample, int C, float* out) {
+extern "C" int tsd_colsum(void* stream, const void* x, int n_samples, int rows_per_sample, int C, float* out,
+                          float* total) {
   int CW = C;
   while (CW > 2048) CW /= 2;
   TSD_CHECK(C % 8 == 0 && C % CW == 0 && 256 % (CW / 8) == 0, "colsum: unsupported C=%d", C);
@@ -264,7 +268,7 @@ extern "C" int tsd_colsum(void* stream, const void* x, int n_samples, int rows_p
   if (rpc < 16) rpc = 16;
   if (rpc > rows_per_sample) rpc = rows_per_sample;
   colsum_kernel<<<dim3(ceil_div(rows_per_sample, rpc), n_samples, C / CW), 256, CW * sizeof(float), (cudaStream_t)stream>>>(
-      (const bf16*)x, rows_per_sample, C, CW, rpc, out);
+      (const bf16*)x, rows_per_sample, C, CW, rpc, out, total);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -169,11 +169,11 @@ def zero_stuff2(x, n_img, H, W):
     return out
 
 
-def colsum(x, n_samples, rows_per_sample):
-    """[n_samples*rows_per_sample, C] bf16 -> fp32 [n_samples, C]"""
+def colsum(x, n_samples, rows_per_sample, total=None):
+    """[n_samples*rows_per_sample, C] bf16 -> fp32 [n_samples, C]; total[C] += the sum over all samples (optional)"""
     C = x.shape[1]
     out = torch.zeros(n_samples, C, device=x.device, dtype=F32)
-    call("tsd_colsum", _chk(x, BF16), n_samples, rows_per_sample, C, out)
+    call("tsd_colsum", _chk(x, BF16), n_samples, rows_per_sample, C, out, None if total is None else _chk(total, F32))
     return out
 
 
@@ -184,9 +184,7 @@ def reduce_rows_into(src, dst):
 
 def bias_grad(dy, n_samples, rows_per_sample, db):
     """db[c] += sum over all rows of dy; returns the per-sample sums."""
-    per = colsum(dy, n_samples, rows_per_sample)
-    reduce_rows_into(per, db)
-    return per
+    return colsum(dy, n_samples, rows_per_sample, total=db)
 
 
 # ------------------------------------------------------------------ conditioning (fp32, small)

@@ -124,8 +124,9 @@ int tsd_upsample2_fwd(void* stream, const void* in, void* out, int n_img, int H,
 int tsd_upsample2_bwd(void* stream, const void* dout, void* din, int n_img, int H, int W, int C);
 /* zero-stuffing [n][H][W][C] -> [n][2H][2W][C]: turns the stride-2 conv data gradient into a stride-1 one */
 int tsd_zero_stuff2(void* stream, const void* in, void* out, int n_img, int H, int W, int C);
-/* out[n][C] += column sums of sample n's rows (bias gradients, time-bias gradient); out[C] += sum_n in[n][C] */
-int tsd_colsum(void* stream, const void* x, int n_samples, int rows_per_sample, int C, float* out);
+/* out[n][C] += column sums of sample n's rows (time-bias / cross-attention gradients) and, when total != NULL,
+ * total[C] += the sums over all samples (bias gradients); tsd_reduce_rows_f32: out[C] += sum_n in[n][C] */
+int tsd_colsum(void* stream, const void* x, int n_samples, int rows_per_sample, int C, float* out, float* total);
 int tsd_reduce_rows_f32(void* stream, const float* in, int n_rows, int C, float* out);
 
 /* ------------------------------------------------------------------------------------------
