@@ -82,9 +82,11 @@ class UNetEngine:
                 out.append((f"decoders.{i}.{j}", b))
         return out
 
-    def packed(self, P):
-        """bf16 GEMM-layout copies of the weights, refreshed when any parameter changed."""
-        sig = self._signature(P)
+    def packed(self, P, save=False):
+        """bf16 GEMM-layout copies of the weights, refreshed when any parameter changed.  The C -> 8C linear of the
+        attention blocks is packed plain when the tape is saved (training: h8 is kept for the backward) and with
+        interleaved value / gate rows for the fused GEGLU epilogue otherwise -- never both."""
+        sig = (bool(save),) + self._signature(P)
         if sig == self._packed_sig:
             return self._packed
         W = {}
@@ -100,10 +102,13 @@ class UNetEngine:
                 if b[1] != b[2]:
                     W[key + ".residual_layer"] = ops.pack_linear(P[key + ".residual_layer.weight"])
             else:
-                for n in ("conv_1.1", "atten_1.1.in_proj", "atten_1.1.out_proj", "linear_1", "linear_2", "conv_output"):
+                for n in ("conv_1.1", "atten_1.1.in_proj", "atten_1.1.out_proj", "linear_2", "conv_output"):
                     W[key + "." + n] = ops.pack_linear(P[f"{key}.{n}.weight"])
-                W[key + ".linear_1.geglu"] = ops.pack_linear(P[key + ".linear_1.weight"], geglu=True)
-                W[key + ".linear_1.geglu_bias"] = ops.pack_geglu_bias(P[key + ".linear_1.bias"])
+                if save:
+                    W[key + ".linear_1"] = ops.pack_linear(P[key + ".linear_1.weight"])
+                else:
+                    W[key + ".linear_1.geglu"] = ops.pack_linear(P[key + ".linear_1.weight"], geglu=True)
+                    W[key + ".linear_1.geglu_bias"] = ops.pack_geglu_bias(P[key + ".linear_1.bias"])
         self._packed, self._packed_sig = W, sig
         return W
 
@@ -184,7 +189,7 @@ class UNetEngine:
         conv_1, LayerNorm, in_proj and the L = H*W self-attention -- is computed once on n/2 rows and duplicated."""
         m = self.model
         P = self.params()
-        W = self.packed(P)
+        W = self.packed(P, save)
         n, ci, H, Wd = x.shape
         assert ci == m.channel_img
         dev = x.device
