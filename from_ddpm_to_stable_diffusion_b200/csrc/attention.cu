@@ -1569,6 +1569,21 @@ static int attn_bwd_impl(void* stream, const void* qkv, const void* out, const v
     const char* f = getenv("TSD_ATTN_BWD_FUSED");
     if (f) bwd_fused = atoi(f);
   }
+  static int bwd_tc = -1;
+  if (bwd_tc < 0) {
+    const char* e = getenv("TSD_ATTN_BWD_TC");
+    bwd_tc = e ? atoi(e) : 0;
+  }
+  if (bwd_tc && ws != nullptr && attn_bwd_tc_supported(L, C, heads)) {
+    // one-pass backward on tcgen05: dK/dV in TMEM, dQ through the fp32 workspace [B][heads][L][16]
+    TSD_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)B * L * C, st));
+    if (launch_attn_bwd_tc(st, qkv, dout, lse2, delta, dqkv, ws, B, L, C, heads)) return 1;
+    int cg = (int)((total + 255) / 256);
+    if (cg > num_sms() * 16) cg = num_sms() * 16;
+    attn_dq_convert_kernel<<<cg, 256, 0, st>>>(ws, (bf16*)dqkv, B, L, C);
+    TSD_LAUNCH_CHECK();
+    return 0;
+  }
   if (bwd_fused && ws != nullptr && dh == 16 && L % 256 == 0) {
     // one-pass backward: dK/dV in registers, dQ through the fp32 workspace [B][heads][L][16]
     static bool cfgd = false;

@@ -1,0 +1,407 @@
+// tcgen05 / TMEM self-attention backward for head_dim 16 with L % 256 == 0: one pass, every contraction on the 5th-gen
+// tensor cores, the softmax warps do nothing but the element-wise part.
+//
+// Reference: autograd of SelfAttention.forward, diffusion.py:46-58.  Same contract as attn_bwd_fused_kernel (attention.cu):
+// qkv bf16 [B*L][3C], dout bf16 [B*L][C], lse2 / delta fp32 [B][heads][L]; dK / dV go to dqkv as bf16, dQ is reduced
+// into the fp32 workspace [B][heads][L][16] (bulk reduce-add) and converted by attn_dq_convert_kernel.
+//
+// A CTA owns 256 keys of one (sample, head) as two 128-key halves (TMEM lanes = keys) and walks over all 128-query
+// tiles; one "sub-tile" t = (query tile j, key half kh):
+//   S^T  [128 k x 64 q] = K_kh Q_g^T          UMMA 128 x 64 x 16, SS (32-byte swizzled TMA tiles), one per warpgroup g
+//   dP^T [128 k x 64 q] = V_kh dO_g^T         same
+//   softmax thread = one key row: P^T = 2^(s c - lse2[q]), dS^T = P^T (dP^T - delta[q]);
+//        P^T  -> TMEM as bf16 (A operand of dV),
+//        dS^T -> shared memory [128 k][128 q] bf16, 128-byte swizzled: read K-major for dK and MN-major for dQ,
+//                so the transposition the mma.sync kernel does with stmatrix/ldmatrix disappears
+//   dV_kh += P^T dO    8 x UMMA 128 x 16 x 16, A from TMEM, B = dO tile MN-major
+//   dK_kh += dS^T Q    8 x UMMA 128 x 16 x 16, A = dS^T tile K-major, B = Q tile MN-major
+//   dQ_j  += dS K_kh   8 x UMMA 128 x 16 x 16, A = dS^T tile MN-major, B = K tile MN-major (accumulated over both halves)
+// dK / dV stay in TMEM for the CTA's life; dQ_j is drained by a separate warpgroup (tcgen05.ld -> staging tile -> one
+// 8 KB cp.reduce.async.bulk add.f32 per query tile).
+//
+// Warps: 0-7 softmax (warpgroup g = warp / 4 owns query columns [64 g, 64 g + 64) of every tile and, in the epilogue,
+// key half g), 8-11 dQ drain, 12 issuer of S^T / dP^T (+ TMA producer, TMEM allocation), 13 / 14 / 15 issuers of the dV /
+// dK / dQ products: a single issuing thread needs ~20 instructions per tcgen05.mma and 28 of them per sub-tile made it the
+// critical path (measured: 2 100 of 3 300 clk per sub-tile), four threads do not.  One CTA per SM (all 512 TMEM columns).
+#include "attention_tc.cuh"
+#include "ptx.cuh"
+#include <cstdlib>
+
+namespace tsd {
+namespace {
+
+constexpr int DH = 16, ROWB = 32;
+constexpr int KT = 128;        // keys per half = TMEM lanes
+constexpr int KH = 2;          // key halves per CTA
+constexpr int QT = 128;        // queries per tile
+constexpr int NWG = 2;         // softmax warpgroups
+constexpr int CW = QT / NWG;   // query columns per warpgroup and tile
+constexpr int NSTQ = 4;        // Q / dO / lse / delta ring
+constexpr int BT_THREADS = NWG * 128 + 128 + 128;
+// TMEM columns (fp32 unless noted)
+constexpr int S_COL = 0;       // + g * 128: S^T [0, 64), dP^T [64, 128)
+constexpr int P_COL = 256;     // + buf * 64: P^T bf16 pairs, 128 queries
+constexpr int DV_COL = 384;    // + kh * 16
+constexpr int DK_COL = 416;    // + kh * 16
+constexpr int DQ_COL = 448;    // + (j & 1) * 16
+constexpr int TMEM_COLS = 512;
+// shared memory (offsets from a 1024-byte aligned base)
+constexpr int OFF_K = 0, OFF_V = KH * KT * ROWB;                 // 8 KB each
+constexpr int OFF_Q = 2 * KH * KT * ROWB;                        // stages: Q 4 KB, dO 4 KB, lse2 512 B, delta 512 B
+constexpr int QSTAGE = 2 * QT * ROWB + 2 * QT * 4;               // 9216
+constexpr int ST_DO = QT * ROWB, ST_LSE = 2 * QT * ROWB, ST_DELTA = 2 * QT * ROWB + QT * 4;
+constexpr int OFF_DS = OFF_Q + NSTQ * QSTAGE;                    // 53248 = 52 * 1024
+constexpr int DS_BYTES = KT * QT * 2;                            // 32 KB, two 64-query chunks of 16 KB
+constexpr int OFF_STG = OFF_DS + 2 * DS_BYTES;                   // dQ staging: 2 x [128 q][16] fp32
+constexpr int STG_BYTES = QT * DH * 4;
+constexpr int OFF_BAR = OFF_STG + 2 * STG_BYTES;
+constexpr int NBAR = 1 + 2 * NSTQ + 6 * 2;
+constexpr int BT_SMEM = 1024 + OFF_BAR + NBAR * 8 + 16;
+static_assert(OFF_DS % 1024 == 0, "dS tile must be 1024-byte aligned (128-byte swizzle atoms)");
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2_(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2_(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(BT_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
+                   float* __restrict__ ws, int L, int C, float scale, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sK = smem_base + OFF_K, sV = smem_base + OFF_V;
+  auto sQ = [&](int s) { return smem_base + OFF_Q + s * QSTAGE; };
+  auto sDS = [&](int buf) { return smem_base + OFF_DS + buf * DS_BYTES; };
+  const uint32_t bar_base = smem_base + OFF_BAR;
+  const uint32_t kv_full = bar_base;
+  auto q_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto q_empty = [&](int s) { return bar_base + 8u * (1 + NSTQ + s); };
+  auto s_full = [&](int g) { return bar_base + 8u * (1 + 2 * NSTQ + g); };
+  auto s_free = [&](int g) { return bar_base + 8u * (3 + 2 * NSTQ + g); };
+  auto pds_full = [&](int buf) { return bar_base + 8u * (5 + 2 * NSTQ + buf); };
+  auto mma_done = [&](int buf) { return bar_base + 8u * (7 + 2 * NSTQ + buf); };
+  auto dq_full = [&](int d) { return bar_base + 8u * (9 + 2 * NSTQ + d); };
+  auto dq_free = [&](int d) { return bar_base + 8u * (11 + 2 * NSTQ + d); };
+  const uint32_t tmem_slot = bar_base + 8u * NBAR;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 8 * NBAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const int kb0 = blockIdx.x * (KH * KT);
+  const int nq = L / QT;
+  const int NT = nq * KH;
+  const int row_base = b * L;
+
+  if (warp == 13 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < NSTQ; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 2);  // the dV and dK issuers read the Q / dO tiles
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(s_free(i), 128);
+      mbar_init(pds_full(i), NWG * 128);
+      mbar_init(mma_done(i), 3);  // one commit per product issuer
+      mbar_init(dq_full(i), 1);
+      mbar_init(dq_free(i), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 12) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  // descriptors: the start-address field is (addr >> 4) in the low word, so a byte offset adds (offset >> 4)
+  auto d32 = [&](uint32_t addr) { return umma_smem_desc_sw(addr, 0, 8 * ROWB, 6); };
+
+  if (warp == 12) {
+    if (lane == 0) {
+      // =========================================================== TMA producer + issuer of S^T / dP^T
+      constexpr uint32_t idescS = umma_idesc_bf16(KT, CW, 0, 0);
+      const float* lse_h = lse2 + ((size_t)b * H + h) * L;
+      const float* delta_h = delta + ((size_t)b * H + h) * L;
+      auto load_q = [&](int j) {
+        const int s = j % NSTQ;
+        mbar_wait(q_empty(s), ((j / NSTQ) & 1) ^ 1);
+        const uint32_t st = sQ(s);
+        mbar_arrive_expect_tx(q_full(s), QSTAGE);
+#pragma unroll
+        for (int i = 0; i < QT / 64; ++i) {
+          tma_load_2d(st + i * 64 * ROWB, &tmQKV, q_full(s), h * DH, row_base + j * QT + i * 64);
+          tma_load_2d(st + ST_DO + i * 64 * ROWB, &tmDO, q_full(s), h * DH, row_base + j * QT + i * 64);
+        }
+        bulk_load_1d(st + ST_LSE, lse_h + j * QT, QT * 4, q_full(s));
+        bulk_load_1d(st + ST_DELTA, delta_h + j * QT, QT * 4, q_full(s));
+      };
+      mbar_arrive_expect_tx(kv_full, 2 * KH * KT * ROWB);
+#pragma unroll
+      for (int i = 0; i < KH * KT / 64; ++i) {
+        tma_load_2d(sK + i * 64 * ROWB, &tmQKV, kv_full, C + h * DH, row_base + kb0 + i * 64);
+        tma_load_2d(sV + i * 64 * ROWB, &tmQKV, kv_full, 2 * C + h * DH, row_base + kb0 + i * 64);
+      }
+      for (int j = 0; j < NSTQ - 1 && j < nq; ++j) load_q(j);
+      const uint64_t dK0 = d32(sK), dV0 = d32(sV);
+      auto issue_S = [&](int t, int g) {
+        const int j = t >> 1, kh = t & 1;
+        const uint64_t dq = d32(sQ(j % NSTQ) + g * CW * ROWB);
+        const uint32_t tS = tmem_base + S_COL + g * 128;
+        umma_bf16(tS, dK0 + (uint64_t)(kh * (KT * ROWB / 16)), dq, idescS, 0u);
+        umma_bf16(tS + 64, dV0 + (uint64_t)(kh * (KT * ROWB / 16)), dq + (uint64_t)(ST_DO / 16), idescS, 0u);
+        umma_commit(s_full(g));
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(q_full(0), 0);
+      tc_fence_after();
+      issue_S(0, 0);
+      issue_S(0, 1);
+      for (int t = 0; t + 1 < NT; ++t) {
+        const int j = t >> 1, kh = t & 1;
+        if (kh == 1) {
+          const int jn = j + 1;
+          mbar_wait(q_full(jn % NSTQ), (jn / NSTQ) & 1);
+        }
+#pragma unroll
+        for (int g = 0; g < NWG; ++g) {
+          mbar_wait(s_free(g), t & 1);  // S^T / dP^T of sub-tile t sit in the softmax warps' registers
+          tc_fence_after();
+          issue_S(t + 1, g);
+        }
+        // refill the ring: tile j + NSTQ - 1 goes where tile j - 1 was (released by its key half 1 products)
+        if (kh == 0 && j + NSTQ - 1 < nq) load_q(j + NSTQ - 1);
+      }
+    }
+  } else if (warp >= 13) {
+    if (lane == 0) {
+      // =========================================================== issuers of dV (13), dK (14), dQ (15)
+      constexpr uint32_t idescKN = umma_idesc_bf16(KT, DH, 0, 1);   // A K-major (or TMEM), B MN-major
+      constexpr uint32_t idescDQ = umma_idesc_bf16(QT, DH, 1, 1);   // A MN-major, B MN-major
+      const int which = warp - 13;
+      mbar_wait(kv_full, 0);
+      const uint64_t dKt = d32(sK);
+      for (int t = 0; t < NT; ++t) {
+        const int j = t >> 1, kh = t & 1, buf = t & 1;
+        const uint32_t st = sQ(j % NSTQ);
+        const uint32_t accKV = j > 0 ? 1u : 0u;
+        mbar_wait(pds_full(buf), (t >> 1) & 1);
+        if (which == 0) {
+          tc_fence_after();
+          const uint32_t tP = tmem_base + P_COL + buf * 64;
+          const uint64_t db = d32(st + ST_DO);
+#pragma unroll
+          for (int k = 0; k < QT / 16; ++k)
+            umma_bf16_ts(tmem_base + DV_COL + kh * 16, tP + k * 8, db + (uint64_t)(k * (16 * ROWB / 16)), idescKN,
+                         k > 0 ? 1u : accKV);
+        } else if (which == 1) {
+          tc_fence_after();
+          const uint64_t da = umma_smem_desc(sDS(buf), 0, 1024);
+          const uint64_t db = d32(st);
+#pragma unroll
+          for (int k = 0; k < QT / 16; ++k)
+            umma_bf16(tmem_base + DK_COL + kh * 16, da + (uint64_t)(((k >> 2) * (DS_BYTES / 2) + (k & 3) * 32) / 16),
+                      db + (uint64_t)(k * (16 * ROWB / 16)), idescKN, k > 0 ? 1u : accKV);
+        } else {
+          if (kh == 0) mbar_wait(dq_free(j & 1), ((j >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint64_t da = umma_smem_desc(sDS(buf), DS_BYTES / 2, 1024);
+          const uint64_t db = dKt + (uint64_t)(kh * (KT * ROWB / 16));
+#pragma unroll
+          for (int k = 0; k < KT / 16; ++k)
+            umma_bf16(tmem_base + DQ_COL + (j & 1) * 16, da + (uint64_t)(k * (2048 / 16)),
+                      db + (uint64_t)(k * (16 * ROWB / 16)), idescDQ, (k > 0 || kh > 0) ? 1u : 0u);
+        }
+        umma_commit(mma_done(buf));
+        if (kh == 1) {
+          if (which == 2) umma_commit(dq_full(j & 1));
+          else umma_commit(q_empty(j % NSTQ));
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // =========================================================== softmax: one key row per thread
+    const int g = warp >> 2, sub = warp & 3;
+    const int r = sub * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
+    const uint32_t tS = lane_base + S_COL + g * 128, tDP = tS + 64;
+    const uint64_t nc2 = pk2(-scale_log2, -scale_log2);
+    const uint64_t m1 = pk2(-1.f, -1.f);
+    const uint32_t ds_row = g * (DS_BYTES / 2) + r * 128;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    for (int t = 0; t < NT; ++t) {
+      const int j = t >> 1, kh = t & 1, buf = t & 1;
+      const int s = j % NSTQ;
+      if (kh == 0) mbar_wait(q_full(s), (j / NSTQ) & 1);
+      mbar_wait(s_full(g), t & 1);
+      tc_fence_after();
+      const float4* sl = reinterpret_cast<const float4*>(smem_gen + OFF_Q + s * QSTAGE + ST_LSE) + g * (CW / 4);
+      const float4* sd = reinterpret_cast<const float4*>(smem_gen + OFF_Q + s * QSTAGE + ST_DELTA) + g * (CW / 4);
+#pragma unroll
+      for (int cc = 0; cc < CW / 32; ++cc) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tS + cc * 32, sv);
+        tmem_ld32(tDP + cc * 32, dv);
+        tmem_ld_wait();
+        if (cc == CW / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(s_free(g));
+        }
+        uint32_t pP[16], pD[16];
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 l4 = sl[cc * 8 + i4];
+          const float4 d4 = sd[cc * 8 + i4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = 2 * i4 + u;
+            const uint64_t lse_p = u == 0 ? pk2(l4.x, l4.y) : pk2(l4.z, l4.w);
+            const uint64_t del_p = u == 0 ? pk2(d4.x, d4.y) : pk2(d4.z, d4.w);
+            // -x = lse2 - s c  (x <= 0 up to rounding: P <= 1)
+            const uint64_t nx = ffma2_(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), nc2, lse_p);
+            float a0, a1;
+            upk2(nx, a0, a1);
+            const float p0 = ex2f(-a0), p1 = ex2f(-a1);
+            const uint64_t tt = ffma2_(del_p, m1, pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])));
+            float e0, e1;
+            upk2(fmul2_(pk2(p0, p1), tt), e0, e1);
+            pP[i] = pack_bf16(p0, p1);
+            pD[i] = pack_bf16(e0, e1);
+          }
+        }
+        if (cc == 0 && t >= 2) {  // P^T / dS^T buffers of sub-tile t - 2 have been consumed
+          mbar_wait(mma_done(buf), ((t >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        tmem_st16(lane_base + P_COL + buf * 64 + (g * CW + cc * 32) / 2, pP);
+        const uint32_t drow = sDS(buf) + ds_row;
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+          sts128(drow + (((cc * 4 + i4) ^ sw) << 4), pD[4 * i4], pD[4 * i4 + 1], pD[4 * i4 + 2], pD[4 * i4 + 3]);
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full(buf));
+    }
+    // ---- epilogue: warpgroup g writes dK / dV of key half g
+    mbar_wait(mma_done(1), ((NT - 1) >> 1) & 1);
+    tc_fence_after();
+    uint32_t a[16], c[16];
+    tmem_ld16(lane_base + DV_COL + g * 16, a);
+    tmem_ld16(lane_base + DK_COL + g * 16, c);
+    tmem_ld_wait();
+    const size_t grow = (size_t)row_base + kb0 + g * KT + r;
+    uint4* dk = reinterpret_cast<uint4*>(dqkv + grow * 3 * C + C + h * DH);
+    uint4* dvp = reinterpret_cast<uint4*>(dqkv + grow * 3 * C + 2 * C + h * DH);
+    uint32_t wk[8], wv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      wk[i] = pack_bf16(__uint_as_float(c[2 * i]) * scale, __uint_as_float(c[2 * i + 1]) * scale);
+      wv[i] = pack_bf16(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1]));
+    }
+    dk[0] = make_uint4(wk[0], wk[1], wk[2], wk[3]);
+    dk[1] = make_uint4(wk[4], wk[5], wk[6], wk[7]);
+    dvp[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    dvp[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+  } else {
+    // =========================================================== dQ drain (warps 8-11): one query row per thread
+    const int sub = warp & 3;
+    const int r = sub * 32 + lane;
+    const int dtid = threadIdx.x - NWG * 128;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
+    float* dq_head = ws + (((size_t)b * H + h) * L) * DH;
+    for (int j = 0; j < nq; ++j) {
+      const int db = j & 1;
+      mbar_wait(dq_full(db), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t o[16];
+      tmem_ld16(lane_base + DQ_COL + db * 16, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_free(db));
+      if (dtid == 0) tma_store_wait_read<1>();  // the reduce issued two tiles ago has read this staging tile
+      named_bar_sync(1, 128);
+      float4* dst = reinterpret_cast<float4*>(smem_gen + OFF_STG + db * STG_BYTES + r * (DH * 4));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dst[i] = make_float4(__uint_as_float(o[4 * i]) * scale, __uint_as_float(o[4 * i + 1]) * scale,
+                             __uint_as_float(o[4 * i + 2]) * scale, __uint_as_float(o[4 * i + 3]) * scale);
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (dtid == 0) {
+        bulk_reduce_add_f32(dq_head + (size_t)j * QT * DH, smem_base + OFF_STG + db * STG_BYTES, STG_BYTES);
+        tma_store_commit();
+      }
+    }
+    if (dtid == 0) tma_store_wait_all<0>();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace
+
+bool attn_bwd_tc_supported(int L, int C, int heads) {
+  return C % heads == 0 && C / heads == DH && L % (KH * KT) == 0 && L >= KH * KT;
+}
+
+int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const float* lse2, const float* delta,
+                       void* dqkv, float* ws, int B, int L, int C, int heads) {
+  TSD_CHECK(attn_bwd_tc_supported(L, C, heads), "attn_bwd_tc: unsupported shape L=%d C=%d heads=%d", L, C, heads);
+  CUtensorMap tmQKV, tmDO;
+  if (make_tmap_2d_sw(&tmQKV, qkv, 2, (uint64_t)B * L, 3 * (uint64_t)C, 3 * (uint64_t)C, DH, 64, ROWB)) return 1;
+  if (make_tmap_2d_sw(&tmDO, dout, 2, (uint64_t)B * L, (uint64_t)C, (uint64_t)C, DH, 64, ROWB)) return 1;
+  static bool configured = false;
+  if (!configured) {
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    configured = true;
+  }
+  const float scale = 1.f / sqrtf((float)DH);
+  attn_bwd_tc_kernel<<<dim3(L / (KH * KT), heads, B), BT_THREADS, BT_SMEM, st>>>(
+      tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, 1.4426950408889634f * scale);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tsd

@@ -11,4 +11,9 @@ bool attn_tc_supported(int L, int C, int heads);
 int launch_attn_fwd_tc(cudaStream_t st, const void* qkv, void* out, float* lse2, float* ws, int B, int L, int C,
                        int heads, int poly);
 
+// one-pass backward, head_dim 16 and L a multiple of 256 (attention_bwd_tc.cu); ws = zeroed fp32 [B][heads][L][16] for dQ
+bool attn_bwd_tc_supported(int L, int C, int heads);
+int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const float* lse2, const float* delta,
+                       void* dqkv, float* ws, int B, int L, int C, int heads);
+
 }  // namespace tsd
