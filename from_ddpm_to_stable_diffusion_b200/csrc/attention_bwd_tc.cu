@@ -6,10 +6,12 @@
 // into the fp32 workspace [B][heads][L][16] (bulk reduce-add) and converted by attn_dq_convert_kernel.
 //
 // A CTA owns 256 keys of one (sample, head) as two 128-key halves (TMEM lanes = keys) and walks over all 128-query
-// tiles; one "sub-tile" t = (query tile j, key half kh):
-//   S^T  [128 k x 64 q] = K_kh Q_g^T          UMMA 128 x 64 x 16, SS (32-byte swizzled TMA tiles), one per warpgroup g
-//   dP^T [128 k x 64 q] = V_kh dO_g^T         same
-//   softmax thread = one key row: P^T = 2^(s c - lse2[q]), dS^T = P^T (dP^T - delta[q]);
+// tiles; one "sub-tile" t = (query tile j, key half kh).  Per sub-tile and softmax warpgroup g (CW query columns):
+//   S'^T  [128 k x CW q] = K_kh Q_g^T - lse2[q] / c      two UMMAs 128 x CW x 16 with A from TMEM: K_kh (copied there
+//   dP'^T [128 k x CW q] = V_kh dO_g^T - delta[q]         once), then a constant tile of ones against a [q][16] tile that
+//        holds -lse2/c (resp. -delta) split into three bf16 pieces: the per-column terms come out of the tensor core
+//        instead of 2 x 128 broadcast shared-memory loads per thread, which saturated the shared-memory pipe;
+//   softmax thread = one key row: P^T = 2^(c S'^T), dS^T = P^T dP'^T;
 //        P^T  -> TMEM as bf16 (A operand of dV),
 //        dS^T -> shared memory [128 k][128 q] bf16, 128-byte swizzled: read K-major for dK and MN-major for dQ,
 //                so the transposition the mma.sync kernel does with stmatrix/ldmatrix disappears
@@ -17,12 +19,11 @@
 //   dK_kh += dS^T Q    8 x UMMA 128 x 16 x 16, A = dS^T tile K-major, B = Q tile MN-major
 //   dQ_j  += dS K_kh   8 x UMMA 128 x 16 x 16, A = dS^T tile MN-major, B = K tile MN-major (accumulated over both halves)
 // dK / dV stay in TMEM for the CTA's life; dQ_j is drained by a separate warpgroup (tcgen05.ld -> staging tile -> one
-// 8 KB cp.reduce.async.bulk add.f32 per query tile).
+// 8 KB cp.reduce.async.bulk add.f32 per query tile), which also builds the split lse2 / delta tiles of the coming tiles.
 //
-// Warps: 0-7 softmax (warpgroup g = warp / 4 owns query columns [64 g, 64 g + 64) of every tile and, in the epilogue,
-// key half g), 8-11 dQ drain, 12 issuer of S^T / dP^T (+ TMA producer, TMEM allocation), 13 / 14 / 15 issuers of the dV /
-// dK / dQ products: a single issuing thread needs ~20 instructions per tcgen05.mma and 28 of them per sub-tile made it the
-// critical path (measured: 2 100 of 3 300 clk per sub-tile), four threads do not.  One CTA per SM (all 512 TMEM columns).
+// Warps: NWG softmax warpgroups (g owns query columns [CW g, CW g + CW) of every tile), one drain warpgroup, NSI issuers of
+// S'^T / dP'^T (the first one is also the TMA producer and allocates TMEM), three issuers for dV / dK / dQ: a single
+// issuing thread needs ~75 clk per tcgen05.mma and was the critical path.  One CTA per SM (all 512 TMEM columns).
 #include "attention_tc.cuh"
 #include "ptx.cuh"
 #include <cstdlib>
@@ -34,30 +35,38 @@ constexpr int DH = 16, ROWB = 32;
 constexpr int KT = 128;        // keys per half = TMEM lanes
 constexpr int KH = 2;          // key halves per CTA
 constexpr int QT = 128;        // queries per tile
-constexpr int NWG = 2;         // softmax warpgroups
+constexpr int NWG = 4;         // softmax warpgroups
 constexpr int CW = QT / NWG;   // query columns per warpgroup and tile
+constexpr int NSI = 2;         // issuers of S'^T / dP'^T, NWG / NSI warpgroups each
 constexpr int NSTQ = 4;        // Q / dO / lse / delta ring
-constexpr int BT_THREADS = NWG * 128 + 128 + 128;
+constexpr int W_DRAIN = NWG * 4, W_S = W_DRAIN + 4, W_P = W_S + NSI;  // first drain warp, S issuer, product issuer
+constexpr int BT_THREADS = (W_P + 3) * 32;
 // TMEM columns (fp32 unless noted)
-constexpr int S_COL = 0;       // + g * 128: S^T [0, 64), dP^T [64, 128)
+constexpr int S_COL = 0;       // + g * 2 CW: S'^T [0, CW), dP'^T [CW, 2 CW)
 constexpr int P_COL = 256;     // + buf * 64: P^T bf16 pairs, 128 queries
 constexpr int DV_COL = 384;    // + kh * 16
 constexpr int DK_COL = 416;    // + kh * 16
-constexpr int DQ_COL = 448;    // + (j & 1) * 16
+constexpr int DQ_COL = 448;
+constexpr int KA_COL = 464;    // bf16 A operands: K_kh at + kh * 8, V_kh at + 16 + kh * 8
+constexpr int ONES_COL = 496;  // bf16 A operand: 1 in K slots 0-2, 0 elsewhere
 constexpr int TMEM_COLS = 512;
 // shared memory (offsets from a 1024-byte aligned base)
 constexpr int OFF_K = 0, OFF_V = KH * KT * ROWB;                 // 8 KB each
-constexpr int OFF_Q = 2 * KH * KT * ROWB;                        // stages: Q 4 KB, dO 4 KB, lse2 512 B, delta 512 B
-constexpr int QSTAGE = 2 * QT * ROWB + 2 * QT * 4;               // 9216
-constexpr int ST_DO = QT * ROWB, ST_LSE = 2 * QT * ROWB, ST_DELTA = 2 * QT * ROWB + QT * 4;
-constexpr int OFF_DS = OFF_Q + NSTQ * QSTAGE;                    // 53248 = 52 * 1024
+constexpr int OFF_Q = 2 * KH * KT * ROWB;                        // ring of stages:
+constexpr int ST_DO = QT * ROWB;                                 //   Q 4 KB, dO 4 KB,
+constexpr int ST_LSE = 2 * QT * ROWB, ST_DELTA = ST_LSE + QT * 4;  // lse2, delta fp32 (512 B each),
+constexpr int ST_LSET = ST_DELTA + QT * 4, ST_DELT = ST_LSET + QT * ROWB;  // their split bf16 tiles [q][16] (4 KB each)
+constexpr int QSTAGE = ST_DELT + QT * ROWB;                      // 17408
+constexpr int Q_TX = ST_LSET;                                    // bytes written by TMA per stage
+constexpr int OFF_DS = OFF_Q + NSTQ * QSTAGE;
 constexpr int DS_BYTES = KT * QT * 2;                            // 32 KB, two 64-query chunks of 16 KB
 constexpr int OFF_STG = OFF_DS + 2 * DS_BYTES;                   // dQ staging: 2 x [128 q][16] fp32
 constexpr int STG_BYTES = QT * DH * 4;
 constexpr int OFF_BAR = OFF_STG + 2 * STG_BYTES;
-constexpr int NBAR = 1 + 2 * NSTQ + 6 * 2;
+constexpr int NBAR = 2 + 3 * NSTQ + 2 * NWG + 2 * 2 + 2;
 constexpr int BT_SMEM = 1024 + OFF_BAR + NBAR * 8 + 16;
-static_assert(OFF_DS % 1024 == 0, "dS tile must be 1024-byte aligned (128-byte swizzle atoms)");
+static_assert(OFF_DS % 1024 == 0 && QSTAGE % 1024 == 0, "swizzled tiles must keep their alignment");
+static_assert(NWG % NSI == 0 && (NWG == 2 || NWG == 4), "warpgroup split");
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -105,15 +114,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   auto sQ = [&](int s) { return smem_base + OFF_Q + s * QSTAGE; };
   auto sDS = [&](int buf) { return smem_base + OFF_DS + buf * DS_BYTES; };
   const uint32_t bar_base = smem_base + OFF_BAR;
-  const uint32_t kv_full = bar_base;
-  auto q_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto q_empty = [&](int s) { return bar_base + 8u * (1 + NSTQ + s); };
-  auto s_full = [&](int g) { return bar_base + 8u * (1 + 2 * NSTQ + g); };
-  auto s_free = [&](int g) { return bar_base + 8u * (3 + 2 * NSTQ + g); };
-  auto pds_full = [&](int buf) { return bar_base + 8u * (5 + 2 * NSTQ + buf); };
-  auto mma_done = [&](int buf) { return bar_base + 8u * (7 + 2 * NSTQ + buf); };
-  auto dq_full = [&](int d) { return bar_base + 8u * (9 + 2 * NSTQ + d); };
-  auto dq_free = [&](int d) { return bar_base + 8u * (11 + 2 * NSTQ + d); };
+  const uint32_t kv_full = bar_base;                 // K / V tiles landed (TMA)
+  const uint32_t ka_full = bar_base + 8u;            // K / V / ones copied to TMEM
+  auto q_full = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto q_empty = [&](int s) { return bar_base + 8u * (2 + NSTQ + s); };
+  auto ld_full = [&](int s) { return bar_base + 8u * (2 + 2 * NSTQ + s); };  // split lse2 / delta tiles built
+  constexpr int B0 = 2 + 3 * NSTQ;
+  auto s_full = [&](int g) { return bar_base + 8u * (B0 + g); };
+  auto s_free = [&](int g) { return bar_base + 8u * (B0 + NWG + g); };
+  auto pds_full = [&](int buf) { return bar_base + 8u * (B0 + 2 * NWG + buf); };
+  auto mma_done = [&](int buf) { return bar_base + 8u * (B0 + 2 * NWG + 2 + buf); };
+  const uint32_t dq_full = bar_base + 8u * (B0 + 2 * NWG + 4);
+  const uint32_t dq_free = bar_base + 8u * (B0 + 2 * NWG + 5);
   const uint32_t tmem_slot = bar_base + 8u * NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 8 * NBAR);
 
@@ -124,25 +136,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const int NT = nq * KH;
   const int row_base = b * L;
 
-  if (warp == 13 && lane == 0) {
+  if (warp == W_P && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     mbar_init(kv_full, 1);
+    mbar_init(ka_full, NWG * 128);
     for (int s = 0; s < NSTQ; ++s) {
       mbar_init(q_full(s), 1);
       mbar_init(q_empty(s), 2);  // the dV and dK issuers read the Q / dO tiles
+      mbar_init(ld_full(s), 128);
+    }
+    for (int g = 0; g < NWG; ++g) {
+      mbar_init(s_full(g), 1);
+      mbar_init(s_free(g), 128);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(s_full(i), 1);
-      mbar_init(s_free(i), 128);
       mbar_init(pds_full(i), NWG * 128);
       mbar_init(mma_done(i), 3);  // one commit per product issuer
-      mbar_init(dq_full(i), 1);
-      mbar_init(dq_free(i), 128);
     }
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 128);
     fence_mbar_init();
   }
-  if (warp == 12) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == W_S) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -150,17 +166,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   // descriptors: the start-address field is (addr >> 4) in the low word, so a byte offset adds (offset >> 4)
   auto d32 = [&](uint32_t addr) { return umma_smem_desc_sw(addr, 0, 8 * ROWB, 6); };
 
-  if (warp == 12) {
+  if (warp >= W_S && warp < W_P) {
     if (lane == 0) {
-      // =========================================================== TMA producer + issuer of S^T / dP^T
+      // =========================================================== issuers of S'^T / dP'^T (the first one also feeds TMA)
       constexpr uint32_t idescS = umma_idesc_bf16(KT, CW, 0, 0);
+      const int si = warp - W_S;
+      const int g_lo = si * (NWG / NSI);
       const float* lse_h = lse2 + ((size_t)b * H + h) * L;
       const float* delta_h = delta + ((size_t)b * H + h) * L;
       auto load_q = [&](int j) {
         const int s = j % NSTQ;
         mbar_wait(q_empty(s), ((j / NSTQ) & 1) ^ 1);
         const uint32_t st = sQ(s);
-        mbar_arrive_expect_tx(q_full(s), QSTAGE);
+        mbar_arrive_expect_tx(q_full(s), Q_TX);
 #pragma unroll
         for (int i = 0; i < QT / 64; ++i) {
           tma_load_2d(st + i * 64 * ROWB, &tmQKV, q_full(s), h * DH, row_base + j * QT + i * 64);
@@ -169,49 +187,55 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         bulk_load_1d(st + ST_LSE, lse_h + j * QT, QT * 4, q_full(s));
         bulk_load_1d(st + ST_DELTA, delta_h + j * QT, QT * 4, q_full(s));
       };
-      mbar_arrive_expect_tx(kv_full, 2 * KH * KT * ROWB);
+      if (si == 0) {
+        mbar_arrive_expect_tx(kv_full, 2 * KH * KT * ROWB);
 #pragma unroll
-      for (int i = 0; i < KH * KT / 64; ++i) {
-        tma_load_2d(sK + i * 64 * ROWB, &tmQKV, kv_full, C + h * DH, row_base + kb0 + i * 64);
-        tma_load_2d(sV + i * 64 * ROWB, &tmQKV, kv_full, 2 * C + h * DH, row_base + kb0 + i * 64);
+        for (int i = 0; i < KH * KT / 64; ++i) {
+          tma_load_2d(sK + i * 64 * ROWB, &tmQKV, kv_full, C + h * DH, row_base + kb0 + i * 64);
+          tma_load_2d(sV + i * 64 * ROWB, &tmQKV, kv_full, 2 * C + h * DH, row_base + kb0 + i * 64);
+        }
+        for (int j = 0; j < NSTQ - 1 && j < nq; ++j) load_q(j);
       }
-      for (int j = 0; j < NSTQ - 1 && j < nq; ++j) load_q(j);
-      const uint64_t dK0 = d32(sK), dV0 = d32(sV);
+      const uint32_t tOnes = tmem_base + ONES_COL;
       auto issue_S = [&](int t, int g) {
         const int j = t >> 1, kh = t & 1;
         const uint64_t dq = d32(sQ(j % NSTQ) + g * CW * ROWB);
-        const uint32_t tS = tmem_base + S_COL + g * 128;
-        umma_bf16(tS, dK0 + (uint64_t)(kh * (KT * ROWB / 16)), dq, idescS, 0u);
-        umma_bf16(tS + 64, dV0 + (uint64_t)(kh * (KT * ROWB / 16)), dq + (uint64_t)(ST_DO / 16), idescS, 0u);
+        const uint32_t tS = tmem_base + S_COL + g * 2 * CW;
+        umma_bf16_ts(tS, tmem_base + KA_COL + kh * 8, dq, idescS, 0u);
+        umma_bf16_ts(tS, tOnes, dq + (uint64_t)(ST_LSET / 16), idescS, 1u);
+        umma_bf16_ts(tS + CW, tmem_base + KA_COL + 16 + kh * 8, dq + (uint64_t)(ST_DO / 16), idescS, 0u);
+        umma_bf16_ts(tS + CW, tOnes, dq + (uint64_t)(ST_DELT / 16), idescS, 1u);
         umma_commit(s_full(g));
       };
-      mbar_wait(kv_full, 0);
+      mbar_wait(ka_full, 0);
       mbar_wait(q_full(0), 0);
+      mbar_wait(ld_full(0), 0);
       tc_fence_after();
-      issue_S(0, 0);
-      issue_S(0, 1);
+#pragma unroll
+      for (int gi = 0; gi < NWG / NSI; ++gi) issue_S(0, g_lo + gi);
       for (int t = 0; t + 1 < NT; ++t) {
         const int j = t >> 1, kh = t & 1;
         if (kh == 1) {
           const int jn = j + 1;
           mbar_wait(q_full(jn % NSTQ), (jn / NSTQ) & 1);
+          mbar_wait(ld_full(jn % NSTQ), (jn / NSTQ) & 1);
         }
 #pragma unroll
-        for (int g = 0; g < NWG; ++g) {
-          mbar_wait(s_free(g), t & 1);  // S^T / dP^T of sub-tile t sit in the softmax warps' registers
+        for (int gi = 0; gi < NWG / NSI; ++gi) {
+          mbar_wait(s_free(g_lo + gi), t & 1);  // sub-tile t of this warpgroup sits in its registers
           tc_fence_after();
-          issue_S(t + 1, g);
+          issue_S(t + 1, g_lo + gi);
         }
         // refill the ring: tile j + NSTQ - 1 goes where tile j - 1 was (released by its key half 1 products)
-        if (kh == 0 && j + NSTQ - 1 < nq) load_q(j + NSTQ - 1);
+        if (si == 0 && kh == 0 && j + NSTQ - 1 < nq) load_q(j + NSTQ - 1);
       }
     }
-  } else if (warp >= 13) {
+  } else if (warp >= W_P) {
     if (lane == 0) {
-      // =========================================================== issuers of dV (13), dK (14), dQ (15)
+      // =========================================================== issuers of dV, dK, dQ
       constexpr uint32_t idescKN = umma_idesc_bf16(KT, DH, 0, 1);   // A K-major (or TMEM), B MN-major
       constexpr uint32_t idescDQ = umma_idesc_bf16(QT, DH, 1, 1);   // A MN-major, B MN-major
-      const int which = warp - 13;
+      const int which = warp - W_P;
       mbar_wait(kv_full, 0);
       const uint64_t dKt = d32(sK);
       for (int t = 0; t < NT; ++t) {
@@ -236,123 +260,159 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             umma_bf16(tmem_base + DK_COL + kh * 16, da + (uint64_t)(((k >> 2) * (DS_BYTES / 2) + (k & 3) * 32) / 16),
                       db + (uint64_t)(k * (16 * ROWB / 16)), idescKN, k > 0 ? 1u : accKV);
         } else {
-          if (kh == 0) mbar_wait(dq_free(j & 1), ((j >> 1) & 1) ^ 1);
+          if (kh == 0 && j > 0) mbar_wait(dq_free, (j - 1) & 1);  // dQ of tile j - 1 has left TMEM
           tc_fence_after();
           const uint64_t da = umma_smem_desc(sDS(buf), DS_BYTES / 2, 1024);
           const uint64_t db = dKt + (uint64_t)(kh * (KT * ROWB / 16));
 #pragma unroll
           for (int k = 0; k < KT / 16; ++k)
-            umma_bf16(tmem_base + DQ_COL + (j & 1) * 16, da + (uint64_t)(k * (2048 / 16)),
-                      db + (uint64_t)(k * (16 * ROWB / 16)), idescDQ, (k > 0 || kh > 0) ? 1u : 0u);
+            umma_bf16(tmem_base + DQ_COL, da + (uint64_t)(k * (2048 / 16)), db + (uint64_t)(k * (16 * ROWB / 16)),
+                      idescDQ, (k > 0 || kh > 0) ? 1u : 0u);
         }
         umma_commit(mma_done(buf));
         if (kh == 1) {
-          if (which == 2) umma_commit(dq_full(j & 1));
+          if (which == 2) umma_commit(dq_full);
           else umma_commit(q_empty(j % NSTQ));
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < W_DRAIN) {
     // =========================================================== softmax: one key row per thread
     const int g = warp >> 2, sub = warp & 3;
     const int r = sub * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
-    const uint32_t tS = lane_base + S_COL + g * 128, tDP = tS + 64;
-    const uint64_t nc2 = pk2(-scale_log2, -scale_log2);
-    const uint64_t m1 = pk2(-1.f, -1.f);
-    const uint32_t ds_row = g * (DS_BYTES / 2) + r * 128;
+    // ---- once: K / V rows of both halves (and the ones tile) become TMEM A operands
+    mbar_wait(kv_full, 0);
+    for (int it = g; it < 4; it += NWG) {
+      const int kh = it & 1;
+      const uint32_t src = ((it >> 1) ? OFF_V : OFF_K) + (kh * KT + r) * ROWB;
+      const uint32_t x = static_cast<uint32_t>((r >> 2) & 1) << 4;  // 32-byte swizzle: 16-byte halves swap every 4 rows
+      const uint4 lo = *reinterpret_cast<const uint4*>(smem_gen + src + x);
+      const uint4 hi = *reinterpret_cast<const uint4*>(smem_gen + src + (x ^ 16u));
+      const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      tmem_st8(lane_base + KA_COL + (it >> 1) * 16 + kh * 8, w);
+    }
+    if (g == 0) {
+      const uint32_t w[8] = {0x3f803f80u, 0x00003f80u, 0u, 0u, 0u, 0u, 0u, 0u};
+      tmem_st8(lane_base + ONES_COL, w);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(ka_full);
+
+    const uint32_t tS = lane_base + S_COL + g * 2 * CW, tDP = tS + CW;
+    const uint64_t c2 = pk2(scale_log2, scale_log2);
+    // dS^T tile: 64-query chunk (g * CW) / 64, 16-byte unit ((g * CW) % 64) / 8 + ..., XOR-swizzled with the row
+    const uint32_t ds_row = ((g * CW) >> 6) * (DS_BYTES / 2) + r * 128;
+    const uint32_t u0 = ((g * CW) & 63) >> 3;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     for (int t = 0; t < NT; ++t) {
-      const int j = t >> 1, kh = t & 1, buf = t & 1;
-      const int s = j % NSTQ;
-      if (kh == 0) mbar_wait(q_full(s), (j / NSTQ) & 1);
+      const int buf = t & 1;
       mbar_wait(s_full(g), t & 1);
       tc_fence_after();
-      const float4* sl = reinterpret_cast<const float4*>(smem_gen + OFF_Q + s * QSTAGE + ST_LSE) + g * (CW / 4);
-      const float4* sd = reinterpret_cast<const float4*>(smem_gen + OFF_Q + s * QSTAGE + ST_DELTA) + g * (CW / 4);
 #pragma unroll
-      for (int cc = 0; cc < CW / 32; ++cc) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tS + cc * 32, sv);
-        tmem_ld32(tDP + cc * 32, dv);
+      for (int cc = 0; cc < CW / 16; ++cc) {
+        uint32_t sv[16], dv[16];
+        tmem_ld16(tS + cc * 16, sv);
+        tmem_ld16(tDP + cc * 16, dv);
         tmem_ld_wait();
-        if (cc == CW / 32 - 1) {
+        if (cc == CW / 16 - 1) {
           tc_fence_before();
           mbar_arrive(s_free(g));
         }
-        uint32_t pP[16], pD[16];
+        uint32_t pP[8], pD[8];
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 l4 = sl[cc * 8 + i4];
-          const float4 d4 = sd[cc * 8 + i4];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = 2 * i4 + u;
-            const uint64_t lse_p = u == 0 ? pk2(l4.x, l4.y) : pk2(l4.z, l4.w);
-            const uint64_t del_p = u == 0 ? pk2(d4.x, d4.y) : pk2(d4.z, d4.w);
-            // -x = lse2 - s c  (x <= 0 up to rounding: P <= 1)
-            const uint64_t nx = ffma2_(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), nc2, lse_p);
-            float a0, a1;
-            upk2(nx, a0, a1);
-            const float p0 = ex2f(-a0), p1 = ex2f(-a1);
-            const uint64_t tt = ffma2_(del_p, m1, pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1])));
-            float e0, e1;
-            upk2(fmul2_(pk2(p0, p1), tt), e0, e1);
-            pP[i] = pack_bf16(p0, p1);
-            pD[i] = pack_bf16(e0, e1);
-          }
+        for (int i = 0; i < 8; ++i) {
+          // x = c (s - lse2 / c) <= 0 up to rounding: P <= 1
+          float a0, a1;
+          upk2(fmul2_(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2), a0, a1);
+          const float p0 = ex2f(a0), p1 = ex2f(a1);
+          float e0, e1;
+          upk2(fmul2_(pk2(p0, p1), pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1]))), e0, e1);
+          pP[i] = pack_bf16(p0, p1);
+          pD[i] = pack_bf16(e0, e1);
         }
         if (cc == 0 && t >= 2) {  // P^T / dS^T buffers of sub-tile t - 2 have been consumed
           mbar_wait(mma_done(buf), ((t >> 1) & 1) ^ 1);
           tc_fence_after();
         }
-        tmem_st16(lane_base + P_COL + buf * 64 + (g * CW + cc * 32) / 2, pP);
+        tmem_st8(lane_base + P_COL + buf * 64 + (g * CW + cc * 16) / 2, pP);
         const uint32_t drow = sDS(buf) + ds_row;
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4)
-          sts128(drow + (((cc * 4 + i4) ^ sw) << 4), pD[4 * i4], pD[4 * i4 + 1], pD[4 * i4 + 2], pD[4 * i4 + 3]);
+        for (int i4 = 0; i4 < 2; ++i4)
+          sts128(drow + (((u0 + cc * 2 + i4) ^ sw) << 4), pD[4 * i4], pD[4 * i4 + 1], pD[4 * i4 + 2], pD[4 * i4 + 3]);
       }
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full(buf));
     }
-    // ---- epilogue: warpgroup g writes dK / dV of key half g
+    // ---- epilogue: dV / dK of both key halves, one (matrix, half) per warpgroup round
     mbar_wait(mma_done(1), ((NT - 1) >> 1) & 1);
     tc_fence_after();
-    uint32_t a[16], c[16];
-    tmem_ld16(lane_base + DV_COL + g * 16, a);
-    tmem_ld16(lane_base + DK_COL + g * 16, c);
-    tmem_ld_wait();
-    const size_t grow = (size_t)row_base + kb0 + g * KT + r;
-    uint4* dk = reinterpret_cast<uint4*>(dqkv + grow * 3 * C + C + h * DH);
-    uint4* dvp = reinterpret_cast<uint4*>(dqkv + grow * 3 * C + 2 * C + h * DH);
-    uint32_t wk[8], wv[8];
+    for (int it = g; it < 4; it += NWG) {
+      const int kh_e = it & 1;
+      const bool is_dk = it >= 2;
+      uint32_t a[16];
+      tmem_ld16(lane_base + (is_dk ? DK_COL : DV_COL) + kh_e * 16, a);
+      tmem_ld_wait();
+      const float mul = is_dk ? scale : 1.f;
+      const size_t grow = (size_t)row_base + kb0 + kh_e * KT + r;
+      uint4* dst = reinterpret_cast<uint4*>(dqkv + grow * 3 * C + (is_dk ? C : 2 * C) + h * DH);
+      uint32_t w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      wk[i] = pack_bf16(__uint_as_float(c[2 * i]) * scale, __uint_as_float(c[2 * i + 1]) * scale);
-      wv[i] = pack_bf16(__uint_as_float(a[2 * i]), __uint_as_float(a[2 * i + 1]));
+      for (int i = 0; i < 8; ++i) w[i] = pack_bf16(__uint_as_float(a[2 * i]) * mul, __uint_as_float(a[2 * i + 1]) * mul);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
-    dk[0] = make_uint4(wk[0], wk[1], wk[2], wk[3]);
-    dk[1] = make_uint4(wk[4], wk[5], wk[6], wk[7]);
-    dvp[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-    dvp[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
   } else {
-    // =========================================================== dQ drain (warps 8-11): one query row per thread
+    // =========================================================== drain warpgroup: one query row per thread
     const int sub = warp & 3;
     const int r = sub * 32 + lane;
-    const int dtid = threadIdx.x - NWG * 128;
+    const int dtid = threadIdx.x - W_DRAIN * 32;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
     float* dq_head = ws + (((size_t)b * H + h) * L) * DH;
+    const float inv_c = 1.f / scale_log2;
+    // -v as three bf16 pieces (24 significant bits), the same 16 bytes in both halves of the 32-byte row so that the
+    // tile reads the same with or without the 32-byte swizzle
+    auto split3 = [](float v, uint32_t& w0, uint32_t& w1) {
+      const bf16 b0 = __float2bfloat16_rn(v);
+      const float r1 = v - __bfloat162float(b0);
+      const bf16 b1 = __float2bfloat16_rn(r1);
+      const bf16 b2 = __float2bfloat16_rn(r1 - __bfloat162float(b1));
+      w0 = static_cast<uint32_t>(__bfloat16_as_ushort(b0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
+      w1 = static_cast<uint32_t>(__bfloat16_as_ushort(b2));
+    };
+    auto build = [&](int j) {
+      const int s = j % NSTQ;
+      mbar_wait(q_full(s), (j / NSTQ) & 1);
+      uint8_t* st = smem_gen + OFF_Q + s * QSTAGE;
+      const float lv = reinterpret_cast<const float*>(st + ST_LSE)[r];
+      const float dl = reinterpret_cast<const float*>(st + ST_DELTA)[r];
+      uint32_t w0, w1;
+      split3(-lv * inv_c, w0, w1);
+      uint4* row = reinterpret_cast<uint4*>(st + ST_LSET + r * ROWB);
+      row[0] = make_uint4(w0, w1, 0u, 0u);
+      row[1] = make_uint4(w0, w1, 0u, 0u);
+      split3(-dl, w0, w1);
+      row = reinterpret_cast<uint4*>(st + ST_DELT + r * ROWB);
+      row[0] = make_uint4(w0, w1, 0u, 0u);
+      row[1] = make_uint4(w0, w1, 0u, 0u);
+      fence_proxy_async_smem();
+      mbar_arrive(ld_full(s));
+    };
+    build(0);
+    if (nq > 1) build(1);
     for (int j = 0; j < nq; ++j) {
       const int db = j & 1;
-      mbar_wait(dq_full(db), (j >> 1) & 1);
+      if (j + 2 < nq) build(j + 2);
+      mbar_wait(dq_full, j & 1);
       tc_fence_after();
       uint32_t o[16];
-      tmem_ld16(lane_base + DQ_COL + db * 16, o);
+      tmem_ld16(lane_base + DQ_COL, o);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(dq_free(db));
+      mbar_arrive(dq_free);
       if (dtid == 0) tma_store_wait_read<1>();  // the reduce issued two tiles ago has read this staging tile
       named_bar_sync(1, 128);
       float4* dst = reinterpret_cast<float4*>(smem_gen + OFF_STG + db * STG_BYTES + r * (DH * 4));
@@ -373,8 +433,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
-    __syncwarp();
+  if (warp == W_S) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
