@@ -129,7 +129,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const uint32_t tmem_slot = bar_base + 8u * NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_BAR + 8 * NBAR);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform for the compiler: the issuer warps run converged and only elect a lane around the async instructions
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
   const int kb0 = blockIdx.x * (KH * KT);
   const int nq = L / QT;
@@ -167,7 +169,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   auto d32 = [&](uint32_t addr) { return umma_smem_desc_sw(addr, 0, 8 * ROWB, 6); };
 
   if (warp >= W_S && warp < W_P) {
-    if (lane == 0) {
+    {
       // =========================================================== issuers of S'^T / dP'^T (the first one also feeds TMA)
       constexpr uint32_t idescS = umma_idesc_bf16(KT, CW, 0, 0);
       const int si = warp - W_S;
@@ -178,22 +180,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const int s = j % NSTQ;
         mbar_wait(q_empty(s), ((j / NSTQ) & 1) ^ 1);
         const uint32_t st = sQ(s);
-        mbar_arrive_expect_tx(q_full(s), Q_TX);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full(s), Q_TX);
 #pragma unroll
-        for (int i = 0; i < QT / 64; ++i) {
-          tma_load_2d(st + i * 64 * ROWB, &tmQKV, q_full(s), h * DH, row_base + j * QT + i * 64);
-          tma_load_2d(st + ST_DO + i * 64 * ROWB, &tmDO, q_full(s), h * DH, row_base + j * QT + i * 64);
+          for (int i = 0; i < QT / 64; ++i) {
+            tma_load_2d(st + i * 64 * ROWB, &tmQKV, q_full(s), h * DH, row_base + j * QT + i * 64);
+            tma_load_2d(st + ST_DO + i * 64 * ROWB, &tmDO, q_full(s), h * DH, row_base + j * QT + i * 64);
+          }
+          bulk_load_1d(st + ST_LSE, lse_h + j * QT, QT * 4, q_full(s));
+          bulk_load_1d(st + ST_DELTA, delta_h + j * QT, QT * 4, q_full(s));
         }
-        bulk_load_1d(st + ST_LSE, lse_h + j * QT, QT * 4, q_full(s));
-        bulk_load_1d(st + ST_DELTA, delta_h + j * QT, QT * 4, q_full(s));
+        __syncwarp();
       };
       if (si == 0) {
-        mbar_arrive_expect_tx(kv_full, 2 * KH * KT * ROWB);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(kv_full, 2 * KH * KT * ROWB);
 #pragma unroll
-        for (int i = 0; i < KH * KT / 64; ++i) {
-          tma_load_2d(sK + i * 64 * ROWB, &tmQKV, kv_full, C + h * DH, row_base + kb0 + i * 64);
-          tma_load_2d(sV + i * 64 * ROWB, &tmQKV, kv_full, 2 * C + h * DH, row_base + kb0 + i * 64);
+          for (int i = 0; i < KH * KT / 64; ++i) {
+            tma_load_2d(sK + i * 64 * ROWB, &tmQKV, kv_full, C + h * DH, row_base + kb0 + i * 64);
+            tma_load_2d(sV + i * 64 * ROWB, &tmQKV, kv_full, 2 * C + h * DH, row_base + kb0 + i * 64);
+          }
         }
+        __syncwarp();
         for (int j = 0; j < NSTQ - 1 && j < nq; ++j) load_q(j);
       }
       const uint32_t tOnes = tmem_base + ONES_COL;
@@ -201,11 +209,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const int j = t >> 1, kh = t & 1;
         const uint64_t dq = d32(sQ(j % NSTQ) + g * CW * ROWB);
         const uint32_t tS = tmem_base + S_COL + g * 2 * CW;
-        umma_bf16_ts(tS, tmem_base + KA_COL + kh * 8, dq, idescS, 0u);
-        umma_bf16_ts(tS, tOnes, dq + (uint64_t)(ST_LSET / 16), idescS, 1u);
-        umma_bf16_ts(tS + CW, tmem_base + KA_COL + 16 + kh * 8, dq + (uint64_t)(ST_DO / 16), idescS, 0u);
-        umma_bf16_ts(tS + CW, tOnes, dq + (uint64_t)(ST_DELT / 16), idescS, 1u);
-        umma_commit(s_full(g));
+        if (elect_one()) {
+          umma_bf16_ts(tS, tmem_base + KA_COL + kh * 8, dq, idescS, 0u);
+          umma_bf16_ts(tS, tOnes, dq + (uint64_t)(ST_LSET / 16), idescS, 1u);
+          umma_bf16_ts(tS + CW, tmem_base + KA_COL + 16 + kh * 8, dq + (uint64_t)(ST_DO / 16), idescS, 0u);
+          umma_bf16_ts(tS + CW, tOnes, dq + (uint64_t)(ST_DELT / 16), idescS, 1u);
+          umma_commit(s_full(g));
+        }
+        __syncwarp();
       };
       mbar_wait(ka_full, 0);
       mbar_wait(q_full(0), 0);
@@ -231,7 +242,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
     }
   } else if (warp >= W_P) {
-    if (lane == 0) {
+    {
       // =========================================================== issuers of dV, dK, dQ
       constexpr uint32_t idescKN = umma_idesc_bf16(KT, DH, 0, 1);   // A K-major (or TMEM), B MN-major
       constexpr uint32_t idescDQ = umma_idesc_bf16(QT, DH, 1, 1);   // A MN-major, B MN-major
@@ -243,8 +254,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const uint32_t st = sQ(j % NSTQ);
         const uint32_t accKV = j > 0 ? 1u : 0u;
         mbar_wait(pds_full(buf), (t >> 1) & 1);
-        if (which == 0) {
-          tc_fence_after();
+        if (which == 2 && kh == 0 && j > 0) mbar_wait(dq_free, (j - 1) & 1);  // dQ of tile j - 1 has left TMEM
+        tc_fence_after();
+        if (!elect_one()) {
+        } else if (which == 0) {
           const uint32_t tP = tmem_base + P_COL + buf * 64;
           const uint64_t db = d32(st + ST_DO);
 #pragma unroll
@@ -252,7 +265,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             umma_bf16_ts(tmem_base + DV_COL + kh * 16, tP + k * 8, db + (uint64_t)(k * (16 * ROWB / 16)), idescKN,
                          k > 0 ? 1u : accKV);
         } else if (which == 1) {
-          tc_fence_after();
           const uint64_t da = umma_smem_desc(sDS(buf), 0, 1024);
           const uint64_t db = d32(st);
 #pragma unroll
@@ -260,8 +272,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             umma_bf16(tmem_base + DK_COL + kh * 16, da + (uint64_t)(((k >> 2) * (DS_BYTES / 2) + (k & 3) * 32) / 16),
                       db + (uint64_t)(k * (16 * ROWB / 16)), idescKN, k > 0 ? 1u : accKV);
         } else {
-          if (kh == 0 && j > 0) mbar_wait(dq_free, (j - 1) & 1);  // dQ of tile j - 1 has left TMEM
-          tc_fence_after();
           const uint64_t da = umma_smem_desc(sDS(buf), DS_BYTES / 2, 1024);
           const uint64_t db = dKt + (uint64_t)(kh * (KT * ROWB / 16));
 #pragma unroll
@@ -269,11 +279,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             umma_bf16(tmem_base + DQ_COL, da + (uint64_t)(k * (2048 / 16)), db + (uint64_t)(k * (16 * ROWB / 16)),
                       idescDQ, (k > 0 || kh > 0) ? 1u : 0u);
         }
-        umma_commit(mma_done(buf));
-        if (kh == 1) {
-          if (which == 2) umma_commit(dq_full);
-          else umma_commit(q_empty(j % NSTQ));
+        if (elect_one()) {
+          umma_commit(mma_done(buf));
+          if (kh == 1) {
+            if (which == 2) umma_commit(dq_full);
+            else umma_commit(q_empty(j % NSTQ));
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp < W_DRAIN) {
