@@ -41,9 +41,9 @@ def test_attention_fwd_bwd_vs_sdpa(cuda, B, L, C):
 
 
 def test_attention_backward_one_pass_vs_two_pass(cuda):
-    """head_dim 16, L % 256 == 0: tsd_attn_bwd_ws (one pass: dK/dV in registers, dQ through the fp32 workspace by bulk
-    reduce-add) against tsd_attn_bwd (two deterministic passes) and SDPA.  dK / dV come from the same arithmetic in both
-    (bit-identical); dQ is summed in a different order (fp32) and rounded once to bf16."""
+    """head_dim 16, L % 256 == 0: tsd_attn_bwd_ws (one pass on tcgen05: dK/dV accumulate in TMEM, dQ goes through the fp32
+    workspace by bulk reduce-add) against tsd_attn_bwd (two deterministic mma.sync passes) and SDPA.  dK / dV are
+    reproducible run to run; dQ is summed in arrival order (fp32) and rounded once to bf16."""
     from from_ddpm_to_stable_diffusion_b200 import _lib
     B, L, C, H = 3, 1024, 128, 8
     dh = C // H
@@ -56,8 +56,8 @@ def test_attention_backward_one_pass_vs_two_pass(cuda):
     delta = torch.empty(B, H, L, device=cuda, dtype=torch.float32)
     _lib.call("tsd_attn_bwd", qkv, out, dout, lse, delta, d2, B, L, C, H)     # two passes (no workspace)
     torch.cuda.synchronize()
-    assert torch.equal(d1[:, C:], d2[:, C:])                                 # dK, dV
-    assert _rel(d1[:, :C], d2[:, :C]) < 8e-3                                 # dQ: one bf16 ulp of the largest entry
+    assert _rel(d1[:, C:], d2[:, C:]) < 8e-3                                 # dK, dV: one bf16 ulp of the largest entry
+    assert _rel(d1[:, :C], d2[:, :C]) < 8e-3                                 # dQ
     x = qkv.float().view(B, L, 3, H, dh).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
     ref = F.scaled_dot_product_attention(x[0], x[1], x[2])
     ref.backward(dout.float().view(B, L, H, dh).permute(0, 2, 1, 3))
@@ -65,6 +65,43 @@ def test_attention_backward_one_pass_vs_two_pass(cuda):
     assert _rel(d1, ref_d) < 1.2e-2 and _rel(d2, ref_d) < 1.2e-2
     d3 = ops.attn_bwd(qkv, out, dout, lse, B, L, C, H)                       # run-to-run: dK / dV exact, dQ to fp32 order
     assert torch.equal(d1[:, C:], d3[:, C:]) and _rel(d1[:, :C], d3[:, :C]) < 8e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 128), (1, 4096, 128), (2, 1024, 256)])
+def test_attention_backward_tc_shapes(cuda, shape):
+    """The tcgen05 backward at its smallest sequence (one 256-key block, two query tiles), the 64x64 sequence
+    (16 key blocks reducing into the same dQ rows) and 16 heads; extreme lse2 / delta values exercise the three-piece
+    bf16 split that carries them through the tensor core."""
+    B, L, C = shape
+    H = C // 16
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = (torch.randn(B * L, 3 * C, device=cuda, generator=g) * 1.3).to(BF)
+    qkv[: L // 2, :C] *= 3.0  # peaked rows: large lse2, P close to one-hot
+    dout = (torch.randn(B * L, C, device=cuda, generator=g) * 4.0).to(BF)
+    out, lse = ops.attn_fwd(qkv, B, L, C, H, need_lse=True)
+    d = ops.attn_bwd(qkv, out, dout, lse, B, L, C, H)
+    x = qkv.float().view(B, L, 3, H, 16).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+    ref = F.scaled_dot_product_attention(x[0], x[1], x[2])
+    ref.backward(dout.float().view(B, L, H, 16).permute(0, 2, 1, 3))
+    ref_d = x.grad.permute(1, 3, 0, 2, 4).reshape(B * L, 3 * C)
+    assert torch.isfinite(d).all()
+    for sl in (slice(0, C), slice(C, 2 * C), slice(2 * C, 3 * C)):
+        assert _rel(d[:, sl], ref_d[:, sl]) < 1.5e-2
+
+
+def test_attention_backward_mma_sync_one_pass_subprocess(cuda):
+    """The mma.sync one-pass kernel (TSD_ATTN_BWD_TC=0) stays the fallback for the same shapes; the switch is read once
+    per process, so it is exercised in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TSD_ATTN_BWD_TC="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "attn_bwd_check.py"), "2,512,128"], env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    errs = [float(line.split("rel max err")[1].split()[0]) for line in r.stdout.splitlines() if "rel max err" in line]
+    assert len(errs) == 3 and max(errs) < 1.2e-2, r.stdout
 
 
 def _sdpa_ref(qkv, B, L, C, H):

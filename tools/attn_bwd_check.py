@@ -20,7 +20,7 @@ dout = torch.randn(B * L, C, device=dev, generator=g).to(torch.bfloat16)
 out, lse = ops.attn_fwd(qkv, B, L, C, H, need_lse=True)
 d = ops.attn_bwd(qkv, out, dout, lse, B, L, C, H)
 torch.cuda.synchronize()
-tag = f"TC={os.environ.get('TSD_ATTN_BWD_TC', '0')} FUSED={os.environ.get('TSD_ATTN_BWD_FUSED', '1')}"
+tag = f"TC={os.environ.get('TSD_ATTN_BWD_TC', '1')} FUSED={os.environ.get('TSD_ATTN_BWD_FUSED', '1')}"
 if not time_only:
     nb = min(B, 2)
     x = qkv[:nb * L].float().view(nb, L, 3, H, dh).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
