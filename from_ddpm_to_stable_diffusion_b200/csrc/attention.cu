@@ -1572,7 +1572,7 @@ static int attn_bwd_impl(void* stream, const void* qkv, const void* out, const v
   static int bwd_tc = -1;
   if (bwd_tc < 0) {
     const char* e = getenv("TSD_ATTN_BWD_TC");
-    bwd_tc = e ? atoi(e) : 0;
+    bwd_tc = e ? atoi(e) : 1;
   }
   if (bwd_tc && ws != nullptr && attn_bwd_tc_supported(L, C, heads)) {
     // one-pass backward on tcgen05: dK/dV in TMEM, dQ through the fp32 workspace [B][heads][L][16]

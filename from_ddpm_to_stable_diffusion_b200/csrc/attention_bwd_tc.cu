@@ -18,8 +18,9 @@
 //   dV_kh += P^T dO    8 x UMMA 128 x 16 x 16, A from TMEM, B = dO tile MN-major
 //   dK_kh += dS^T Q    8 x UMMA 128 x 16 x 16, A = dS^T tile K-major, B = Q tile MN-major
 //   dQ_j  += dS K_kh   8 x UMMA 128 x 16 x 16, A = dS^T tile MN-major, B = K tile MN-major (accumulated over both halves)
-// dK / dV stay in TMEM for the CTA's life; dQ_j is drained by a separate warpgroup (tcgen05.ld -> staging tile -> one
-// 8 KB cp.reduce.async.bulk add.f32 per query tile), which also builds the split lse2 / delta tiles of the coming tiles.
+// dK / dV stay in TMEM for the CTA's life; dQ_j is drained by a separate warpgroup (tcgen05.ld -> red.global.add.v4.f32
+// into the workspace: the shared-memory pipe is the busiest unit of this kernel, so the drain stays off it), which also
+// builds the split lse2 / delta tiles of the coming tiles.
 //
 // Warps: NWG softmax warpgroups (g owns query columns [CW g, CW g + CW) of every tile), one drain warpgroup, NSI issuers of
 // S'^T / dP'^T (the first one is also the TMA producer and allocates TMEM), three issuers for dV / dK / dQ: a single
@@ -60,9 +61,7 @@ constexpr int QSTAGE = ST_DELT + QT * ROWB;                      // 17408
 constexpr int Q_TX = ST_LSET;                                    // bytes written by TMA per stage
 constexpr int OFF_DS = OFF_Q + NSTQ * QSTAGE;
 constexpr int DS_BYTES = KT * QT * 2;                            // 32 KB, two 64-query chunks of 16 KB
-constexpr int OFF_STG = OFF_DS + 2 * DS_BYTES;                   // dQ staging: 2 x [128 q][16] fp32
-constexpr int STG_BYTES = QT * DH * 4;
-constexpr int OFF_BAR = OFF_STG + 2 * STG_BYTES;
+constexpr int OFF_BAR = OFF_DS + 2 * DS_BYTES;
 constexpr int NBAR = 2 + 3 * NSTQ + 2 * NWG + 2 * 2 + 2;
 constexpr int BT_SMEM = 1024 + OFF_BAR + NBAR * 8 + 16;
 static_assert(OFF_DS % 1024 == 0 && QSTAGE % 1024 == 0, "swizzled tiles must keep their alignment");
@@ -81,11 +80,6 @@ __device__ __forceinline__ uint64_t pk2(float a, float b) {
 __device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
 }
-__device__ __forceinline__ uint64_t ffma2_(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
 __device__ __forceinline__ uint64_t fmul2_(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -95,9 +89,8 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, uint32_t ssrc, uint32_t bytes) {
-  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-               ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -382,7 +375,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     // =========================================================== drain warpgroup: one query row per thread
     const int sub = warp & 3;
     const int r = sub * 32 + lane;
-    const int dtid = threadIdx.x - W_DRAIN * 32;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
     float* dq_head = ws + (((size_t)b * H + h) * L) * DH;
     const float inv_c = 1.f / scale_log2;
@@ -404,20 +396,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       const float dl = reinterpret_cast<const float*>(st + ST_DELTA)[r];
       uint32_t w0, w1;
       split3(-lv * inv_c, w0, w1);
+      const int x = (r >> 2) & 1;  // which half goes first: 8 consecutive rows then cover 8 distinct 16-byte bank groups
       uint4* row = reinterpret_cast<uint4*>(st + ST_LSET + r * ROWB);
-      row[0] = make_uint4(w0, w1, 0u, 0u);
-      row[1] = make_uint4(w0, w1, 0u, 0u);
+      row[x] = make_uint4(w0, w1, 0u, 0u);
+      row[x ^ 1] = make_uint4(w0, w1, 0u, 0u);
       split3(-dl, w0, w1);
       row = reinterpret_cast<uint4*>(st + ST_DELT + r * ROWB);
-      row[0] = make_uint4(w0, w1, 0u, 0u);
-      row[1] = make_uint4(w0, w1, 0u, 0u);
+      row[x] = make_uint4(w0, w1, 0u, 0u);
+      row[x ^ 1] = make_uint4(w0, w1, 0u, 0u);
       fence_proxy_async_smem();
       mbar_arrive(ld_full(s));
     };
     build(0);
     if (nq > 1) build(1);
     for (int j = 0; j < nq; ++j) {
-      const int db = j & 1;
       if (j + 2 < nq) build(j + 2);
       mbar_wait(dq_full, j & 1);
       tc_fence_after();
@@ -426,21 +418,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(dq_free);
-      if (dtid == 0) tma_store_wait_read<1>();  // the reduce issued two tiles ago has read this staging tile
-      named_bar_sync(1, 128);
-      float4* dst = reinterpret_cast<float4*>(smem_gen + OFF_STG + db * STG_BYTES + r * (DH * 4));
+      float* dst = dq_head + ((size_t)j * QT + r) * DH;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        dst[i] = make_float4(__uint_as_float(o[4 * i]) * scale, __uint_as_float(o[4 * i + 1]) * scale,
-                             __uint_as_float(o[4 * i + 2]) * scale, __uint_as_float(o[4 * i + 3]) * scale);
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (dtid == 0) {
-        bulk_reduce_add_f32(dq_head + (size_t)j * QT * DH, smem_base + OFF_STG + db * STG_BYTES, STG_BYTES);
-        tma_store_commit();
-      }
+        red_add_v4(dst + 4 * i, __uint_as_float(o[4 * i]) * scale, __uint_as_float(o[4 * i + 1]) * scale,
+                   __uint_as_float(o[4 * i + 2]) * scale, __uint_as_float(o[4 * i + 3]) * scale);
     }
-    if (dtid == 0) tma_store_wait_all<0>();
   }
 
   __syncwarp();

@@ -152,7 +152,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made warp-uniform for the compiler: the issuer warps run converged and elect a lane only around the
+  // async instructions, so the UMMAs issue back to back from uniform registers (no per-instruction elect loop)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
   const int q0 = blockIdx.x * (NWG * QT);
   const int nkb = L / KB;
@@ -179,7 +182,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp >= 8) {
-    if (lane == 0) {
+    {
       // =========================================================== MMA issuer of warpgroup g (g == 0 also feeds TMA)
       // The softmax warps raise their events in program order (s_free(j), p_full(j), s_free(j+1), ...), so the issuer
       // simply blocks on them in that order: no polling, and one issuer per warpgroup keeps the two independent.
@@ -191,15 +194,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       auto load_kv = [&](int jn) {
         const int s = jn % NST;
         mbar_wait(kv_empty(s), ((jn / NST) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full(s), STAGE_BYTES);
-        tma_load_2d(sKV + s * STAGE_BYTES, &tmQKV, kv_full(s), C + h * DH, row_base + jn * KB);
-        tma_load_2d(sKV + s * STAGE_BYTES + KV_BYTES, &tmQKV, kv_full(s), 2 * C + h * DH, row_base + jn * KB);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(kv_full(s), STAGE_BYTES);
+          tma_load_2d(sKV + s * STAGE_BYTES, &tmQKV, kv_full(s), C + h * DH, row_base + jn * KB);
+          tma_load_2d(sKV + s * STAGE_BYTES + KV_BYTES, &tmQKV, kv_full(s), 2 * C + h * DH, row_base + jn * KB);
+        }
+        __syncwarp();
       };
       if (g == 0) {
-        mbar_arrive_expect_tx(q_full, Q_BYTES);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full, Q_BYTES);
 #pragma unroll
-        for (int i = 0; i < NWG * QT / 64; ++i)
-          tma_load_2d(sQ + i * 64 * ROWB, &tmQKV, q_full, h * DH, row_base + q0 + i * 64);
+          for (int i = 0; i < NWG * QT / 64; ++i)
+            tma_load_2d(sQ + i * 64 * ROWB, &tmQKV, q_full, h * DH, row_base + q0 + i * 64);
+        }
+        __syncwarp();
         for (int jn = 0; jn < AHEAD && jn < nkb; ++jn) load_kv(jn);
       }
       const uint64_t descQ = umma_smem_desc_sw(sQ + g * QT * ROWB, 0, 8 * ROWB, SWZ);
@@ -208,11 +217,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         const int s = j % NST;
         mbar_wait(kv_full(s), (j / NST) & 1);
         tc_fence_after();
+        if (elect_one()) {
+          const uint64_t descK = umma_smem_desc_sw(sKV + s * STAGE_BYTES, 0, 8 * ROWB, SWZ);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)  // K-major: a 16-element k-step is 32 bytes further along the swizzled row
-          umma_bf16(tW + S_COL, descQ + (uint64_t)(k * 2), umma_smem_desc_sw(sKV + s * STAGE_BYTES + k * 32, 0, 8 * ROWB, SWZ),
-                    idescS, k > 0 ? 1u : 0u);
-        umma_commit(s_full(g));
+          for (int k = 0; k < DH / 16; ++k)  // K-major: a 16-element k-step is 32 bytes further along the swizzled row
+            umma_bf16(tW + S_COL, descQ + (uint64_t)(k * 2), descK + (uint64_t)(k * 2), idescS, k > 0 ? 1u : 0u);
+          umma_commit(s_full(g));
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_S(0);
@@ -225,12 +237,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         tc_fence_after();
         const int s = j % NST;
         const uint32_t sV = sKV + s * STAGE_BYTES + KV_BYTES;
+        if (elect_one()) {
+          const uint64_t descV = umma_smem_desc_sw(sV, 0, 8 * ROWB, SWZ);
 #pragma unroll
-        for (int k = 0; k < KB / 16; ++k)
-          umma_bf16_ts(tW + O_COL, tW + P_COL + k * 8, umma_smem_desc_sw(sV + k * 16 * ROWB, 0, 8 * ROWB, SWZ), idescPV,
-                       (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(pv_done(g));
-        umma_commit(kv_empty(s));
+          for (int k = 0; k < KB / 16; ++k)
+            umma_bf16_ts(tW + O_COL, tW + P_COL + k * 8, descV + (uint64_t)(k * (16 * ROWB / 16)), idescPV,
+                         (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(pv_done(g));
+          umma_commit(kv_empty(s));
+        }
+        __syncwarp();
         if (g == 0 && j + AHEAD < nkb) load_kv(j + AHEAD);  // its stage was released by block j - 2
       }
     }

@@ -47,7 +47,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  const int warp = threadIdx.x >> 5;
+  // warp index made warp-uniform for the compiler: the MMA warp runs converged and elects a lane only around the
+  // tcgen05 instructions, so the four UMMAs of a k-block issue back to back from uniform registers (a lane-0 branch
+  // costs an elect loop and vector-to-uniform moves per instruction: ~75 clk per UMMA, more than the UMMA itself)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -163,8 +166,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // =========================================================== MMA issuer
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (whole warp, one elected lane issues)
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
     // K-major: 32 B per UMMA_K step inside the 128 B swizzle row; MN-major: 16 k-rows of 128 B.
     constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32;
@@ -188,16 +191,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         const uint32_t sa = smem_stage0 + stage * STAGE_BYTES;
         const uint32_t sb = sa + A_STAGE_BYTES;
+        if (elect_one()) {
+          const uint64_t da = umma_smem_desc(sa, A_LBO, 1024);
+          const uint64_t db = umma_smem_desc(sb, B_LBO, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = umma_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
-          const uint64_t db = umma_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
-          umma_bf16(d_tmem, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k)  // the start-address field holds addr >> 4
+            umma_bf16(d_tmem, da + (uint64_t)(k * (A_KSTEP / 16)), db + (uint64_t)(k * (B_KSTEP / 16)), idesc,
+                      (kb > kb_begin || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+          if (kb + 1 == kb_end) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         }
-        umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      if (kb_end <= kb_begin) {  // empty K range (never produced by the host-side split): keep the hand-off alive
+        if (elect_one()) umma_commit(tfull_bar(acc));
+        __syncwarp();
+      }
     }
   } else if (warp >= 4) {
     // =========================================================== epilogue
