@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 CFG = dict(channel_img=3, channel_multy=[1, 2, 2, 2], channel_base=128, num_class=3, dropout=0.1,
            T=1000, beta_1=0.0015, beta_T=0.0195, w=1.8, lr=2e-6, weight_decay=1e-5, grad_clip=1.0, img=64)
 FWD_GF_PER_SAMPLE = 62.60  # necessary forward work, SURVEY 8(d)
+BWD_TC_TRAFFIC_B256 = 2.712e9  # dram__bytes_read.sum + dram__bytes_write.sum of one attn_bwd_tc_kernel launch at batch 256
 TRAIN_GF_PER_SAMPLE = 187.8
 
 
@@ -251,11 +252,11 @@ def run_ours(args):
     att_flops = 4.0 * B * L * L * Cc  # QK^T + PV per forward launch; backward = 2.5x (5 matmuls)
     att_exps = float(B) * Hh * L * L  # per pass; the one-pass backward evaluates them once
     ach = (nf * att_flops + nb * 2.5 * att_flops) / ((tfw + tb) * 1e-3) / 1e12
-    roof = {"kernel": "attn_fwd_tc_kernel (tcgen05/TMEM) + attn_bwd_fused_kernel (one-pass, mma.sync), L=4096, head_dim 16, %d launches/step" % (nf + nb),
+    roof = {"kernel": "attn_fwd_tc_kernel + attn_bwd_tc_kernel (tcgen05/TMEM; one-pass backward), L=4096, head_dim 16, %d launches/step" % (nf + nb),
             "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
             # DRAM bytes per launch (read + write) of the backward kernel at this shape, from ncu
-            # (profiles/r01_attn_dram_traffic_b256.csv); the forward kernel moves 1.088e9 (qkv once, out + lse once)
-            "traffic": 2.713e9 if B == 256 else None,
+            # (profiles/r01_attn_bwd_tc_dram_traffic_b256.csv); the forward kernel moves 1.088e9 (qkv once, out + lse once)
+            "traffic": BWD_TC_TRAFFIC_B256 if B == 256 else None,
             "peak_source": how + " (bf16_tflops_sustained)", "share_of_step": (tfw + tb) / tot_ms,
             "avg_launch_ms": {"fwd": tfw / max(nf, 1), "bwd": tb / max(nb, 1)},
             "exp_bound": {"achieved_texp_s": (nf + nb) * att_exps / ((tfw + tb) * 1e-3) / 1e12, "mufu_peak_texp_s": 4.64,
