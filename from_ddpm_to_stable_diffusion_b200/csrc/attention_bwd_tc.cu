@@ -99,7 +99,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __global__ void __launch_bounds__(BT_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
-                   float* __restrict__ ws, int L, int C, float scale, float scale_log2) {
+                   float* __restrict__ ws, int L, int C, float scale, float scale_log2, int stagger) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -214,6 +214,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_wait(ka_full, 0);
       mbar_wait(q_full(0), 0);
       mbar_wait(ld_full(0), 0);
+      // stagger: the second issuer's warpgroups start half a sub-tile after the first one's, so that the four softmax
+      // warps of a scheduler are not all in the same phase (TMEM load / exponentials / stores) at the same time
+      if (stagger && si > 0) mbar_wait(s_free(0), 0);
       tc_fence_after();
 #pragma unroll
       for (int gi = 0; gi < NWG / NSI; ++gi) issue_S(0, g_lo + gi);
@@ -452,9 +455,14 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     configured = true;
   }
+  static int stagger = -1;
+  if (stagger < 0) {
+    const char* e = getenv("TSD_ATTN_BWD_TC_STAGGER");
+    stagger = e ? atoi(e) : 0;
+  }
   const float scale = 1.f / sqrtf((float)DH);
   attn_bwd_tc_kernel<<<dim3(L / (KH * KT), heads, B), BT_THREADS, BT_SMEM, st>>>(
-      tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, 1.4426950408889634f * scale);
+      tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, 1.4426950408889634f * scale, stagger);
   TSD_LAUNCH_CHECK();
   return 0;
 }
