@@ -17,5 +17,6 @@ except ImportError:  # pragma: no cover
 
 from from_ddpm_to_stable_diffusion_b200.utils import SamplerDDPM, TrainerDDPM, extract  # noqa: E402,F401
 from from_ddpm_to_stable_diffusion_b200.optim import FusedClipAdamW  # noqa: E402,F401
-from from_ddpm_to_stable_diffusion_b200.training import (CosineWarmupScheduler, EMA, denormalize, generate_grid,  # noqa: E402,F401
-                                                          image_grid_u8, means, normalize_u8, stds, train_step)
+from from_ddpm_to_stable_diffusion_b200.training import (CosineWarmupScheduler, EMA, GraphedTrainStep, denormalize,  # noqa: E402,F401
+                                                          generate_grid, image_grid_u8, load_training_state, means,
+                                                          normalize_u8, stds, train_step, training_state)

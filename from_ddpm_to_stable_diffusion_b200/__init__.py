@@ -4,7 +4,7 @@ Mirrors the reference's Python surface (06_tiny_stable_diffusion/diffusion.py, u
 ``Diffusion``, ``TrainerDDPM``, ``SamplerDDPM``, ``extract``.
 """
 __all__ = ["Diffusion", "TrainerDDPM", "SamplerDDPM", "extract", "EMA", "CosineWarmupScheduler", "denormalize",
-           "normalize_u8", "image_grid_u8", "train_step", "generate_grid", "means", "stds"]
+           "normalize_u8", "image_grid_u8", "train_step", "generate_grid", "means", "stds", "GraphedTrainStep", "training_state", "load_training_state"]
 
 
 def __getattr__(name):
@@ -15,7 +15,7 @@ def __getattr__(name):
         from . import utils
         return getattr(utils, name)
     if name in ("EMA", "CosineWarmupScheduler", "denormalize", "normalize_u8", "image_grid_u8", "train_step",
-                "generate_grid", "means", "stds"):
+                "generate_grid", "means", "stds", "GraphedTrainStep", "training_state", "load_training_state"):
         from . import training
         return getattr(training, name)
     raise AttributeError(name)

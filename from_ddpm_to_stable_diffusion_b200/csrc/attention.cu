@@ -1404,10 +1404,10 @@ static int launch_fwd(cudaStream_t st, dim3 grid, dim3 block, const void* qkv, v
                       float scale_log2) {
   auto kern = attn_fwd_kernel<DH, MT, NSUB>;
   constexpr int smem = 2 * 2 * KV_TILE * NSUB * (DH * 2 + 16);
-  static bool configured = false;
-  if (!configured) {
+  static tsd::PerDeviceFlag configured;
+  if (!configured.cur()) {
     TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.cur() = true;
   }
   kern<<<grid, block, smem, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
   TSD_LAUNCH_CHECK();
@@ -1419,10 +1419,10 @@ static int launch_fwd2(cudaStream_t st, int B, int heads, const void* qkv, void*
                        float scale_log2) {
   auto kern = attn_fwd2_kernel<DH, MT, NSUB, POLY, NTHR, MINB>;
   constexpr int smem = 2 * 2 * KV_TILE * NSUB * (DH * 2 + 16);
-  static bool configured = false;
-  if (!configured) {
+  static tsd::PerDeviceFlag configured;
+  if (!configured.cur()) {
     TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.cur() = true;
   }
   dim3 grid(ceil_div(L, (NTHR / 32) * 16 * MT), heads, B);
   kern<<<grid, NTHR, smem, st>>>((const bf16*)qkv, (bf16*)out, lse2, L, C, scale_log2);
@@ -1509,15 +1509,15 @@ static int launch_bwd(cudaStream_t st, dim3 grid, dim3 block, int dh, const void
   const int smem_dq16 = 4 * KV_TILE * NSUB * 48, smem_dq32 = 4 * KV_TILE * NSUB * 80, smem_dq64 = 4 * KV_TILE * NSUB * 144;
   const int smem_kv16 = smem_dq16 + 4 * KV_TILE * NSUB * 4, smem_kv32 = smem_dq32 + 4 * KV_TILE * NSUB * 4;
   const int smem_kv64 = smem_dq64 + 4 * KV_TILE * NSUB * 4;
-  static bool configured = false;
-  if (!configured) {
+  static tsd::PerDeviceFlag configured;
+  if (!configured.cur()) {
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<16, NSUB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq16));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<32, NSUB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq32));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<16, NSUB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv16));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<32, NSUB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv32));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<64, NSUB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq64));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<64, NSUB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv64));
-    configured = true;
+    configured.cur() = true;
   }
   if (dh == 16) {
     attn_bwd_dq_kernel<16, NSUB, 3><<<grid, block, smem_dq16, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2);
@@ -1586,10 +1586,10 @@ static int attn_bwd_impl(void* stream, const void* qkv, const void* out, const v
   }
   if (bwd_fused && ws != nullptr && dh == 16 && L % 256 == 0) {
     // one-pass backward: dK/dV in registers, dQ through the fp32 workspace [B][heads][L][16]
-    static bool cfgd = false;
-    if (!cfgd) {
+    static tsd::PerDeviceFlag cfgd;
+    if (!cfgd.cur()) {
       TSD_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM));
-      cfgd = true;
+      cfgd.cur() = true;
     }
     TSD_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)B * L * C, st));
     attn_bwd_fused_kernel<<<dim3(L / 256, heads, B), FB_NTHR, FB_SMEM, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta,
@@ -1606,8 +1606,8 @@ static int attn_bwd_impl(void* stream, const void* qkv, const void* out, const v
     const int smem_q = 4 * KV_TILE * 4 * 48, smem_k = smem_q + 4 * KV_TILE * 4 * 4;
 #define TSD_BWD_LAUNCH(KERN, MT, NT, SM)                                                                          \
     do {                                                                                                          \
-      static bool cfgd = false;                                                                                   \
-      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); cfgd = true; } \
+      static tsd::PerDeviceFlag cfgd;                                                                                   \
+      if (!cfgd.cur()) { TSD_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); cfgd.cur() = true; } \
       dim3 gr(ceil_div(L, (NT / 32) * 16 * MT), heads, B);                                                        \
       KERN<<<gr, NT, SM, st>>>((const bf16*)qkv, (const bf16*)dout, lse2, delta, (bf16*)dqkv, L, C, scale, scale_log2); \
       TSD_LAUNCH_CHECK();                                                                                         \

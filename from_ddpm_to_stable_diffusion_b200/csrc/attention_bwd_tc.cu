@@ -450,10 +450,10 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
   CUtensorMap tmQKV, tmDO;
   if (make_tmap_2d_sw(&tmQKV, qkv, 2, (uint64_t)B * L, 3 * (uint64_t)C, 3 * (uint64_t)C, DH, 64, ROWB)) return 1;
   if (make_tmap_2d_sw(&tmDO, dout, 2, (uint64_t)B * L, (uint64_t)C, (uint64_t)C, DH, 64, ROWB)) return 1;
-  static bool configured = false;
-  if (!configured) {
+  static tsd::PerDeviceFlag configured;
+  if (!configured.cur()) {
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
-    configured = true;
+    configured.cur() = true;
   }
   static int stagger = -1;
   if (stagger < 0) {

@@ -409,10 +409,10 @@ template <int DH, int POLY>
 int launch_fwd_t(cudaStream_t st, const CUtensorMap& tm, void* out, float* lse2, const float* knmax2, int B, int L,
                  int C, int heads, float scale_log2) {
   auto kern = attn_fwd_tc_kernel<DH, POLY>;
-  static bool configured = false;
-  if (!configured) {
+  static tsd::PerDeviceFlag configured;
+  if (!configured.cur()) {
     TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<DH>::SMEM_BYTES));
-    configured = true;
+    configured.cur() = true;
   }
   dim3 grid(L / (NWG * QT), heads, B);
   kern<<<grid, TC_THREADS, Geo<DH>::SMEM_BYTES, st>>>(tm, (bf16*)out, lse2, knmax2, L, C, scale_log2);

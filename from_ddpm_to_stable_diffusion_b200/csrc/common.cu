@@ -26,13 +26,12 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return cached;
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cached[dev & 63];
+  if (!c) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+  return c;
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -113,6 +112,6 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t N, uint64_t H, u
 }  // namespace tsd
 
 extern "C" const char* tsd_last_error() { return tsd::g_err; }
-extern "C" int tsd_abi_version() { return 1; }
+extern "C" int tsd_abi_version() { return 2; }
 // number of kernel launches issued by this library so far (host-side counter)
 extern "C" unsigned long long tsd_launch_count() { return tsd::g_launches; }

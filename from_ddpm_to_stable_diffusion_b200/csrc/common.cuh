@@ -36,6 +36,15 @@ void count_launch();
   } while (0)
 
 int num_sms();
+// "done once" flag per CUDA device (cudaFuncSetAttribute and friends are per device, not per process)
+struct PerDeviceFlag {
+  bool done[64] = {};
+  bool& cur() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return done[d & 63];
+  }
+};
 
 // Tensor-map (TMA descriptor) builders; bf16 / f32 elements, SWIZZLE_128B, zero OOB fill.
 // 2-D: tensor [rows][cols] with cols contiguous; box = box_cols x box_rows.
@@ -144,6 +153,18 @@ struct Philox {
     return make_uint4(c0, c1, c2, c3);
   }
 };
+// Device-resident part of a Philox stream position: {number of calls so far, global index of this rank's first sample}.
+// Kernels that draw random numbers take an optional pointer to it, so that (a) a captured CUDA graph draws fresh
+// numbers on every replay (the counter is advanced by a kernel inside the graph) and (b) the numbers of a sample depend
+// on its GLOBAL index only -- a batch sharded over N ranks draws exactly what one rank would.
+struct RngPos {
+  uint64_t calls, sample0;
+};
+__device__ __forceinline__ RngPos load_rng_pos(const uint64_t* p) {
+  RngPos r{0ull, 0ull};
+  if (p) { r.calls = p[0]; r.sample0 = p[1]; }
+  return r;
+}
 // Two uniform u32 -> two N(0,1) via Box-Muller.
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   float u1 = (a + 0.5f) * 2.3283064365386963e-10f;  // (0,1)

@@ -79,144 +79,11 @@ __global__ void __launch_bounds__(256) head_conv_fwd_kernel(const float* __restr
   }
 }
 
-// dW[co][ci][3][3] += sum_p dy[p][co] * x[p+tap][ci], db[co] += sum_p dy[p][co].  thread = output channel.
-__global__ void __launch_bounds__(HEAD_CO) head_conv_wgrad_kernel(const bf16* __restrict__ dy, const float* __restrict__ x,
-                                                                  float* __restrict__ dw, float* __restrict__ db,
-                                                                  int n_img, int ci, int H, int W, int co,
-                                                                  int pix_per_cta) {
-  const int o = threadIdx.x;
-  const int total = n_img * H * W;
-  const int p0 = blockIdx.x * pix_per_cta;
-  const int p1 = min(p0 + pix_per_cta, total);
-  float acc[MAX_CI * 9];
-#pragma unroll
-  for (int i = 0; i < MAX_CI * 9; ++i) acc[i] = 0.f;
-  float accb = 0.f;
-  for (int p = p0; p < p1; ++p) {
-    const int xx = p % W;
-    const int yy = (p / W) % H;
-    const int n = p / (W * H);
-    const float d = __bfloat162float(dy[(size_t)p * co + o]);
-    accb += d;
-#pragma unroll
-    for (int c = 0; c < MAX_CI; ++c) {
-      if (c >= ci) break;
-      const float* xp = x + ((size_t)n * ci + c) * H * W;
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
-        const float v = (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) ? 0.f : __ldg(xp + (size_t)y2 * W + x2);
-        acc[c * 9 + tap] += d * v;
-      }
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < MAX_CI; ++c) {
-    if (c >= ci) break;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) atomicAdd(&dw[((size_t)o * ci + c) * 9 + tap], acc[c * 9 + tap]);
-  }
-  atomicAdd(&db[o], accb);
-}
 
 // ------------------------------------------------------------------------------------------ tail conv
-// a bf16 NHWC [n][H][W][128] (already GroupNorm+SiLU'ed) -> out fp32 NCHW [n][co][H][W], co <= 4.
-// One warp walks 32 consecutive pixels; lanes split the 128 input channels (4 each).
-template <int CO>
-__global__ void __launch_bounds__(256) tail_conv_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
-                                                            const float* __restrict__ bias, float* __restrict__ out,
-                                                            int n_img, int H, int W) {
-  constexpr int C = 128;
-  __shared__ float sw[CO * 9 * C];  // [co][tap][c]
-  for (int i = threadIdx.x; i < CO * C * 9; i += blockDim.x) {
-    const int o = i / (C * 9), r = i - o * (C * 9), c = r / 9, tap = r - c * 9;  // OIHW
-    sw[(o * 9 + tap) * C + c] = w[i];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int total = n_img * H * W;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int base = warp_global * 32; base < total; base += nwarps * 32) {
-    float mine[CO];
-#pragma unroll
-    for (int o = 0; o < CO; ++o) mine[o] = 0.f;
-    for (int i = 0; i < 32; ++i) {
-      const int p = base + i;
-      if (p >= total) break;
-      const int xx = p % W;
-      const int yy = (p / W) % H;
-      const size_t nbase = (size_t)(p / (W * H)) * H * W;
-      float acc[CO];
-#pragma unroll
-      for (int o = 0; o < CO; ++o) acc[o] = 0.f;
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
-        if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
-        const uint2 u = *reinterpret_cast<const uint2*>(a + (nbase + (size_t)y2 * W + x2) * C + lane * 4);
-        const float2 v0 = unpack_bf16(u.x), v1 = unpack_bf16(u.y);
-#pragma unroll
-        for (int o = 0; o < CO; ++o) {
-          const float4 wv = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + lane * 4);
-          acc[o] += v0.x * wv.x + v0.y * wv.y + v1.x * wv.z + v1.y * wv.w;
-        }
-      }
-#pragma unroll
-      for (int o = 0; o < CO; ++o) {
-        const float s = warp_sum(acc[o]);
-        if (lane == i) mine[o] = s;
-      }
-    }
-    const int p = base + lane;
-    if (p < total) {
-      const size_t n = p / (W * H), rem = p - n * (size_t)W * H;
-#pragma unroll
-      for (int o = 0; o < CO; ++o) out[(n * CO + o) * (size_t)H * W + rem] = mine[o] + bias[o];
-    }
-  }
-}
-
-// da[p][c] = sum_tap sum_co dy[p - off(tap)][co] * w[co][c][tap]; thread = (pixel, 8 channels)
-template <int CO>
-__global__ void __launch_bounds__(256) tail_conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                              bf16* __restrict__ da, int n_img, int H, int W) {
-  constexpr int C = 128;
-  __shared__ float sw[CO * 9 * C];  // [co][tap][c]
-  for (int i = threadIdx.x; i < CO * C * 9; i += blockDim.x) {
-    const int o = i / (C * 9), r = i - o * (C * 9), c = r / 9, tap = r - c * 9;
-    sw[(o * 9 + tap) * C + c] = w[i];
-  }
-  __syncthreads();
-  const int total = n_img * H * W * (C / 8);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int cv = (i % (C / 8)) * 8;
-    const int p = i / (C / 8);
-    const int xx = p % W;
-    const int yy = (p / W) % H;
-    const size_t n = p / (W * H);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      // forward: out[q] += a[q + off(tap)] * w[tap]  =>  da[p] += dy[p - off(tap)] * w[tap]
-      const int y2 = yy - (tap / 3 - 1), x2 = xx - (tap % 3 - 1);
-      if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
-#pragma unroll
-      for (int o = 0; o < CO; ++o) {
-        const float d = __ldg(dy + ((n * CO + o) * H + y2) * (size_t)W + x2);
-        const float* wr = sw + (o * 9 + tap) * C + cv;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += d * wr[j];
-      }
-    }
-    *reinterpret_cast<uint4*>(da + (size_t)i * 8) =
-        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]), pack_bf16(acc[6], acc[7]));
-  }
-}
-
-// Same, register-blocked: thread = (4 consecutive pixels of a row, 8 channels).  Every weight vector read from shared
-// memory serves 4 pixels and every dy value up to 3 taps (the one-pixel version is bound by its shared-memory reads:
-// 4 B per FMA).  W % 4 == 0.
+// Data gradient of the tail conv: da[p][c] = sum_tap sum_co dy[p - off(tap)][co] * w[co][c][tap], register-blocked:
+// thread = (4 consecutive pixels of a row, 8 channels).  Every weight vector read from shared memory serves 4 pixels
+// and every dy value up to 3 taps.  W % 4 == 0.
 template <int CO>
 __global__ void __launch_bounds__(256) tail_conv_dgrad4_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                bf16* __restrict__ da, int n_img, int H, int W) {
@@ -277,58 +144,19 @@ __global__ void __launch_bounds__(256) tail_conv_dgrad4_kernel(const float* __re
   }
 }
 
-// dW[co][c][3][3] += sum_p dy[p][co] * a[p+off][c]; db[co] += sum dy.  thread = input channel c.
-template <int CO>
-__global__ void __launch_bounds__(128) tail_conv_wgrad_kernel(const float* __restrict__ dy, const bf16* __restrict__ a,
-                                                              float* __restrict__ dw, float* __restrict__ db, int n_img,
-                                                              int H, int W, int pix_per_cta) {
-  constexpr int C = 128;
-  const int c = threadIdx.x;
-  const int total = n_img * H * W;
-  const int p0 = blockIdx.x * pix_per_cta;
-  const int p1 = min(p0 + pix_per_cta, total);
-  float acc[CO * 9];
-#pragma unroll
-  for (int i = 0; i < CO * 9; ++i) acc[i] = 0.f;
-  float accb[CO];
-#pragma unroll
-  for (int o = 0; o < CO; ++o) accb[o] = 0.f;
-  for (int p = p0; p < p1; ++p) {
-    const int xx = p % W;
-    const int yy = (p / W) % H;
-    const size_t n = p / (W * H);
-    float d[CO];
-#pragma unroll
-    for (int o = 0; o < CO; ++o) {
-      d[o] = __ldg(dy + ((n * CO + o) * H + yy) * (size_t)W + xx);
-      accb[o] += d[o];
-    }
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
-      if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
-      const float v = __bfloat162float(a[((n * H + y2) * (size_t)W + x2) * C + c]);
-#pragma unroll
-      for (int o = 0; o < CO; ++o) acc[o * 9 + tap] += d[o] * v;
-    }
-  }
-#pragma unroll
-  for (int o = 0; o < CO; ++o)
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) atomicAdd(&dw[((size_t)o * C + c) * 9 + tap], acc[o * 9 + tap]);
-  if (c == 0) {
-#pragma unroll
-    for (int o = 0; o < CO; ++o) atomicAdd(&db[o], accb[o]);
-  }
-}
 
 // ------------------------------------------------------------------------------------------ DDPM elementwise
 // x_t = sqrt_ab[t_n] * x0 + sqrt_1mab[t_n] * noise (utils.py:115-116); noise ~ N(0,1) from Philox unless given.
 __global__ void q_sample_kernel(const float* __restrict__ x0, const int64_t* __restrict__ t,
                                 const float* __restrict__ sqrt_ab, const float* __restrict__ sqrt_1mab,
                                 const float* __restrict__ noise_in, uint64_t seed, uint64_t offset,
-                                float* __restrict__ x_t, float* __restrict__ noise_out, size_t per_sample, size_t total4) {
+                                float* __restrict__ x_t, float* __restrict__ noise_out, size_t per_sample, size_t total4,
+                                const uint64_t* __restrict__ rng_dev) {
   const Philox rng(seed);
+  // stream position: (call counter, global sample index, element) -- see RngPos
+  const RngPos pos = load_rng_pos(rng_dev);
+  const uint64_t ctr_hi = 0x71ULL | (pos.calls << 8);
+  const uint64_t base = offset + pos.sample0 * (uint64_t)(per_sample / 4);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const size_t e = i * 4;
     const int n = (int)(e / per_sample);
@@ -339,7 +167,7 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const int64_t* __r
     if (noise_in) {
       z = *reinterpret_cast<const float4*>(noise_in + e);
     } else {
-      const uint4 r = rng(offset + i, 0x71ULL);
+      const uint4 r = rng(base + i, ctr_hi);
       const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
       z = make_float4(z0.x, z0.y, z1.x, z1.y);
     }
@@ -375,11 +203,14 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
                                       const float* __restrict__ c1, const float* __restrict__ c2,
                                       const float* __restrict__ sigma, float w, const float* __restrict__ noise_in,
                                       uint64_t seed, float* __restrict__ x_out, int* __restrict__ nan_flag, size_t total4,
-                                      int clip_last, int dup) {
+                                      int clip_last, int dup, const uint64_t* __restrict__ rng_dev, int n_img) {
   const int step = *step_ptr;
   const float k1 = c1[step], k2 = c2[step], sg = sigma[step];
   const float w1 = 1.f + w;
   const Philox rng(seed);
+  const RngPos pos = load_rng_pos(rng_dev);
+  const uint64_t ctr_hi = ((uint64_t)step + 1) | (pos.calls << 16);  // fresh stream per step and per sampler call
+  const uint64_t base = pos.sample0 * (uint64_t)(total4 / (size_t)(n_img > 0 ? n_img : 1));
   bool bad = false;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const size_t e = i * 4;
@@ -391,7 +222,7 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
       if (noise_in) {
         z = *reinterpret_cast<const float4*>(noise_in + e);
       } else {
-        const uint4 r = rng(i, (uint64_t)step + 1);  // fresh stream per step
+        const uint4 r = rng(base + i, ctr_hi);
         const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
         z = make_float4(z0.x, z0.y, z1.x, z1.y);
       }
@@ -414,102 +245,6 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
   if (bad) atomicOr(nan_flag, 1);
 }
 
-// Fused sampling tail (north star K7): final conv 128 -> CO on the GroupNorm+SiLU'ed features of BOTH halves of the
-// 2B batch (conditional rows n, unconditional rows n + B), and in the epilogue, per pixel and channel,
-//   eps = (1+w) eps_c - w eps_u;  x' = c1[t] x - c2[t] eps + sigma[t] z;  NaN flag;  clip at t = 0
-// with z from Philox keyed by (seed, t, element).  x (fp32 NCHW, [2B] with both halves equal) is read once and
-// written once per step; eps never goes to HBM.
-template <int CO>
-__global__ void __launch_bounds__(256) tail_conv_sample_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
-                                                               const float* __restrict__ bias, float* __restrict__ x,
-                                                               const int* __restrict__ step_ptr, const float* __restrict__ c1,
-                                                               const float* __restrict__ c2, const float* __restrict__ sigma,
-                                                               float wcfg, const float* __restrict__ noise_in, uint64_t seed,
-                                                               int* __restrict__ nan_flag, float* __restrict__ eps_out,
-                                                               int B, int H, int W, int clip_last) {
-  constexpr int C = 128;
-  __shared__ float sw[CO * 9 * C];  // [co][tap][c]
-  for (int i = threadIdx.x; i < CO * C * 9; i += blockDim.x) {
-    const int o = i / (C * 9), r = i - o * (C * 9), c = r / 9, tap = r - c * 9;  // OIHW
-    sw[(o * 9 + tap) * C + c] = w[i];
-  }
-  __syncthreads();
-  const int step = *step_ptr;
-  const float k1 = c1[step], k2 = c2[step], sg = sigma[step], w1 = 1.f + wcfg;
-  const Philox rng(seed);
-  const int lane = threadIdx.x & 31;
-  const int HW = H * W;
-  const int total = B * HW;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  bool bad = false;
-  for (int base = warp_global * 32; base < total; base += nwarps * 32) {
-    float mine[2][CO];
-#pragma unroll
-    for (int o = 0; o < CO; ++o) mine[0][o] = mine[1][o] = 0.f;
-    for (int i = 0; i < 32; ++i) {
-      const int p = base + i;
-      if (p >= total) break;
-      const int xx = p % W;
-      const int yy = (p / W) % H;
-      const int n = p / HW;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const size_t nbase = (size_t)(n + half * B) * HW;
-        float acc[CO];
-#pragma unroll
-        for (int o = 0; o < CO; ++o) acc[o] = 0.f;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int y2 = yy + tap / 3 - 1, x2 = xx + tap % 3 - 1;
-          if (y2 < 0 || y2 >= H || x2 < 0 || x2 >= W) continue;
-          const uint2 u = *reinterpret_cast<const uint2*>(a + (nbase + (size_t)y2 * W + x2) * C + lane * 4);
-          const float2 v0 = unpack_bf16(u.x), v1 = unpack_bf16(u.y);
-#pragma unroll
-          for (int o = 0; o < CO; ++o) {
-            const float4 wv = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + lane * 4);
-            acc[o] += v0.x * wv.x + v0.y * wv.y + v1.x * wv.z + v1.y * wv.w;
-          }
-        }
-#pragma unroll
-        for (int o = 0; o < CO; ++o) {
-          const float s = warp_sum(acc[o]);
-          if (lane == i) mine[half][o] = s;
-        }
-      }
-    }
-    const int p = base + lane;
-    if (p < total) {
-      const int n = p / HW, rem = p - n * HW;
-#pragma unroll
-      for (int o = 0; o < CO; ++o) {
-        const size_t e = ((size_t)n * CO + o) * HW + rem;  // element index inside the [B, CO, H, W] image tensor
-        const float ec = mine[0][o] + bias[o], eu = mine[1][o] + bias[o];
-        if (eps_out) {
-          eps_out[e] = ec;
-          eps_out[(size_t)B * CO * HW + e] = eu;
-        }
-        float z = 0.f;
-        if (step > 0) {
-          if (noise_in) {
-            z = noise_in[e];
-          } else {
-            const uint4 r = rng(e, (uint64_t)step + 1);
-            z = box_muller(r.x, r.y).x;
-          }
-        }
-        const float ep = __fsub_rn(__fmul_rn(w1, ec), __fmul_rn(wcfg, eu));
-        const float mean = __fsub_rn(__fmul_rn(k1, x[e]), __fmul_rn(k2, ep));
-        float v = __fadd_rn(mean, __fmul_rn(sg, z));
-        bad |= (v != v);
-        if (clip_last && step == 0) v = fminf(fmaxf(v, -1.f), 1.f);
-        x[e] = v;
-        x[(size_t)B * CO * HW + e] = v;  // the unconditional copy of the 2B batch
-      }
-    }
-  }
-  if (bad) atomicOr(nan_flag, 1);
-}
 
 // ------------------------------------------------------------------------------------------ tail conv on tensor cores
 // The same convolution as an implicit GEMM on warp-level MMA (m16n8k16, bf16 in, fp32 accumulate): M = 128 output
@@ -543,7 +278,8 @@ tail_conv_mma_kernel(const bf16* __restrict__ a, const float* __restrict__ w, co
                      float* __restrict__ out /* SAMPLE: x (updated in place, both halves); else eps */,
                      const int* __restrict__ step_ptr, const float* __restrict__ c1, const float* __restrict__ c2,
                      const float* __restrict__ sigma, float wcfg, const float* __restrict__ noise_in, uint64_t seed,
-                     int* __restrict__ nan_flag, float* __restrict__ eps_out, int B, int H, int W, int clip_last) {
+                     int* __restrict__ nan_flag, float* __restrict__ eps_out, int B, int H, int W, int clip_last,
+                     const uint64_t* __restrict__ rng_dev) {
   using namespace tcv;
   extern __shared__ __align__(16) uint8_t smem_tc[];
   const int TH = 128 / W;                 // output rows per CTA
@@ -611,6 +347,9 @@ tail_conv_mma_kernel(const bf16* __restrict__ a, const float* __restrict__ w, co
   }
   const float w1 = 1.f + wcfg;
   const Philox rng(seed);
+  const RngPos pos = load_rng_pos(rng_dev);
+  const uint64_t ctr_hi = ((uint64_t)step + 1) | (pos.calls << 16);
+  const uint64_t ebase = pos.sample0 * (uint64_t)(CO * HW);  // z depends on the GLOBAL sample index
   bool bad = false;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -635,7 +374,7 @@ tail_conv_mma_kernel(const bf16* __restrict__ a, const float* __restrict__ w, co
           if (noise_in) {
             z = noise_in[e];
           } else {
-            const uint4 rr = rng(e, (uint64_t)step + 1);
+            const uint4 rr = rng(ebase + e, ctr_hi);
             z = box_muller(rr.x, rr.y).x;
           }
         }
@@ -652,10 +391,9 @@ tail_conv_mma_kernel(const bf16* __restrict__ a, const float* __restrict__ w, co
   if (SAMPLE && bad) atomicOr(nan_flag, 1);
 }
 
+// the tail conv tiles an image into 128-pixel row blocks
 static bool tail_mma_ok(int H, int W) {
-  static int enabled = -1;  // TSD_TAIL_MMA=0: the CUDA-core kernels (A/B comparison)
-  if (enabled < 0) { const char* e = getenv("TSD_TAIL_MMA"); enabled = e ? atoi(e) : 1; }
-  return enabled && (W == 16 || W == 32 || W == 64) && (H * W) % 128 == 0 && H % (128 / W) == 0;
+  return (W == 16 || W == 32 || W == 64) && (H * W) % 128 == 0 && H % (128 / W) == 0;
 }
 static int tail_mma_smem(int W) { return 8 * tcv::WPITCH * 2 + (128 / W + 2) * (W + 2) * tcv::PITCH; }
 
@@ -705,6 +443,17 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ src, bf16* __r
 }
 
 __global__ void step_counter_kernel(int* step_ptr, int delta) { *step_ptr += delta; }
+__global__ void counter_add_u64_kernel(uint64_t* p, uint64_t delta) { *p += delta; }
+// t[n] ~ U{0..T-1} (utils.py:112), a function of (seed, call counter, GLOBAL sample index) only
+__global__ void draw_timesteps_kernel(int64_t* __restrict__ t, int n, int T, uint64_t seed,
+                                      const uint64_t* __restrict__ rng_dev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Philox rng(seed);
+  const RngPos pos = load_rng_pos(rng_dev);
+  const uint4 r = rng(pos.sample0 + (uint64_t)i, 0x72ULL | (pos.calls << 8));
+  t[i] = (int64_t)(((uint64_t)r.x * (uint64_t)T) >> 32);
+}
 // out[0:len] = table[*step][0:len]  (per-step conditioning rows, indexed on the device so a CUDA graph can replay)
 __global__ void gather_row_kernel(const float* __restrict__ table, const int* __restrict__ step_ptr, int len,
                                   float* __restrict__ out) {
@@ -726,76 +475,53 @@ extern "C" int tsd_head_conv_fwd(void* stream, const float* x, const float* w, c
                                  int ci, int H, int W, int co) {
   TSD_CHECK(ci <= MAX_CI && co % 8 == 0 && W % 4 == 0, "head_conv_fwd: unsupported shape ci=%d co=%d W=%d", ci, co, W);
   const size_t smem = (size_t)(ci * 9 * co + co) * sizeof(float);
-  head_conv_fwd_kernel<<<ew_grid((size_t)n_img * H * (W / 4) * (co / 8)), 256, smem, (cudaStream_t)stream>>>(x, w, bias, (bf16*)out, n_img, ci, H, W, co);
+  const size_t total = (size_t)n_img * H * (W / 4) * (co / 8);
+  head_conv_fwd_kernel<<<ew_grid(total), 256, smem, (cudaStream_t)stream>>>(x, w, bias, (bf16*)out, n_img, ci, H, W, co);
   TSD_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int tsd_head_conv_wgrad(void* stream, const void* dy, const float* x, float* dw, float* db, int n_img, int ci,
-                                   int H, int W, int co) {
-  TSD_CHECK(ci <= MAX_CI && co == HEAD_CO, "head_conv_wgrad: unsupported channels ci=%d co=%d", ci, co);
-  const size_t total = (size_t)n_img * H * W;
-  int ppc = (int)((total + 4 * num_sms() - 1) / (4 * num_sms()));
-  if (ppc < 64) ppc = 64;
-  head_conv_wgrad_kernel<<<(int)((total + ppc - 1) / ppc), HEAD_CO, 0, (cudaStream_t)stream>>>((const bf16*)dy, x, dw, db, n_img, ci, H, W, co, ppc);
-  TSD_LAUNCH_CHECK();
-  return 0;
-}
+#define TSD_TAIL_SMEM_ATTR(KERN)                                                                              \
+  do {                                                                                                        \
+    static tsd::PerDeviceFlag cfgd;                                                                           \
+    if (!cfgd.cur()) {                                                                                        \
+      TSD_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));          \
+      cfgd.cur() = true;                                                                                      \
+    }                                                                                                         \
+  } while (0)
 extern "C" int tsd_tail_conv_fwd(void* stream, const void* a, const float* w, const float* bias, float* out, int n_img,
                                  int H, int W, int c_in, int co) {
   TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_fwd: unsupported channels c_in=%d co=%d", c_in, co);
-  if (tail_mma_ok(H, W)) {  // tensor-core implicit GEMM
-    const int smem = tail_mma_smem(W);
-    const int grid_tc = n_img * (H * W / 128);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (co == 3) {
-      static bool cfgd = false;
-      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfgd = true; }
-      tail_conv_mma_kernel<3, 0><<<grid_tc, 256, smem, st>>>((const bf16*)a, w, bias, out, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, 0, H, W, 0);
-    } else {
-      static bool cfgd = false;
-      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfgd = true; }
-      tail_conv_mma_kernel<4, 0><<<grid_tc, 256, smem, st>>>((const bf16*)a, w, bias, out, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, 0, H, W, 0);
-    }
-    TSD_LAUNCH_CHECK();
-    return 0;
-  }
-  const size_t total = (size_t)n_img * H * W;
-  int grid = (int)((total + 255) / 256);  // 8 warps x 32 pixels per CTA pass
-  if (grid > num_sms() * 8) grid = num_sms() * 8;
-  if (co == 3) tail_conv_fwd_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, w, bias, out, n_img, H, W);
-  else tail_conv_fwd_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, w, bias, out, n_img, H, W);
-  TSD_LAUNCH_CHECK();
-  return 0;
-}
-extern "C" int tsd_tail_conv_bwd(void* stream, const float* dy, const void* a, const float* w, void* da, float* dw,
-                                 float* db, int n_img, int H, int W, int c_in, int co) {
-  TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_bwd: unsupported channels c_in=%d co=%d", c_in, co);
+  TSD_CHECK(tail_mma_ok(H, W), "tail_conv_fwd: unsupported image size %dx%d (W in {16,32,64}, H*W %% 128 == 0)", H, W);
+  const int smem = tail_mma_smem(W);
+  const int grid_tc = n_img * (H * W / 128);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t total = (size_t)n_img * H * W;
-  const int g1 = ew_grid(total * 16);
-  int ppc = (int)((total + 4 * num_sms() - 1) / (4 * num_sms()));
-  if (ppc < 64) ppc = 64;
-  const int g2 = (int)((total + ppc - 1) / ppc);
   if (co == 3) {
-    if (W % 4 == 0) tail_conv_dgrad4_kernel<3><<<ew_grid(total * 4), 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
-    else tail_conv_dgrad_kernel<3><<<g1, 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
-    TSD_LAUNCH_CHECK();
-    tail_conv_wgrad_kernel<3><<<g2, 128, 0, st>>>(dy, (const bf16*)a, dw, db, n_img, H, W, ppc);
+    TSD_TAIL_SMEM_ATTR((tail_conv_mma_kernel<3, 0>));
+    tail_conv_mma_kernel<3, 0><<<grid_tc, 256, smem, st>>>((const bf16*)a, w, bias, out, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, 0, H, W, 0, nullptr);
   } else {
-    if (W % 4 == 0) tail_conv_dgrad4_kernel<4><<<ew_grid(total * 4), 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
-    else tail_conv_dgrad_kernel<4><<<g1, 256, 0, st>>>(dy, w, (bf16*)da, n_img, H, W);
-    TSD_LAUNCH_CHECK();
-    tail_conv_wgrad_kernel<4><<<g2, 128, 0, st>>>(dy, (const bf16*)a, dw, db, n_img, H, W, ppc);
+    TSD_TAIL_SMEM_ATTR((tail_conv_mma_kernel<4, 0>));
+    tail_conv_mma_kernel<4, 0><<<grid_tc, 256, smem, st>>>((const bf16*)a, w, bias, out, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, 0, H, W, 0, nullptr);
   }
   TSD_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int tsd_q_sample(void* stream, const float* x0, const int64_t* t, const float* sqrt_ab, const float* sqrt_1mab,
                             const float* noise_in, uint64_t seed, uint64_t offset, float* x_t, float* noise_out,
-                            int n_img, int64_t per_sample) {
+                            int n_img, int64_t per_sample, const uint64_t* rng_dev) {
   TSD_CHECK(per_sample % 4 == 0, "q_sample: per-sample element count must be a multiple of 4");
   const size_t total4 = (size_t)n_img * per_sample / 4;
-  q_sample_kernel<<<ew_grid(total4), 256, 0, (cudaStream_t)stream>>>(x0, t, sqrt_ab, sqrt_1mab, noise_in, seed, offset, x_t, noise_out, per_sample, total4);
+  q_sample_kernel<<<ew_grid(total4), 256, 0, (cudaStream_t)stream>>>(x0, t, sqrt_ab, sqrt_1mab, noise_in, seed, offset, x_t, noise_out, per_sample, total4, rng_dev);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_draw_timesteps(void* stream, int64_t* t, int n, int T, uint64_t seed, const uint64_t* rng_dev) {
+  TSD_CHECK(n > 0 && T > 0, "draw_timesteps: n=%d T=%d", n, T);
+  draw_timesteps_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(t, n, T, seed, rng_dev);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_counter_add_u64(void* stream, uint64_t* counter, uint64_t delta) {
+  counter_add_u64_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
   TSD_LAUNCH_CHECK();
   return 0;
 }
@@ -812,9 +538,11 @@ extern "C" int tsd_mse_bwd(void* stream, const float* pred, const float* noise, 
 }
 extern "C" int tsd_sampler_update(void* stream, const float* x, const float* eps, const int* step_ptr, const float* c1,
                                   const float* c2, const float* sigma, float w, const float* noise_in, uint64_t seed,
-                                  float* x_out, int* nan_flag, int64_t total, int clip_last, int dup) {
+                                  float* x_out, int* nan_flag, int64_t total, int clip_last, int dup,
+                                  const uint64_t* rng_dev, int n_img) {
   TSD_CHECK(total % 4 == 0, "sampler_update: element count must be a multiple of 4");
-  sampler_update_kernel<<<ew_grid(total / 4), 256, 0, (cudaStream_t)stream>>>(x, eps, step_ptr, c1, c2, sigma, w, noise_in, seed, x_out, nan_flag, total / 4, clip_last, dup);
+  TSD_CHECK(rng_dev == nullptr || (n_img > 0 && (total / 4) % n_img == 0), "sampler_update: n_img=%d does not divide the batch", n_img);
+  sampler_update_kernel<<<ew_grid(total / 4), 256, 0, (cudaStream_t)stream>>>(x, eps, step_ptr, c1, c2, sigma, w, noise_in, seed, x_out, nan_flag, total / 4, clip_last, dup, rng_dev, n_img);
   TSD_LAUNCH_CHECK();
   return 0;
 }
@@ -831,32 +559,20 @@ extern "C" int tsd_gather_row_f32(void* stream, const float* table, const int* s
 extern "C" int tsd_tail_conv_sample(void* stream, const void* a, const float* w, const float* bias, float* x,
                                     const int* step_ptr, const float* c1, const float* c2, const float* sigma, float wcfg,
                                     const float* noise_in, uint64_t seed, int* nan_flag, float* eps_out, int B, int H, int W,
-                                    int c_in, int co, int clip_last) {
+                                    int c_in, int co, int clip_last, const uint64_t* rng_dev) {
   TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_sample: unsupported channels c_in=%d co=%d", c_in, co);
-  if (tail_mma_ok(H, W)) {  // tensor-core implicit GEMM, both halves of the CFG pair per CTA
-    const int smem = tail_mma_smem(W);
-    const int grid_tc = B * (H * W / 128);
-    cudaStream_t stt = (cudaStream_t)stream;
-    if (co == 3) {
-      static bool cfgd = false;
-      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfgd = true; }
-      tail_conv_mma_kernel<3, 1><<<grid_tc, 256, smem, stt>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
-    } else {
-      static bool cfgd = false;
-      if (!cfgd) { TSD_CUDA(cudaFuncSetAttribute(tail_conv_mma_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfgd = true; }
-      tail_conv_mma_kernel<4, 1><<<grid_tc, 256, smem, stt>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
-    }
-    TSD_LAUNCH_CHECK();
-    return 0;
+  TSD_CHECK(tail_mma_ok(H, W), "tail_conv_sample: unsupported image size %dx%d (W in {16,32,64}, H*W %% 128 == 0)", H, W);
+  // tensor-core implicit GEMM, both halves of the CFG pair per CTA
+  const int smem = tail_mma_smem(W);
+  const int grid_tc = B * (H * W / 128);
+  cudaStream_t stt = (cudaStream_t)stream;
+  if (co == 3) {
+    TSD_TAIL_SMEM_ATTR((tail_conv_mma_kernel<3, 1>));
+    tail_conv_mma_kernel<3, 1><<<grid_tc, 256, smem, stt>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last, rng_dev);
+  } else {
+    TSD_TAIL_SMEM_ATTR((tail_conv_mma_kernel<4, 1>));
+    tail_conv_mma_kernel<4, 1><<<grid_tc, 256, smem, stt>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last, rng_dev);
   }
-  const size_t total = (size_t)B * H * W;
-  int grid = (int)((total + 255) / 256);
-  if (grid > num_sms() * 8) grid = num_sms() * 8;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (co == 3)
-    tail_conv_sample_kernel<3><<<grid, 256, 0, st>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
-  else
-    tail_conv_sample_kernel<4><<<grid, 256, 0, st>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last);
   TSD_LAUNCH_CHECK();
   return 0;
 }
@@ -875,13 +591,10 @@ extern "C" int tsd_nchw_to_nhwc_pad(void* stream, const float* src, void* dst, i
 extern "C" int tsd_tail_conv_dgrad(void* stream, const float* dy, const float* w, void* da, int n_img, int H, int W,
                                    int c_in, int co) {
   TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_dgrad: unsupported channels c_in=%d co=%d", c_in, co);
+  TSD_CHECK(W % 4 == 0, "tail_conv_dgrad: W=%d must be a multiple of 4", W);
   const size_t total = (size_t)n_img * H * W;
-  const int g1 = ew_grid(total * 16);
-  if (W % 4 == 0) {
-    if (co == 3) tail_conv_dgrad4_kernel<3><<<ew_grid(total * 4), 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
-    else tail_conv_dgrad4_kernel<4><<<ew_grid(total * 4), 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
-  } else if (co == 3) tail_conv_dgrad_kernel<3><<<g1, 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
-  else tail_conv_dgrad_kernel<4><<<g1, 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
+  if (co == 3) tail_conv_dgrad4_kernel<3><<<ew_grid(total * 4), 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
+  else tail_conv_dgrad4_kernel<4><<<ew_grid(total * 4), 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -384,10 +384,10 @@ static int launch_t(cudaStream_t stream, const CUtensorMap& tmA0, const CUtensor
                     const CUtensorMap& tmR, const GemmParams& p) {
   auto kern = gemm_tc_kernel<A_MN, B_MN, OUT_F32>;
   constexpr int smem = Cfg<OUT_F32>::SMEM_BYTES;
-  static bool configured = false;
-  if (!configured) {
+  static tsd::PerDeviceFlag configured;
+  if (!configured.cur()) {
     TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.cur() = true;
   }
   const int total = p.tiles_m * p.tiles_n * p.splits;
   const int grid = total < num_sms() ? total : num_sms();

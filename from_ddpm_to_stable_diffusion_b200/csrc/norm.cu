@@ -111,9 +111,9 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, float* __rest
 
 // Keep/scale factors for the 8 consecutive elements starting at flat index ebase (ebase % 8 == 0): one Philox call,
 // one 16-bit uniform per element (keep probability quantised to 1/65536).  The backward kernels regenerate the mask.
-__device__ __forceinline__ void dropout_scales8(const Philox& rng, uint64_t ebase, float p, float inv_keep,
-                                                float* sc) {
-  const uint4 r = rng.rounds<7>(ebase >> 3, 0x5eedULL);
+__device__ __forceinline__ void dropout_scales8(const Philox& rng, uint64_t ebase, uint64_t ctr_hi, float p,
+                                                float inv_keep, float* sc) {
+  const uint4 r = rng.rounds<7>(ebase >> 3, ctr_hi);
   const uint32_t thr = (uint32_t)(p * 65536.f);
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                                                        int c1, int hw, int pix_per_cta, const float* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int act_silu, float drop_p, uint64_t seed,
-                                                       bf16* __restrict__ out) {
+                                                       bf16* __restrict__ out, const uint64_t* __restrict__ rng_dev) {
   const int C = c0 + c1;
   const int cpg = C / GROUPS;
   const int vec_per_pix = C / 8;
@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 8; ++j) { fa[j] = s_ab[cv + j]; fb[j] = s_ab[C + cv + j]; }
   const Philox rng(seed);
+  // mask = f(seed, call counter, GLOBAL sample index, element): identical for any sharding of the batch (RngPos)
+  const RngPos rpos = load_rng_pos(rng_dev);
+  const uint64_t ctr_hi = 0x5eedULL | (rpos.calls << 16);
+  const size_t ng = (size_t)n + (size_t)rpos.sample0;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(hw, p_begin + pix_per_cta);
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
       }
       if (drop_p > 0.f) {
         float sc[8];
-        dropout_scales8(rng, ((size_t)n * hw + pix) * C + cv, drop_p, inv_keep, sc);
+        dropout_scales8(rng, (ng * hw + pix) * C + cv, ctr_hi, drop_p, inv_keep, sc);
 #pragma unroll
         for (int j = 0; j < 8; ++j) e[j] *= sc[j];
       }
@@ -203,7 +207,8 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_sums_kernel(const bf16* __restr
                                                           int pix_per_cta, const float* __restrict__ stats,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           int act_silu, float drop_p, uint64_t seed,
-                                                          float* __restrict__ ab /* [n][C][2] */) {
+                                                          float* __restrict__ ab /* [n][C][2] */,
+                                                          const uint64_t* __restrict__ rng_dev) {
   const int C = c0 + c1;
   const int cpg = C / GROUPS;
   const int vec_per_pix = C / 8;
@@ -212,6 +217,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_sums_kernel(const bf16* __restr
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_ab[i] = 0.f;
   __syncthreads();
   const Philox rng(seed);
+  // mask = f(seed, call counter, GLOBAL sample index, element): identical for any sharding of the batch (RngPos)
+  const RngPos rpos = load_rng_pos(rng_dev);
+  const uint64_t ctr_hi = 0x5eedULL | (rpos.calls << 16);
+  const size_t ng = (size_t)n + (size_t)rpos.sample0;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(hw, p_begin + pix_per_cta);
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_sums_kernel(const bf16* __restr
         d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = dd.x; d[7] = dd.y; }
       if (drop_p > 0.f) {
         float sc[8];
-        dropout_scales8(rng, ((size_t)n * hw + pix) * C + cv, drop_p, inv_keep, sc);
+        dropout_scales8(rng, (ng * hw + pix) * C + cv, ctr_hi, drop_p, inv_keep, sc);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] *= sc[j];
       }
@@ -292,7 +301,8 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            int act_silu, float drop_p, uint64_t seed,
                                                            const float* __restrict__ ab, const bf16* __restrict__ radd,
-                                                           bf16* __restrict__ dx0, bf16* __restrict__ dx1) {
+                                                           bf16* __restrict__ dx0, bf16* __restrict__ dx1,
+                                                           const uint64_t* __restrict__ rng_dev) {
   const int C = c0 + c1;
   const int cpg = C / GROUPS;
   const int vec_per_pix = C / 8;
@@ -312,6 +322,10 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
   }
   __syncthreads();
   const Philox rng(seed);
+  // mask = f(seed, call counter, GLOBAL sample index, element): identical for any sharding of the batch (RngPos)
+  const RngPos rpos = load_rng_pos(rng_dev);
+  const uint64_t ctr_hi = 0x5eedULL | (rpos.calls << 16);
+  const size_t ng = (size_t)n + (size_t)rpos.sample0;
   const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const int slots = blockDim.x / vec_per_pix;
   const int cv = (threadIdx.x % vec_per_pix) * 8;
@@ -364,7 +378,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
         r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y; r[6] = dd.x; r[7] = dd.y; }
       if (drop_p > 0.f) {
         float sc[8];
-        dropout_scales8(rng, full_base + (size_t)pix * C, drop_p, inv_keep, sc);
+        dropout_scales8(rng, (ng * hw + pix) * C + cv, ctr_hi, drop_p, inv_keep, sc);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] *= sc[j];
       }
@@ -577,14 +591,14 @@ extern "C" int tsd_gn_stats(void* stream, const void* x0, const void* x1, int c0
 
 extern "C" int tsd_gn_apply(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int hw,
                             const float* stats, const float* gamma, const float* beta, int act_silu, float drop_p,
-                            uint64_t seed, void* out) {
+                            uint64_t seed, void* out, const uint64_t* rng_dev) {
   const int C = c0 + c1;
   TSD_CHECK(C % 64 == 0 && c0 % 8 == 0, "gn_apply: unsupported channels c0=%d c1=%d", c0, c1);
   TSD_CHECK(C <= 2048 && 256 % (C / 8) == 0, "gn_apply: unsupported channel count %d", C);
   int ppc;
   const int gx = gn_grid_x(hw, C, n_img, &ppc);
   gn_apply_kernel<<<dim3(gx, n_img), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc, stats, gamma, beta, act_silu, drop_p, seed, (bf16*)out);
+      (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc, stats, gamma, beta, act_silu, drop_p, seed, (bf16*)out, rng_dev);
   TSD_LAUNCH_CHECK();
   return 0;
 }
@@ -593,7 +607,7 @@ extern "C" int tsd_gn_apply(void* stream, const void* x0, const void* x1, int c0
 extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1, int n_img,
                           int hw, const float* stats, const float* gamma, const float* beta, int act_silu,
                           float drop_p, uint64_t seed, float* ab, const void* radd, void* dx0, void* dx1,
-                          float* dgamma, float* dbeta) {
+                          float* dgamma, float* dbeta, const uint64_t* rng_dev) {
   const int C = c0 + c1;
   TSD_CHECK(C % 128 == 0 && c0 % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "gn_bwd: unsupported channels c0=%d c1=%d", c0, c1);
   cudaStream_t st = (cudaStream_t)stream;
@@ -601,11 +615,11 @@ extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const vo
   int ppc;
   const int gx = gn_grid_x(hw, C, n_img, &ppc);
   gn_bwd_sums_kernel<<<dim3(gx, n_img), 256, 2 * C * sizeof(float), st>>>(
-      (const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc, stats, gamma, beta, act_silu, drop_p, seed, ab);
+      (const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc, stats, gamma, beta, act_silu, drop_p, seed, ab, rng_dev);
   TSD_LAUNCH_CHECK();
   gn_bwd_apply_kernel<<<dim3(gx, n_img), 256, 0, st>>>((const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc,
                                                        stats, gamma, beta, act_silu, drop_p, seed, ab, (const bf16*)radd,
-                                                       (bf16*)dx0, (bf16*)dx1);
+                                                       (bf16*)dx0, (bf16*)dx1, rng_dev);
   TSD_LAUNCH_CHECK();
   if (dgamma) {
     gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ab, n_img, C, dgamma, dbeta);

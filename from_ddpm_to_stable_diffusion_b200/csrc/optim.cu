@@ -30,10 +30,20 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 
 // torch.optim.AdamW semantics (decoupled weight decay, bias-corrected), gradient pre-scaled by the
 // clip coefficient min(1, max_norm / (||g|| + 1e-6)) of torch.nn.utils.clip_grad_norm_.
+// lr_dev / step_dev (optional): learning rate and step count read from DEVICE memory, so that a captured CUDA graph
+// of the training iteration follows the LR schedule and the bias correction on every replay.
 __global__ void __launch_bounds__(256) adamw_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                          float* __restrict__ v, size_t n, float lr, float beta1, float beta2,
                                                          float eps, float wd, float bc1, float bc2_sqrt, float max_norm,
-                                                         const float* __restrict__ sumsq, int write_clipped_grad) {
+                                                         const float* __restrict__ sumsq, int write_clipped_grad,
+                                                         const float* __restrict__ lr_dev, const int* __restrict__ step_dev) {
+  if (lr_dev) lr = *lr_dev;
+  if (step_dev) {
+    // same expressions as the host path below (fp32 powf), evaluated once per thread: a handful of instructions
+    const float st = (float)(*step_dev);
+    bc1 = 1.f - powf(beta1, st);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, st));
+  }
   float coef = 1.f;
   if (max_norm > 0.f) {
     coef = max_norm / (sqrtf(*sumsq) + 1e-6f);
@@ -121,7 +131,16 @@ extern "C" int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float*
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   adamw_clip_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt,
-                                                                 max_norm, sumsq, write_clipped_grad);
+                                                                 max_norm, sumsq, write_clipped_grad, nullptr, nullptr);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_adamw_clip_dev(void* stream, float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev,
+                                  const int* step_dev, float beta1, float beta2, float eps, float wd, float max_norm,
+                                  const float* sumsq, int write_clipped_grad) {
+  TSD_CHECK(lr_dev != nullptr && step_dev != nullptr, "adamw_clip_dev: lr / step device pointers are required");
+  adamw_clip_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, 0.f, beta1, beta2, eps, wd, 1.f, 1.f,
+                                                                 max_norm, sumsq, write_clipped_grad, lr_dev, step_dev);
   TSD_LAUNCH_CHECK();
   return 0;
 }

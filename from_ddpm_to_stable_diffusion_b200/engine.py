@@ -13,8 +13,40 @@ import math
 import torch
 
 from . import ops
+from .rng import DeviceRng
 
 F32 = torch.float32
+
+
+class _ZeroArena:
+    """Zero-initialised fp32 scratch of one backward pass, carved out of a single buffer that is cleared by ONE memset
+    (instead of one ``torch.zeros`` per weight-gradient partial: ~100 small fills per step)."""
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+        self.high = 0
+
+    def begin(self, dev):
+        want = max(self.high, 1 << 20)
+        if self.buf is None or self.buf.device != dev or self.buf.numel() < want:
+            self.buf = torch.zeros(want + want // 8, device=dev, dtype=F32)
+        else:
+            self.buf.zero_()
+        self.off = 0
+        self.high = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        n4 = (n + 3) // 4 * 4  # keep every slice 16-byte aligned
+        self.high += n4
+        if self.buf is not None and self.off + n4 <= self.buf.numel():
+            out = self.buf[self.off:self.off + n].view(*shape)
+            self.off += n4
+            return out
+        return torch.zeros(*shape, device=self.buf.device, dtype=F32)  # first pass only: the arena grows next time
 
 
 class _Rec:
@@ -35,16 +67,27 @@ class UNetEngine:
     def __init__(self, model):
         # weak-ish back reference (the engine is owned by the model)
         object.__setattr__(self, "_model_ref", model)
-        self._packed = {}
-        self._packed_sig = None
+        self._packed = {}          # save flag -> packed weight dict (training and inference packings coexist)
+        self._packed_sig = {}
         self._epoch = 0
-        self._scratch = None
+        self._generation = 0       # bumped whenever a cached device buffer (packed weights, scratch) is REPLACED:
+        self._scratch = None       # captured CUDA graphs that baked the old pointers must be dropped (sampling.py)
         self._freqs = None
         self._flat_grad = None
         self._grad_views = None
         self._fn = None
-        self.seed = 0x1234ABCD
-        self._drop_calls = 0
+        self._arena = _ZeroArena()
+        # dropout masks: Philox keyed by (seed of the layer, call counter on the device, global sample index, element)
+        self.rng = DeviceRng(salt=0xD20F)
+        self.section_hook = None   # callable(section) fired by backward() when a parameter section's grads are final
+
+    @property
+    def seed(self):
+        return self.rng.seed
+
+    @seed.setter
+    def seed(self, v):
+        self.rng.seed = int(v)
 
     # ------------------------------------------------------------------ parameters
     @property
@@ -52,12 +95,14 @@ class UNetEngine:
         return self._model_ref
 
     def invalidate(self):
-        self._packed_sig = None
+        self._packed_sig = {}
+        self._packed = {}
         self._dgrad_sig = None
         self._flat_grad = None
         self._grad_views = None
         self._scratch = None
         self._freqs = None
+        self._generation += 1
 
     def bump(self):
         """Call after parameters were modified through raw pointers (fused optimiser)."""
@@ -86,9 +131,10 @@ class UNetEngine:
         """bf16 GEMM-layout copies of the weights, refreshed when any parameter changed.  The C -> 8C linear of the
         attention blocks is packed plain when the tape is saved (training: h8 is kept for the backward) and with
         interleaved value / gate rows for the fused GEGLU epilogue otherwise -- never both."""
-        sig = (bool(save),) + self._signature(P)
-        if sig == self._packed_sig:
-            return self._packed
+        save = bool(save)
+        sig = self._signature(P)
+        if sig == self._packed_sig.get(save):
+            return self._packed[save]
         W = {}
         for key, b in self._block_list():
             if b[0] == "conv":
@@ -109,7 +155,8 @@ class UNetEngine:
                 else:
                     W[key + ".linear_1.geglu"] = ops.pack_linear(P[key + ".linear_1.weight"], geglu=True)
                     W[key + ".linear_1.geglu_bias"] = ops.pack_geglu_bias(P[key + ".linear_1.bias"])
-        self._packed, self._packed_sig = W, sig
+        self._packed[save], self._packed_sig[save] = W, sig
+        self._generation += 1
         return W
 
     def packed_dgrad(self, P):
@@ -130,9 +177,11 @@ class UNetEngine:
         return D
 
     def _get_scratch(self, n_img, dev):
-        need = (8 * 160 + n_img) * 64 + 64  # >= tsd_gn_scratch_floats(n_img): per-CTA GroupNorm partials
-        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != dev:
+        if self._scratch is None or self._scratch_imgs < n_img or self._scratch.device != dev:
+            need = ops.gn_scratch_floats(n_img)  # per-CTA GroupNorm partials, sized by the library for this device
             self._scratch = torch.zeros(max(need, 4096), device=dev, dtype=F32)
+            self._scratch_imgs = n_img
+            self._generation += 1
         return self._scratch
 
     def _get_freqs(self, dev):
@@ -198,6 +247,12 @@ class UNetEngine:
         tape = []
         x = x.contiguous().float()
         n_full = n
+        drop_pos = None
+        if training and m.dropout > 0.0:
+            # one stream position per forward, snapshotted so that the backward regenerates the same masks whatever
+            # happens to the counter in between (a second forward before the backward, graph replays)
+            drop_pos = self.rng.advance(dev).clone()
+        layer_no = [0]
         first_attn = None
         if shared_prefix:
             assert not save and tb_override is not None and cb_override is not None and n % 2 == 0
@@ -228,11 +283,11 @@ class UNetEngine:
                                row_bias=tb, rows_per_sample=rps)
             st2 = ops.gn_stats(hmid, n, hw, 1e-5, scratch)
             seed = 0
+            layer_no[0] += 1
             if p_drop > 0.0:
-                self._drop_calls += 1
-                seed = (self.seed * 1000003 + self._drop_calls) & 0xFFFFFFFFFFFFFFFF
+                seed = (self.rng.seed * 1000003 + layer_no[0]) & 0xFFFFFFFFFFFFFFFF
             a2 = ops.gn_apply(hmid, n, hw, st2, P[key + ".conv_2.0.weight"], P[key + ".conv_2.0.bias"], True,
-                              drop_p=p_drop, seed=seed)
+                              drop_p=p_drop, seed=seed, rng=drop_pos)
             if ci_ != co:
                 sc = ops.gemm(x0, W[key + ".residual_layer"], co, a1=x1, bias=P[key + ".residual_layer.bias"])
             else:
@@ -240,7 +295,7 @@ class UNetEngine:
             out = ops.conv3x3(a2, n, h, w, W[key + ".conv_2.3"], co, bias=P[key + ".conv_2.3.bias"], residual=sc)
             if save:
                 tape.append(_Rec("res", key, b=b, x0=x0, x1=x1, st1=st1, a1=a1, hmid=hmid, st2=st2, a2=a2,
-                                 p_drop=p_drop, seed=seed, h=h, w=w))
+                                 p_drop=p_drop, seed=seed, pos=drop_pos, h=h, w=w))
             return out
 
         def run_attn(key, b, x0, h, w):
@@ -365,6 +420,10 @@ class UNetEngine:
                 G[k] = torch.zeros_like(p)
         return G, total
 
+    def _bias_grad(self, dy, n_samples, rows_per_sample, db):
+        """db[c] += column sums of dy; returns the per-sample sums (their zeroed destination comes from the arena)."""
+        return ops.colsum(dy, n_samples, rows_per_sample, total=db, out=self._arena.take(n_samples, dy.shape[1]))
+
     def backward(self, saved, deps):
         m = self.model
         P, W, n, scratch = saved["P"], saved["W"], saved["n"], saved["scratch"]
@@ -375,21 +434,29 @@ class UNetEngine:
         D = self.packed_dgrad(P)
         saved["D"] = D
         dev = x.device
-        d_temb = torch.zeros(n, m.time_emb_dim, device=dev, dtype=F32)
-        d_ctx = torch.zeros(n, m.time_emb_dim, device=dev, dtype=F32)
+        arena = self._arena
+        arena.begin(dev)
+        d_temb = arena.take(n, m.time_emb_dim)
+        d_ctx = arena.take(n, m.time_emb_dim)
         temb, ctx = crec["temb"], crec["ctx"]
         packed_wgrads = []  # (packed fp32 grad, OIHW grad view) to unpack at the end
 
         def conv_wgrad(dy, x0, key_w, hh, ww, x1=None, stride=1):
             gw = G[key_w]
-            tmp = torch.zeros(gw.shape[0], 9 * gw.shape[1], device=dev, dtype=F32)
+            tmp = arena.take(gw.shape[0], 9 * gw.shape[1])
             ops.conv3x3_wgrad(dy, x0, n, hh, ww, tmp, x1=x1, stride=stride)
             ops.unpack_conv3x3_grad(tmp, gw)
 
         dcur = None
         skip_grads = []
+        section = "decoders"  # the tail sits right behind the decoders in the flat gradient buffer
         for rec in reversed(tape):
             kind, key = rec.kind, rec.key
+            if key and self.section_hook is not None:
+                sec = key.split(".", 1)[0]
+                if sec in ("bottleneck", "encoders") and sec != section:
+                    self.section_hook(section)  # every gradient of the section just left is final
+                    section = sec
             if kind == "tail":
                 hh, ww = rec.h, rec.w
                 # tail conv backward: data gradient on CUDA cores (N = 3), weight gradient on the tensor cores through
@@ -398,11 +465,11 @@ class UNetEngine:
                 da = ops.tail_conv_dgrad(deps_c, rec.a, P["tail.2.weight"], n, hh, ww)
                 co_img = P["tail.2.weight"].shape[0]
                 dyp = ops.nchw_to_nhwc_pad(deps_c, 64)
-                tmpw = torch.zeros(64, 9 * rec.a.shape[1], device=dev, dtype=F32)
+                tmpw = arena.take(64, 9 * rec.a.shape[1])
                 ops.conv3x3_wgrad(dyp, rec.a, n, hh, ww, tmpw)
                 ops.unpack_conv3x3_grad(tmpw[:co_img], G["tail.2.weight"])
-                tmpb = torch.zeros(64, device=dev, dtype=F32)
-                ops.bias_grad(dyp, n, hh * ww, tmpb)
+                tmpb = arena.take(64)
+                self._bias_grad(dyp, n, hh * ww, tmpb)
                 ops.add_cols(G["tail.2.bias"], tmpb, 1, co_img, co_img, 64)
                 dcur, _ = ops.gn_bwd(da, rec.xin, n, hh * ww, rec.st, P["tail.0.weight"], P["tail.0.bias"], True,
                                      G["tail.0.weight"], G["tail.0.bias"])
@@ -422,7 +489,7 @@ class UNetEngine:
             elif kind == "conv":
                 b, hh, ww = rec.b, rec.h, rec.w
                 s = b[3]
-                ops.bias_grad(dcur, n, (hh // s) * (ww // s), G[key + ".bias"])
+                self._bias_grad(dcur, n, (hh // s) * (ww // s), G[key + ".bias"])
                 conv_wgrad(dcur, rec.x0, key + ".weight", hh, ww, stride=s)
                 if s == 2:
                     zs = ops.zero_stuff2(dcur, n, hh // 2, ww // 2)
@@ -431,7 +498,7 @@ class UNetEngine:
                     dcur = ops.conv3x3(dcur, n, hh, ww, D[key], b[1])
             elif kind == "up":
                 hh, ww = rec.h, rec.w
-                ops.bias_grad(dcur, n, 4 * hh * ww, G[key + ".conv.bias"])
+                self._bias_grad(dcur, n, 4 * hh * ww, G[key + ".conv.bias"])
                 conv_wgrad(dcur, rec.u, key + ".conv.weight", 2 * hh, 2 * ww)
                 du = ops.conv3x3(dcur, n, 2 * hh, 2 * ww, D[key + ".conv"], rec.b[1])
                 dcur = ops.upsample2_bwd(du, n, hh, ww)
@@ -439,10 +506,10 @@ class UNetEngine:
                 # head conv weight gradient on the tensor cores: dW[co][c*9+tap] = dY^T * im2col(x)
                 gw = G[key + ".weight"]
                 patch = ops.im2col_head(x, 128)
-                tmpw = torch.zeros(gw.shape[0], 128, device=dev, dtype=F32)
+                tmpw = arena.take(gw.shape[0], 128)
                 ops.gemm_wgrad(dcur, patch, tmpw)
                 ops.add_cols(gw, tmpw, gw.shape[0], gw.shape[1] * 9, gw.shape[1] * 9, 128)
-                ops.bias_grad(dcur, n, dcur.shape[0] // n, G[key + ".bias"])
+                self._bias_grad(dcur, n, dcur.shape[0] // n, G[key + ".bias"])
                 dcur = None
         assert not skip_grads
         # conditioning backward (time / label MLPs, embedding)
@@ -462,6 +529,8 @@ class UNetEngine:
         for k, p in P.items():
             if p.grad is not None and p.grad.data_ptr() != G[k].data_ptr():
                 p.grad.add_(G[k])
+        if self.section_hook is not None:
+            self.section_hook("rest")  # encoders + the conditioning MLPs: everything that is left
 
     def _res_bwd(self, rec, dout, P, W, G, n, temb, d_temb, conv_wgrad, D):
         key, b = rec.key, rec.b
@@ -469,13 +538,13 @@ class UNetEngine:
         hh, ww = rec.h, rec.w
         hw = hh * ww
         # conv_2 (+ shortcut bias share the same column sums of dout)
-        per = ops.bias_grad(dout, n, hw, G[key + ".conv_2.3.bias"])
+        per = self._bias_grad(dout, n, hw, G[key + ".conv_2.3.bias"])
         conv_wgrad(dout, rec.a2, key + ".conv_2.3.weight", hh, ww)
         da2 = ops.conv3x3(dout, n, hh, ww, D[key + ".conv_2.3"], co)
         dh, _ = ops.gn_bwd(da2, rec.hmid, n, hw, rec.st2, P[key + ".conv_2.0.weight"], P[key + ".conv_2.0.bias"], True,
-                           G[key + ".conv_2.0.weight"], G[key + ".conv_2.0.bias"], drop_p=rec.p_drop, seed=rec.seed)
+                           G[key + ".conv_2.0.weight"], G[key + ".conv_2.0.bias"], drop_p=rec.p_drop, seed=rec.seed, rng=rec.pos)
         # time bias: per-sample column sums of dh feed linear_time; their sum over samples is conv_1's bias grad
-        dtb = ops.bias_grad(dh, n, hw, G[key + ".conv_1.2.bias"])
+        dtb = self._bias_grad(dh, n, hw, G[key + ".conv_1.2.bias"])
         ops.small_linear_bwd(dtb, temb, P[key + ".linear_time.1.weight"], d_temb, G[key + ".linear_time.1.weight"],
                              G[key + ".linear_time.1.bias"], silu_in=True, accumulate_dx=True)
         conv_wgrad(dh, rec.a1, key + ".conv_1.2.weight", hh, ww)
@@ -496,20 +565,20 @@ class UNetEngine:
         L = rec.h * rec.w
         k = key
         # conv_output (1x1) + long residual
-        ops.bias_grad(dout, n, L, G[k + ".conv_output.bias"])
+        self._bias_grad(dout, n, L, G[k + ".conv_output.bias"])
         ops.gemm_wgrad(dout, rec.t3, G[k + ".conv_output.weight"].view(C, C))
         dt3 = ops.gemm_dgrad(dout, W[k + ".conv_output"], C)
         # linear_2 (+ short residual to t2)
-        ops.bias_grad(dt3, n, L, G[k + ".linear_2.bias"])
+        self._bias_grad(dt3, n, L, G[k + ".linear_2.bias"])
         ops.gemm_wgrad(dt3, rec.gg, G[k + ".linear_2.weight"])
         dgg = ops.gemm_dgrad(dt3, W[k + ".linear_2"], 4 * C)
         dh8 = ops.geglu_bwd(rec.h8, dgg)
-        ops.bias_grad(dh8, n, L, G[k + ".linear_1.bias"])
+        self._bias_grad(dh8, n, L, G[k + ".linear_1.bias"])
         ops.gemm_wgrad(dh8, rec.l3, G[k + ".linear_1.weight"])
         dl3 = ops.gemm_dgrad(dh8, W[k + ".linear_1"], C)
         dt2 = ops.ln_bwd(dl3, rec.t2, P[k + ".norm_3.weight"], G[k + ".norm_3.weight"], G[k + ".norm_3.bias"], radd=dt3)
         # out_proj (+ cross-attention vector + residual t0)
-        dcb = ops.bias_grad(dt2, n, L, G[k + ".atten_1.1.out_proj.bias"])  # per-sample sums = grad of the cross vector
+        dcb = self._bias_grad(dt2, n, L, G[k + ".atten_1.1.out_proj.bias"])  # per-sample sums = grad of the cross vector
         ops.gemm_wgrad(dt2, rec.o, G[k + ".atten_1.1.out_proj.weight"])
         do = ops.gemm_dgrad(dt2, W[k + ".atten_1.1.out_proj"], C)
         dqkv = ops.attn_bwd(rec.qkv, rec.o, do, rec.lse, n, L, C, self.model.N_HEAD)
@@ -518,7 +587,7 @@ class UNetEngine:
         dt0 = ops.ln_bwd(dl1, rec.t0, P[k + ".atten_1.0.weight"], G[k + ".atten_1.0.weight"], G[k + ".atten_1.0.bias"],
                          radd=dt2)
         # conv_1.1 (1x1) and GroupNorm (eps 1e-6, no activation), + long residual
-        ops.bias_grad(dt0, n, L, G[k + ".conv_1.1.bias"])
+        self._bias_grad(dt0, n, L, G[k + ".conv_1.1.bias"])
         ops.gemm_wgrad(dt0, rec.g, G[k + ".conv_1.1.weight"].view(C, C))
         dg = ops.gemm_dgrad(dt0, W[k + ".conv_1.1"], C)
         dx, _ = ops.gn_bwd(dg, rec.x0, n, L, rec.st, P[k + ".conv_1.0.weight"], P[k + ".conv_1.0.bias"], False,

@@ -77,22 +77,22 @@ def gn_stats(x0, n_img, hw, eps, scratch, x1=None):
     return stats
 
 
-def gn_apply(x0, n_img, hw, stats, gamma, beta, silu, x1=None, drop_p=0.0, seed=0):
+def gn_apply(x0, n_img, hw, stats, gamma, beta, silu, x1=None, drop_p=0.0, seed=0, rng=None):
     c0 = x0.shape[1]
     c1 = x1.shape[1] if x1 is not None else 0
     out = empty_bf16(n_img * hw, c0 + c1, like=x0)
-    call("tsd_gn_apply", x0, x1, c0, c1, n_img, hw, stats, gamma, beta, int(silu), f32(drop_p), u64(seed), out)
+    call("tsd_gn_apply", x0, x1, c0, c1, n_img, hw, stats, gamma, beta, int(silu), f32(drop_p), u64(seed), out, rng)
     return out
 
 
-def gn_bwd(dy, x0, n_img, hw, stats, gamma, beta, silu, dgamma, dbeta, x1=None, drop_p=0.0, seed=0, radd=None):
+def gn_bwd(dy, x0, n_img, hw, stats, gamma, beta, silu, dgamma, dbeta, x1=None, drop_p=0.0, seed=0, radd=None, rng=None):
     c0 = x0.shape[1]
     c1 = x1.shape[1] if x1 is not None else 0
     ab = torch.empty(n_img, c0 + c1, 2, device=x0.device, dtype=F32)
     dx0 = empty_bf16(n_img * hw, c0, like=x0)
     dx1 = empty_bf16(n_img * hw, c1, like=x0) if c1 else None
     call("tsd_gn_bwd", _chk(dy, BF16), x0, x1, c0, c1, n_img, hw, stats, gamma, beta, int(silu), f32(drop_p), u64(seed),
-         ab, radd, dx0, dx1, dgamma, dbeta)
+         ab, radd, dx0, dx1, dgamma, dbeta, rng)
     return dx0, dx1
 
 
@@ -169,10 +169,12 @@ def zero_stuff2(x, n_img, H, W):
     return out
 
 
-def colsum(x, n_samples, rows_per_sample, total=None):
-    """[n_samples*rows_per_sample, C] bf16 -> fp32 [n_samples, C]; total[C] += the sum over all samples (optional)"""
+def colsum(x, n_samples, rows_per_sample, total=None, out=None):
+    """[n_samples*rows_per_sample, C] bf16 -> fp32 [n_samples, C]; total[C] += the sum over all samples (optional).
+    ``out`` (zero-filled fp32 [n_samples, C]) may be supplied by the caller."""
     C = x.shape[1]
-    out = torch.zeros(n_samples, C, device=x.device, dtype=F32)
+    if out is None:
+        out = torch.zeros(n_samples, C, device=x.device, dtype=F32)
     call("tsd_colsum", _chk(x, BF16), n_samples, rows_per_sample, C, out, None if total is None else _chk(total, F32))
     return out
 
@@ -231,11 +233,6 @@ def head_conv_fwd(x, w, bias):
     return out
 
 
-def head_conv_wgrad(dy, x, dw, db):
-    n, ci, H, W = x.shape
-    call("tsd_head_conv_wgrad", _chk(dy, BF16), x, _chk(dw, F32), db, n, ci, H, W, dw.shape[0])
-
-
 def im2col_head(x, KP=128):
     n, ci, H, W = x.shape
     patch = torch.empty(n * H * W, KP, device=x.device, dtype=BF16)
@@ -258,25 +255,30 @@ def tail_conv_fwd(a, w, bias, n, H, W, out=None):
     return out
 
 
-def tail_conv_bwd(dy, a, w, dw, db, n, H, W):
-    da = torch.empty_like(a)
-    call("tsd_tail_conv_bwd", _chk(dy, F32), a, w, da, dw, db, n, H, W, a.shape[1], w.shape[0])
-    return da
-
-
 def tail_conv_dgrad(dy, a, w, n, H, W):
     da = torch.empty_like(a)
     call("tsd_tail_conv_dgrad", _chk(dy, F32), w, da, n, H, W, a.shape[1], w.shape[0])
     return da
 
 
-def q_sample(x0, t, sqrt_ab, sqrt_1mab, seed=0, offset=0, noise=None):
+def q_sample(x0, t, sqrt_ab, sqrt_1mab, seed=0, offset=0, noise=None, rng=None):
     n = x0.shape[0]
     x_t = torch.empty_like(x0)
     noise_out = torch.empty_like(x0) if noise is None else None
     call("tsd_q_sample", _chk(x0, F32), _chk(t, torch.int64), sqrt_ab, sqrt_1mab, noise, u64(seed), u64(offset), x_t,
-         noise_out, n, i64(x0.numel() // n))
+         noise_out, n, i64(x0.numel() // n), rng)
     return x_t, (noise if noise is not None else noise_out)
+
+
+def draw_timesteps(n, T, seed, rng, device):
+    """t ~ U{0..T-1} per sample (utils.py:112) from the device Philox stream -> int64 [n]"""
+    t = torch.empty(n, device=device, dtype=torch.int64)
+    call("tsd_draw_timesteps", t, n, int(T), u64(seed), rng)
+    return t
+
+
+def counter_add_u64(counter, delta):
+    call("tsd_counter_add_u64", _chk(counter, torch.int64), u64(delta))
 
 
 def mse_fwd(pred, noise):
@@ -291,16 +293,17 @@ def mse_bwd(pred, noise, gout):
     return dpred
 
 
-def sampler_update(x, eps, step_ptr, c1, c2, sigma, w, x_out, nan_flag, noise=None, seed=0, clip_last=True, dup=False):
+def sampler_update(x, eps, step_ptr, c1, c2, sigma, w, x_out, nan_flag, noise=None, seed=0, clip_last=True, dup=False,
+                   rng=None):
     total = eps.numel() // 2
     call("tsd_sampler_update", _chk(x, F32), _chk(eps, F32), step_ptr, c1, c2, sigma, f32(w), noise, u64(seed), x_out,
-         nan_flag, i64(total), int(clip_last), int(dup))
+         nan_flag, i64(total), int(clip_last), int(dup), rng, eps.shape[0] // 2)
 
 
 def tail_conv_sample(a, w, bias, x, B, H, W, step_ptr, c1, c2, sigma, wcfg, nan_flag, noise=None, seed=0, eps_out=None,
-                     clip_last=True):
+                     clip_last=True, rng=None):
     call("tsd_tail_conv_sample", _chk(a, BF16), _chk(w, F32), bias, _chk(x, F32), step_ptr, c1, c2, sigma, f32(wcfg), noise,
-         u64(seed), nan_flag, eps_out, B, H, W, a.shape[1], w.shape[0], int(clip_last))
+         u64(seed), nan_flag, eps_out, B, H, W, a.shape[1], w.shape[0], int(clip_last), rng)
 
 
 def step_add(step_ptr, delta):
@@ -360,6 +363,18 @@ def sumsq(g, out):
 def adamw_clip(p, g, m, v, lr, beta1, beta2, eps, wd, step, max_norm, sumsq_buf, write_clipped_grad=True):
     call("tsd_adamw_clip", p, g, m, v, i64(p.numel()), f32(lr), f32(beta1), f32(beta2), f32(eps), f32(wd), int(step),
          f32(max_norm), sumsq_buf, int(write_clipped_grad))
+
+
+def adamw_clip_dev(p, g, m, v, lr_dev, step_dev, beta1, beta2, eps, wd, max_norm, sumsq_buf, write_clipped_grad=True):
+    """clip + AdamW with lr (fp32 [1]) and the step count (int32 [1], already incremented) read on the device"""
+    call("tsd_adamw_clip_dev", p, g, m, v, i64(p.numel()), _chk(lr_dev, F32), _chk(step_dev, torch.int32), f32(beta1),
+         f32(beta2), f32(eps), f32(wd), f32(max_norm), sumsq_buf, int(write_clipped_grad))
+
+
+def gn_scratch_floats(n_img):
+    fn = _lib.lib().tsd_gn_scratch_floats
+    fn.restype = __import__("ctypes").c_int64
+    return int(fn(int(n_img)))
 
 
 # ------------------------------------------------------------------ image input / output (csrc/imageio.cu)

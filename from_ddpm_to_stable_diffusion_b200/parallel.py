@@ -45,6 +45,15 @@ def gather_batch(local, total, group=None):
     return torch.cat([o[: e - b] for o, (b, e) in zip(outs, sizes)], dim=0)
 
 
+def set_shard(obj, sample0):
+    """Tell a TrainerDDPM / SamplerDDPM (and the UNet engine behind it) the GLOBAL index of its first local sample:
+    random numbers are keyed by global sample index, so N ranks draw what one rank would on the same global batch."""
+    obj.rng.set_sample0(sample0)
+    eng = getattr(getattr(obj, "model", None), "_engine", None)
+    if eng is not None:
+        eng.rng.set_sample0(sample0)
+
+
 def dp_loss_scale(global_batch):
     """The reference normalises the summed loss by bs**2 (02_train_direct.py:70); under data parallelism every
     rank uses the global batch so that the all-reduced (summed) gradient equals the single-process one."""

@@ -9,8 +9,15 @@ changes versus the reference's loop, not its arithmetic:
     ResBlock's linear_time for all T steps ([T, sum Cout] table), the label MLP and the ten
     cross-attention vectors (constant over the loop);
   * the per-step scalars (coeff1, coeff2, sigma) and the time rows are indexed on the device by a
-    step counter, so one captured graph replays for every step; Philox noise is keyed by that step;
+    step counter, so one captured graph replays for every step; Philox noise is keyed by (seed, sampler call
+    counter, step, GLOBAL sample index), the call counter and the shard offset living in device memory too: every
+    call draws a fresh z sequence (the reference's ``randn_like``, utils.py:163) and a batch sharded over ranks
+    draws what a single rank would (SURVEY 8e);
   * the per-step host sync of utils.py:167 becomes a device flag checked once after the loop.
+
+The captured graph bakes pointers (packed weights, GroupNorm scratch, conditioning tables) and scalars (w, seed): the
+plan keeps strong references to those buffers and drops the graph whenever the engine replaces one of them
+(``engine._generation``) or a baked scalar changes.
 """
 import torch
 
@@ -32,6 +39,8 @@ class SamplingPlan:
         self.nan_flag = torch.zeros(1, device=device, dtype=torch.int32)
         self.c1, self.c2, self.sigma = sampler._f32_tables(device)
         self.graph = None
+        self.graph_sig = None
+        self._held = None  # buffers whose addresses the captured graph uses (kept alive with it)
         self.tb_table = None
         self.cond_sig = None
         self.fused_tail = getattr(sampler, "fused_tail", True)
@@ -78,19 +87,31 @@ class SamplingPlan:
             for k in cb:
                 self.cb_override[k].copy_(cb[k])
 
+    def _graph_signature(self):
+        """Everything a captured step bakes in besides the plan's own buffers."""
+        eng = self.sampler.model._engine
+        P = eng.params()
+        # touch the caches first so that a pending refresh happens here, outside any capture
+        W = eng.packed(P, save=False)
+        scratch = eng._get_scratch(2 * self.shape[0], self.device)
+        sig = (float(self.sampler.w), int(self.sampler.seed), bool(self.fused_tail), bool(self.shared_prefix),
+               eng._generation, self.cond_sig)
+        return sig, (W, scratch, P)
+
     def _one_step(self, noise=None):
         model = self.sampler.model
+        pos = self.sampler.rng.tensor(self.device)
         ops.gather_row(self.tb_table, self.step, self.tb_cur)
         if self.fused_tail:
             tail = dict(step_ptr=self.step, c1=self.c1, c2=self.c2, sigma=self.sigma, wcfg=float(self.sampler.w),
-                        nan_flag=self.nan_flag, noise=noise, seed=self.sampler.seed, clip_last=True)
+                        nan_flag=self.nan_flag, noise=noise, seed=self.sampler.seed, clip_last=True, rng=pos)
             model._engine.forward(self.x2, None, None, save=False, tb_override=self.tb_override,
                                   cb_override=self.cb_override, sample_tail=tail, shared_prefix=self.shared_prefix)
         else:
             model._engine.forward(self.x2, None, None, save=False, tb_override=self.tb_override,
                                   cb_override=self.cb_override, eps_out=self.eps, shared_prefix=self.shared_prefix)
             ops.sampler_update(self.x2, self.eps, self.step, self.c1, self.c2, self.sigma, float(self.sampler.w), self.x2,
-                               self.nan_flag, noise=noise, seed=self.sampler.seed, clip_last=True, dup=True)
+                               self.nan_flag, noise=noise, seed=self.sampler.seed, clip_last=True, dup=True, rng=pos)
         ops.step_add(self.step, -1)
 
     def run(self, x_T, labels, steps=None, noise_fn=None):
@@ -100,6 +121,7 @@ class SamplingPlan:
         assert all(0 <= s < T for s in steps)
         contiguous_desc = all(steps[i] - 1 == steps[i + 1] for i in range(len(steps) - 1))
         self._prepare(labels)
+        self.sampler.rng.advance(self.device)  # a new z sequence for this call (outside the captured step)
         x = x_T.contiguous().float()
         self.x2[:B].copy_(x)
         self.x2[B:].copy_(x)
@@ -114,6 +136,9 @@ class SamplingPlan:
         else:
             self.step.fill_(steps[0])
             remaining = len(steps)
+            sig, held = self._graph_signature()
+            if self.graph is not None and sig != self.graph_sig:
+                self.graph = None  # a baked pointer or scalar changed: capture again
             if self.graph is None:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
@@ -125,6 +150,7 @@ class SamplingPlan:
                 with torch.cuda.graph(g):
                     self._one_step()
                 self.graph = g
+                self.graph_sig, self._held = sig, held
             for _ in range(remaining):
                 self.graph.replay()
         if int(self.nan_flag.item()) != 0:

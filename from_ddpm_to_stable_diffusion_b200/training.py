@@ -9,9 +9,11 @@ import math
 
 import numpy as np
 import torch
+import torch.distributed as dist
 from torch.optim.lr_scheduler import CosineAnnealingLR, LRScheduler
 
 from . import ops
+from .parallel import set_shard, world_info
 
 means = [0.485, 0.456, 0.406]
 stds = [0.229, 0.224, 0.225]
@@ -170,18 +172,152 @@ def train_step(trainer, optimizer, images, labels, train_rand=0.0, grad_clip=Non
     tensor (the reference reads it with ``.item()``).  ``optimizer`` is either ``FusedClipAdamW`` (clip and AdamW in one
     sweep, ``grad_clip`` taken from its ``max_norm``) or any torch optimizer (then ``grad_clip`` is applied here)."""
     optimizer.zero_grad()
-    bs = images.shape[0]
+    # data parallel: every rank holds bs images of a world * bs batch; the reference's normalisation sum / B^2 uses the
+    # GLOBAL batch so that the summed (all-reduced) gradient equals the single-process one (parallel.dp_loss_scale)
+    rank, world = world_info()
+    bs = images.shape[0] * world
+    set_shard(trainer, rank * images.shape[0])
     labels = labels + 1
     if rng.rand() < train_rand:
         labels = torch.zeros_like(labels)
+    finish = optimizer.overlap_all_reduce() if hasattr(optimizer, "overlap_all_reduce") else None
     loss = trainer(images, labels).sum() / bs ** 2.
     loss.backward()
-    if hasattr(optimizer, "all_reduce_grads"):
-        optimizer.all_reduce_grads()
+    if finish is not None:
+        finish()
     elif grad_clip is not None:
         torch.nn.utils.clip_grad_norm_(trainer.model.parameters(), grad_clip)
     optimizer.step()
     return loss
+
+
+class GraphedTrainStep:
+    """The whole training iteration of 02_train_direct.py:64-74 as replayed CUDA graphs.
+
+    ``step(images, labels)`` does what ``train_step`` does -- label shift / whole-batch label drop, q_sample,
+    UNet forward, noise-MSE normalised by the global batch squared, backward, gradient all-reduce, clip + AdamW
+    (+ EMA) -- but the ~1 100 kernel launches of one iteration are captured once and replayed, so the host issues a
+    handful of calls per step.  What makes the capture replayable: timesteps, q_sample noise and dropout masks are
+    drawn on the device from Philox streams whose call counters live in device memory (rng.DeviceRng), the learning
+    rate and the AdamW step count are read from device memory (optim.FusedClipAdamW), inputs are copied into static
+    buffers, and the label-drop decision (host RNG, as in the reference) is a device flag.
+
+    ``micro_batches`` > 1 accumulates gradients over equal slices of the local batch (BASELINE configs[3]: global
+    batch 2048 on 2 / 4 GPUs); the exchange happens once, after the last slice.  With ``overlap=True`` the all-reduce
+    runs in buckets on a side stream inside the captured backward (NCCL captures into the graph); otherwise it is
+    issued eagerly between the backward graph and the optimiser graph.
+    """
+
+    def __init__(self, trainer, optimizer, train_rand=0.0, micro_batches=1, overlap=True, group=None, rng=np.random):
+        if not hasattr(optimizer, "sync_lr"):
+            raise RuntimeError("GraphedTrainStep needs optim.FusedClipAdamW (learning rate and step count on the device)")
+        self.trainer, self.opt = trainer, optimizer
+        self.train_rand, self.micro, self.overlap, self.group, self.host_rng = train_rand, int(micro_batches), overlap, group, rng
+        self.rank, self.world = world_info()
+        self._graphs = None
+        self._shape = None
+
+    # -------------------------------------------------------------- pieces of one iteration
+    def _fwd_bwd(self):
+        labels = (self._y + 1) * self._keep
+        loss = self.trainer(self._x, labels).sum() * self._scale
+        loss.backward()
+        self.loss.add_(loss.detach())
+
+    def _fwd_bwd_exchange(self):
+        finish = self.opt.overlap_all_reduce(self.group)
+        self._fwd_bwd()
+        finish()
+
+    def _build(self, images):
+        dev = self.trainer.sqrt_alphas_bar.device
+        B = images.shape[0]
+        assert B % self.micro == 0, "local batch must be divisible by micro_batches"
+        mb = B // self.micro
+        self._shape = tuple(images.shape)
+        self._mb = mb
+        self._x = torch.empty((mb,) + tuple(images.shape[1:]), device=dev, dtype=torch.float32)
+        self._y = torch.zeros(mb, device=dev, dtype=torch.int64)
+        self._keep = torch.ones(1, device=dev, dtype=torch.int64)
+        self.loss = torch.zeros((), device=dev, dtype=torch.float32)
+        self._scale = 1.0 / float(B * self.world) ** 2
+        eng = self.trainer.model._engine
+        # ---- warm-up: one eager forward + backward on a side stream (lazy initialisation, flat gradient buffer, arena
+        # sizing, NCCL communicator), with the random streams put back so that the first replay draws what an eager
+        # first step would
+        saved = (self.trainer.rng.state_dict(), eng.rng.state_dict())
+        self._x.normal_()
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.opt.zero_grad()
+            for _ in range(2):  # the second pass runs with the arena at its final size
+                if self.world > 1 and self.overlap:
+                    self._fwd_bwd_exchange()  # also creates the side stream and the NCCL communicator before capture
+                else:
+                    self._fwd_bwd()
+            if self.world > 1:
+                dist.all_reduce(self.loss.clone(), group=self.group)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.trainer.rng.load_state_dict(saved[0])
+        eng.rng.load_state_dict(saved[1])
+        torch.cuda.empty_cache()
+        # ---- capture.  Gradients stay attached to the flat buffer (no zero_grad inside: zeroing is one eager memset)
+        mode = "thread_local" if self.world > 1 else "global"
+        pool = None
+        graphs = {}
+
+        def capture(name, fn):
+            nonlocal pool
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, capture_error_mode=mode):
+                fn()
+            pool = g.pool()
+            graphs[name] = g
+
+        exchange_in_graph = self.world > 1 and self.overlap
+        if self.world == 1 and self.micro == 1:
+            capture("full", lambda: (self._fwd_bwd(), self.opt.step()))
+        else:
+            if self.micro > 1 or not exchange_in_graph:
+                capture("fb", self._fwd_bwd)
+            if exchange_in_graph:
+                capture("fb_last", self._fwd_bwd_exchange)
+            capture("opt", self.opt.step)
+        self._graphs = graphs
+        self._exchange_in_graph = exchange_in_graph
+
+    # -------------------------------------------------------------- the call
+    def __call__(self, images, labels):
+        if self._graphs is None or tuple(images.shape) != self._shape:
+            self._build(images)
+        eng = self.trainer.model._engine
+        g = self._graphs
+        keep = 0 if self.host_rng.rand() < self.train_rand else 1
+        self._keep.fill_(keep)
+        self.opt.sync_lr()
+        eng._flat_grad.zero_()
+        self.loss.zero_()
+        mb, B = self._mb, self._shape[0]
+        for i in range(self.micro):
+            self._x.copy_(images[i * mb:(i + 1) * mb], non_blocking=True)
+            self._y.copy_(labels[i * mb:(i + 1) * mb], non_blocking=True)
+            set_shard(self.trainer, self.rank * B + i * mb)
+            last = i == self.micro - 1
+            if "full" in g:
+                g["full"].replay()
+            elif last and self._exchange_in_graph:
+                g["fb_last"].replay()
+            else:
+                g["fb"].replay()
+        if "full" not in g:
+            if not self._exchange_in_graph:
+                self.opt.all_reduce_grads(self.group)
+            g["opt"].replay()
+        eng.bump()  # the replay changed the parameters behind the host's back: packed copies held by eager paths are stale
+        return self.loss
 
 
 @torch.no_grad()
@@ -192,3 +328,25 @@ def generate_grid(sampler, num_class, nrow, img_channel, img_size, device, x_T=N
         x_T = torch.randn(size=[num_class * nrow, img_channel, img_size, img_size], device=device)
     img_sample = sampler(x_T, values)
     return image_grid_u8(img_sample, nrow=nrow, padding=0)
+
+
+# ------------------------------------------------------------------ checkpoint / resume (02_train_direct.py:40-50,85-88)
+def training_state(trainer, optimizer):
+    """Everything needed to resume a run bit-identically.  The reference saves only ``diffusion.state_dict()``
+    (02_train_direct.py:85-88) and restarts Adam and the random streams on resume; this adds the optimiser moments,
+    the step count, the EMA shadow and the positions of the device Philox streams (timesteps, q_sample noise, dropout).
+    ``state['model']`` alone is the reference's ``ckpt_XXX.pth`` content (same 425 keys)."""
+    eng = trainer.model._engine
+    return {"model": {k: v.detach().clone() for k, v in trainer.model.state_dict().items()},
+            "optimizer": optimizer.state_dict(),
+            "rng": {"trainer": trainer.rng.state_dict(), "dropout": eng.rng.state_dict()}}
+
+
+def load_training_state(trainer, optimizer, state):
+    trainer.model.load_state_dict(state["model"], strict=False)
+    if hasattr(optimizer, "_check_homed"):
+        optimizer._check_homed()
+    optimizer.load_state_dict(state["optimizer"])
+    trainer.rng.load_state_dict(state["rng"]["trainer"])
+    trainer.model._engine.rng.load_state_dict(state["rng"]["dropout"])
+    trainer.model._engine.bump()

@@ -10,6 +10,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .rng import DeviceRng
 
 
 def extract(v, t, x_shape):
@@ -44,8 +45,17 @@ class TrainerDDPM(nn.Module):
         self.register_buffer('sqrt_alphas_bar', torch.sqrt(alphas_bar))
         self.register_buffer('sqrt_one_minus_alphas_bar', torch.sqrt(1. - alphas_bar))
         self._tables = None
-        self._calls = 0
-        self.seed = 0x5EED0001
+        # timesteps and q_sample noise: Philox keyed by (seed, call counter on the device, GLOBAL sample index); the
+        # seed derives from torch.initial_seed(), so torch.manual_seed() selects the stream as in the reference
+        self.rng = DeviceRng(salt=0x5EED0001)
+
+    @property
+    def seed(self):
+        return self.rng.seed
+
+    @seed.setter
+    def seed(self, v):
+        self.rng.seed = int(v)
 
     def _f32_tables(self, device):
         # extract() gathers the f64 table then casts to fp32; casting the table first gives the same bits
@@ -56,16 +66,17 @@ class TrainerDDPM(nn.Module):
 
     def forward(self, x_0, labels, t=None, noise=None):
         """Returns the un-reduced noise-MSE [B,C,H,W] (utils.py:111-119).  ``t`` / ``noise`` may be injected
-        for parity tests; by default t ~ U{0..T-1} (torch.randint, as the reference) and the noise comes
-        from the on-device Philox stream fused into the q_sample kernel."""
+        for parity tests; by default t ~ U{0..T-1} per sample and noise ~ N(0,1) come from the on-device Philox
+        stream (the noise fused into the q_sample kernel), a function of (seed, call number, global sample index)."""
         if not x_0.is_cuda:
             raise RuntimeError("TrainerDDPM (B200) runs on CUDA only; there is no CPU fallback")
+        dev = x_0.device
+        pos = self.rng.advance(dev)
         if t is None:
-            t = torch.randint(self.T, size=(x_0.shape[0],), device=x_0.device)
-        sa, sb = self._f32_tables(x_0.device)
-        self._calls += 1
+            t = ops.draw_timesteps(x_0.shape[0], self.T, self.rng.seed, pos, dev)
+        sa, sb = self._f32_tables(dev)
         x_0 = x_0.contiguous().float()
-        x_t, noise = ops.q_sample(x_0, t.contiguous(), sa, sb, seed=self.seed, offset=self._calls * (1 << 40),
+        x_t, noise = ops.q_sample(x_0, t.contiguous(), sa, sb, seed=self.rng.seed, rng=pos,
                                   noise=None if noise is None else noise.contiguous().float())
         pred_noise = self.model(x_t, t, labels)
         return _MseFn.apply(pred_noise, noise)
@@ -84,24 +95,20 @@ class SamplerDDPM(nn.Module):
         self.register_buffer('coeff1', torch.sqrt(1. / alphas))
         self.register_buffer('coeff2', self.coeff1 * (1. - alphas) / torch.sqrt(1. - alphas_bar))
         self.register_buffer('posterior_var', self.betas * (1. - alphas_bar_prev) / (1. - alphas_bar))
-        self.seed = 0x5EED0002
+        # per-step z: Philox keyed by (seed, call counter, time step, GLOBAL sample index): two sampler calls never
+        # reuse a noise sequence and a batch sharded over ranks draws what one rank would
+        self.rng = DeviceRng(salt=0x5EED0002)
         self.use_cuda_graph = True
         self.fused_tail = True  # final conv + CFG + posterior update + noise as one kernel
         self._plan = None
 
-    # reference helpers kept for API parity (utils.py:143-155) ------------------------------------
-    def predict_xt_prev_mean_from_eps(self, x_t, t, eps):
-        assert x_t.shape == eps.shape
-        return extract(self.coeff1, t, x_t.shape) * x_t - extract(self.coeff2, t, x_t.shape) * eps
+    @property
+    def seed(self):
+        return self.rng.seed
 
-    def p_mean_variance(self, x_t, t, labels):
-        var = torch.cat([self.posterior_var[1:2], self.betas[1:]])
-        var = extract(var, t, x_t.shape)
-        eps = self.model(x_t, t, labels)
-        nonEps = self.model(x_t, t, torch.zeros_like(labels).to(labels.device))
-        eps = (1. + self.w) * eps - self.w * nonEps
-        xt_prev_mean = self.predict_xt_prev_mean_from_eps(x_t, t, eps=eps)
-        return xt_prev_mean, var
+    @seed.setter
+    def seed(self, v):
+        self.rng.seed = int(v)
 
     # device tables -----------------------------------------------------------------------------
     def _f32_tables(self, device):

@@ -80,15 +80,23 @@ int tsd_conv3x3_wgrad(void* stream, const void* dy, const void* x0, const void* 
 int64_t tsd_gn_scratch_floats(int n_img);
 int tsd_gn_stats(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int hw, float eps,
                  float* scratch, float* stats);
+/* Random-stream position kept in DEVICE memory: rng_dev[0] = number of calls so far, rng_dev[1] = GLOBAL index of this
+ * rank's first sample.  Every kernel that draws random numbers (dropout, q_sample noise, timesteps, sampler z) takes an
+ * optional pointer to it (NULL = {0, 0}): a captured CUDA graph then draws fresh numbers on each replay (advance the
+ * counter with tsd_counter_add_u64 inside the graph), and what a sample draws depends on its global index only, so a
+ * batch sharded over N ranks reproduces the single-rank stream. */
+int tsd_counter_add_u64(void* stream, uint64_t* counter, uint64_t delta);
+
 /* out = dropout_p(silu?(gamma * (x - mean) * rstd + beta)), bf16 [n*hw][c0+c1].  The dropout mask is a
- * counter-based Philox function of (seed, element index); nn.SiLU / nn.Dropout at diffusion.py:91,96-97. */
+ * counter-based Philox function of (seed, rng_dev position, element index); nn.SiLU / nn.Dropout at diffusion.py:91,96-97. */
 int tsd_gn_apply(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int hw, const float* stats,
-                 const float* gamma, const float* beta, int act_silu, float drop_p, uint64_t seed, void* out);
+                 const float* gamma, const float* beta, int act_silu, float drop_p, uint64_t seed, void* out,
+                 const uint64_t* rng_dev);
 /* Backward of tsd_gn_apply (+ optional residual add `radd` [n*hw][c0+c1]); dx is written split as dx0 [.., c0],
  * dx1 [.., c1]; dgamma/dbeta (fp32 [c0+c1]) are accumulated.  ab: fp32 scratch [n_img][c0+c1][2]. */
 int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1, int n_img, int hw,
                const float* stats, const float* gamma, const float* beta, int act_silu, float drop_p, uint64_t seed,
-               float* ab, const void* radd, void* dx0, void* dx1, float* dgamma, float* dbeta);
+               float* ab, const void* radd, void* dx0, void* dx1, float* dgamma, float* dbeta, const uint64_t* rng_dev);
 /* LayerNorm over C in {128, 256, 512} per token row; nn.LayerNorm at diffusion.py:127,132 */
 int tsd_ln_fwd(void* stream, const void* x, int M, int C, const float* gamma, const float* beta, float eps, void* out);
 int tsd_ln_bwd(void* stream, const void* dy, const void* x, int M, int C, const float* gamma, float eps,
@@ -150,24 +158,23 @@ int tsd_embedding_bwd(void* stream, const int64_t* idx, const float* dy, float* 
 /* head conv channel_img(<=4) -> co (diffusion.py:206); weights OIHW fp32 */
 int tsd_head_conv_fwd(void* stream, const float* x, const float* w, const float* bias, void* out, int n_img, int ci,
                       int H, int W, int co);
-int tsd_head_conv_wgrad(void* stream, const void* dy, const float* x, float* dw, float* db, int n_img, int ci, int H,
-                        int W, int co);
 /* operands that put the two skinny weight gradients on the tensor cores: patch[p][c*9+tap] (bf16, zero-padded to KP
  * columns) of the fp32 NCHW image for tsd_gemm_wgrad, and d(eps) as bf16 NHWC padded to CP channels for tsd_conv3x3_wgrad */
 int tsd_im2col_head(void* stream, const float* x, void* patch, int n_img, int ci, int H, int W, int KP);
 int tsd_nchw_to_nhwc_pad(void* stream, const float* src, void* dst, int n_img, int co, int HW, int CP);
-/* tail conv 128 -> co in {3,4} on the GroupNorm+SiLU'ed features (diffusion.py:260); out fp32 NCHW */
+/* tail conv 128 -> co in {3,4} on the GroupNorm+SiLU'ed features (diffusion.py:260); out fp32 NCHW; image width in
+ * {16, 32, 64} and H*W a multiple of 128 (tensor-core implicit GEMM, 128-pixel row blocks) */
 int tsd_tail_conv_fwd(void* stream, const void* a, const float* w, const float* bias, float* out, int n_img, int H,
                       int W, int c_in, int co);
 int tsd_tail_conv_dgrad(void* stream, const float* dy, const float* w, void* da, int n_img, int H, int W, int c_in,
                         int co);
-int tsd_tail_conv_bwd(void* stream, const float* dy, const void* a, const float* w, void* da, float* dw, float* db,
-                      int n_img, int H, int W, int c_in, int co);
 /* x_t = sqrt_ab[t_n] x0 + sqrt_1mab[t_n] noise (utils.py:115-116); noise_in NULL => Philox N(0,1), written to
  * noise_out.  Tables are the fp32 casts of the reference's fp64 buffers (what extract() returns). */
 int tsd_q_sample(void* stream, const float* x0, const int64_t* t, const float* sqrt_ab, const float* sqrt_1mab,
                  const float* noise_in, uint64_t seed, uint64_t offset, float* x_t, float* noise_out, int n_img,
-                 int64_t per_sample);
+                 int64_t per_sample, const uint64_t* rng_dev);
+/* t[n] ~ U{0..T-1} (torch.randint at utils.py:112), Philox keyed by (seed, rng_dev position, n) */
+int tsd_draw_timesteps(void* stream, int64_t* t, int n, int T, uint64_t seed, const uint64_t* rng_dev);
 /* loss = (pred - noise)^2 un-reduced (utils.py:118); dpred = 2 (pred - noise) gout */
 int tsd_mse_fwd(void* stream, const float* pred, const float* noise, float* loss, int64_t total);
 int tsd_mse_bwd(void* stream, const float* pred, const float* noise, const float* gout, float* dpred, int64_t total);
@@ -177,7 +184,8 @@ int tsd_mse_bwd(void* stream, const float* pred, const float* noise, const float
  * dup also writes x' to x_out[total:2 total] (the unconditional copy of the 2B batch). */
 int tsd_sampler_update(void* stream, const float* x, const float* eps, const int* step_ptr, const float* c1,
                        const float* c2, const float* sigma, float w, const float* noise_in, uint64_t seed,
-                       float* x_out, int* nan_flag, int64_t total, int clip_last, int dup);
+                       float* x_out, int* nan_flag, int64_t total, int clip_last, int dup, const uint64_t* rng_dev,
+                       int n_img);
 /* Fused sampling tail: final conv 128 -> co over BOTH halves of the 2B batch `a` (rows [0,B) conditional, [B,2B)
  * unconditional; diffusion.py:260) with the reverse-step update above in its epilogue: x ([2B,co,H,W] fp32, both
  * halves identical) is read once and overwritten once per step and eps never reaches HBM (eps_out != NULL dumps
@@ -185,7 +193,7 @@ int tsd_sampler_update(void* stream, const float* x, const float* eps, const int
 int tsd_tail_conv_sample(void* stream, const void* a, const float* w, const float* bias, float* x, const int* step_ptr,
                          const float* c1, const float* c2, const float* sigma, float wcfg, const float* noise_in,
                          uint64_t seed, int* nan_flag, float* eps_out, int B, int H, int W, int c_in, int co,
-                         int clip_last);
+                         int clip_last, const uint64_t* rng_dev);
 int tsd_step_add(void* stream, int* step_ptr, int delta);
 /* out[0:len] = table[*step_ptr][0:len] (per-step time-embedding rows, indexed on the device) */
 int tsd_gather_row_f32(void* stream, const float* table, const int* step_ptr, int len, float* out);
@@ -204,6 +212,11 @@ int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out);
 /* clip_grad_norm_(max_norm) + torch.optim.AdamW step over flat fp32 buffers; sumsq = squared global grad norm */
 int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float wd, int step, float max_norm, const float* sumsq, int write_clipped_grad);
+/* Same with the learning rate and the step count (already incremented, >= 1) read from device memory: the launch can
+ * be replayed from a CUDA graph while the LR schedule and the bias correction advance */
+int tsd_adamw_clip_dev(void* stream, float* p, float* g, float* m, float* v, int64_t n, const float* lr_dev,
+                       const int* step_dev, float beta1, float beta2, float eps, float wd, float max_norm,
+                       const float* sumsq, int write_clipped_grad);
 int tsd_scale_f32(void* stream, float* x, int64_t n, float s);
 /* shadow = (1-decay)*p + decay*shadow over a flat fp32 buffer (EMA.update, utils.py:54-58); one_minus_decay is the
  * host's float(1.0 - decay) and every step is separately rounded, so the result equals the torch expression bit for bit */

@@ -174,7 +174,7 @@ def state_dict_digest(sd: Dict[str, Tensor]) -> float:
 def timestep_embedding(t: Tensor, dim: int, dtype, max_period: float = 10000.0) -> Tensor:
     """diffusion.py:23-31.  freqs are built in fp32 exactly like the reference, then promoted."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     return emb.to(dtype)

@@ -44,16 +44,16 @@ def test_trainer_vs_reference(cuda):
     tr = TrainerDDPM(m, 0.0015, 0.0195, 1000).to(cuda)
     loss = tr(f["x0"].to(cuda), f["labels"].to(cuda), t=f["t"].to(cuda), noise=f["noise"].to(cuda))
     assert loss.shape == f["loss"].shape
-    assert abs(loss.sum().item() - f["loss"].sum().item()) / f["loss"].sum().item() < 5e-3
+    assert abs(loss.sum().item() - f["loss"].sum().item()) / f["loss"].sum().item() < 1e-3  # 0.1 %
     (loss.sum() / 2 ** 2).backward()
     P = dict(m.named_parameters())
     for k, ref in f["grads"].items():
         got = P[k].grad.float().cpu()
         cos = (got.flatten() @ ref.flatten() / (got.norm() * ref.norm() + 1e-30)).item()
-        assert cos > 0.99, (k, cos)
+        assert cos > 0.995, (k, cos)
     n_ref = sum(v ** 2 for v in f["grad_norms"].values()) ** 0.5
     n_got = sum(float(p.grad.double().pow(2).sum()) for p in P.values()) ** 0.5
-    assert abs(n_got - n_ref) / n_ref < 2e-2
+    assert abs(n_got - n_ref) / n_ref < 1e-3
 
 
 def test_sampler_vs_reference(cuda):

@@ -77,7 +77,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 45
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/tinysd_b200.h but not exported"
-    assert lib.tsd_abi_version() == 1
+    assert lib.tsd_abi_version() == 2
 
 
 def test_every_exported_symbol_is_declared():

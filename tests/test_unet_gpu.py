@@ -31,12 +31,17 @@ def _inputs(B, C, H, seed=1234, num_class=3):
 
 
 def test_forward_blocks_64(cuda):
-    """Every block output against the fp32 oracle (bf16 tolerance: rel-L2 <= 2e-2 per block, eps <= 2e-2)."""
+    """Every block output against the fp32 oracle (bf16 tolerance: rel-L2 <= 2e-2 per block, eps <= 2e-2), and the
+    SURVEY 8c gate: eps error vs the fp64 oracle <= 1.5x the error of torch's own bf16 autocast on the same inputs."""
     m, sd = _model(cuda)
     x, t, y = _inputs(2, 3, 64)
     taps_ref = {}
     with torch.no_grad():
         ref = R.unet_forward(sd, x, t, y, MULTY, taps=taps_ref)
+        ref64 = R.unet_forward({k: v.double() for k, v in sd.items()}, x.double(), t, y, MULTY)
+        sdc = {k: v.to(cuda) for k, v in sd.items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            tbf = R.unet_forward(sdc, x.to(cuda), t.to(cuda), y.to(cuda), MULTY).float().cpu()
         taps = {}
         eps, _ = m._engine.forward(x.to(cuda), t.to(cuda), y.to(cuda), save=False, taps=taps)
     torch.cuda.synchronize()
@@ -45,9 +50,12 @@ def test_forward_blocks_64(cuda):
         got = v.float().view(2, h, w, -1).permute(0, 3, 1, 2)
         e = _rel_l2(got, taps_ref[k])
         worst = max(worst, e)
-        assert e < 3e-2, f"block {k}: rel-L2 {e}"
+        assert e < 2e-2, f"block {k}: rel-L2 {e}"
     e = _rel_l2(eps, ref)
     assert e < 2e-2, f"eps rel-L2 {e} (worst block {worst})"
+    e64, ebf = _rel_l2(eps, ref64), _rel_l2(tbf, ref64)
+    print(f"eps rel-L2 vs fp64: ours {e64:.3e}, torch bf16 autocast {ebf:.3e}, worst block {worst:.3e}")
+    assert e64 <= 1.5 * ebf, f"eps error {e64} exceeds 1.5x torch-bf16's own error {ebf}"
 
 
 def test_forward_latent_16(cuda):
@@ -76,7 +84,7 @@ def test_backward_32(cuda):
     loss = trainer(x0.to(cuda), y.to(cuda), t=t.to(cuda), noise=noise.to(cuda)).sum() / B ** 2
     loss.backward()
     torch.cuda.synchronize()
-    assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) < 5e-3, (loss.item(), loss_ref.item())
+    assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) < 1e-3, (loss.item(), loss_ref.item())
     dead = (".norm_2.", ".atten_2.q_proj.", ".atten_2.k_proj.")
     cos = {}
     gn_ref = gn_got = 0.0
@@ -92,11 +100,14 @@ def test_backward_32(cuda):
             assert gg[0].abs().max().item() == 0.0
         denom = gr.norm() * gg.norm()
         cos[k] = (gr.flatten() @ gg.flatten() / denom).item() if denom > 0 else 1.0
-    bad = {k: v for k, v in cos.items() if v < 0.99}
-    assert not bad, f"low-cosine grads: {sorted(bad.items(), key=lambda kv: kv[1])[:10]}"
     vals = sorted(cos.values())
-    assert vals[len(vals) // 2] > 0.999, f"median cosine {vals[len(vals) // 2]}"
-    assert abs(gn_got ** 0.5 - gn_ref ** 0.5) / gn_ref ** 0.5 < 2e-2, (gn_got ** 0.5, gn_ref ** 0.5)
+    print(f"grad cosine: min {vals[0]:.5f} median {vals[len(vals) // 2]:.6f}; grad-norm rel err "
+          f"{abs(gn_got ** 0.5 - gn_ref ** 0.5) / gn_ref ** 0.5:.2e}")
+    # SURVEY 8c gates: per-tensor cosine >= 0.995, median >= 0.9995, loss and global grad norm within 0.1 %
+    bad = {k: v for k, v in cos.items() if v < 0.995}
+    assert not bad, f"low-cosine grads: {sorted(bad.items(), key=lambda kv: kv[1])[:10]}"
+    assert vals[len(vals) // 2] > 0.9995, f"median cosine {vals[len(vals) // 2]}"
+    assert abs(gn_got ** 0.5 - gn_ref ** 0.5) / gn_ref ** 0.5 < 1e-3, (gn_got ** 0.5, gn_ref ** 0.5)
 
 
 def test_sampler_step_teacher_forced(cuda):
@@ -137,9 +148,9 @@ def test_sampler_graph_matches_eager(cuda):
     s2 = SamplerDDPM(m, 0.0015, 0.0195, 1000, w=1.8).to(cuda)
     s2.use_cuda_graph = False
     b = s2(xT, y, steps=steps)
-    # GroupNorm statistics are reduced with float atomics, so replay and eager runs differ in the last bits
+    # same kernels on the same data (the forward path has no atomics): replay and eager stepping agree bit for bit
     assert torch.isfinite(a).all()
-    assert (a - b).abs().max().item() < 5e-3
+    assert torch.equal(a, b), (a - b).abs().max().item()
 
 
 def test_fused_clip_adamw_matches_torch(cuda):
@@ -192,7 +203,7 @@ def test_data_parallel_gradient_additivity(cuda):
     full = grads(slice(0, B))
     parts = sum(grads(slice(*shard_range(B, r, 2))) for r in range(2))
     rel = ((parts - full).norm() / full.norm()).item()
-    assert rel < 2e-2, rel  # bf16 wgrad partial sums are re-associated, nothing else differs
+    assert rel < 1e-3, rel  # fp32 wgrad partial sums are re-associated, nothing else differs
 
 
 def test_fused_sampling_tail_matches_unfused(cuda):
