@@ -6,9 +6,12 @@
 
 Workload (BASELINE.json configs[1]): one DDPM training step of the tiny UNet on synthetic 3x64x64
 images, batch 256 per GPU, bf16 activations / fp32 accumulate, dropout 0.1, AdamW + grad clip -- the
-reference's step body 02_train_direct.py:64-74.  A "step" = zero_grad, trainer (q_sample + UNet forward
-+ noise-MSE), backward, [gradient all-reduce], clip + AdamW.  The same line also carries the sampling
-throughput (DDPM 64x64 images/s at T=1000, CFG w=1.8) under "sampling".
+reference's step body 02_train_direct.py:64-74.  A "step" = zero_grad, label shift/drop, trainer (timesteps +
+q_sample + UNet forward + noise-MSE), backward, [bucketed gradient all-reduce], clip + AdamW, replayed as a
+captured CUDA graph (training.GraphedTrainStep).  The same line carries, under "sampling", the other half of
+BASELINE's metric: DDPM 64x64 images/s over the reverse process (T=1000, CFG w=1.8; the full 1000 steps are run
+and timed at N=1), plus the latent-space figure (configs[4]) and, as context, the reference's own modules run
+eagerly on the same GPU ("gpu_eager_baseline") and on the host CPU ("cpu_baseline").
 """
 import argparse
 import json
@@ -84,11 +87,57 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_train_sample(n_img, steps, warmup, threads):
-    """The reference path (oracle port, torch CPU fp32) on a bounded sample: `n_img` images per step."""
+# ---------------------------------------------------------------------------------------------- reference legs
+def _reference_modules():
+    """The reference's own diffusion.py / utils.py, staged under oracle/_ref by oracle/make_ref.py (None if absent)."""
+    try:
+        from oracle import make_ref
+        if make_ref.available():
+            return make_ref.load_tiny_sd()
+    except Exception:
+        pass
+    return None
+
+
+def reference_train_sample(device, n_img, steps, warmup, autocast=None):
+    """The UNMODIFIED reference (Diffusion + TrainerDDPM + the step body of 02_train_direct.py:64-74) on `device`."""
+    D, U = _reference_modules()
+    torch.manual_seed(0)
+    model = D.Diffusion(channel_img=CFG["channel_img"], channel_base=CFG["channel_base"], num_class=CFG["num_class"],
+                        channel_multy=CFG["channel_multy"], dropout=CFG["dropout"]).to(device)
+    opt = torch.optim.AdamW(model.parameters(), lr=CFG["lr"], weight_decay=CFG["weight_decay"])
+    trainer = U.TrainerDDPM(model, CFG["beta_1"], CFG["beta_T"], CFG["T"]).to(device)
+    g = torch.Generator().manual_seed(1234)
+    x0 = torch.randn(n_img, CFG["channel_img"], CFG["img"], CFG["img"], generator=g).to(device)
+    y = torch.randint(0, CFG["num_class"], (n_img,), generator=g).to(device)
+
+    def step():
+        opt.zero_grad()
+        labels = y + 1
+        if autocast is not None:
+            with torch.autocast(device.type, dtype=autocast):
+                loss = trainer(x0, labels).sum() / n_img ** 2.
+        else:
+            loss = trainer(x0, labels).sum() / n_img ** 2.
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), CFG["grad_clip"])
+        opt.step()
+        return loss.item()
+
+    for _ in range(warmup):
+        step()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()  # .item() synchronises every step, as the reference loop does
+    dt = (time.perf_counter() - t0) / steps
+    return n_img / dt, dt
+
+
+def port_train_sample(n_img, steps, warmup):
+    """Fallback when oracle/_ref is absent: the oracle port (functional restatement) of the same step on the CPU."""
     from oracle import ref_unet as R
-    torch.set_num_threads(threads)
     sd = R.init_state_dict(0, CFG["channel_img"], CFG["channel_multy"], CFG["channel_base"], CFG["num_class"])
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     opt = torch.optim.AdamW(list(params.values()), lr=CFG["lr"], weight_decay=CFG["weight_decay"])
@@ -117,6 +166,16 @@ def cpu_train_sample(n_img, steps, warmup, threads):
     return n_img / dt, dt
 
 
+def cpu_train_sample(n_img, steps, warmup, threads):
+    """(samples/s, s/step, kind): the reference path on the host cores, on a bounded sample of the workload."""
+    torch.set_num_threads(threads)
+    if _reference_modules() is not None:
+        v, dt = reference_train_sample(torch.device("cpu"), n_img, steps, warmup)
+        return v, dt, "reference"
+    v, dt = port_train_sample(n_img, steps, warmup)
+    return v, dt, "port"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -125,14 +184,16 @@ def run_reference(args):
     n_img = 8
     steps = max(1, min(args.steps, 5))
     warmup = 1 if args.warmup > 0 else 0
-    val, dt = cpu_train_sample(n_img, steps, warmup, threads)
+    val, dt, kind = cpu_train_sample(n_img, steps, warmup, threads)
+    what = ("the unmodified reference modules (oracle/_ref: diffusion.py + utils.py, step body of 02_train_direct.py:64-74)"
+            if kind == "reference" else "oracle port of the reference path")
     line = {
         "impl": "reference", "metric": "train_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "tiny UNet DDPM training step 3x64x64 (reference CPU path, oracle port), "
+        "config": {"workload": f"tiny UNet DDPM training step 3x64x64 on the host CPU, {what}, "
                                f"bounded sample: batch {n_img} per step", "global_batch": n_img, "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": kind,
                          "sample": f"{steps} training step(s) of batch {n_img} (fwd+bwd+clip+AdamW), torch CPU fp32"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -142,9 +203,13 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
+    import ctypes
+
     import torch.distributed as dist
     from from_ddpm_to_stable_diffusion_b200 import Diffusion, SamplerDDPM, TrainerDDPM, _lib
     from from_ddpm_to_stable_diffusion_b200.optim import FusedClipAdamW
+    from from_ddpm_to_stable_diffusion_b200.parallel import set_shard
+    from from_ddpm_to_stable_diffusion_b200.training import GraphedTrainStep, train_step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -154,25 +219,18 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    torch.manual_seed(0)
+    torch.manual_seed(0)  # same weights and same Philox seeds on every rank; the streams are offset by global sample index
     model = Diffusion(CFG["channel_img"], CFG["channel_multy"], CFG["channel_base"], num_class=CFG["num_class"],
                       dropout=CFG["dropout"]).to(dev).train()
     trainer = TrainerDDPM(model, CFG["beta_1"], CFG["beta_T"], CFG["T"]).to(dev)
     opt = FusedClipAdamW(model, lr=CFG["lr"], weight_decay=CFG["weight_decay"], max_norm=CFG["grad_clip"])
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(B, CFG["channel_img"], CFG["img"], CFG["img"], generator=g).pin_memory()
-    y_host = torch.randint(1, CFG["num_class"] + 1, (B,), generator=g).pin_memory()
+    y_host = torch.randint(0, CFG["num_class"], (B,), generator=g).pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
     global_b = B * world
-
-    def step(x, y):
-        opt.zero_grad()
-        loss = trainer(x, y).sum() / global_b ** 2  # reference normalisation with the GLOBAL batch (02_train_direct.py:70)
-        loss.backward()
-        if world > 1:
-            opt.all_reduce_grads()
-        opt.step()
-        return loss
+    overlap = bool(int(os.environ.get("TSD_DP_OVERLAP", "1")))
+    stepper = GraphedTrainStep(trainer, opt, train_rand=0.05, overlap=overlap)
 
     def barrier():
         if world > 1:
@@ -193,17 +251,17 @@ def run_ours(args):
         return ms.item()
 
     lib = _lib.lib()
-    lib.tsd_launch_count.restype = __import__("ctypes").c_ulonglong
-    for _ in range(args.warmup):
-        step(x_dev, y_dev)
+    lib.tsd_launch_count.restype = ctypes.c_ulonglong
+    for _ in range(max(args.warmup, 1)):
+        stepper(x_dev, y_dev)  # the first call captures the graphs
     clocks = ClockSampler(local)
     clocks.start()
-    n0 = lib.tsd_launch_count()
-    ms = timed(lambda: step(x_dev, y_dev), args.steps)
-    launches = lib.tsd_launch_count() - n0
+    ms = timed(lambda: stepper(x_dev, y_dev), args.steps)
     clk = clocks.stop()
+    launches = stepper.launches_per_step() * args.steps
     ms_per_step = ms / args.steps
     value = global_b / (ms_per_step / 1e3)
+    assert bool(torch.isfinite(stepper.loss)), "training loss is not finite"
 
     # end-to-end: pinned host inputs -> H2D every step, loss read back every step (02_train_direct.py:66-74)
     # The loss of step i is copied to pinned host memory right after the step and read by the host while step i+1
@@ -215,9 +273,7 @@ def run_ours(args):
 
     def e2e_step():
         i = e2e_state["i"]
-        x = x_host.to(dev, non_blocking=True)
-        y = y_host.to(dev, non_blocking=True)
-        loss = step(x, y)
+        loss = stepper(x_host, y_host)  # copies the pinned host batch into the graph's static buffers (H2D, async)
         loss_host[i & 1].copy_(loss.detach(), non_blocking=True)
         loss_evt[i & 1].record()
         if i > 0:
@@ -230,12 +286,18 @@ def run_ours(args):
     assert len(e2e_state["losses"]) == args.steps and all(v == v for v in e2e_state["losses"])
     e2e_val = global_b / (e2e_ms / 1e3)
 
-    # Per-kernel rooflines, measured live: one extra (untimed) step with a CUDA-event pair around every C-ABI call
+    # the same iteration issued eagerly from Python (one C-ABI call per kernel), for the launch-overhead comparison
+    set_shard(trainer, rank * B)
+    for _ in range(2):
+        train_step(trainer, opt, x_dev, y_dev, train_rand=0.05)
+    eager_ms = timed(lambda: train_step(trainer, opt, x_dev, y_dev, train_rand=0.05), 3) / 3
+
+    # Per-kernel rooflines, measured live: one extra (untimed) eager step with a CUDA-event pair around every C-ABI call
     # on the launching stream, aggregated per entry point and shape.
     hbm, tf, how = peaks()
     _lib.PROFILE = True
     _lib.profile_report()
-    step(x_dev, y_dev)
+    train_step(trainer, opt, x_dev, y_dev, train_rand=0.0)
     agg = _lib.profile_report()
     _lib.PROFILE = False
     tot_ms = sum(v[1] for v in agg.values())
@@ -274,39 +336,83 @@ def run_ours(args):
         extra.append({"kernel": "gn_apply_kernel C=128 @64x64 (GroupNorm+SiLU(+dropout))", "bound": "hbm",
                       "achieved": by * n2 / (t2 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                       "frac": by * n2 / (t2 * 1e-3) / 1e9 / hbm, "launches": n2})
-    n3, t3 = fam("tsd_adamw_clip")
+    n3, t3 = fam("tsd_adamw_clip_dev")
     if n3:
         by = 30945155 * 7 * 4.0
         extra.append({"kernel": "adamw_clip_kernel (clip + AdamW, 30.9 M params)", "bound": "hbm",
                       "achieved": by / (t3 * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": by / (t3 * 1e-3) / 1e9 / hbm,
                       "launches": n3})
     step_tf = TRAIN_GF_PER_SAMPLE * B / (ms_per_step / 1e3) / 1e3
+    del stepper
+    torch.cuda.empty_cache()
 
-    # sampling throughput (same model, eval mode): DDPM 64x64 images/s at T=1000, CFG w=1.8, 2 forwards per step
+    # sampling throughput (same model, eval mode): DDPM 64x64 images/s, CFG w=1.8, 2 forwards per step.  At N=1 the whole
+    # reverse process (T=1000 steps) is executed and timed; at N>1 a prefix of `--sample-steps-multi` steps is timed and
+    # scaled to T (every reverse step costs the same: same kernels, same shapes).
     sampling = None
-    if args.sample_steps > 0:
+    k = args.sample_steps if world == 1 else min(args.sample_steps, args.sample_steps_multi)
+    if k > 0:
         model.eval()
         Bs = args.sample_batch
         sampler = SamplerDDPM(model, CFG["beta_1"], CFG["beta_T"], CFG["T"], w=CFG["w"]).to(dev)
+        set_shard(sampler, rank * Bs)
         xT = torch.randn(Bs, CFG["channel_img"], CFG["img"], CFG["img"], device=dev)
         ys = torch.randint(1, CFG["num_class"] + 1, (Bs,), device=dev)
-        k = args.sample_steps
+        k = min(k, CFG["T"])
         sampler(xT, ys, steps=range(CFG["T"] - 1, CFG["T"] - 1 - 4, -1))  # capture + warm-up
-        s_ms = timed(lambda: sampler(xT, ys, steps=range(CFG["T"] - 1, CFG["T"] - 1 - k, -1)), 1) / k
-        sampling = {"images_per_s": Bs * world / (s_ms / 1e3 * CFG["T"]), "ms_per_reverse_step": s_ms,
-                    "batch_per_gpu": Bs, "T": CFG["T"], "w": CFG["w"], "timed_reverse_steps": k,
+        n0 = lib.tsd_launch_count()
+        out = []
+        s_ms = timed(lambda: out.append(sampler(xT, ys, steps=range(CFG["T"] - 1, CFG["T"] - 1 - k, -1))), 1)
+        assert bool(torch.isfinite(out[0]).all())
+        per = s_ms / k
+        sampling = {"metric": "ddpm_64x64_images_per_sec_T1000", "images_per_s": Bs * world / (per / 1e3 * CFG["T"]),
+                    "ms_per_reverse_step": per, "batch_per_gpu": Bs, "T": CFG["T"], "w": CFG["w"],
+                    "timed_reverse_steps": k, "full_reverse_process_timed": k == CFG["T"],
+                    "wall_s_timed": s_ms / 1e3,
                     # executed work: the label-independent prefix (11.57 GF: head conv, first ResBlock, first attention
                     # block up to its self-attention) runs once for the conditional / unconditional pair
                     "gflop_per_image_step_executed": 2 * FWD_GF_PER_SAMPLE - 11.57,
-                    "tflops": (2 * FWD_GF_PER_SAMPLE - 11.57) * Bs / (s_ms / 1e3) / 1e3}
+                    "tflops": (2 * FWD_GF_PER_SAMPLE - 11.57) * Bs / (per / 1e3) / 1e3}
+        del sampler, out
+        torch.cuda.empty_cache()
+        # BASELINE configs[4]: latent-space DDPM, 4x16x16 latents, batch 4096 (sharded over the ranks), num_class 10
+        if args.latent_steps > 0:
+            torch.manual_seed(1)
+            lm = Diffusion(4, CFG["channel_multy"], CFG["channel_base"], num_class=10, dropout=0.0).to(dev).eval()
+            ls = SamplerDDPM(lm, CFG["beta_1"], CFG["beta_T"], CFG["T"], w=CFG["w"]).to(dev)
+            Bl = 4096 // world
+            set_shard(ls, rank * Bl)
+            zT = torch.randn(Bl, 4, 16, 16, device=dev)
+            yl = torch.randint(1, 11, (Bl,), device=dev)
+            kl = args.latent_steps
+            ls(zT, yl, steps=range(CFG["T"] - 1, CFG["T"] - 1 - 4, -1))
+            l_ms = timed(lambda: ls(zT, yl, steps=range(CFG["T"] - 1, CFG["T"] - 1 - kl, -1)), 1) / kl
+            sampling["latent_4x16x16"] = {"images_per_s": 4096 / (l_ms / 1e3 * CFG["T"]), "ms_per_reverse_step": l_ms,
+                                          "global_batch": 4096, "timed_reverse_steps": kl,
+                                          "note": "BASELINE configs[4]; scaled from the timed prefix to T=1000"}
+            del ls, lm
+            torch.cuda.empty_cache()
         model.train()
 
-    cpu = None
+    cpu = gpu_eager = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if _reference_modules() is not None:
+            # context: the reference's own modules run eagerly on this GPU (the ATen/cuDNN/SDPA kernel set it would hit)
+            gpu_eager = {"batch": 32, "unit": "samples/s", "what": "unmodified reference modules (oracle/_ref), eager "
+                         "torch on this GPU, training step of batch 32 (fwd+bwd+clip+AdamW)"}
+            for name, ac in (("fp32_tf32conv", None), ("bf16_autocast", torch.bfloat16)):
+                try:
+                    v, _ = reference_train_sample(dev, 32, 5, 2, autocast=ac)
+                    gpu_eager[name] = v
+                except Exception as e:  # context only: never fails the benchmark
+                    gpu_eager[name] = f"failed: {type(e).__name__}: {e}"[:200]
+                torch.cuda.empty_cache()
         threads = os.cpu_count() or 1
-        v, dt = cpu_train_sample(8, 3, 1, threads)
-        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": "1 warm-up + 3 timed training steps of batch 8 (fwd+bwd+clip+AdamW), oracle port on torch CPU fp32, all host threads"}
+        v, dt, kind = cpu_train_sample(8, 3, 1, threads)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": kind,
+               "sample": "1 warm-up + 3 timed training steps of batch 8 (fwd+bwd+clip+AdamW), "
+                         + ("unmodified reference modules (oracle/_ref)" if kind == "reference" else "oracle port")
+                         + " on torch CPU fp32, all host threads"}
 
     if rank == 0:
         line = {
@@ -315,16 +421,21 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"tiny UNet DDPM training step bf16 3x64x64, batch {B} per GPU (BASELINE configs[1])",
                        "global_batch": global_b, "parallelism": f"dp{world}", "dropout": CFG["dropout"],
-                       "optimizer": "clip_grad_norm(1.0)+AdamW fused", "l2": "inputs larger than L2 (activations >> 126 MB)"},
+                       "optimizer": "clip_grad_norm(1.0)+AdamW fused", "l2": "inputs larger than L2 (activations >> 126 MB)",
+                       "issue": "whole iteration replayed as a CUDA graph"
+                                + ("" if world == 1 else (", bucketed NCCL all-reduce captured inside the backward"
+                                                          if overlap else ", NCCL all-reduce between two graphs"))},
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
+            "sampling": sampling,
+            "eager_issue_ms_per_step": eager_ms,
             "roofline": roof,
             "roofline_other_kernels": extra,
             "step_necessary_tflops": step_tf,
             "cpu_baseline": cpu,
-            "sampling": sampling,
+            "gpu_eager_baseline": gpu_eager,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -339,7 +450,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="training batch per GPU")
     ap.add_argument("--sample-batch", type=int, default=256, help="images per GPU for the sampling figure")
-    ap.add_argument("--sample-steps", type=int, default=8, help="timed reverse steps (0 = skip sampling figure)")
+    ap.add_argument("--sample-steps", type=int, default=1000, help="timed reverse steps at N=1 (0 = skip sampling figure)")
+    ap.add_argument("--sample-steps-multi", type=int, default=200, help="timed reverse steps when N>1")
+    ap.add_argument("--latent-steps", type=int, default=50, help="timed reverse steps of the latent config (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -96,6 +96,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// SHARED: the score products of a sub-tile are issued ONCE for all warpgroups (four UMMAs with N = 128 instead of
+// sixteen with N = 32: the in-order tensor pipe is paid per instruction, not per column), the warpgroups read their
+// 32-column slices of the shared S'^T / dP'^T regions and hand them back together.
+template <bool SHARED>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
@@ -143,7 +147,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     }
     for (int g = 0; g < NWG; ++g) {
       mbar_init(s_full(g), 1);
-      mbar_init(s_free(g), 128);
+      mbar_init(s_free(g), SHARED ? NWG * 128 : 128);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(pds_full(i), NWG * 128);
@@ -161,7 +165,71 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   // descriptors: the start-address field is (addr >> 4) in the low word, so a byte offset adds (offset >> 4)
   auto d32 = [&](uint32_t addr) { return umma_smem_desc_sw(addr, 0, 8 * ROWB, 6); };
 
-  if (warp >= W_S && warp < W_P) {
+  if (SHARED && warp >= W_S && warp < W_P) {
+    if (warp == W_S) {
+      // =========================================================== one issuer of S'^T / dP'^T for all warpgroups (+ TMA)
+      constexpr uint32_t idescS = umma_idesc_bf16(KT, QT, 0, 0);
+      const float* lse_h = lse2 + ((size_t)b * H + h) * L;
+      const float* delta_h = delta + ((size_t)b * H + h) * L;
+      auto load_q = [&](int j) {
+        const int s = j % NSTQ;
+        mbar_wait(q_empty(s), ((j / NSTQ) & 1) ^ 1);
+        const uint32_t st = sQ(s);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full(s), Q_TX);
+#pragma unroll
+          for (int i = 0; i < QT / 64; ++i) {
+            tma_load_2d(st + i * 64 * ROWB, &tmQKV, q_full(s), h * DH, row_base + j * QT + i * 64);
+            tma_load_2d(st + ST_DO + i * 64 * ROWB, &tmDO, q_full(s), h * DH, row_base + j * QT + i * 64);
+          }
+          bulk_load_1d(st + ST_LSE, lse_h + j * QT, QT * 4, q_full(s));
+          bulk_load_1d(st + ST_DELTA, delta_h + j * QT, QT * 4, q_full(s));
+        }
+        __syncwarp();
+      };
+      if (elect_one()) {
+        mbar_arrive_expect_tx(kv_full, 2 * KH * KT * ROWB);
+#pragma unroll
+        for (int i = 0; i < KH * KT / 64; ++i) {
+          tma_load_2d(sK + i * 64 * ROWB, &tmQKV, kv_full, C + h * DH, row_base + kb0 + i * 64);
+          tma_load_2d(sV + i * 64 * ROWB, &tmQKV, kv_full, 2 * C + h * DH, row_base + kb0 + i * 64);
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < NSTQ - 1 && j < nq; ++j) load_q(j);
+      const uint32_t tOnes = tmem_base + ONES_COL;
+      auto issue_S = [&](int t) {
+        const int j = t >> 1, kh = t & 1;
+        const uint64_t dq = d32(sQ(j % NSTQ));
+        const uint32_t tS = tmem_base + S_COL, tDP = tS + QT;
+        if (elect_one()) {
+          umma_bf16_ts(tS, tmem_base + KA_COL + kh * 8, dq, idescS, 0u);
+          umma_bf16_ts(tS, tOnes, dq + (uint64_t)(ST_LSET / 16), idescS, 1u);
+          umma_bf16_ts(tDP, tmem_base + KA_COL + 16 + kh * 8, dq + (uint64_t)(ST_DO / 16), idescS, 0u);
+          umma_bf16_ts(tDP, tOnes, dq + (uint64_t)(ST_DELT / 16), idescS, 1u);
+          umma_commit(s_full(0));
+        }
+        __syncwarp();
+      };
+      mbar_wait(ka_full, 0);
+      mbar_wait(q_full(0), 0);
+      mbar_wait(ld_full(0), 0);
+      tc_fence_after();
+      issue_S(0);
+      for (int t = 0; t + 1 < NT; ++t) {
+        const int j = t >> 1, kh = t & 1;
+        if (kh == 1) {
+          const int jn = j + 1;
+          mbar_wait(q_full(jn % NSTQ), (jn / NSTQ) & 1);
+          mbar_wait(ld_full(jn % NSTQ), (jn / NSTQ) & 1);
+        }
+        mbar_wait(s_free(0), t & 1);  // every warpgroup holds its slice of sub-tile t in registers
+        tc_fence_after();
+        issue_S(t + 1);
+        if (kh == 0 && j + NSTQ - 1 < nq) load_q(j + NSTQ - 1);
+      }
+    }
+  } else if (warp >= W_S && warp < W_P) {
     {
       // =========================================================== issuers of S'^T / dP'^T (the first one also feeds TMA)
       constexpr uint32_t idescS = umma_idesc_bf16(KT, CW, 0, 0);
@@ -309,7 +377,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     tc_fence_before();
     mbar_arrive(ka_full);
 
-    const uint32_t tS = lane_base + S_COL + g * 2 * CW, tDP = tS + CW;
+    const uint32_t tS = lane_base + S_COL + (SHARED ? g * CW : g * 2 * CW), tDP = SHARED ? tS + QT : tS + CW;
+    const int gs = SHARED ? 0 : g;  // whose score barriers this warpgroup uses
     const uint64_t c2 = pk2(scale_log2, scale_log2);
     // dS^T tile: 64-query chunk (g * CW) / 64, 16-byte unit ((g * CW) % 64) / 8 + ..., XOR-swizzled with the row
     const uint32_t ds_row = ((g * CW) >> 6) * (DS_BYTES / 2) + r * 128;
@@ -317,7 +386,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const uint32_t sw = static_cast<uint32_t>(r & 7);
     for (int t = 0; t < NT; ++t) {
       const int buf = t & 1;
-      mbar_wait(s_full(g), t & 1);
+      mbar_wait(s_full(gs), t & 1);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < CW / 16; ++cc) {
@@ -327,7 +396,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         tmem_ld_wait();
         if (cc == CW / 16 - 1) {
           tc_fence_before();
-          mbar_arrive(s_free(g));
+          mbar_arrive(s_free(gs));
         }
         uint32_t pP[8], pD[8];
 #pragma unroll
@@ -452,17 +521,25 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
   if (make_tmap_2d_sw(&tmDO, dout, 2, (uint64_t)B * L, (uint64_t)C, (uint64_t)C, DH, 64, ROWB)) return 1;
   static tsd::PerDeviceFlag configured;
   if (!configured.cur()) {
-    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     configured.cur() = true;
   }
-  static int stagger = -1;
+  static int stagger = -1, shared = -1;
   if (stagger < 0) {
     const char* e = getenv("TSD_ATTN_BWD_TC_STAGGER");
     stagger = e ? atoi(e) : 0;
+    e = getenv("TSD_ATTN_BWD_TC_SHARED");  // 1: score products issued once per sub-tile for all warpgroups (N = 128)
+    shared = e ? atoi(e) : 1;
   }
   const float scale = 1.f / sqrtf((float)DH);
-  attn_bwd_tc_kernel<<<dim3(L / (KH * KT), heads, B), BT_THREADS, BT_SMEM, st>>>(
-      tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, 1.4426950408889634f * scale, stagger);
+  const dim3 grid(L / (KH * KT), heads, B);
+  if (shared)
+    attn_bwd_tc_kernel<true><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale,
+                                                                 1.4426950408889634f * scale, stagger);
+  else
+    attn_bwd_tc_kernel<false><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale,
+                                                                  1.4426950408889634f * scale, stagger);
   TSD_LAUNCH_CHECK();
   return 0;
 }

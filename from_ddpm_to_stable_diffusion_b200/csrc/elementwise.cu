@@ -212,6 +212,59 @@ __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ src, float*
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// All weight packings of a step in ONE launch.  The UNet has ~140 GEMM weights; refreshing their bf16 copies one
+// tensor at a time costs ~140 launch latencies per optimiser step for 0.3 GB of traffic.  A descriptor per tensor
+// (built once on the host; the parameter and packed buffers do not move) turns it into a single grid-stride pass.
+// ------------------------------------------------------------------------------------------
+struct PackDesc {
+  const float* src;
+  void* dst;
+  long long begin;  // first flat output element of this tensor
+  int rows, cols;   // linear: [rows][cols]; conv: rows = co, cols = ci
+  int kind;         // TSD_PACK_*
+  int pad_;
+};
+__global__ void __launch_bounds__(256) pack_many_kernel(const PackDesc* __restrict__ table, int n_desc, long long total) {
+  extern __shared__ long long s_begin[];  // [n_desc + 1]
+  for (int i = threadIdx.x; i < n_desc; i += blockDim.x) s_begin[i] = table[i].begin;
+  if (threadIdx.x == 0) s_begin[n_desc] = total;
+  __syncthreads();
+  int d = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (!(i >= s_begin[d] && i < s_begin[d + 1])) {  // consecutive elements mostly stay in the same tensor
+      int lo = 0, hi = n_desc - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_begin[mid] <= i) lo = mid; else hi = mid - 1;
+      }
+      d = lo;
+    }
+    const PackDesc t = table[d];
+    const long long e = i - t.begin;
+    if (t.kind == TSD_PACK_LINEAR || t.kind == TSD_PACK_LINEAR_GEGLU) {
+      const int r = (int)(e / t.cols), c = (int)(e - (long long)r * t.cols);
+      int sr = r;
+      if (t.kind == TSD_PACK_LINEAR_GEGLU) {  // packed tile q (128 rows) = value rows [64q, 64q+64) then gate rows H + [64q, ..)
+        const int q = r >> 7, j = r & 127, H = t.rows >> 1;
+        sr = j < 64 ? q * 64 + j : H + q * 64 + (j - 64);
+      }
+      reinterpret_cast<bf16*>(t.dst)[e] = __float2bfloat16(t.src[(size_t)sr * t.cols + c]);
+    } else if (t.kind == TSD_PACK_CONV3X3) {  // OIHW -> [co][tap][ci]
+      const int ci = t.cols;
+      const int c = (int)(e % ci), tap = (int)((e / ci) % 9), o = (int)(e / ((long long)ci * 9));
+      reinterpret_cast<bf16*>(t.dst)[e] = __float2bfloat16(t.src[((size_t)o * ci + c) * 9 + tap]);
+    } else if (t.kind == TSD_PACK_CONV3X3_DGRAD) {  // OIHW -> [ci][8 - tap][co]
+      const int co = t.rows, ci = t.cols;
+      const int o = (int)(e % co), tap = (int)((e / co) % 9), c = (int)(e / ((long long)co * 9));
+      reinterpret_cast<bf16*>(t.dst)[e] = __float2bfloat16(t.src[((size_t)o * ci + c) * 9 + (8 - tap)]);
+    } else {  // TSD_PACK_GEGLU_BIAS: fp32 vector, same row permutation as the GEGLU weight
+      const int r = (int)e, q = r >> 7, j = r & 127, H = t.rows >> 1;
+      reinterpret_cast<float*>(t.dst)[e] = t.src[j < 64 ? q * 64 + j : H + q * 64 + (j - 64)];
+    }
+  }
+}
+
 inline int ew_grid(size_t work_items) {
   size_t g = (work_items + 255) / 256;
   const size_t cap = (size_t)num_sms() * 16;
@@ -300,6 +353,14 @@ extern "C" int tsd_unpack_conv3x3_grad(void* stream, const float* src, float* ds
 }
 extern "C" int tsd_pack_conv3x3_dgrad(void* stream, const float* src, void* dst, int co, int ci) {
   pack_conv3x3_dgrad_kernel<<<ew_grid((size_t)co * ci * 9), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, co, ci);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_pack_many(void* stream, const void* table_dev, int n_desc, int64_t total) {
+  TSD_CHECK(n_desc > 0 && n_desc <= 4096 && total > 0, "pack_many: n_desc=%d total=%lld", n_desc, (long long)total);
+  static_assert(sizeof(PackDesc) == 40, "PackDesc layout is part of the C ABI (host side builds the table)");
+  pack_many_kernel<<<ew_grid((size_t)total / 4), 256, (n_desc + 1) * sizeof(long long), (cudaStream_t)stream>>>(
+      reinterpret_cast<const PackDesc*>(table_dev), n_desc, (long long)total);
   TSD_LAUNCH_CHECK();
   return 0;
 }

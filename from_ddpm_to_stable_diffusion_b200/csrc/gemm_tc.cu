@@ -328,6 +328,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               f[q * 8 + 4] += c.x; f[q * 8 + 5] += c.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
             }
           }
+          if (p.act == ACT_LRELU) {  // nn.LeakyReLU() default slope 0.01
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.01f * f[j];
+          } else if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          } else if (p.act == ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);  // rel. err 2^-11, below the bf16 rounding of the result
+          }
           uint8_t* dst = staging + (ch >> 1) * (BM * 128) + ep_tid * 128;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

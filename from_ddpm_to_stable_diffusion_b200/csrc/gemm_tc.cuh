@@ -24,6 +24,7 @@ namespace tsd {
 enum : int { A_K2D = 0, A_KCONV = 1, A_MN2D = 2 };
 enum : int { B_K2D = 0, B_MN2D = 1, B_MNCONV = 2 };
 enum : int { EPI_NONE = 0, EPI_GEGLU = 1 };
+enum : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH = 3 };  // applied last: act(acc + bias + residual)
 
 struct GemmParams {
   int M, N;              // rows / cols of D (GEGLU: N counts the 2x-wide pre-activation columns)
@@ -50,8 +51,7 @@ struct GemmParams {
   int rows_per_sample;
   const bf16* residual;   // [M][ldr] or null
   int ldr;
-  float* gn_sums;         // null, or [M / rows_per_sample][32][2] (sum, sum of squares) to accumulate
-  int gn_cpg;             // channels per group when gn_sums != null
+  int act;                // ACT_*: pointwise activation on the finished value (codec convolutions, vqvae models.py:286-341)
 };
 
 // Host launcher (defined in gemm_tc.cu).  tm* are fully-built tensor maps.

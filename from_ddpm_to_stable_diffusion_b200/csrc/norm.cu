@@ -395,18 +395,30 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
   }
 }
 
-// dgamma[c] += sum_n A[n][c];  dbeta[c] += sum_n B[n][c]
-__global__ void gn_bwd_params_kernel(const float* __restrict__ ab, int n_img, int C, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// dgamma[c] += sum_n A[n][c];  dbeta[c] += sum_n B[n][c].  CTA = 32 channels x 8 image lanes (a single thread per
+// channel walking all images serially made this 30 us of pure load latency, 39 times per step).
+__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ ab, int n_img, int C,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int cx = threadIdx.x & 31, ny = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float a = 0.f, b = 0.f;
-  for (int n = 0; n < n_img; ++n) {
-    a += ab[((size_t)n * C + c) * 2];
-    b += ab[((size_t)n * C + c) * 2 + 1];
+  if (c < C) {
+    for (int n = ny; n < n_img; n += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(ab + ((size_t)n * C + c) * 2);
+      a += v.x;
+      b += v.y;
+    }
   }
-  dgamma[c] += a;
-  dbeta[c] += b;
+  __shared__ float sa[8][32], sb[8][32];
+  sa[ny][cx] = a;
+  sb[ny][cx] = b;
+  __syncthreads();
+  if (ny == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { a += sa[k][cx]; b += sb[k][cx]; }  // fixed order: reproducible
+    dgamma[c] += a;
+    dbeta[c] += b;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -622,7 +634,7 @@ extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const vo
                                                        (bf16*)dx0, (bf16*)dx1, rng_dev);
   TSD_LAUNCH_CHECK();
   if (dgamma) {
-    gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ab, n_img, C, dgamma, dbeta);
+    gn_bwd_params_kernel<<<ceil_div(C, 32), 256, 0, st>>>(ab, n_img, C, dgamma, dbeta);
     TSD_LAUNCH_CHECK();
   }
   return 0;

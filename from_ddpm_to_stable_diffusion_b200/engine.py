@@ -67,8 +67,7 @@ class UNetEngine:
     def __init__(self, model):
         # weak-ish back reference (the engine is owned by the model)
         object.__setattr__(self, "_model_ref", model)
-        self._packed = {}          # save flag -> packed weight dict (training and inference packings coexist)
-        self._packed_sig = {}
+        self._packs = {}           # 'train' / 'infer' / 'dgrad' -> packed bf16 weights + descriptor table (persistent)
         self._epoch = 0
         self._generation = 0       # bumped whenever a cached device buffer (packed weights, scratch) is REPLACED:
         self._scratch = None       # captured CUDA graphs that baked the old pointers must be dropped (sampling.py)
@@ -95,9 +94,7 @@ class UNetEngine:
         return self._model_ref
 
     def invalidate(self):
-        self._packed_sig = {}
-        self._packed = {}
-        self._dgrad_sig = None
+        self._packs = {}
         self._flat_grad = None
         self._grad_views = None
         self._scratch = None
@@ -127,54 +124,78 @@ class UNetEngine:
                 out.append((f"decoders.{i}.{j}", b))
         return out
 
-    def packed(self, P, save=False):
-        """bf16 GEMM-layout copies of the weights, refreshed when any parameter changed.  The C -> 8C linear of the
-        attention blocks is packed plain when the tape is saved (training: h8 is kept for the backward) and with
-        interleaved value / gate rows for the fused GEGLU epilogue otherwise -- never both."""
-        save = bool(save)
-        sig = self._signature(P)
-        if sig == self._packed_sig.get(save):
-            return self._packed[save]
-        W = {}
+    # ------------------------------------------------------------------ packed bf16 weights
+    def _pack_entries(self, P, which):
+        """[(name, source parameter, kind, rows, cols, dst shape, dst dtype)] of one packing set.
+        'train' / 'infer': forward GEMM weights (the C -> 8C linear of the attention blocks is packed plain when the
+        tape is saved -- h8 is kept for the backward -- and with interleaved value / gate rows plus a permuted bias for
+        the fused GEGLU epilogue otherwise); 'dgrad': data-gradient weights of the 3x3 convs ([ci][mirrored tap][co])."""
+        BF = torch.bfloat16
+        E = []
+
+        def lin(name, key, kind=ops.PACK_LINEAR):
+            w = P[key]
+            rows = w.shape[0]
+            E.append((name, w, kind, rows, w.numel() // rows, (rows, w.numel() // rows), BF))
+
+        def conv(name, key, kind):
+            w = P[key]
+            co, ci = w.shape[:2]
+            shape = (co, 9 * ci) if kind == ops.PACK_CONV3X3 else (ci, 9 * co)
+            E.append((name, w, kind, co, ci, shape, BF))
+
+        ck = ops.PACK_CONV3X3_DGRAD if which == "dgrad" else ops.PACK_CONV3X3
         for key, b in self._block_list():
             if b[0] == "conv":
                 if b[1] % 64 == 0:  # the head conv (3/4 input channels) runs on CUDA cores from fp32
-                    W[key] = ops.pack_conv3x3(P[key + ".weight"])
+                    conv(key, key + ".weight", ck)
             elif b[0] == "up":
-                W[key + ".conv"] = ops.pack_conv3x3(P[key + ".conv.weight"])
+                conv(key + ".conv", key + ".conv.weight", ck)
             elif b[0] == "res":
-                W[key + ".conv_1.2"] = ops.pack_conv3x3(P[key + ".conv_1.2.weight"])
-                W[key + ".conv_2.3"] = ops.pack_conv3x3(P[key + ".conv_2.3.weight"])
-                if b[1] != b[2]:
-                    W[key + ".residual_layer"] = ops.pack_linear(P[key + ".residual_layer.weight"])
-            else:
+                conv(key + ".conv_1.2", key + ".conv_1.2.weight", ck)
+                conv(key + ".conv_2.3", key + ".conv_2.3.weight", ck)
+                if b[1] != b[2] and which != "dgrad":
+                    lin(key + ".residual_layer", key + ".residual_layer.weight")
+            elif which != "dgrad":
                 for n in ("conv_1.1", "atten_1.1.in_proj", "atten_1.1.out_proj", "linear_2", "conv_output"):
-                    W[key + "." + n] = ops.pack_linear(P[f"{key}.{n}.weight"])
-                if save:
-                    W[key + ".linear_1"] = ops.pack_linear(P[key + ".linear_1.weight"])
+                    lin(key + "." + n, f"{key}.{n}.weight")
+                if which == "train":
+                    lin(key + ".linear_1", key + ".linear_1.weight")
                 else:
-                    W[key + ".linear_1.geglu"] = ops.pack_linear(P[key + ".linear_1.weight"], geglu=True)
-                    W[key + ".linear_1.geglu_bias"] = ops.pack_geglu_bias(P[key + ".linear_1.bias"])
-        self._packed[save], self._packed_sig[save] = W, sig
-        self._generation += 1
-        return W
+                    lin(key + ".linear_1.geglu", key + ".linear_1.weight", ops.PACK_LINEAR_GEGLU)
+                    b1 = P[key + ".linear_1.bias"]
+                    E.append((key + ".linear_1.geglu_bias", b1, ops.PACK_GEGLU_BIAS, b1.shape[0], 1, (b1.shape[0],), F32))
+        return E
+
+    def _pack_set(self, P, which):
+        """Packed copies of one set, refreshed by ONE kernel launch when any parameter changed.  The destination buffers
+        and the descriptor table are allocated once and never move (captured CUDA graphs keep using them)."""
+        st = self._packs.get(which)
+        sig = self._signature(P)
+        if st is not None and sig != st["sig"] and st["ptrs"] != tuple(w.data_ptr() for w in st["srcs"]):
+            st = None  # a parameter was re-homed behind our back: the descriptor table points at the old storage
+        if st is None:
+            E = self._pack_entries(P, which)
+            dev = E[0][1].device
+            W, rows, begin = {}, [], 0
+            for name, w, kind, r, c, shape, dt in E:
+                W[name] = torch.empty(shape, device=dev, dtype=dt)
+                rows.append((w.data_ptr(), W[name].data_ptr(), begin, r, c, kind))
+                begin += W[name].numel()
+            st = dict(W=W, table=ops.pack_table(rows, dev), n=len(rows), total=begin, sig=None,
+                      srcs=[w for _, w, *_ in E], ptrs=tuple(w.data_ptr() for _, w, *_ in E))
+            self._packs[which] = st
+            self._generation += 1
+        if sig != st["sig"]:
+            ops.pack_many(st["table"], st["n"], st["total"])
+            st["sig"] = sig
+        return st["W"]
+
+    def packed(self, P, save=False):
+        return self._pack_set(P, "train" if save else "infer")
 
     def packed_dgrad(self, P):
-        """bf16 data-gradient weights of the 3x3 convs ([ci][mirrored tap][co]); training only."""
-        sig = self._signature(P)
-        if sig == getattr(self, "_dgrad_sig", None):
-            return self._dgrad
-        D = {}
-        for key, b in self._block_list():
-            if b[0] == "conv" and b[1] % 64 == 0:
-                D[key] = ops.pack_conv3x3_dgrad(P[key + ".weight"])
-            elif b[0] == "up":
-                D[key + ".conv"] = ops.pack_conv3x3_dgrad(P[key + ".conv.weight"])
-            elif b[0] == "res":
-                D[key + ".conv_1.2"] = ops.pack_conv3x3_dgrad(P[key + ".conv_1.2.weight"])
-                D[key + ".conv_2.3"] = ops.pack_conv3x3_dgrad(P[key + ".conv_2.3.weight"])
-        self._dgrad, self._dgrad_sig = D, sig
-        return D
+        return self._pack_set(P, "dgrad")
 
     def _get_scratch(self, n_img, dev):
         if self._scratch is None or self._scratch_imgs < n_img or self._scratch.device != dev:

@@ -315,6 +315,25 @@ def gather_row(table, step_ptr, out):
 
 
 # ------------------------------------------------------------------ weight packing / optimiser
+PACK_LINEAR, PACK_LINEAR_GEGLU, PACK_CONV3X3, PACK_CONV3X3_DGRAD, PACK_GEGLU_BIAS = range(5)  # TSD_PACK_* in the header
+
+
+def pack_table(rows, device):
+    """Device copy of the tsd_pack_many descriptor table; rows = [(src_ptr, dst_ptr, begin, rows, cols, kind)]."""
+    import numpy as np
+    dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("begin", "<i8"), ("rows", "<i4"), ("cols", "<i4"), ("kind", "<i4"),
+                   ("pad", "<i4")])
+    assert dt.itemsize == 40
+    arr = np.zeros(len(rows), dtype=dt)
+    for i, (s, d, b, r, c, k) in enumerate(rows):
+        arr[i] = (s, d, b, r, c, k, 0)
+    return torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+
+
+def pack_many(table, n_desc, total):
+    call("tsd_pack_many", table, int(n_desc), i64(total))
+
+
 def pack_linear(w, geglu=False):
     rows = w.shape[0]
     cols = w.numel() // rows

@@ -191,6 +191,15 @@ def train_step(trainer, optimizer, images, labels, train_rand=0.0, grad_clip=Non
     return loss
 
 
+def _launch_count():
+    import ctypes
+
+    from . import _lib
+    fn = _lib.lib().tsd_launch_count
+    fn.restype = ctypes.c_ulonglong
+    return int(fn())
+
+
 class GraphedTrainStep:
     """The whole training iteration of 02_train_direct.py:64-74 as replayed CUDA graphs.
 
@@ -219,6 +228,10 @@ class GraphedTrainStep:
 
     # -------------------------------------------------------------- pieces of one iteration
     def _fwd_bwd(self):
+        if torch.cuda.is_current_stream_capturing():
+            # the optimiser inside the graph changes the parameters on every replay: the refresh of the packed bf16
+            # weights must be part of the captured work, whatever the host-side change tracking believes right now
+            self.trainer.model._engine.bump()
         labels = (self._y + 1) * self._keep
         loss = self.trainer(self._x, labels).sum() * self._scale
         loss.backward()
@@ -269,11 +282,15 @@ class GraphedTrainStep:
         pool = None
         graphs = {}
 
+        self.launches = {}  # kernels of this library per replay of each graph (for bench.py's gpu_launches)
+
         def capture(name, fn):
             nonlocal pool
             g = torch.cuda.CUDAGraph()
+            n0 = _launch_count()
             with torch.cuda.graph(g, pool=pool, capture_error_mode=mode):
                 fn()
+            self.launches[name] = _launch_count() - n0
             pool = g.pool()
             graphs[name] = g
 
@@ -288,6 +305,14 @@ class GraphedTrainStep:
             capture("opt", self.opt.step)
         self._graphs = graphs
         self._exchange_in_graph = exchange_in_graph
+
+    def launches_per_step(self):
+        """Library kernels executed by one call (replayed graph nodes; torch glue and NCCL not counted)."""
+        L = self.launches
+        if "full" in L:
+            return L["full"]
+        fb_last = L["fb_last"] if self._exchange_in_graph else L["fb"]
+        return (self.micro - 1) * L.get("fb", 0) + fb_last + L["opt"]
 
     # -------------------------------------------------------------- the call
     def __call__(self, images, labels):

@@ -201,6 +201,16 @@ int tsd_gather_row_f32(void* stream, const float* table, const int* step_ptr, in
 /* ------------------------------------------------------------------------------------------
  * Weight packing and the caller-side optimiser step (02_train_direct.py:72-73).
  * ------------------------------------------------------------------------------------------ */
+/* Every weight packing of a step in one launch.  table_dev: DEVICE array of n_desc records
+ *   struct { const float* src; void* dst; int64_t begin; int32_t rows, cols, kind, pad; }   (40 bytes)
+ * sorted by `begin` (first flat output element of the tensor; total = sum of all element counts).  kind selects the
+ * layouts of the single-tensor entry points below; conv tensors pass rows = co, cols = ci. */
+#define TSD_PACK_LINEAR 0
+#define TSD_PACK_LINEAR_GEGLU 1
+#define TSD_PACK_CONV3X3 2
+#define TSD_PACK_CONV3X3_DGRAD 3
+#define TSD_PACK_GEGLU_BIAS 4
+int tsd_pack_many(void* stream, const void* table_dev, int n_desc, int64_t total);
 int tsd_pack_linear(void* stream, const float* src, void* dst, int rows, int cols, int geglu);
 int tsd_pack_geglu_bias(void* stream, const float* src, float* dst, int rows);
 int tsd_pack_conv3x3(void* stream, const float* src, void* dst, int co, int ci);          /* OIHW -> [co][tap][ci] */
