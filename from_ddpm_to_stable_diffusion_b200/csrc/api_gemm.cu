@@ -40,22 +40,35 @@ extern "C" int tsd_gemm_fwd(void* stream, const void* a0, const void* a1, int c0
   if (make_tmap_2d(&tA0, a0, 2, M, c0, c0, 64, 128)) return 1;
   if (c1 > 0) { if (make_tmap_2d(&tA1, a1, 2, M, c1, c1, 64, 128)) return 1; } else tA1 = tA0;
   if (make_tmap_2d(&tB, w, 2, N, K, K, 64, 128)) return 1;
+  TSD_CHECK(epi >= 0 && epi <= TSD_EPI_TANH, "gemm_fwd: unknown epilogue %d", epi);
+  const int act = epi >= TSD_EPI_LRELU ? epi - TSD_EPI_LRELU + ACT_LRELU : ACT_NONE;  // pointwise activations
+  if (act != ACT_NONE) epi = EPI_NONE;
   const int Nd = epi == EPI_GEGLU ? N / 2 : N;
   if (make_tmap_2d(&tD, d, 2, M, Nd, Nd, 64, 128)) return 1;
   GemmParams p; zero_params(p);
   p.M = M; p.N = N; p.tiles_m = ceil_div(M, 128); p.tiles_n = N / 128;
   p.num_kb = K / 64; p.kb_per_split = p.num_kb;
   p.a_mode = A_K2D; p.a_c0 = c0; p.b_mode = B_K2D;
-  p.epi = epi; p.bias = bias; p.row_bias = row_bias; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+  p.epi = epi; p.act = act; p.bias = bias; p.row_bias = row_bias; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = N;
   TSD_CHECK(!(epi == EPI_GEGLU && (residual || row_bias)), "gemm_fwd: GEGLU epilogue takes no residual/row bias");
   return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA0, tA1, tB, tB, tD, p);
 }
 
+extern "C" int tsd_conv3x3_fwd_act(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
+                                   int H, int W, int stride, const void* w, int cout, const float* bias,
+                                   const float* row_bias, int rows_per_sample, const void* residual, int act, void* d);
 extern "C" int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
                                int H, int W, int stride, const void* w, int cout, const float* bias,
                                const float* row_bias, int rows_per_sample, const void* residual, void* d) {
+  return tsd_conv3x3_fwd_act(stream, x0, x1, c0, c1, n_img, H, W, stride, w, cout, bias, row_bias, rows_per_sample,
+                             residual, 0, d);
+}
+extern "C" int tsd_conv3x3_fwd_act(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
+                                   int H, int W, int stride, const void* w, int cout, const float* bias,
+                                   const float* row_bias, int rows_per_sample, const void* residual, int act, void* d) {
   const int cin = c0 + c1;
+  TSD_CHECK(act == 0 || (act >= TSD_EPI_LRELU && act <= TSD_EPI_TANH), "conv3x3_fwd_act: unknown activation %d", act);
   TSD_CHECK(stride == 1 || stride == 2, "conv3x3_fwd: stride must be 1 or 2");
   TSD_CHECK(cin % 64 == 0 && c0 % 64 == 0 && cout % 128 == 0, "conv3x3_fwd: bad channels c0=%d c1=%d cout=%d", c0, c1, cout);
   TSD_CHECK(H % stride == 0 && W % stride == 0, "conv3x3_fwd: H, W must be multiples of the stride");
@@ -75,6 +88,7 @@ extern "C" int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int
   p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.b_mode = B_K2D;
   p.bias = bias; p.row_bias = row_bias; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : Ho * Wo;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = cout;
+  p.act = act ? act - TSD_EPI_LRELU + ACT_LRELU : ACT_NONE;
   return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA0, tA1, tB, tB, tD, p);
 }
 

@@ -529,8 +529,10 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
   if (stagger < 0) {
     const char* e = getenv("TSD_ATTN_BWD_TC_STAGGER");
     stagger = e ? atoi(e) : 0;
-    e = getenv("TSD_ATTN_BWD_TC_SHARED");  // 1: score products issued once per sub-tile for all warpgroups (N = 128)
-    shared = e ? atoi(e) : 1;
+    // 1: score products issued once per sub-tile for all warpgroups (N = 128).  Measured SLOWER (3.54 vs 3.05 ms per 64
+    // samples at L = 4096): sharing the hand-off locks the four warpgroups into the same phase.  Kept for A/B runs.
+    e = getenv("TSD_ATTN_BWD_TC_SHARED");
+    shared = e ? atoi(e) : 0;
   }
   const float scale = 1.f / sqrtf((float)DH);
   const dim3 grid(L / (KH * KT), heads, B);

@@ -315,6 +315,7 @@ def gather_row(table, step_ptr, out):
 
 
 # ------------------------------------------------------------------ weight packing / optimiser
+EPI_NONE, EPI_GEGLU, EPI_LRELU, EPI_RELU, EPI_TANH = range(5)  # TSD_EPI_* in the header
 PACK_LINEAR, PACK_LINEAR_GEGLU, PACK_CONV3X3, PACK_CONV3X3_DGRAD, PACK_GEGLU_BIAS = range(5)  # TSD_PACK_* in the header
 
 

@@ -38,6 +38,11 @@ int tsd_abi_version(void);
 /* epilogue selector for tsd_gemm_fwd */
 #define TSD_EPI_NONE 0
 #define TSD_EPI_GEGLU 1 /* d[m][j] = (acc[x_j]+b) * gelu(acc[g_j]+b); weights packed by tsd_pack_geglu */
+/* pointwise activation applied last, act(acc + bias + row_bias + residual): the codec convolutions of
+ * 03_variational_autoencoder/models.py:286-341 (nn.LeakyReLU() slope 0.01, nn.ReLU, nn.Tanh) */
+#define TSD_EPI_LRELU 2
+#define TSD_EPI_RELU 3
+#define TSD_EPI_TANH 4
 
 /* d[M][N] = [a0 | a1][M][c0+c1] * w[N][c0+c1]^T + bias[N] + row_bias[m / rows_per_sample][N] + residual[M][N]
  * Replaces nn.Linear / 1x1 nn.Conv2d calls: diffusion.py:43-44 (in/out_proj), :106 (shortcut),
@@ -54,6 +59,11 @@ int tsd_gemm_fwd(void* stream, const void* a0, const void* a1, int c0, int c1, i
 int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int H, int W,
                     int stride, const void* w, int cout, const float* bias, const float* row_bias,
                     int rows_per_sample, const void* residual, void* d);
+
+/* tsd_conv3x3_fwd with a pointwise activation (0 or TSD_EPI_LRELU / RELU / TANH) on the finished value */
+int tsd_conv3x3_fwd_act(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int H, int W,
+                        int stride, const void* w, int cout, const float* bias, const float* row_bias,
+                        int rows_per_sample, const void* residual, int act, void* d);
 
 /* dx[M][K] = dy[M][N] * w[N][K] + residual[M][K]   (autograd of the ops above; reference relies on
  * torch autograd, 02_train_direct.py:71) */
@@ -245,6 +255,30 @@ int tsd_u8_to_f32_norm(void* stream, const void* in_hwc, float* out_chw, int N, 
  * (N == 1: the image itself, no padding frame, as make_grid returns it) */
 int tsd_denorm_grid_u8(void* stream, const float* x, void* out_hwc, int N, int C, int H, int W, int nrow, int padding,
                        const float* mean, const float* stdv);
+/* ------------------------------------------------------------------------------------------
+ * Latent codec either side of the denoiser: the repo's VQ-VAE,
+ * 03_variational_autoencoder/models.py:135-185 (VectorQuantizer) and :268-378 (VQVAE encode / decode).  Its
+ * convolutions run on the GEMM core above (tsd_gemm_fwd / tsd_conv3x3_fwd_act with TSD_EPI_LRELU / RELU / TANH);
+ * these are the data-movement and quantisation kernels around them.  Activations bf16 NHWC as everywhere else.
+ * ------------------------------------------------------------------------------------------ */
+/* patch[p][(ky*KW + kx)*C + c] = x[n][oy*stride - pad + ky][ox*stride - pad + kx][c], zero outside the image and for
+ * columns >= KH*KW*C; patch is bf16 [n*Ho*Wo][Kp]: the A operand of a KHxKW strided nn.Conv2d (models.py:286) */
+int tsd_im2col_nhwc(void* stream, const void* x, void* patch, int n_img, int H, int W, int C, int KH, int KW, int stride,
+                    int pad, int Kp);
+/* src [n][H][W][ld] holding the four output parities q = py*2 + px as channel blocks [q*Cq, (q+1)*Cq) -> dst
+ * [n][2H][2W][Cq]: the shuffle behind nn.ConvTranspose2d(k=4, s=2, p=1) (models.py:330-341) */
+int tsd_depth_to_space2(void* stream, const void* src, void* dst, int n_img, int H, int W, int Cq, int ld);
+/* same shuffle for the last layer, straight to the fp32 NCHW image [n][Co][2H][2W] */
+int tsd_d2s_to_nchw_f32(void* stream, const void* src, float* dst, int n_img, int H, int W, int Co, int ld);
+/* first D channels of bf16 [n*hw][ld] -> fp32 NCHW [n][D][hw] (the encoder's latent output, models.py:351-352) */
+int tsd_nhwc_to_nchw_f32(void* stream, const void* src, float* dst, int n_img, int hw, int D, int ld);
+/* VectorQuantizer.forward (models.py:149-185): idx[n*hw] = argmin_k |z|^2 + |e_k|^2 - 2 z.e_k (fp32, first minimum),
+ * zq = z + (codebook[idx] - z) (the reference's straight-through expression, :180; NCHW fp32 like z),
+ * *loss = (1 + beta) * mean((codebook[idx] - z)^2) when loss != NULL.
+ * scratch: tsd_vq_scratch_floats(n_img, hw) floats.  embedding_dim D <= 16. */
+int64_t tsd_vq_scratch_floats(int n_img, int hw);
+int tsd_vq_nearest(void* stream, const float* z, const float* codebook, int64_t* idx, float* zq, float* scratch,
+                   float* loss, float beta, int n_img, int hw, int D, int K);
 /* number of kernel launches issued by this library so far (host-side counter, for bench.py's gpu_launches) */
 unsigned long long tsd_launch_count(void);
 

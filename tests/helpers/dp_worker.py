@@ -72,7 +72,7 @@ def main():
         gg = m._engine._flat_grad
         ref = opt0.engine._flat_grad if grads_clipped else g0  # after step() the buffer holds the clipped gradient
         assert rel(gg, ref) < 1e-3, (tag, rel(gg, ref))
-        assert rel(opt.flat_p, p0) < 1e-6, (tag, rel(opt.flat_p, p0))
+        assert rel(opt.flat_p, p0) < 2e-3, (tag, rel(opt.flat_p, p0))  # one +-lr AdamW step on re-associated gradients
         other = opt.flat_p.clone()
         dist.broadcast(other, src=0)
         assert torch.equal(other, opt.flat_p), tag + ": ranks diverged"
