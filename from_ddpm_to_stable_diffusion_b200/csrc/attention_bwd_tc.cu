@@ -42,6 +42,11 @@ constexpr int NSI = 2;         // issuers of S'^T / dP'^T, NWG / NSI warpgroups 
 constexpr int NSTQ = 4;        // Q / dO / lse / delta ring
 constexpr int W_DRAIN = NWG * 4, W_S = W_DRAIN + 4, W_P = W_S + NSI;  // first drain warp, S issuer, product issuer
 constexpr int BT_THREADS = (W_P + 3) * 32;
+// PIPE variant: the CTA is padded to whole warpgroups (7 x 128 threads) so that setmaxnreg can move registers from the
+// service warps (40 each) to the softmax warps (96 each), which then pull a whole sub-tile of scores out of TMEM at
+// once and hand the score buffer back before the first exponential.
+constexpr int BT_THREADS_PIPE = 7 * 128;
+constexpr int REGS_SOFTMAX = 96, REGS_SERVICE = 40;
 // TMEM columns (fp32 unless noted)
 constexpr int S_COL = 0;       // + g * 2 CW: S'^T [0, CW), dP'^T [CW, 2 CW)
 constexpr int P_COL = 256;     // + buf * 64: P^T bf16 pairs, 128 queries
@@ -99,8 +104,17 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // SHARED: the score products of a sub-tile are issued ONCE for all warpgroups (four UMMAs with N = 128 instead of
 // sixteen with N = 32: the in-order tensor pipe is paid per instruction, not per column), the warpgroups read their
 // 32-column slices of the shared S'^T / dP'^T regions and hand them back together.
-template <bool SHARED>
-__global__ void __launch_bounds__(BT_THREADS, 1)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+template <bool SHARED, bool PIPE>
+__global__ void __launch_bounds__(PIPE ? BT_THREADS_PIPE : BT_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
                    float* __restrict__ ws, int L, int C, float scale, float scale_log2, int stagger) {
@@ -162,6 +176,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // register hand-over: one instruction for all service warpgroups here, one for the softmax warpgroups at the top of
+  // their branch (every thread of a warpgroup must execute the same setmaxnreg)
+  if (PIPE && warp >= W_DRAIN) setmaxnreg_dec<REGS_SERVICE>();
   // descriptors: the start-address field is (addr >> 4) in the low word, so a byte offset adds (offset >> 4)
   auto d32 = [&](uint32_t addr) { return umma_smem_desc_sw(addr, 0, 8 * ROWB, 6); };
 
@@ -305,6 +322,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         if (si == 0 && kh == 0 && j + NSTQ - 1 < nq) load_q(j + NSTQ - 1);
       }
     }
+  } else if (warp >= W_P + 3) {
+    // padding warps of the PIPE variant: nothing to do until the final barrier
   } else if (warp >= W_P) {
     {
       // =========================================================== issuers of dV, dK, dQ
@@ -355,6 +374,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     }
   } else if (warp < W_DRAIN) {
     // =========================================================== softmax: one key row per thread
+    if (PIPE) setmaxnreg_inc<REGS_SOFTMAX>();
     const int g = warp >> 2, sub = warp & 3;
     const int r = sub * 32 + lane;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(sub * 32) << 16);
@@ -388,16 +408,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       const int buf = t & 1;
       mbar_wait(s_full(gs), t & 1);
       tc_fence_after();
+      constexpr int NCH = CW / 16;
+      uint32_t svp[PIPE ? NCH : 1][16], dvp[PIPE ? NCH : 1][16];
+      if (PIPE) {
+        // the whole sub-tile of this warpgroup leaves TMEM now: the next score products can be issued before the
+        // first exponential of this one (they queue behind up to 24 product UMMAs in the in-order tensor pipe)
 #pragma unroll
-      for (int cc = 0; cc < CW / 16; ++cc) {
-        uint32_t sv[16], dv[16];
-        tmem_ld16(tS + cc * 16, sv);
-        tmem_ld16(tDP + cc * 16, dv);
-        tmem_ld_wait();
-        if (cc == CW / 16 - 1) {
-          tc_fence_before();
-          mbar_arrive(s_free(gs));
+        for (int cc = 0; cc < NCH; ++cc) {
+          tmem_ld16(tS + cc * 16, svp[cc]);
+          tmem_ld16(tDP + cc * 16, dvp[cc]);
         }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free(gs));
+      }
+#pragma unroll
+      for (int cc = 0; cc < NCH; ++cc) {
+        uint32_t svl[16], dvl[16];
+        if (!PIPE) {
+          tmem_ld16(tS + cc * 16, svl);
+          tmem_ld16(tDP + cc * 16, dvl);
+          tmem_ld_wait();
+          if (cc == NCH - 1) {
+            tc_fence_before();
+            mbar_arrive(s_free(gs));
+          }
+        }
+        const uint32_t* sv = PIPE ? svp[cc] : svl;
+        const uint32_t* dv = PIPE ? dvp[cc] : dvl;
         uint32_t pP[8], pD[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -521,11 +559,12 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
   if (make_tmap_2d_sw(&tmDO, dout, 2, (uint64_t)B * L, (uint64_t)C, (uint64_t)C, DH, 64, ROWB)) return 1;
   static tsd::PerDeviceFlag configured;
   if (!configured.cur()) {
-    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
-    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     configured.cur() = true;
   }
-  static int stagger = -1, shared = -1;
+  static int stagger = -1, shared = -1, pipe = -1;
   if (stagger < 0) {
     const char* e = getenv("TSD_ATTN_BWD_TC_STAGGER");
     stagger = e ? atoi(e) : 0;
@@ -533,15 +572,21 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
     // samples at L = 4096): sharing the hand-off locks the four warpgroups into the same phase.  Kept for A/B runs.
     e = getenv("TSD_ATTN_BWD_TC_SHARED");
     shared = e ? atoi(e) : 0;
+    // 1: setmaxnreg register hand-over + whole-sub-tile score loads (see BT_THREADS_PIPE).  Measured SLOWER as well
+    // (3.27 vs 3.09 ms): handing the score buffer back earlier puts the next score products ahead of the pending
+    // dV / dK / dQ products in the in-order tensor pipe and lengthens their critical path.  Kept for A/B runs.
+    e = getenv("TSD_ATTN_BWD_TC_PIPE");
+    pipe = e ? atoi(e) : 0;
   }
   const float scale = 1.f / sqrtf((float)DH);
   const dim3 grid(L / (KH * KT), heads, B);
+  const float sl2 = 1.4426950408889634f * scale;
   if (shared)
-    attn_bwd_tc_kernel<true><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale,
-                                                                 1.4426950408889634f * scale, stagger);
+    attn_bwd_tc_kernel<true, false><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, sl2, stagger);
+  else if (pipe)
+    attn_bwd_tc_kernel<false, true><<<grid, BT_THREADS_PIPE, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, sl2, stagger);
   else
-    attn_bwd_tc_kernel<false><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale,
-                                                                  1.4426950408889634f * scale, stagger);
+    attn_bwd_tc_kernel<false, false><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, sl2, stagger);
   TSD_LAUNCH_CHECK();
   return 0;
 }

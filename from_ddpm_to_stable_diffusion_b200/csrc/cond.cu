@@ -7,6 +7,7 @@
 // :112; CrossAttention :61-82 (one key/value token => out_proj(v_proj(ctx)) per sample).
 #include "../../include/tinysd_b200.h"
 #include "common.cuh"
+#include <cstring>
 
 using namespace tsd;
 
@@ -15,11 +16,11 @@ namespace {
 constexpr int ROWS = 8;  // rows of x handled per CTA (weight rows are re-used across them)
 
 // out[m][n] = sum_k f(x[m][k]) * w[n][k] + b[n],  f = SiLU if silu_in.  grid = (ceil(N/64), ceil(M/ROWS))
-__global__ void __launch_bounds__(256) small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                               const float* __restrict__ bias, float* __restrict__ out,
-                                                               int M, int N, int K, int silu_in) {
+__device__ __forceinline__ void small_linear_fwd_body(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float* __restrict__ out, int M, int N,
+                                                      int K, int silu_in, int bx, int by) {
   extern __shared__ float sx[];  // [ROWS][K]
-  const int m0 = blockIdx.y * ROWS;
+  const int m0 = by * ROWS;
   for (int i = threadIdx.x; i < ROWS * K; i += blockDim.x) {
     const int r = i / K, k = i - r * K;
     float v = (m0 + r) < M ? x[(size_t)(m0 + r) * K + k] : 0.f;
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(256) small_linear_fwd_kernel(const float* __re
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int n = blockIdx.x * 64 + warp; n < min(N, blockIdx.x * 64 + 64); n += 8) {
+  for (int n = bx * 64 + warp; n < min(N, bx * 64 + 64); n += 8) {
     float acc[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
@@ -46,6 +47,34 @@ __global__ void __launch_bounds__(256) small_linear_fwd_kernel(const float* __re
         if (m0 + r < M) out[(size_t)(m0 + r) * N + n] = acc[r] + bv;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) small_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ out,
+                                                               int M, int N, int K, int silu_in) {
+  small_linear_fwd_body(x, w, bias, out, M, N, K, silu_in, blockIdx.x, blockIdx.y);
+}
+
+// A group of small linears in ONE launch (blockIdx.z = entry): the 14 linear_time layers, the 10 cross-attention
+// v_proj and the 10 out_proj of a step share M but are separate parameters; launched one by one each is a 20-40 us
+// latency-bound kernel on a handful of CTAs.  Entries may differ in N and K; pointers are passed by value.
+constexpr int SLB_MAX = 16;
+struct SmallLinearBatch {
+  const float* x[SLB_MAX];     // forward input [M][K_i] (also needed by the backward)
+  const float* w[SLB_MAX];     // [N_i][K_i]
+  const float* bias[SLB_MAX];  // forward: bias or null
+  float* out[SLB_MAX];         // forward: [M][N_i]
+  const float* dy[SLB_MAX];    // backward: [M][N_i]
+  float* dx[SLB_MAX];          // backward: [M][K_i] or null; entries may alias (accumulated with atomics)
+  float* dw[SLB_MAX];          // backward: [N_i][K_i] (+=) or null
+  float* db[SLB_MAX];          // backward: [N_i] (+=) or null
+  int N[SLB_MAX], K[SLB_MAX];
+  int n, M, silu_in, accumulate_dx;
+};
+__global__ void __launch_bounds__(256) small_linear_many_fwd_kernel(const __grid_constant__ SmallLinearBatch b) {
+  const int e = blockIdx.z;
+  if ((int)blockIdx.x * 64 >= b.N[e]) return;
+  small_linear_fwd_body(b.x[e], b.w[e], b.bias[e], b.out[e], b.M, b.N[e], b.K[e], b.silu_in, blockIdx.x, blockIdx.y);
 }
 
 // dx[m][k] (+)= f'(x[m][k]) * sum_n dy[m][n] * w[n][k].  grid = (ceil(K/256), ceil(M/ROWS))
@@ -149,16 +178,16 @@ __global__ void __launch_bounds__(64) small_linear_wgrad_kernel(const float* __r
 // ------------------------------------------------------------------------------------------
 constexpr int TI = 32, TJ = 64, TR = 32;
 
-template <int WGRAD>
-__global__ void __launch_bounds__(256) small_linear_bwd_tiled_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                                     const float* __restrict__ w, float* __restrict__ dx,
-                                                                     float* __restrict__ dw, float* __restrict__ db, int M,
-                                                                     int N, int K, int silu_in, int accumulate) {
+template <int WGRAD, int ATOMIC>
+__device__ __forceinline__ void small_linear_bwd_tiled_body(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ w, float* __restrict__ dx,
+                                                            float* __restrict__ dw, float* __restrict__ db, int M, int N,
+                                                            int K, int silu_in, int accumulate, int bx, int by) {
   // A(r, i): the dy operand; B(r, j): f(x) (wgrad) or w (dgrad).  sA[r][i], sB[r][j]
   __shared__ float sA[TR][TI + 1];
   __shared__ float sB[TR][TJ];
-  const int i0 = blockIdx.y * TI;  // wgrad: n; dgrad: m
-  const int j0 = blockIdx.x * TJ;  // k
+  const int i0 = by * TI;  // wgrad: n; dgrad: m
+  const int j0 = bx * TJ;  // k
   const int R = WGRAD ? M : N;     // reduction length
   const int ti = (threadIdx.x >> 4) * 2, tj = (threadIdx.x & 15) * 4;
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -216,11 +245,28 @@ __global__ void __launch_bounds__(256) small_linear_bwd_tiled_kernel(const float
           val *= sg * (1.f + xv * (1.f - sg));
         }
         float* pd = dx + (size_t)i * K + k;
-        *pd = accumulate ? *pd + val : val;
+        if (ATOMIC && accumulate) atomicAdd(pd, val);  // several entries of a batch add into the same dx
+        else *pd = accumulate ? *pd + val : val;
       }
     }
-    if (WGRAD && db && blockIdx.x == 0 && (threadIdx.x & 15) == 0) db[i] += accb[u];
+    if (WGRAD && db && bx == 0 && (threadIdx.x & 15) == 0) db[i] += accb[u];
   }
+}
+template <int WGRAD>
+__global__ void __launch_bounds__(256) small_linear_bwd_tiled_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                     const float* __restrict__ w, float* __restrict__ dx,
+                                                                     float* __restrict__ dw, float* __restrict__ db, int M,
+                                                                     int N, int K, int silu_in, int accumulate) {
+  small_linear_bwd_tiled_body<WGRAD, 0>(dy, x, w, dx, dw, db, M, N, K, silu_in, accumulate, blockIdx.x, blockIdx.y);
+}
+// grid = (ceil(max K / TJ), ceil(max(N or M) / TI), entries)
+template <int WGRAD>
+__global__ void __launch_bounds__(256) small_linear_many_bwd_kernel(const __grid_constant__ SmallLinearBatch b) {
+  const int e = blockIdx.z;
+  if ((int)blockIdx.x * TJ >= b.K[e] || (int)blockIdx.y * TI >= (WGRAD ? b.N[e] : b.M)) return;
+  if (WGRAD ? b.dw[e] == nullptr : b.dx[e] == nullptr) return;
+  small_linear_bwd_tiled_body<WGRAD, 1>(b.dy[e], b.x[e], b.w[e], b.dx[e], b.dw[e], b.db[e], b.M, b.N[e], b.K[e], b.silu_in,
+                                        b.accumulate_dx, blockIdx.x, blockIdx.y);
 }
 
 // emb[m][0:half] = cos(t*f_i), emb[m][half:] = sin(t*f_i), f_i = exp(-ln(10000) * i / half)  (diffusion.py:24-28)
@@ -286,6 +332,55 @@ extern "C" int tsd_small_linear_bwd(void* stream, const float* dy, const float* 
       dim3 grid(ceil_div(K, 64), ceil_div(N, NT));
       small_linear_wgrad_kernel<<<grid, 64, 0, st>>>(dy, x, dw, db, M, N, K, silu_in);
     }
+    TSD_LAUNCH_CHECK();
+  }
+  return 0;
+}
+static int slb_fill(SmallLinearBatch& b, int n, const float* const* x, const float* const* w, const int* N, const int* K,
+                    int M, int silu_in) {
+  TSD_CHECK(n >= 1 && n <= SLB_MAX, "small_linear_many: %d entries (1..%d)", n, SLB_MAX);
+  memset(&b, 0, sizeof(b));
+  b.n = n; b.M = M; b.silu_in = silu_in;
+  for (int i = 0; i < n; ++i) {
+    TSD_CHECK(N[i] > 0 && K[i] > 0 && K[i] <= 4096 && N[i] <= 4096, "small_linear_many: entry %d has N=%d K=%d", i, N[i], K[i]);
+    b.x[i] = x[i]; b.w[i] = w[i]; b.N[i] = N[i]; b.K[i] = K[i];
+  }
+  return 0;
+}
+extern "C" int tsd_small_linear_many_fwd(void* stream, int n, const float* const* x, const float* const* w,
+                                         const float* const* bias, float* const* out, const int* N, const int* K, int M,
+                                         int silu_in) {
+  SmallLinearBatch b;
+  if (slb_fill(b, n, x, w, N, K, M, silu_in)) return 1;
+  int maxN = 0, maxK = 0;
+  for (int i = 0; i < n; ++i) { b.bias[i] = bias ? bias[i] : nullptr; b.out[i] = out[i]; maxN = max(maxN, N[i]); maxK = max(maxK, K[i]); }
+  dim3 grid(ceil_div(maxN, 64), ceil_div(M, ROWS), n);
+  small_linear_many_fwd_kernel<<<grid, 256, ROWS * maxK * sizeof(float), (cudaStream_t)stream>>>(b);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int tsd_small_linear_many_bwd(void* stream, int n, const float* const* dy, const float* const* x,
+                                         const float* const* w, float* const* dx, float* const* dw, float* const* db,
+                                         const int* N, const int* K, int M, int silu_in, int accumulate_dx) {
+  TSD_CHECK(M >= 32, "small_linear_many_bwd: batch-sized M only (M=%d); use tsd_small_linear_bwd per layer", M);
+  SmallLinearBatch b;
+  if (slb_fill(b, n, x, w, N, K, M, silu_in)) return 1;
+  b.accumulate_dx = accumulate_dx;
+  int maxN = 0, maxK = 0;
+  bool any_dx = false, any_dw = false;
+  for (int i = 0; i < n; ++i) {
+    b.dy[i] = dy[i];
+    b.dx[i] = dx ? dx[i] : nullptr; b.dw[i] = dw ? dw[i] : nullptr; b.db[i] = db ? db[i] : nullptr;
+    any_dx |= b.dx[i] != nullptr; any_dw |= b.dw[i] != nullptr;
+    maxN = max(maxN, N[i]); maxK = max(maxK, K[i]);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (any_dx) {
+    small_linear_many_bwd_kernel<0><<<dim3(ceil_div(maxK, TJ), ceil_div(M, TI), n), 256, 0, st>>>(b);
+    TSD_LAUNCH_CHECK();
+  }
+  if (any_dw) {
+    small_linear_many_bwd_kernel<1><<<dim3(ceil_div(maxK, TJ), ceil_div(maxN, TI), n), 256, 0, st>>>(b);
     TSD_LAUNCH_CHECK();
   }
   return 0;

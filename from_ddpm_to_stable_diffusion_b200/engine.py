@@ -285,6 +285,17 @@ class UNetEngine:
 
         if tb_override is None:
             temb, ctx, crec = self.conditioning(P, t.contiguous(), labels.contiguous(), save)
+            # every per-block conditioning vector of this forward in three launches: the 14 linear_time rows, the 10
+            # cross-attention v_proj and out_proj vectors (separate parameters, same batch)
+            blocks = self._block_list()
+            rkeys = [k for k, b in blocks if b[0] == "res"]
+            akeys = [k for k, b in blocks if b[0] == "attn"]
+            tbs = dict(zip(rkeys, ops.small_linear_many([temb] * len(rkeys), [P[k + ".linear_time.1.weight"] for k in rkeys],
+                                                        [P[k + ".linear_time.1.bias"] for k in rkeys], silu_in=True)))
+            vvs = ops.small_linear_many([ctx] * len(akeys), [P[k + ".atten_2.v_proj.weight"] for k in akeys])
+            cbs = ops.small_linear_many(vvs, [P[k + ".atten_2.out_proj.weight"] for k in akeys],
+                                        [P[k + ".atten_2.out_proj.bias"] for k in akeys])
+            vvs, cbs = dict(zip(akeys, vvs)), dict(zip(akeys, cbs))
         else:
             temb = ctx = None
             crec = {}
@@ -293,7 +304,7 @@ class UNetEngine:
             ci_, co = b[1], b[2]
             hw = h * w
             if tb_override is None:
-                tb, rps = self.time_bias(P, key, temb), hw
+                tb, rps = tbs[key], hw
             else:
                 tb, rps = tb_override[key]
             p_drop = m.dropout if (b[3] and training) else 0.0
@@ -324,7 +335,7 @@ class UNetEngine:
             C = b[1]
             L = h * w
             if cb_override is None:
-                vv, cb = self.cross_bias(P, key, ctx)
+                vv, cb = vvs[key], cbs[key]
             else:
                 vv, cb = None, cb_override[key]
             st = ops.gn_stats(x0, n, L, 1e-6, scratch)
@@ -470,13 +481,38 @@ class UNetEngine:
 
         dcur = None
         skip_grads = []
+        pend_time, pend_cross = [], []  # (dtb, key) / (dcb, vv, key): conditioning backward, batched per section
+
+        def flush_conditioning():
+            if pend_time:
+                ks = [k for _, k in pend_time]
+                ops.small_linear_many_bwd([d for d, _ in pend_time], [temb] * len(ks),
+                                          [P[k + ".linear_time.1.weight"] for k in ks], [d_temb] * len(ks),
+                                          [G[k + ".linear_time.1.weight"] for k in ks],
+                                          [G[k + ".linear_time.1.bias"] for k in ks], silu_in=True, accumulate_dx=True)
+                pend_time.clear()
+            if pend_cross:
+                ks = [k for _, _, k in pend_cross]
+                dvvs = [torch.empty_like(v) for _, v, _ in pend_cross]
+                # cb = out_proj(v_proj(ctx)) + bias   (norm_2, q_proj, k_proj get exact zeros)
+                ops.small_linear_many_bwd([d for d, _, _ in pend_cross], [v for _, v, _ in pend_cross],
+                                          [P[k + ".atten_2.out_proj.weight"] for k in ks], dvvs,
+                                          [G[k + ".atten_2.out_proj.weight"] for k in ks],
+                                          [G[k + ".atten_2.out_proj.bias"] for k in ks])
+                ops.small_linear_many_bwd(dvvs, [ctx] * len(ks), [P[k + ".atten_2.v_proj.weight"] for k in ks],
+                                          [d_ctx] * len(ks), [G[k + ".atten_2.v_proj.weight"] for k in ks], None,
+                                          accumulate_dx=True)
+                pend_cross.clear()
+
         section = "decoders"  # the tail sits right behind the decoders in the flat gradient buffer
         for rec in reversed(tape):
             kind, key = rec.kind, rec.key
-            if key and self.section_hook is not None:
+            if key:
                 sec = key.split(".", 1)[0]
                 if sec in ("bottleneck", "encoders") and sec != section:
-                    self.section_hook(section)  # every gradient of the section just left is final
+                    flush_conditioning()  # the linear_time / cross-attention gradients of the section just left
+                    if self.section_hook is not None:
+                        self.section_hook(section)  # every gradient of that section is final now
                     section = sec
             if kind == "tail":
                 hh, ww = rec.h, rec.w
@@ -504,9 +540,9 @@ class UNetEngine:
                 dskip = skip_grads.pop()
                 dcur = ops.add(dcur, dskip) if dcur is not None else dskip
             elif kind == "res":
-                dcur = self._res_bwd(rec, dcur, P, W, G, n, temb, d_temb, conv_wgrad, D)
+                dcur = self._res_bwd(rec, dcur, P, W, G, n, pend_time, conv_wgrad, D)
             elif kind == "attn":
-                dcur = self._attn_bwd(rec, dcur, P, W, G, n, ctx, d_ctx)
+                dcur = self._attn_bwd(rec, dcur, P, W, G, n, pend_cross)
             elif kind == "conv":
                 b, hh, ww = rec.b, rec.h, rec.w
                 s = b[3]
@@ -533,6 +569,7 @@ class UNetEngine:
                 self._bias_grad(dcur, n, dcur.shape[0] // n, G[key + ".bias"])
                 dcur = None
         assert not skip_grads
+        flush_conditioning()
         # conditioning backward (time / label MLPs, embedding)
         dh1 = torch.empty_like(crec["h1"])
         ops.small_linear_bwd(d_temb, crec["h1"], P["time_embedding.mlp.2.weight"], dh1, G["time_embedding.mlp.2.weight"],
@@ -553,7 +590,7 @@ class UNetEngine:
         if self.section_hook is not None:
             self.section_hook("rest")  # encoders + the conditioning MLPs: everything that is left
 
-    def _res_bwd(self, rec, dout, P, W, G, n, temb, d_temb, conv_wgrad, D):
+    def _res_bwd(self, rec, dout, P, W, G, n, pend_time, conv_wgrad, D):
         key, b = rec.key, rec.b
         ci, co = b[1], b[2]
         hh, ww = rec.h, rec.w
@@ -566,8 +603,7 @@ class UNetEngine:
                            G[key + ".conv_2.0.weight"], G[key + ".conv_2.0.bias"], drop_p=rec.p_drop, seed=rec.seed, rng=rec.pos)
         # time bias: per-sample column sums of dh feed linear_time; their sum over samples is conv_1's bias grad
         dtb = self._bias_grad(dh, n, hw, G[key + ".conv_1.2.bias"])
-        ops.small_linear_bwd(dtb, temb, P[key + ".linear_time.1.weight"], d_temb, G[key + ".linear_time.1.weight"],
-                             G[key + ".linear_time.1.bias"], silu_in=True, accumulate_dx=True)
+        pend_time.append((dtb, key))  # linear_time backward: batched with the other blocks of this section
         conv_wgrad(dh, rec.a1, key + ".conv_1.2.weight", hh, ww)
         da1 = ops.conv3x3(dh, n, hh, ww, D[key + ".conv_1.2"], ci)
         if ci != co:
@@ -580,7 +616,7 @@ class UNetEngine:
                               G[key + ".conv_1.0.weight"], G[key + ".conv_1.0.bias"], x1=rec.x1, radd=radd)
         return (dx0, dx1) if rec.x1 is not None else dx0
 
-    def _attn_bwd(self, rec, dout, P, W, G, n, ctx, d_ctx):
+    def _attn_bwd(self, rec, dout, P, W, G, n, pend_cross):
         key, b = rec.key, rec.b
         C = b[1]
         L = rec.h * rec.w
@@ -613,12 +649,7 @@ class UNetEngine:
         dg = ops.gemm_dgrad(dt0, W[k + ".conv_1.1"], C)
         dx, _ = ops.gn_bwd(dg, rec.x0, n, L, rec.st, P[k + ".conv_1.0.weight"], P[k + ".conv_1.0.bias"], False,
                            G[k + ".conv_1.0.weight"], G[k + ".conv_1.0.bias"], radd=dout)
-        # degenerate cross attention: cb = out_proj(v_proj(ctx)) + bias   (norm_2, q_proj, k_proj get exact zeros)
-        dvv = torch.empty_like(rec.vv)
-        ops.small_linear_bwd(dcb, rec.vv, P[k + ".atten_2.out_proj.weight"], dvv, G[k + ".atten_2.out_proj.weight"],
-                             G[k + ".atten_2.out_proj.bias"])
-        ops.small_linear_bwd(dvv, ctx, P[k + ".atten_2.v_proj.weight"], d_ctx, G[k + ".atten_2.v_proj.weight"], None,
-                             accumulate_dx=True)
+        pend_cross.append((dcb, rec.vv, k))  # degenerate cross attention backward: batched per section
         return dx
 
 

@@ -205,6 +205,51 @@ def small_linear_bwd(dy, x, w, dx, dw, db, silu_in=False, accumulate_dx=False):
          int(accumulate_dx))
 
 
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def _int_array(vals):
+    import ctypes
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def small_linear_many(xs, ws, biases=None, silu_in=False):
+    """[f(x_i) w_i^T + b_i] for up to 16 layers that share the batch dimension, one launch (fp32)."""
+    outs = []
+    for c in range(0, len(xs), 16):
+        x, w = xs[c:c + 16], ws[c:c + 16]
+        b = None if biases is None else biases[c:c + 16]
+        M = x[0].shape[0]
+        out = [torch.empty(M, wi.shape[0], device=wi.device, dtype=F32) for wi in w]
+        for xi, wi in zip(x, w):
+            _chk(xi, F32), _chk(wi, F32)
+        call("tsd_small_linear_many_fwd", len(x), _ptr_array(x), _ptr_array(w), None if b is None else _ptr_array(b),
+             _ptr_array(out), _int_array([wi.shape[0] for wi in w]), _int_array([wi.shape[1] for wi in w]), M, int(silu_in))
+        outs += out
+    return outs
+
+
+def small_linear_many_bwd(dys, xs, ws, dxs, dws, dbs, silu_in=False, accumulate_dx=False):
+    """Backward of small_linear_many.  dxs / dws / dbs: lists (entries may be None; dx entries may alias when
+    accumulate_dx).  Batch-sized M goes through one launch per direction, tiny M through the per-layer kernels."""
+    M = dys[0].shape[0]
+    n = len(dys)
+    dxs = dxs or [None] * n
+    dws = dws or [None] * n
+    dbs = dbs or [None] * n
+    if M < 32:
+        for i in range(n):
+            small_linear_bwd(dys[i], xs[i], ws[i], dxs[i], dws[i], dbs[i], silu_in=silu_in, accumulate_dx=accumulate_dx)
+        return
+    for c in range(0, n, 16):
+        sl = slice(c, c + 16)
+        call("tsd_small_linear_many_bwd", len(dys[sl]), _ptr_array(dys[sl]), _ptr_array(xs[sl]), _ptr_array(ws[sl]),
+             _ptr_array(dxs[sl]), _ptr_array(dws[sl]), _ptr_array(dbs[sl]), _int_array([w.shape[0] for w in ws[sl]]),
+             _int_array([w.shape[1] for w in ws[sl]]), M, int(silu_in), int(accumulate_dx))
+
+
 def timestep_embedding(t, freqs):
     M = t.shape[0]
     half = freqs.shape[0]

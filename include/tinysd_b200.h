@@ -157,6 +157,15 @@ int tsd_small_linear_fwd(void* stream, const float* x, const float* w, const flo
 /* dx (=|+=) f'(x) * (dy * w); dw += dy^T f(x); db += colsum(dy).  dx, dw, db may each be NULL. */
 int tsd_small_linear_bwd(void* stream, const float* dy, const float* x, const float* w, float* dx, float* dw,
                          float* db, int M, int N, int K, int silu_in, int accumulate_dx);
+/* n (<= 16) independent small linears with a common M in one launch each way (the 14 linear_time layers of the
+ * ResBlocks, the 10 v_proj and 10 out_proj of the degenerate cross-attention: separate parameters, same batch).  x, w,
+ * bias, out, dy, dx, dw, db are HOST arrays of n device pointers, N / K host arrays of n ints; entries of dx may alias
+ * (accumulate_dx: summed with atomics), NULL entries of dx / dw / db are skipped.  Backward needs M >= 32. */
+int tsd_small_linear_many_fwd(void* stream, int n, const float* const* x, const float* const* w, const float* const* bias,
+                              float* const* out, const int* N, const int* K, int M, int silu_in);
+int tsd_small_linear_many_bwd(void* stream, int n, const float* const* dy, const float* const* x, const float* const* w,
+                              float* const* dx, float* const* dw, float* const* db, const int* N, const int* K, int M,
+                              int silu_in, int accumulate_dx);
 /* emb[m] = [cos(t_m * freqs), sin(t_m * freqs)] (cos first, diffusion.py:28); freqs built by the host shell */
 int tsd_timestep_embedding(void* stream, const int64_t* t, const float* freqs, float* emb, int M, int half);
 int tsd_embedding_fwd(void* stream, const int64_t* idx, const float* table, float* out, int M, int D);
