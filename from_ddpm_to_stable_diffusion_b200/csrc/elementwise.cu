@@ -43,14 +43,25 @@ __global__ void geglu_fwd_kernel(const bf16* __restrict__ h8, bf16* __restrict__
     store8(out + row * H + c, v);
   }
 }
-// dh8 = [dout * gelu(gate), dout * value * gelu'(gate)]
-__global__ void geglu_bwd_kernel(const bf16* __restrict__ h8, const bf16* __restrict__ dout, bf16* __restrict__ dh8,
-                                 size_t M, int H) {
+// dh8 = [dout * gelu(gate), dout * value * gelu'(gate)]; optionally dbias[2H] += column sums of dh8 (the bias gradient
+// of the C -> 8C linear, diffusion.py:133: a separate pass over the 8C-wide tensor otherwise).  A thread owns one
+// 8-column vector of both halves and walks rows, so the sums stay in registers.  blockDim = 256, 256 % (H / 8) == 0.
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const bf16* __restrict__ h8, const bf16* __restrict__ dout,
+                                                        bf16* __restrict__ dh8, size_t M, int H, size_t rows_per_cta,
+                                                        float* __restrict__ dbias) {
+  extern __shared__ float s_db[];  // [2H], only when dbias != null
   const int vec_per_row = H / 8;
-  const size_t total = M * vec_per_row;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t row = i / vec_per_row;
-    const int c = (int)(i - row * vec_per_row) * 8;
+  const int slots = blockDim.x / vec_per_row;
+  const int c = (threadIdx.x % vec_per_row) * 8;
+  const int slot = threadIdx.x / vec_per_row;
+  if (dbias) {
+    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) s_db[i] = 0.f;
+    __syncthreads();
+  }
+  float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const size_t r0 = blockIdx.x * rows_per_cta;
+  const size_t r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+  for (size_t row = r0 + slot; row < r1; row += slots) {
     float v[8], g[8], d[8], dv[8], dg[8];
     load8(h8 + row * 2 * H + c, v);
     load8(h8 + row * 2 * H + H + c, g);
@@ -59,9 +70,20 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ h8, const bf16* __rest
     for (int j = 0; j < 8; ++j) {
       dv[j] = d[j] * gelu_f(g[j]);
       dg[j] = d[j] * v[j] * gelu_grad_f(g[j]);
+      sv[j] += dv[j];
+      sg[j] += dg[j];
     }
     store8(dh8 + row * 2 * H + c, dv);
     store8(dh8 + row * 2 * H + H + c, dg);
+  }
+  if (dbias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_db[c + j], sv[j]);
+      atomicAdd(&s_db[H + c + j], sg[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) atomicAdd(&dbias[i], s_db[i]);
   }
 }
 
@@ -287,9 +309,16 @@ extern "C" int tsd_geglu_fwd(void* stream, const void* h8, void* out, int64_t M,
   TSD_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int tsd_geglu_bwd(void* stream, const void* h8, const void* dout, void* dh8, int64_t M, int H) {
-  TSD_CHECK(H % 8 == 0, "geglu_bwd: H must be a multiple of 8");
-  geglu_bwd_kernel<<<ew_grid(M * (H / 8)), 256, 0, (cudaStream_t)stream>>>((const bf16*)h8, (const bf16*)dout, (bf16*)dh8, M, H);
+extern "C" int tsd_geglu_bwd(void* stream, const void* h8, const void* dout, void* dh8, int64_t M, int H, float* dbias) {
+  TSD_CHECK(H % 8 == 0 && H / 8 <= 256 && 256 % (H / 8) == 0, "geglu_bwd: H=%d (H / 8 must divide 256)", H);
+  const int slots = 256 / (H / 8);
+  size_t ctas = (size_t)num_sms() * 8;
+  size_t rpc = ((size_t)M + ctas - 1) / ctas;
+  rpc = (rpc + slots - 1) / slots * slots;
+  if (rpc < (size_t)slots) rpc = slots;
+  const int grid = (int)(((size_t)M + rpc - 1) / rpc);
+  geglu_bwd_kernel<<<grid, 256, dbias ? 2 * H * sizeof(float) : 0, (cudaStream_t)stream>>>(
+      (const bf16*)h8, (const bf16*)dout, (bf16*)dh8, (size_t)M, H, rpc, dbias);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
                                                            int act_silu, float drop_p, uint64_t seed,
                                                            const float* __restrict__ ab, const bf16* __restrict__ radd,
                                                            bf16* __restrict__ dx0, bf16* __restrict__ dx1,
-                                                           const uint64_t* __restrict__ rng_dev) {
+                                                           const uint64_t* __restrict__ rng_dev,
+                                                           float* __restrict__ cs_out, float* __restrict__ cs_total) {
   const int C = c0 + c1;
   const int cpg = C / GROUPS;
   const int vec_per_pix = C / 8;
@@ -353,6 +354,14 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
   bf16* dst_base = from0 ? dx0 + (size_t)n * hw * c0 + cv : dx1 + (size_t)n * hw * c1 + (cv - c0);
   const int src_ld = from0 ? c0 : c1;
   const size_t full_base = (size_t)n * hw * C + cv;
+  // optional by-product: column sums of dx per image (cs_out [n][C]) and over all images (cs_total [C]) -- the
+  // time-embedding / bias gradients that a separate pass over dx would otherwise compute (diffusion.py:112-113)
+  extern __shared__ float s_cs[];  // [C], only when cs_out != null
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (cs_out) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_cs[i] = 0.f;
+    __syncthreads();
+  }
   constexpr int UNROLL = 4;
   for (int pix0 = p_begin + my_slot; pix0 < p_end; pix0 += slots * UNROLL) {
     uint4 u[UNROLL], gq[UNROLL], rq[UNROLL];
@@ -388,9 +397,19 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const bf16* __rest
         if (act_silu) dz *= silu_grad_f(fmaf(e[j], fa[j], fb[j]));
         const float xhat = fmaf(e[j], rs[j >> 2], ms[j >> 2]);
         e[j] = fmaf(fa[j], dz, r[j]) - fmaf(xhat, k2[j >> 2], k1[j >> 2]);
+        cs[j] += e[j];
       }
       *reinterpret_cast<uint4*>(dst_base + (size_t)pix * src_ld) =
           make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+    }
+  }
+  if (cs_out) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_cs[cv + j], cs[j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      atomicAdd(&cs_out[(size_t)n * C + i], s_cs[i]);
+      if (cs_total) atomicAdd(&cs_total[i], s_cs[i]);
     }
   }
 }
@@ -619,7 +638,7 @@ extern "C" int tsd_gn_apply(void* stream, const void* x0, const void* x1, int c0
 extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1, int n_img,
                           int hw, const float* stats, const float* gamma, const float* beta, int act_silu,
                           float drop_p, uint64_t seed, float* ab, const void* radd, void* dx0, void* dx1,
-                          float* dgamma, float* dbeta, const uint64_t* rng_dev) {
+                          float* dgamma, float* dbeta, const uint64_t* rng_dev, float* colsum_out, float* colsum_total) {
   const int C = c0 + c1;
   TSD_CHECK(C % 128 == 0 && c0 % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "gn_bwd: unsupported channels c0=%d c1=%d", c0, c1);
   cudaStream_t st = (cudaStream_t)stream;
@@ -629,9 +648,9 @@ extern "C" int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const vo
   gn_bwd_sums_kernel<<<dim3(gx, n_img), 256, 2 * C * sizeof(float), st>>>(
       (const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc, stats, gamma, beta, act_silu, drop_p, seed, ab, rng_dev);
   TSD_LAUNCH_CHECK();
-  gn_bwd_apply_kernel<<<dim3(gx, n_img), 256, 0, st>>>((const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc,
-                                                       stats, gamma, beta, act_silu, drop_p, seed, ab, (const bf16*)radd,
-                                                       (bf16*)dx0, (bf16*)dx1, rng_dev);
+  gn_bwd_apply_kernel<<<dim3(gx, n_img), 256, colsum_out ? C * sizeof(float) : 0, st>>>(
+      (const bf16*)dy, (const bf16*)x0, (const bf16*)x1, c0, c1, hw, ppc, stats, gamma, beta, act_silu, drop_p, seed, ab,
+      (const bf16*)radd, (bf16*)dx0, (bf16*)dx1, rng_dev, colsum_out, colsum_total);
   TSD_LAUNCH_CHECK();
   if (dgamma) {
     gn_bwd_params_kernel<<<ceil_div(C, 32), 256, 0, st>>>(ab, n_img, C, dgamma, dbeta);

@@ -599,10 +599,12 @@ class UNetEngine:
         per = self._bias_grad(dout, n, hw, G[key + ".conv_2.3.bias"])
         conv_wgrad(dout, rec.a2, key + ".conv_2.3.weight", hh, ww)
         da2 = ops.conv3x3(dout, n, hh, ww, D[key + ".conv_2.3"], co)
+        # time bias: per-sample column sums of dh feed linear_time; their sum over samples is conv_1's bias grad -- both
+        # come out of the GroupNorm backward kernel that writes dh
+        dtb = self._arena.take(n, co)
         dh, _ = ops.gn_bwd(da2, rec.hmid, n, hw, rec.st2, P[key + ".conv_2.0.weight"], P[key + ".conv_2.0.bias"], True,
-                           G[key + ".conv_2.0.weight"], G[key + ".conv_2.0.bias"], drop_p=rec.p_drop, seed=rec.seed, rng=rec.pos)
-        # time bias: per-sample column sums of dh feed linear_time; their sum over samples is conv_1's bias grad
-        dtb = self._bias_grad(dh, n, hw, G[key + ".conv_1.2.bias"])
+                           G[key + ".conv_2.0.weight"], G[key + ".conv_2.0.bias"], drop_p=rec.p_drop, seed=rec.seed, rng=rec.pos,
+                           colsum_out=dtb, colsum_total=G[key + ".conv_1.2.bias"])
         pend_time.append((dtb, key))  # linear_time backward: batched with the other blocks of this section
         conv_wgrad(dh, rec.a1, key + ".conv_1.2.weight", hh, ww)
         da1 = ops.conv3x3(dh, n, hh, ww, D[key + ".conv_1.2"], ci)
@@ -629,8 +631,7 @@ class UNetEngine:
         self._bias_grad(dt3, n, L, G[k + ".linear_2.bias"])
         ops.gemm_wgrad(dt3, rec.gg, G[k + ".linear_2.weight"])
         dgg = ops.gemm_dgrad(dt3, W[k + ".linear_2"], 4 * C)
-        dh8 = ops.geglu_bwd(rec.h8, dgg)
-        self._bias_grad(dh8, n, L, G[k + ".linear_1.bias"])
+        dh8 = ops.geglu_bwd(rec.h8, dgg, dbias=G[k + ".linear_1.bias"])  # bias gradient as a by-product
         ops.gemm_wgrad(dh8, rec.l3, G[k + ".linear_1.weight"])
         dl3 = ops.gemm_dgrad(dh8, W[k + ".linear_1"], C)
         dt2 = ops.ln_bwd(dl3, rec.t2, P[k + ".norm_3.weight"], G[k + ".norm_3.weight"], G[k + ".norm_3.bias"], radd=dt3)

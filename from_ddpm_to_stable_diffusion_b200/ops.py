@@ -85,14 +85,15 @@ def gn_apply(x0, n_img, hw, stats, gamma, beta, silu, x1=None, drop_p=0.0, seed=
     return out
 
 
-def gn_bwd(dy, x0, n_img, hw, stats, gamma, beta, silu, dgamma, dbeta, x1=None, drop_p=0.0, seed=0, radd=None, rng=None):
+def gn_bwd(dy, x0, n_img, hw, stats, gamma, beta, silu, dgamma, dbeta, x1=None, drop_p=0.0, seed=0, radd=None, rng=None,
+           colsum_out=None, colsum_total=None):
     c0 = x0.shape[1]
     c1 = x1.shape[1] if x1 is not None else 0
     ab = torch.empty(n_img, c0 + c1, 2, device=x0.device, dtype=F32)
     dx0 = empty_bf16(n_img * hw, c0, like=x0)
     dx1 = empty_bf16(n_img * hw, c1, like=x0) if c1 else None
     call("tsd_gn_bwd", _chk(dy, BF16), x0, x1, c0, c1, n_img, hw, stats, gamma, beta, int(silu), f32(drop_p), u64(seed),
-         ab, radd, dx0, dx1, dgamma, dbeta, rng)
+         ab, radd, dx0, dx1, dgamma, dbeta, rng, colsum_out, colsum_total)
     return dx0, dx1
 
 
@@ -142,9 +143,10 @@ def geglu_fwd(h8):
     return out
 
 
-def geglu_bwd(h8, dout):
+def geglu_bwd(h8, dout, dbias=None):
+    """dh8 of the GEGLU; dbias (fp32 [8C]) += column sums of dh8 when given (bias gradient of the C -> 8C linear)"""
     dh8 = torch.empty_like(h8)
-    call("tsd_geglu_bwd", h8, _chk(dout, BF16), dh8, i64(h8.shape[0]), h8.shape[1] // 2)
+    call("tsd_geglu_bwd", h8, _chk(dout, BF16), dh8, i64(h8.shape[0]), h8.shape[1] // 2, dbias)
     return dh8
 
 

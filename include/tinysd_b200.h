@@ -103,10 +103,13 @@ int tsd_gn_apply(void* stream, const void* x0, const void* x1, int c0, int c1, i
                  const float* gamma, const float* beta, int act_silu, float drop_p, uint64_t seed, void* out,
                  const uint64_t* rng_dev);
 /* Backward of tsd_gn_apply (+ optional residual add `radd` [n*hw][c0+c1]); dx is written split as dx0 [.., c0],
- * dx1 [.., c1]; dgamma/dbeta (fp32 [c0+c1]) are accumulated.  ab: fp32 scratch [n_img][c0+c1][2]. */
+ * dx1 [.., c1]; dgamma/dbeta (fp32 [c0+c1]) are accumulated.  ab: fp32 scratch [n_img][c0+c1][2].
+ * colsum_out (optional, fp32 [n_img][c0+c1], +=) / colsum_total (optional, [c0+c1], +=): column sums of dx per image and
+ * over all images as a by-product (the time-embedding and conv-bias gradients of diffusion.py:112-113). */
 int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const void* x1, int c0, int c1, int n_img, int hw,
                const float* stats, const float* gamma, const float* beta, int act_silu, float drop_p, uint64_t seed,
-               float* ab, const void* radd, void* dx0, void* dx1, float* dgamma, float* dbeta, const uint64_t* rng_dev);
+               float* ab, const void* radd, void* dx0, void* dx1, float* dgamma, float* dbeta, const uint64_t* rng_dev,
+               float* colsum_out, float* colsum_total);
 /* LayerNorm over C in {128, 256, 512} per token row; nn.LayerNorm at diffusion.py:127,132 */
 int tsd_ln_fwd(void* stream, const void* x, int M, int C, const float* gamma, const float* beta, float eps, void* out);
 int tsd_ln_bwd(void* stream, const void* dy, const void* x, int M, int C, const float* gamma, float eps,
@@ -136,7 +139,8 @@ int tsd_attn_bwd_ws(void* stream, const void* qkv, const void* out, const void* 
 int tsd_add_bf16(void* stream, const void* a, const void* b, void* out, int64_t numel);
 /* GEGLU: out[M][H] = h8[:, :H] * gelu(h8[:, H:]) (exact erf GELU; diffusion.py:151-152) and its backward */
 int tsd_geglu_fwd(void* stream, const void* h8, void* out, int64_t M, int H);
-int tsd_geglu_bwd(void* stream, const void* h8, const void* dout, void* dh8, int64_t M, int H);
+/* dbias (optional, fp32 [2H]) += column sums of dh8: the bias gradient of the C -> 8C linear as a by-product */
+int tsd_geglu_bwd(void* stream, const void* h8, const void* dout, void* dh8, int64_t M, int H, float* dbias);
 /* nearest x2 upsample (F.interpolate, diffusion.py:167) and its adjoint (2x2 block sums) */
 int tsd_upsample2_fwd(void* stream, const void* in, void* out, int n_img, int H, int W, int C);
 int tsd_upsample2_bwd(void* stream, const void* dout, void* din, int n_img, int H, int W, int C);

@@ -159,11 +159,13 @@ def test_groupnorm_fwd_bwd(cuda, n, hw, c0, c1, silu, eps):
     beta = torch.randn(C, device=cuda, generator=g) * 0.2
     dy = torch.randn(n * hw, C, device=cuda, generator=g).to(BF)
     radd = torch.randn(n * hw, C, device=cuda, generator=g).to(BF)
-    scratch = torch.zeros((8 * 160 + n) * 64 + 64, device=cuda)
+    scratch = torch.zeros(ops.gn_scratch_floats(n), device=cuda)
     stats = ops.gn_stats(x0, n, hw, eps, scratch, x1=x1)
     out = ops.gn_apply(x0, n, hw, stats, gamma, beta, silu, x1=x1)
     dg, db = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
-    dx0, dx1 = ops.gn_bwd(dy, x0, n, hw, stats, gamma, beta, silu, dg, db, x1=x1, radd=radd)
+    cs_out, cs_tot = torch.zeros(n, C, device=cuda), torch.zeros(C, device=cuda)
+    dx0, dx1 = ops.gn_bwd(dy, x0, n, hw, stats, gamma, beta, silu, dg, db, x1=x1, radd=radd, colsum_out=cs_out,
+                          colsum_total=cs_tot)
     xr = x.float().view(n, hw, C).permute(0, 2, 1).contiguous().requires_grad_(True)  # [n, C, hw]
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     y = F.group_norm(xr, 32, gr, br, eps=eps)
@@ -177,6 +179,11 @@ def test_groupnorm_fwd_bwd(cuda, n, hw, c0, c1, silu, eps):
     got_dx = dx0 if dx1 is None else torch.cat([dx0, dx1], 1)
     assert _rel(got_dx, ref_dx) < 1.5e-2
     assert _rel(dg, gr.grad) < 1e-2 and _rel(db, br.grad) < 1e-2
+    # by-product: column sums of dx per image and over the batch (time-embedding / conv-bias gradients)
+    ref_cs = ref_dx.view(n, hw, C).sum(1)
+    tol = 2e-2 * ref_dx.abs().mean().item() * hw ** 0.5 + 1e-3
+    assert (cs_out - ref_cs).abs().max().item() < tol * 3 and (cs_tot - ref_cs.sum(0)).abs().max().item() < tol * 3 * n ** 0.5
+    assert (cs_out - got_dx.float().view(n, hw, C).sum(1)).abs().max().item() < tol
     # statistics themselves
     m_ref = xr.detach().view(n, 32, -1).mean(-1)
     assert (stats[..., 0] - m_ref).abs().max().item() < 1e-3
@@ -209,13 +216,16 @@ def test_geglu_and_elementwise(cuda):
     h8 = torch.randn(M, 2 * H, device=cuda, generator=g).to(BF)
     dout = torch.randn(M, H, device=cuda, generator=g).to(BF)
     out = ops.geglu_fwd(h8)
-    dh8 = ops.geglu_bwd(h8, dout)
+    dbias = torch.ones(2 * H, device=cuda)  # accumulated into: starts from a non-zero value
+    dh8 = ops.geglu_bwd(h8, dout, dbias=dbias)
+    assert torch.equal(dh8, ops.geglu_bwd(h8, dout))
     hr = h8.float().requires_grad_(True)
     a, gate = hr.chunk(2, dim=-1)
     y = a * F.gelu(gate)  # exact erf GELU (diffusion.py:152)
     y.backward(dout.float())
     torch.cuda.synchronize()
     assert _rel(out, y) < 1e-2 and _rel(dh8, hr.grad) < 1e-2
+    assert _rel(dbias - 1.0, hr.grad.sum(0)) < 5e-3  # bias gradient of the C -> 8C linear as a by-product
     # nearest upsample and its adjoint, zero stuffing, column sums
     n, Hh, Ww, C = 3, 8, 8, 128
     x = torch.randn(n * Hh * Ww, C, device=cuda, generator=g).to(BF)
