@@ -346,6 +346,24 @@ def run_ours(args):
     del stepper
     torch.cuda.empty_cache()
 
+    # BASELINE configs[3]: data-parallel training at a FIXED global batch of 2048 on 2 / 4 GPUs (8 GPUs: the main line
+    # above is that configuration).  2048 / N images per rank are processed as micro-batches of `B` with gradient
+    # accumulation; one all-reduce and one optimiser step per global batch.
+    cfg3 = None
+    if world in (2, 4) and 2048 % (world * B) == 0 and args.cfg3_steps > 0:
+        k = 2048 // (world * B)
+        g3 = torch.Generator().manual_seed(4321 + rank)
+        x3 = torch.randn(k * B, CFG["channel_img"], CFG["img"], CFG["img"], generator=g3).pin_memory()
+        y3 = torch.randint(0, CFG["num_class"], (k * B,), generator=g3).pin_memory()
+        st3 = GraphedTrainStep(trainer, opt, train_rand=0.05, micro_batches=k, overlap=overlap)
+        st3(x3, y3)
+        ms3 = timed(lambda: st3(x3, y3), args.cfg3_steps) / args.cfg3_steps
+        cfg3 = {"global_batch": 2048, "micro_batches_per_rank": k, "micro_batch": B, "ms_per_step": ms3,
+                "samples_per_s": 2048 / (ms3 / 1e3), "timed_steps": args.cfg3_steps,
+                "note": "BASELINE configs[3]; inputs from pinned host memory every micro-batch"}
+        del st3, x3, y3
+        torch.cuda.empty_cache()
+
     # sampling throughput (same model, eval mode): DDPM 64x64 images/s, CFG w=1.8, 2 forwards per step.  At N=1 the whole
     # reverse process (T=1000 steps) is executed and timed; at N>1 a prefix of `--sample-steps-multi` steps is timed and
     # scaled to T (every reverse step costs the same: same kernels, same shapes).
@@ -430,6 +448,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "sampling": sampling,
+            "cfg3_global_batch_2048": cfg3,
             "eager_issue_ms_per_step": eager_ms,
             "roofline": roof,
             "roofline_other_kernels": extra,
@@ -453,6 +472,7 @@ def main():
     ap.add_argument("--sample-steps", type=int, default=1000, help="timed reverse steps at N=1 (0 = skip sampling figure)")
     ap.add_argument("--sample-steps-multi", type=int, default=200, help="timed reverse steps when N>1")
     ap.add_argument("--latent-steps", type=int, default=50, help="timed reverse steps of the latent config (0 = skip)")
+    ap.add_argument("--cfg3-steps", type=int, default=3, help="timed steps of the fixed-global-batch-2048 line at N=2/4 (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

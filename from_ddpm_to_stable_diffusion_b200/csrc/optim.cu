@@ -7,7 +7,12 @@ using namespace tsd;
 
 namespace {
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n4, size_t n, float* __restrict__ out) {
+// Global sum of squares, bit-reproducible: every CTA writes its partial to scratch[1 + blockIdx.x]; the CTA that finishes
+// last (ticket counter in scratch[0]) adds the partials in index order.  Data-parallel ranks hold identical all-reduced
+// gradients and must derive the identical clip coefficient from them, or their weights drift apart ulp by ulp (a float
+// atomicAdd across CTAs sums in arrival order).
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n4, size_t n, float* __restrict__ out,
+                                                    float* __restrict__ scratch) {
   float acc = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = *reinterpret_cast<const float4*>(g + i * 4);
@@ -17,14 +22,31 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     for (size_t i = n4 * 4; i < n; ++i) acc += g[i] * g[i];
   acc = warp_sum(acc);
   __shared__ float s[8];
+  __shared__ bool s_last;
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x < 8) {
-    float v = s[threadIdx.x];
-    v += __shfl_xor_sync(0xffu, v, 4);
-    v += __shfl_xor_sync(0xffu, v, 2);
-    v += __shfl_xor_sync(0xffu, v, 1);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s[w];
+    scratch[1 + blockIdx.x] = v;
+    __threadfence();
+    const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(scratch), 1u);
+    s_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    // fixed-order reduction of the per-CTA partials by one warp (lane-strided partial sums, then a shuffle tree)
+    if (threadIdx.x < 32) {
+      float t = 0.f;
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) t += __ldcg(scratch + 1 + i);
+      t = warp_sum(t);
+      if (threadIdx.x == 0) {
+        out[0] += t;
+        *reinterpret_cast<unsigned*>(scratch) = 0u;  // ready for the next call
+      }
+    }
   }
 }
 
@@ -117,10 +139,14 @@ inline int ew_grid(size_t items) {
 
 }  // namespace
 
-// out[0] += sum g^2   (out must be zeroed by the caller)
-extern "C" int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out) {
+// out[0] += sum g^2   (out zeroed by the caller; scratch: tsd_sumsq_scratch_floats() floats, zero before the FIRST call)
+extern "C" int64_t tsd_sumsq_scratch_floats(void) { return 1 + 16 * 1024; }
+extern "C" int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out, float* scratch) {
   TSD_CHECK((reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: buffer must be 16-byte aligned");
-  sumsq_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(g, n / 4, n, out);
+  TSD_CHECK(scratch != nullptr, "sumsq: scratch buffer required (deterministic reduction)");
+  const int grid = ew_grid(n / 4);
+  TSD_CHECK(grid <= 16 * 1024, "sumsq: grid %d exceeds the scratch size", grid);
+  sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, n / 4, n, out, scratch);
   TSD_LAUNCH_CHECK();
   return 0;
 }

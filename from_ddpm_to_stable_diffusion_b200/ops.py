@@ -423,8 +423,18 @@ def ema_update(ema, p, decay):
     call("tsd_ema_update", _chk(ema, F32), _chk(p, F32), i64(p.numel()), f32(decay), f32(1.0 - decay))
 
 
-def sumsq(g, out):
-    call("tsd_sumsq_f32", _chk(g, F32), i64(g.numel()), out)
+_sumsq_scratch = {}
+
+
+def sumsq(g, out, scratch=None):
+    """out[0] += sum g^2, reduced in a fixed order (bit-identical on every data-parallel rank)"""
+    if scratch is None:
+        scratch = _sumsq_scratch.get(g.device)
+        if scratch is None:
+            fn = _lib.lib().tsd_sumsq_scratch_floats
+            fn.restype = __import__("ctypes").c_int64
+            scratch = _sumsq_scratch[g.device] = torch.zeros(int(fn()), device=g.device, dtype=F32)
+    call("tsd_sumsq_f32", _chk(g, F32), i64(g.numel()), out, scratch)
 
 
 def adamw_clip(p, g, m, v, lr, beta1, beta2, eps, wd, step, max_norm, sumsq_buf, write_clipped_grad=True):

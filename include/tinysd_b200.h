@@ -240,8 +240,11 @@ int tsd_pack_conv3x3(void* stream, const float* src, void* dst, int co, int ci);
 /* OIHW -> [ci][8-tap][co]: the data gradient of a stride-1 3x3 conv is tsd_conv3x3_fwd(dy, this weight) */
 int tsd_pack_conv3x3_dgrad(void* stream, const float* src, void* dst, int co, int ci);
 int tsd_unpack_conv3x3_grad(void* stream, const float* src, float* dst, int co, int ci);  /* dst(OIHW) += src */
-/* out[0] += sum g^2 */
-int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out);
+/* out[0] += sum g^2, bit-reproducible (fixed-order reduction of per-CTA partials through `scratch`,
+ * tsd_sumsq_scratch_floats() floats, zero-filled once before the first call): data-parallel ranks must derive the
+ * identical clip coefficient from their identical all-reduced gradients */
+int64_t tsd_sumsq_scratch_floats(void);
+int tsd_sumsq_f32(void* stream, const float* g, int64_t n, float* out, float* scratch);
 /* clip_grad_norm_(max_norm) + torch.optim.AdamW step over flat fp32 buffers; sumsq = squared global grad norm */
 int tsd_adamw_clip(void* stream, float* p, float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float wd, int step, float max_norm, const float* sumsq, int write_clipped_grad);

@@ -87,7 +87,10 @@ def main():
         st = GraphedTrainStep(tr2, opt2, overlap=overlap, rng=NoDrop)
         l2 = st(x[lo:hi], y[lo:hi]).clone()
         check(tag, l2, m2, opt2, True)
-    # (4) sampling shards, no collective in the loop
+    # (4) sampling shards, no collective in the loop.  The model must be the same on every rank: m1 went through the
+    # data-parallel step above (check() asserted bit-identical weights across ranks), whereas every rank trained its own
+    # m0 on the full batch and dQ's arrival-order sums make those copies differ in the last bits.
+    m0 = m1
     m0.eval()
     xT = torch.randn(B, 3, 32, 32, generator=g).to(dev)
     ys = torch.randint(1, 4, (B,), generator=g).to(dev)

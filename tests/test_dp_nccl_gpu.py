@@ -16,4 +16,11 @@ def test_two_ranks_match_one(cuda):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "helpers", "dp_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0 and "DP_NCCL_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
+    if r.returncode != 0 or "DP_NCCL_OK" not in r.stdout:
+        # the worker's own traceback sits far above torchrun's summary: keep the whole log and show the relevant lines
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "dp_worker_failure.log"), "w") as f:
+            f.write(r.stdout + "\n==== stderr ====\n" + r.stderr)
+        keep = [ln for ln in r.stderr.splitlines() if any(k in ln for k in ("Error", "assert", "dp_worker.py", "rank"))]
+        pytest.fail("dp_worker failed:\n" + "\n".join(keep[-40:]))
