@@ -500,20 +500,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
                                                      const float* __restrict__ gamma, float eps,
                                                      const bf16* __restrict__ radd, bf16* __restrict__ dx,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                     int rows_per_cta) {
+                                                     int rows_per_cta, int rows_per_sample, float* __restrict__ cs_out,
+                                                     float* __restrict__ cs_total) {
   constexpr int C = 128 * VEC;
-  __shared__ float s_dg[C], s_db[C];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __shared__ float s_dg[C], s_db[C], s_cs[C];
+  // optional by-product (cs_out / cs_total != null): column sums of dx per sample and over all rows -- the gradients
+  // of the bias / per-sample vector added in front of this LayerNorm (diffusion.py:141-148); rows_per_cta then divides
+  // rows_per_sample, so a CTA's rows belong to one sample
+  const bool want_cs = cs_out != nullptr || cs_total != nullptr;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; s_cs[i] = 0.f; }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float adg[4 * VEC], adb[4 * VEC], gm[4 * VEC];
+  float adg[4 * VEC], adb[4 * VEC], gm[4 * VEC], acs[4 * VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     const float4 g = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
     gm[4 * i] = g.x; gm[4 * i + 1] = g.y; gm[4 * i + 2] = g.z; gm[4 * i + 3] = g.w;
   }
 #pragma unroll
-  for (int i = 0; i < 4 * VEC; ++i) { adg[i] = 0.f; adb[i] = 0.f; }
+  for (int i = 0; i < 4 * VEC; ++i) { adg[i] = 0.f; adb[i] = 0.f; acs[i] = 0.f; }
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(M, r_begin + rows_per_cta);
   constexpr int RPW = VEC == 1 ? 4 : 2;  // rows per warp per pass: all loads of these rows are issued before the first is used
@@ -570,6 +575,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
           const float2 a = unpack_bf16(ur[r][i].x), b = unpack_bf16(ur[r][i].y);
           o[0] += a.x; o[1] += a.y; o[2] += b.x; o[3] += b.y;
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acs[4 * i + j] += o[j];
         *reinterpret_cast<uint2*>(dx + off) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
       }
     }
@@ -580,11 +587,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     for (int j = 0; j < 4; ++j) {
       atomicAdd(&s_dg[(i * 32 + lane) * 4 + j], adg[4 * i + j]);
       atomicAdd(&s_db[(i * 32 + lane) * 4 + j], adb[4 * i + j]);
+      if (want_cs) atomicAdd(&s_cs[(i * 32 + lane) * 4 + j], acs[4 * i + j]);
     }
   __syncthreads();
+  const int sample = want_cs ? r_begin / rows_per_sample : 0;
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     atomicAdd(&dgamma[i], s_dg[i]);
     atomicAdd(&dbeta[i], s_db[i]);
+    if (cs_out) atomicAdd(&cs_out[(size_t)sample * C + i], s_cs[i]);
+    if (cs_total) atomicAdd(&cs_total[i], s_cs[i]);
   }
 }
 
@@ -673,17 +684,23 @@ extern "C" int tsd_ln_fwd(void* stream, const void* x, int M, int C, const float
 }
 
 extern "C" int tsd_ln_bwd(void* stream, const void* dy, const void* x, int M, int C, const float* gamma, float eps,
-                          const void* radd, void* dx, float* dgamma, float* dbeta) {
+                          const void* radd, void* dx, float* dgamma, float* dbeta, int rows_per_sample, float* colsum_out,
+                          float* colsum_total) {
   cudaStream_t st = (cudaStream_t)stream;
   int rows_per_cta = ceil_div(M, 8 * num_sms());  // 8 CTAs (64 warps) per SM: the per-row shuffle chains are latency bound
   if (rows_per_cta < 8) rows_per_cta = 8;
+  if (colsum_out || colsum_total) {
+    TSD_CHECK(rows_per_sample > 0 && M % rows_per_sample == 0, "ln_bwd: rows_per_sample=%d does not divide M=%d", rows_per_sample, M);
+    if (rows_per_cta > rows_per_sample) rows_per_cta = rows_per_sample;
+    while (rows_per_sample % rows_per_cta != 0) --rows_per_cta;  // a CTA never straddles two samples
+  }
   const int grid = ceil_div(M, rows_per_cta);
   if (C == 128)
-    ln_bwd_kernel<1><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, M, gamma, eps, (const bf16*)radd, (bf16*)dx, dgamma, dbeta, rows_per_cta);
+    ln_bwd_kernel<1><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, M, gamma, eps, (const bf16*)radd, (bf16*)dx, dgamma, dbeta, rows_per_cta, rows_per_sample, colsum_out, colsum_total);
   else if (C == 256)
-    ln_bwd_kernel<2><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, M, gamma, eps, (const bf16*)radd, (bf16*)dx, dgamma, dbeta, rows_per_cta);
+    ln_bwd_kernel<2><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, M, gamma, eps, (const bf16*)radd, (bf16*)dx, dgamma, dbeta, rows_per_cta, rows_per_sample, colsum_out, colsum_total);
   else if (C == 512)
-    ln_bwd_kernel<4><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, M, gamma, eps, (const bf16*)radd, (bf16*)dx, dgamma, dbeta, rows_per_cta);
+    ln_bwd_kernel<4><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, M, gamma, eps, (const bf16*)radd, (bf16*)dx, dgamma, dbeta, rows_per_cta, rows_per_sample, colsum_out, colsum_total);
   else TSD_CHECK(false, "ln_bwd: C=%d not in {128,256,512}", C);
   TSD_LAUNCH_CHECK();
   return 0;

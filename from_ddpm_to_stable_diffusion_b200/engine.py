@@ -634,18 +634,19 @@ class UNetEngine:
         dh8 = ops.geglu_bwd(rec.h8, dgg, dbias=G[k + ".linear_1.bias"])  # bias gradient as a by-product
         ops.gemm_wgrad(dh8, rec.l3, G[k + ".linear_1.weight"])
         dl3 = ops.gemm_dgrad(dh8, W[k + ".linear_1"], C)
-        dt2 = ops.ln_bwd(dl3, rec.t2, P[k + ".norm_3.weight"], G[k + ".norm_3.weight"], G[k + ".norm_3.bias"], radd=dt3)
-        # out_proj (+ cross-attention vector + residual t0)
-        dcb = self._bias_grad(dt2, n, L, G[k + ".atten_1.1.out_proj.bias"])  # per-sample sums = grad of the cross vector
+        # out_proj (+ cross-attention vector + residual t0): the per-sample column sums of dt2 are the gradient of the
+        # cross-attention vector, their total the out_proj bias gradient -- by-products of the LayerNorm backward
+        dcb = self._arena.take(n, C)
+        dt2 = ops.ln_bwd(dl3, rec.t2, P[k + ".norm_3.weight"], G[k + ".norm_3.weight"], G[k + ".norm_3.bias"], radd=dt3,
+                         rows_per_sample=L, colsum_out=dcb, colsum_total=G[k + ".atten_1.1.out_proj.bias"])
         ops.gemm_wgrad(dt2, rec.o, G[k + ".atten_1.1.out_proj.weight"])
         do = ops.gemm_dgrad(dt2, W[k + ".atten_1.1.out_proj"], C)
         dqkv = ops.attn_bwd(rec.qkv, rec.o, do, rec.lse, n, L, C, self.model.N_HEAD)
         ops.gemm_wgrad(dqkv, rec.l1, G[k + ".atten_1.1.in_proj.weight"])
         dl1 = ops.gemm_dgrad(dqkv, W[k + ".atten_1.1.in_proj"], C)
         dt0 = ops.ln_bwd(dl1, rec.t0, P[k + ".atten_1.0.weight"], G[k + ".atten_1.0.weight"], G[k + ".atten_1.0.bias"],
-                         radd=dt2)
+                         radd=dt2, rows_per_sample=L, colsum_total=G[k + ".conv_1.1.bias"])
         # conv_1.1 (1x1) and GroupNorm (eps 1e-6, no activation), + long residual
-        self._bias_grad(dt0, n, L, G[k + ".conv_1.1.bias"])
         ops.gemm_wgrad(dt0, rec.g, G[k + ".conv_1.1.weight"].view(C, C))
         dg = ops.gemm_dgrad(dt0, W[k + ".conv_1.1"], C)
         dx, _ = ops.gn_bwd(dg, rec.x0, n, L, rec.st, P[k + ".conv_1.0.weight"], P[k + ".conv_1.0.bias"], False,

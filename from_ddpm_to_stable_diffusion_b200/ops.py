@@ -104,10 +104,11 @@ def ln_fwd(x, gamma, beta, eps=1e-5):
     return out
 
 
-def ln_bwd(dy, x, gamma, dgamma, dbeta, eps=1e-5, radd=None):
+def ln_bwd(dy, x, gamma, dgamma, dbeta, eps=1e-5, radd=None, rows_per_sample=0, colsum_out=None, colsum_total=None):
     M, C = x.shape
     dx = torch.empty_like(x)
-    call("tsd_ln_bwd", _chk(dy, BF16), x, M, C, gamma, f32(eps), radd, dx, dgamma, dbeta)
+    call("tsd_ln_bwd", _chk(dy, BF16), x, M, C, gamma, f32(eps), radd, dx, dgamma, dbeta, int(rows_per_sample), colsum_out,
+         colsum_total)
     return dx
 
 

@@ -112,8 +112,11 @@ int tsd_gn_bwd(void* stream, const void* dy, const void* x0, const void* x1, int
                float* colsum_out, float* colsum_total);
 /* LayerNorm over C in {128, 256, 512} per token row; nn.LayerNorm at diffusion.py:127,132 */
 int tsd_ln_fwd(void* stream, const void* x, int M, int C, const float* gamma, const float* beta, float eps, void* out);
+/* colsum_out (optional, fp32 [M / rows_per_sample][C], +=) / colsum_total (optional, [C], +=): column sums of dx per
+ * sample and over all rows as a by-product (gradients of the bias / per-sample vector added before the LayerNorm) */
 int tsd_ln_bwd(void* stream, const void* dy, const void* x, int M, int C, const float* gamma, float eps,
-               const void* radd, void* dx, float* dgamma, float* dbeta);
+               const void* radd, void* dx, float* dgamma, float* dbeta, int rows_per_sample, float* colsum_out,
+               float* colsum_total);
 
 /* ------------------------------------------------------------------------------------------
  * Self-attention, head_dim 16 / 32 (SelfAttention.forward, diffusion.py:46-58).

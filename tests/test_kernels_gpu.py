@@ -200,6 +200,14 @@ def test_layernorm_fwd_bwd(cuda, M, C):
     out = ops.ln_fwd(x, gamma, beta)
     dg, db = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
     dx = ops.ln_bwd(dy, x, gamma, dg, db, radd=radd)
+    rps = {4096: 512, 1000: 250, 77: 11}[M]  # rows per "sample": column sums of dx per sample and in total as by-products
+    cs, ct = torch.zeros(M // rps, C, device=cuda), torch.zeros(C, device=cuda)
+    dg2, db2 = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+    dx2 = ops.ln_bwd(dy, x, gamma, dg2, db2, radd=radd, rows_per_sample=rps, colsum_out=cs, colsum_total=ct)
+    assert torch.equal(dx2, dx)
+    ref_cs = dx.float().view(M // rps, rps, C).sum(1)
+    assert (cs - ref_cs).abs().max().item() < 0.05 * rps ** 0.5 and (ct - ref_cs.sum(0)).abs().max().item() < 0.05 * M ** 0.5
+    assert _rel(cs, ref_cs) < 1e-2
     xr = x.float().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     y = F.layer_norm(xr, (C,), gr, br, eps=1e-5)
