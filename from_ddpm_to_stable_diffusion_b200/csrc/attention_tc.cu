@@ -44,7 +44,8 @@ struct Geo {
   static constexpr int Q_BYTES = NWG * QT * ROWB;
   static constexpr int KV_BYTES = KB * ROWB;
   static constexpr int STAGE_BYTES = 2 * KV_BYTES;
-  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + NST * STAGE_BYTES + 256;
+  static constexpr int ONES_BYTES = KB * ROWB;  // LSUM: constant [64 keys][16] tile, 1 in column 0 (see the kernel)
+  static constexpr int SMEM_BYTES = 1024 + Q_BYTES + NST * STAGE_BYTES + ONES_BYTES + 256;
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -128,7 +129,11 @@ __global__ void __launch_bounds__(512) attn_knorm_kernel(const bf16* __restrict_
   if (threadIdx.x < H) atomicMax(reinterpret_cast<int*>(knmax2) + b * H + threadIdx.x, s_max[threadIdx.x]);
 }
 
-template <int DH, int POLY>
+// LSUM (head_dim 16 only): the softmax row sum comes out of the tensor core instead of one FADD per score.  The P V
+// product is issued with N = 32: the second 16-column chunk of its MN-major B operand is a constant tile (leading-
+// dimension byte offset of the descriptor pointing at it) with ones in column 0, so TMEM column O_COL + 16 accumulates
+// sum_k bf16(P) next to O -- the same rounded P values that form the numerator.
+template <int DH, int POLY, bool LSUM>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse2,
                    const float* __restrict__ knmax2, int L, int C, float scale_log2) {
@@ -139,7 +144,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
   const uint32_t sKV = smem_base + Q_BYTES;
-  const uint32_t bar_base = sKV + NST * STAGE_BYTES;
+  const uint32_t sOnes = sKV + NST * STAGE_BYTES;
+  const uint32_t bar_base = sOnes + Geo<DH>::ONES_BYTES;
   // barriers (8 B each): q_full, kv_full[NST], kv_empty[NST], s_full[NWG], s_free[NWG], p_full[NWG], pv_done[NWG]
   const uint32_t q_full = bar_base;
   auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
@@ -176,6 +182,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (LSUM) {
+    // 64 rows of 32 bytes: 1.0 in the first element of BOTH 16-byte halves (the 32-byte swizzle may swap the halves of a
+    // row; either way output column 16 -- and its twin, column 24 -- receives the row sum), zero elsewhere
+    for (int i = threadIdx.x; i < Geo<DH>::ONES_BYTES / 4; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(smem_raw + (sOnes - smem_u32(smem_raw)))[i] = (i % 4 == 0) ? 0x00003f80u : 0u;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -188,7 +201,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       // simply blocks on them in that order: no polling, and one issuer per warpgroup keeps the two independent.
       const int g = warp - 8;
       constexpr uint32_t idescS = umma_idesc_bf16(QT, KB, 0, 0);
-      constexpr uint32_t idescPV = umma_idesc_bf16(QT, DH, 0, 1);
+      constexpr uint32_t idescPV = umma_idesc_bf16(QT, LSUM ? 2 * DH : DH, 0, 1);
       constexpr int AHEAD = NST - 2;  // K/V blocks in flight beyond the one being consumed
       const int row_base = b * L;
       auto load_kv = [&](int jn) {
@@ -238,7 +251,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         const int s = j % NST;
         const uint32_t sV = sKV + s * STAGE_BYTES + KV_BYTES;
         if (elect_one()) {
-          const uint64_t descV = umma_smem_desc_sw(sV, 0, 8 * ROWB, SWZ);
+          // MN-major B: 16-column chunks LBO bytes apart -- the second chunk is the constant ones tile (LSUM)
+          const uint64_t descV = umma_smem_desc_sw(sV, LSUM ? sOnes - sV : 0u, 8 * ROWB, SWZ);
 #pragma unroll
           for (int k = 0; k < KB / 16; ++k)
             umma_bf16_ts(tW + O_COL, tW + P_COL + k * 8, descV + (uint64_t)(k * (16 * ROWB / 16)), idescPV,
@@ -313,9 +327,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         if (need) {
           alpha = ex2f(m_ref - bm);  // 0 on the first block
           m_ref = bm;
-          float la, lb;
-          upk2(l2, la, lb);
-          l2 = pk2(la * alpha, lb * alpha);
+          if (!LSUM) {  // (LSUM: the sum lives in TMEM next to O and is rescaled with it)
+            float la, lb;
+            upk2(l2, la, lb);
+            l2 = pk2(la * alpha, lb * alpha);
+          }
         }
       }
       // ---- P = 2^(s*c - m_ref) as bf16 pairs; the S buffer is handed back as soon as it sits in registers
@@ -344,7 +360,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
               p0 = ex2f(a0);
               p1 = ex2f(a1);
             }
-            l2 = fadd2_(l2, pk2(p0, p1));
+            if (!LSUM) l2 = fadd2_(l2, pk2(p0, p1));
             pk[half * 16 + i] = pack_bf16(p0, p1);
           }
         }
@@ -357,7 +373,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         tc_fence_after();
         if (rescale) {
 #pragma unroll
-          for (int part = 0; part < DH / 16; ++part) {
+          for (int part = 0; part < (LSUM ? 2 * DH : DH) / 16; ++part) {
             uint32_t o[16];
             tmem_ld16(tO + part * 16, o);
             tmem_ld_wait();
@@ -375,9 +391,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     // ---- epilogue: O / l -> bf16, lse
     mbar_wait(pv_done(g), (nkb - 1) & 1);
     tc_fence_after();
-    float la, lb;
-    upk2(l2, la, lb);
-    const float l = la + lb;
+    float l;
+    if (LSUM) {
+      uint32_t o2[16];
+      tmem_ld16(tO + DH, o2);
+      tmem_ld_wait();
+      l = __uint_as_float(o2[0]);
+    } else {
+      float la, lb;
+      upk2(l2, la, lb);
+      l = la + lb;
+    }
     const float inv = 1.f / l;
     const size_t grow = (size_t)b * L + q0 + g * QT + row;
     uint4* dst = reinterpret_cast<uint4*>(out + grow * C + h * DH);
@@ -405,10 +429,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   }
 }
 
-template <int DH, int POLY>
+template <int DH, int POLY, bool LSUM>
 int launch_fwd_t(cudaStream_t st, const CUtensorMap& tm, void* out, float* lse2, const float* knmax2, int B, int L,
                  int C, int heads, float scale_log2) {
-  auto kern = attn_fwd_tc_kernel<DH, POLY>;
+  auto kern = attn_fwd_tc_kernel<DH, POLY, LSUM>;
   static tsd::PerDeviceFlag configured;
   if (!configured.cur()) {
     TSD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<DH>::SMEM_BYTES));
@@ -432,11 +456,23 @@ int launch_fwd_dh(cudaStream_t st, const void* qkv, void* out, float* lse2, floa
     attn_knorm_kernel<DH><<<dim3(ceil_div(L, rows_per_block), B), 512, 0, st>>>((const bf16*)qkv, ws, L, C, heads);
     TSD_LAUNCH_CHECK();
   }
+  static int lsum = -1;  // TSD_ATTN_TC_LSUM=1: softmax row sum from the tensor core (head_dim 16)
+  if (lsum < 0) { const char* e = getenv("TSD_ATTN_TC_LSUM"); lsum = e ? atoi(e) : 0; }
+  if constexpr (DH == 16) {
+    if (lsum) {
+      switch (poly) {
+        case 0: return launch_fwd_t<DH, 0, true>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+        case 2: return launch_fwd_t<DH, 2, true>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+        case 3: return launch_fwd_t<DH, 3, true>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+        default: return launch_fwd_t<DH, 4, true>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+      }
+    }
+  }
   switch (poly) {
-    case 0: return launch_fwd_t<DH, 0>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
-    case 2: return launch_fwd_t<DH, 2>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
-    case 3: return launch_fwd_t<DH, 3>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
-    default: return launch_fwd_t<DH, 4>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    case 0: return launch_fwd_t<DH, 0, false>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    case 2: return launch_fwd_t<DH, 2, false>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    case 3: return launch_fwd_t<DH, 3, false>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
+    default: return launch_fwd_t<DH, 4, false>(st, tm, out, lse2, ws, B, L, C, heads, scale_log2);
   }
 }
 
