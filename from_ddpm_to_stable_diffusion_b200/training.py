@@ -309,6 +309,18 @@ class GraphedTrainStep:
             capture("opt", self.opt.step)
         self._graphs = graphs
         self._exchange_in_graph = exchange_in_graph
+        self._held = self._engine_buffers()
+
+    def _engine_buffers(self):
+        """The engine-owned buffers whose addresses the captured graphs use.  Holding them keeps them alive; comparing
+        identities tells when the engine replaced one (load_state_dict, .to(), a re-homed parameter buffer) and the
+        graphs must be captured again."""
+        eng = self.trainer.model._engine
+        return (eng._packs.get("train"), eng._packs.get("dgrad"), eng._flat_grad, eng._arena.buf, eng._scratch,
+                self.opt.flat_p)
+
+    def _stale(self):
+        return any(a is not b for a, b in zip(self._held, self._engine_buffers()))
 
     def launches_per_step(self):
         """Library kernels executed by one call (replayed graph nodes; torch glue and NCCL not counted)."""
@@ -320,7 +332,8 @@ class GraphedTrainStep:
 
     # -------------------------------------------------------------- the call
     def __call__(self, images, labels):
-        if self._graphs is None or tuple(images.shape) != self._shape:
+        if self._graphs is None or tuple(images.shape) != self._shape or self._stale():
+            self._graphs = None  # drop the old graphs (and their memory pool) before capturing again
             self._build(images)
         eng = self.trainer.model._engine
         g = self._graphs

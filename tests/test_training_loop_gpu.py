@@ -228,3 +228,25 @@ def test_trainer_draws_fresh_numbers_per_call_and_per_global_sample(cuda):
     assert 0 <= int(t_full.min()) and int(t_full.max()) < 1000
     big = ops.draw_timesteps(200000, 1000, r.seed, pos, cuda).float()
     assert abs(big.mean().item() - 499.5) < 3.0 and abs(n_full.std().item() - 1.0) < 0.05
+
+
+def test_graph_is_recaptured_when_the_engine_replaces_its_buffers(cuda):
+    """load_state_dict() between two graphed steps drops the engine's packed-weight buffers: the stepper must notice and
+    capture again instead of replaying launches that point at freed memory; the step then equals an eager step from the
+    same state."""
+    from from_ddpm_to_stable_diffusion_b200.training import GraphedTrainStep, train_step
+    data = _batches(3, 4)
+    m1, tr1, opt1 = _setup(cuda, 0.0)
+    step = GraphedTrainStep(tr1, opt1, rng=_NoDrop)
+    step(data[0][0].to(cuda), data[0][1].to(cuda))
+    sd = {k: v.detach().clone() for k, v in m1.state_dict().items()}
+    held = step._held
+    m1.load_state_dict(sd)  # same values, but the engine invalidates every derived buffer
+    junk = [torch.randn(1 << 22, device=cuda) for _ in range(8)]  # recycle whatever was released
+    la = step(data[1][0].to(cuda), data[1][1].to(cuda)).item()
+    assert step._held[0] is not held[0]  # captured again on the new buffers
+    del junk
+    m2, tr2, opt2 = _setup(cuda, 0.0)
+    train_step(tr2, opt2, data[0][0].to(cuda), data[0][1].to(cuda), rng=_NoDrop)
+    lb = train_step(tr2, opt2, data[1][0].to(cuda), data[1][1].to(cuda), rng=_NoDrop).item()
+    assert abs(la - lb) / abs(lb) < 1e-4, (la, lb)
