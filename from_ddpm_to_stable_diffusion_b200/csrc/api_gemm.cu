@@ -55,6 +55,24 @@ extern "C" int tsd_gemm_fwd(void* stream, const void* a0, const void* a1, int c0
   return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA0, tA1, tB, tB, tD, p);
 }
 
+// dh8[M][2H] = backward of GEGLU(a w^T + bias) given d(gg)[M][H], with the pre-activations recomputed by the GEMM and
+// the activation backward in its epilogue (w / bias in the GEGLU packing of tsd_pack_linear(geglu = 1)).
+extern "C" int tsd_gemm_geglu_bwd(void* stream, const void* a, int M, int K, const void* w_geglu, int N,
+                                  const float* bias_geglu, const void* dgg, void* dh8, float* dbias) {
+  TSD_CHECK(M > 0 && N % 256 == 0 && N <= 2048 && K % 64 == 0, "gemm_geglu_bwd: bad shape M=%d N=%d K=%d", M, N, K);
+  CUtensorMap tA, tB, tD;
+  if (make_tmap_2d(&tA, a, 2, M, K, K, 64, 128)) return 1;
+  if (make_tmap_2d(&tB, w_geglu, 2, N, K, K, 64, 128)) return 1;
+  if (make_tmap_2d(&tD, dh8, 2, M, N, N, 64, 128)) return 1;
+  GemmParams p; zero_params(p);
+  p.M = M; p.N = N; p.tiles_m = ceil_div(M, 128); p.tiles_n = N / 128;
+  p.num_kb = K / 64; p.kb_per_split = p.num_kb;
+  p.a_mode = A_K2D; p.a_c0 = K; p.b_mode = B_K2D;
+  p.epi = EPI_GEGLU_BWD; p.bias = bias_geglu; p.rows_per_sample = 1;
+  p.residual = reinterpret_cast<const bf16*>(dgg); p.ldr = N / 2; p.n_half = N / 2; p.colsum = dbias;
+  return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA, tA, tB, tB, tD, p);
+}
+
 extern "C" int tsd_conv3x3_fwd_act(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
                                    int H, int W, int stride, const void* w, int cout, const float* bias,
                                    const float* row_bias, int rows_per_sample, const void* residual, int act, void* d);

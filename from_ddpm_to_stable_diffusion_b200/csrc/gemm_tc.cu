@@ -231,10 +231,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int t2r = tile_idx % tiles_mn;
       const int nb = t2r % p.tiles_n, mb = t2r / p.tiles_n;
       const uint32_t dst = smem_staging + bufsel * (BM * BN * 2);
+      if (p.epi == EPI_GEGLU_BWD) {  // the 64 d(gg) columns that belong to this tile's 64 value + 64 gate columns
+        mbar_arrive_expect_tx(res_bar(bufsel), BM * 64 * 2);
+        tma_load_2d(dst, &tmR, res_bar(bufsel), nb * 64, mb * BM);
+        return;
+      }
       mbar_arrive_expect_tx(res_bar(bufsel), BM * BN * 2);
       tma_load_2d(dst, &tmR, res_bar(bufsel), nb * BN, mb * BM);
       tma_load_2d(dst + BM * 128, &tmR, res_bar(bufsel), nb * BN + 64, mb * BM);
     };
+    float cs_acc[16];  // EPI_GEGLU_BWD: this thread's column-sum partials per n-block (bias gradient), flushed at the end
+#pragma unroll
+    for (int i = 0; i < 16; ++i) cs_acc[i] = 0.f;
     if (has_res && ep_leader && (int)blockIdx.x < total_tiles) prefetch_residual(blockIdx.x, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -275,6 +283,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint4 o = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             *reinterpret_cast<uint4*>(dst + ((q ^ r7) << 4)) = o;
           }
+        }
+      } else if (p.epi == EPI_GEGLU_BWD) {
+        // Backward of value * gelu(gate) with the pre-activations RECOMPUTED by this GEMM (accumulator columns [0,64) =
+        // value x, [64,128) = gate g, same packing as the forward) and d(gg) of the tile TMA-loaded into the staging
+        // buffer: dx = d * gelu(g) goes back over d, dg = d * x * gelu'(g) into the second half; gelu in the tanh form of
+        // the forward epilogue (geglu_fast_f), one MUFU per element for value and derivative together.
+        const int ch = half;
+        uint32_t xv[32], gv[32];
+        tmem_ld32(t_addr + ch * 32, xv);
+        tmem_ld32(t_addr + 64 + ch * 32, gv);
+        tmem_ld_wait();
+        uint8_t* row_d = staging + ep_tid * 128;
+        uint8_t* row_g = staging + BM * 128 + ep_tid * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cj = ch * 4 + q;
+          const uint4 dv4 = *reinterpret_cast<const uint4*>(row_d + ((cj ^ r7) << 4));
+          const uint32_t dw[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
+          uint32_t ox[4], og[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = q * 8 + e * 2;
+            float x[2] = {__uint_as_float(xv[j]), __uint_as_float(xv[j + 1])};
+            float g[2] = {__uint_as_float(gv[j]), __uint_as_float(gv[j + 1])};
+            if (p.bias) {
+              const float2 bx = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + ch * 32 + j));
+              const float2 bg = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + 64 + ch * 32 + j));
+              x[0] += bx.x; x[1] += bx.y; g[0] += bg.x; g[1] += bg.y;
+            }
+            const float2 d = unpack_bf16(dw[e]);
+            const float dd[2] = {d.x, d.y};
+            float rx[2], rg[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float t = g[u] * g[u];
+              const float th = tanh_fast(g[u] * fmaf(0.0347008941f, t, 0.8001570768f));
+              const float hp = fmaf(0.5f, th, 0.5f);                        // 0.5 (1 + tanh z)
+              const float dz = fmaf(0.1041026823f, t, 0.8001570768f);       // dz/dg = a + 3 b g^2
+              const float gp = fmaf(0.5f * g[u] * dz, fmaf(-th, th, 1.f), hp);  // gelu'(g)
+              rx[u] = dd[u] * (g[u] * hp);
+              rg[u] = dd[u] * x[u] * gp;
+            }
+            ox[e] = pack_bf16(rx[0], rx[1]);
+            og[e] = pack_bf16(rg[0], rg[1]);
+          }
+          *reinterpret_cast<uint4*>(row_d + ((cj ^ r7) << 4)) = make_uint4(ox[0], ox[1], ox[2], ox[3]);
+          *reinterpret_cast<uint4*>(row_g + ((cj ^ r7) << 4)) = make_uint4(og[0], og[1], og[2], og[3]);
         }
       } else if (p.epi == EPI_GEGLU) {
         // columns [0,64) = value half, [64,128) = gate half (weights are packed that way)
@@ -364,6 +419,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // (the next tile's residual prefetch and, one tile later, its result are written there)
       if (!OUT_F32 && ep_leader) tma_store_wait_read<0>();
       named_bar_sync(1, EPI_THREADS);
+      if (!OUT_F32 && p.epi == EPI_GEGLU_BWD && p.colsum) {
+        // bias gradient of the C -> 8C linear as a by-product: column sums of the finished tile, read back from the
+        // staging buffer (thread = one column of one 64-row half), kept per n-block in registers across the CTA's tiles
+        const int et = (warp - 4) * 32 + lane;
+        const int col = et & 63, which = (et >> 6) & 1, r_lo = (et >> 7) * 64;
+        const uint8_t* base = staging + which * (BM * 128) + (col & 7) * 2;
+        float part = 0.f;
+#pragma unroll 8
+        for (int r = r_lo; r < r_lo + 64; ++r) {
+          const uint16_t v = *reinterpret_cast<const uint16_t*>(base + r * 128 + (((col >> 3) ^ (r & 7)) << 4));
+          part += __uint_as_float(static_cast<uint32_t>(v) << 16);
+        }
+        cs_acc[n_blk & 15] += part;
+      }
       if (ep_leader) {
         if (OUT_F32) {
 #pragma unroll
@@ -375,6 +444,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (has_res && tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + gridDim.x, sbuf ^ 1);
           if (p.epi == EPI_GEGLU) {
             tma_store_2d(&tmD, staging_s, n0 / 2, m0);
+          } else if (p.epi == EPI_GEGLU_BWD) {  // dh8 in the plain layout: [d value (n_half) | d gate (n_half)]
+            tma_store_2d(&tmD, staging_s, n0 / 2, m0);
+            tma_store_2d(&tmD, staging_s + BM * 128, p.n_half + n0 / 2, m0);
           } else {
             tma_store_2d(&tmD, staging_s, n0, m0);
             tma_store_2d(&tmD, staging_s + BM * 128, n0 + 64, m0);
@@ -384,6 +456,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
     if (ep_leader) tma_store_wait_all<0>();
+    if (!OUT_F32 && p.epi == EPI_GEGLU_BWD && p.colsum) {
+      const int et = (warp - 4) * 32 + lane;
+      const int col = et & 63, which = (et >> 6) & 1;
+      for (int nb = 0; nb < p.tiles_n && nb < 16; ++nb)
+        if (cs_acc[nb] != 0.f) atomicAdd(p.colsum + which * p.n_half + nb * 64 + col, cs_acc[nb]);
+    }
   }
 
   __syncwarp();
@@ -419,8 +497,12 @@ int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUte
   // residual [M][ldr] bf16 is read through its own tensor map (same tiling as D)
   CUtensorMap tmR = tmD;
   if (p.residual && !out_f32) {
-    if (make_tmap_2d(&tmR, p.residual, 2, p.M, p.N, p.ldr, 64, 128)) return 1;
+    // EPI_GEGLU_BWD: the "residual" operand is d(gg) [M][n_half], one 64-column box per tile
+    const int rcols = p.epi == EPI_GEGLU_BWD ? p.n_half : p.N;
+    if (make_tmap_2d(&tmR, p.residual, 2, p.M, rcols, p.ldr, 64, 128)) return 1;
   }
+  TSD_CHECK(p.epi != EPI_GEGLU_BWD || (p.residual && !out_f32 && p.tiles_n <= 16 && p.n_half * 2 == p.N),
+            "gemm: GEGLU backward epilogue needs d(gg), bf16 output and N = 2 * n_half <= 2048");
   TSD_CHECK(p.N % BN == 0, "gemm: N=%d must be a multiple of %d", p.N, BN);
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("TSD_GEMM_DBG"); dbg = e ? atoi(e) : 0; }

@@ -23,7 +23,7 @@ namespace tsd {
 
 enum : int { A_K2D = 0, A_KCONV = 1, A_MN2D = 2 };
 enum : int { B_K2D = 0, B_MN2D = 1, B_MNCONV = 2 };
-enum : int { EPI_NONE = 0, EPI_GEGLU = 1 };
+enum : int { EPI_NONE = 0, EPI_GEGLU = 1, EPI_GEGLU_BWD = 2 };
 enum : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH = 3 };  // applied last: act(acc + bias + residual)
 
 struct GemmParams {
@@ -51,6 +51,8 @@ struct GemmParams {
   int rows_per_sample;
   const bf16* residual;   // [M][ldr] or null
   int ldr;
+  float* colsum;          // EPI_GEGLU_BWD: bias gradient [N] (+=) or null
+  int n_half;             // EPI_GEGLU_BWD: N / 2 (column offset of the gate half in the plain layout)
   int dbg;                // timing experiments only (TSD_GEMM_DBG): 1 = skip B loads, 2 = skip A loads after the ring fill
   int act;                // ACT_*: pointwise activation on the finished value (codec convolutions, vqvae models.py:286-341)
 };

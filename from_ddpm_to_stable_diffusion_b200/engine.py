@@ -79,6 +79,11 @@ class UNetEngine:
         # dropout masks: Philox keyed by (seed of the layer, call counter on the device, global sample index, element)
         self.rng = DeviceRng(salt=0xD20F)
         self.section_hook = None   # callable(section) fired by backward() when a parameter section's grads are final
+        # training GEGLU without the 8C-wide pre-activation tensor: forward through the fused epilogue, backward by
+        # recomputing the pre-activations inside the GEMM that applies the activation gradient (TSD_GEGLU_FUSED_TRAIN=0:
+        # store h8 and run the stand-alone geglu kernels)
+        import os
+        self.fused_geglu_train = bool(int(os.environ.get("TSD_GEGLU_FUSED_TRAIN", "1")))
 
     @property
     def seed(self):
@@ -159,9 +164,9 @@ class UNetEngine:
             elif which != "dgrad":
                 for n in ("conv_1.1", "atten_1.1.in_proj", "atten_1.1.out_proj", "linear_2", "conv_output"):
                     lin(key + "." + n, f"{key}.{n}.weight")
-                if which == "train":
+                if which == "train":  # plain: the B operand of the data gradient dl3 = dh8 W1
                     lin(key + ".linear_1", key + ".linear_1.weight")
-                else:
+                if which == "infer" or self.fused_geglu_train:
                     lin(key + ".linear_1.geglu", key + ".linear_1.weight", ops.PACK_LINEAR_GEGLU)
                     b1 = P[key + ".linear_1.bias"]
                     E.append((key + ".linear_1.geglu_bias", b1, ops.PACK_GEGLU_BIAS, b1.shape[0], 1, (b1.shape[0],), F32))
@@ -351,7 +356,7 @@ class UNetEngine:
             t2 = ops.gemm(o, W[key + ".atten_1.1.out_proj"], C, bias=P[key + ".atten_1.1.out_proj.bias"],
                           row_bias=cb, rows_per_sample=L, residual=t0)
             l3 = ops.ln_fwd(t2, P[key + ".norm_3.weight"], P[key + ".norm_3.bias"])
-            if save:
+            if save and not self.fused_geglu_train:
                 h8 = ops.gemm(l3, W[key + ".linear_1"], 8 * C, bias=P[key + ".linear_1.bias"])
                 gg = ops.geglu_fwd(h8)
             else:
@@ -631,7 +636,11 @@ class UNetEngine:
         self._bias_grad(dt3, n, L, G[k + ".linear_2.bias"])
         ops.gemm_wgrad(dt3, rec.gg, G[k + ".linear_2.weight"])
         dgg = ops.gemm_dgrad(dt3, W[k + ".linear_2"], 4 * C)
-        dh8 = ops.geglu_bwd(rec.h8, dgg, dbias=G[k + ".linear_1.bias"])  # bias gradient as a by-product
+        if rec.h8 is None:  # pre-activations recomputed inside the GEMM whose epilogue applies the activation gradient
+            dh8 = ops.gemm_geglu_bwd(rec.l3, W[k + ".linear_1.geglu"], W[k + ".linear_1.geglu_bias"], dgg,
+                                     dbias=G[k + ".linear_1.bias"])
+        else:
+            dh8 = ops.geglu_bwd(rec.h8, dgg, dbias=G[k + ".linear_1.bias"])  # bias gradient as a by-product
         ops.gemm_wgrad(dh8, rec.l3, G[k + ".linear_1.weight"])
         dl3 = ops.gemm_dgrad(dh8, W[k + ".linear_1"], C)
         # out_proj (+ cross-attention vector + residual t0): the per-sample column sums of dt2 are the gradient of the

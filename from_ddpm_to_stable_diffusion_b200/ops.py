@@ -31,6 +31,15 @@ def gemm(a0, w, n_out, a1=None, bias=None, row_bias=None, rows_per_sample=1, res
     return d
 
 
+def gemm_geglu_bwd(a, w_geglu, bias_geglu, dgg, dbias=None):
+    """dh8 [M, 8C] of the GEGLU feed-forward input, pre-activations recomputed (no stored h8); dbias (+=) optional."""
+    M, K = a.shape
+    N = w_geglu.shape[0]
+    dh8 = empty_bf16(M, N, like=a)
+    call("tsd_gemm_geglu_bwd", _chk(a, BF16), M, K, _chk(w_geglu, BF16), N, bias_geglu, _chk(dgg, BF16), dh8, dbias)
+    return dh8
+
+
 def conv3x3(x0, n_img, H, W, w, cout, x1=None, stride=1, bias=None, row_bias=None, rows_per_sample=0, residual=None):
     c0 = x0.shape[1]
     c1 = x1.shape[1] if x1 is not None else 0

@@ -60,6 +60,13 @@ int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int c0, int c1
                     int stride, const void* w, int cout, const float* bias, const float* row_bias,
                     int rows_per_sample, const void* residual, void* d);
 
+/* Backward of the GEGLU feed-forward input (diffusion.py:151-152) without a stored pre-activation tensor:
+ * dh8[M][N] = d/dh8 of (value * gelu(gate)) where h8 = a[M][K] w^T + bias is RECOMPUTED by this GEMM (w_geglu /
+ * bias_geglu in the packing of tsd_pack_linear(geglu = 1) / tsd_pack_geglu_bias) and dgg[M][N/2] is the gradient of
+ * the GEGLU output; the activation backward runs in the epilogue (tanh-form gelu, as the forward epilogue).  dh8 is
+ * written in the plain layout [d value (N/2) | d gate (N/2)]; dbias (optional, fp32 [N], +=) receives its column sums. */
+int tsd_gemm_geglu_bwd(void* stream, const void* a, int M, int K, const void* w_geglu, int N, const float* bias_geglu,
+                       const void* dgg, void* dh8, float* dbias);
 /* tsd_conv3x3_fwd with a pointwise activation (0 or TSD_EPI_LRELU / RELU / TANH) on the finished value */
 int tsd_conv3x3_fwd_act(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int H, int W,
                         int stride, const void* w, int cout, const float* bias, const float* row_bias,

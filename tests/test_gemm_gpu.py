@@ -68,6 +68,33 @@ def test_gemm_geglu(cuda):
     _close(d, ref)
 
 
+@pytest.mark.parametrize("M,C", [(1000, 128), (4096, 256), (77, 128)])
+def test_gemm_geglu_bwd_recompute(cuda, M, C):
+    """Backward of value * gelu(gate) with the pre-activations recomputed inside the GEMM (no stored 8C-wide tensor)
+    and the bias gradient as a by-product, against torch autograd of the erf-form GEGLU on the same bf16 inputs."""
+    from from_ddpm_to_stable_diffusion_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    H = 4 * C
+    a = _bf(torch.randn(M, C, device=cuda, generator=g))
+    w = torch.randn(8 * C, C, device=cuda, generator=g) * 0.1
+    b = torch.randn(8 * C, device=cuda, generator=g) * 0.1
+    dgg = _bf(torch.randn(M, H, device=cuda, generator=g))
+    wp = ops.pack_linear(w.contiguous(), geglu=True)
+    bp = ops.pack_geglu_bias(b.contiguous())
+    dbias = torch.ones(8 * C, device=cuda)
+    dh8 = ops.gemm_geglu_bwd(a, wp, bp, dgg, dbias=dbias)
+    h = (a.float() @ _bf(w).float().t() + b).requires_grad_(True)
+    (h[:, :H] * F.gelu(h[:, H:])).backward(dgg.float())
+    torch.cuda.synchronize()
+    assert dh8.shape == (M, 8 * C)
+    _close(dh8, h.grad, tol=1.5e-2)
+    rel = ((dh8.float() - h.grad).norm() / h.grad.norm()).item()
+    assert rel < 1e-2, rel
+    cs_ref = h.grad.sum(0)
+    assert ((dbias - 1.0) - cs_ref).abs().max().item() < 2e-2 * cs_ref.abs().max().item() + 0.05 * M ** 0.5 * 0.05
+    assert torch.equal(ops.gemm_geglu_bwd(a, wp, bp, dgg), dh8)  # the by-product does not change the result
+
+
 @pytest.mark.parametrize("n,H,W,c0,c1,cout,stride", [
     (2, 16, 16, 64, 0, 128, 1), (3, 8, 8, 128, 128, 256, 1), (1, 64, 64, 64, 64, 128, 1),
     (2, 32, 32, 128, 0, 128, 2), (2, 16, 16, 64, 0, 128, 2), (4, 4, 4, 64, 0, 128, 1), (8, 2, 2, 64, 0, 128, 1),
