@@ -30,9 +30,17 @@ void zero_params(GemmParams& p) { memset(&p, 0, sizeof(p)); p.splits = 1; p.b_cp
 
 }  // namespace
 
+extern "C" int tsd_gemm_fwd_gn(void* stream, const void* a0, const void* a1, int c0, int c1, int M,
+                               const void* w, int N, const float* bias, const float* row_bias,
+                               int rows_per_sample, const void* residual, int epi, void* d, float* gn_part);
 extern "C" int tsd_gemm_fwd(void* stream, const void* a0, const void* a1, int c0, int c1, int M,
                             const void* w, int N, const float* bias, const float* row_bias,
                             int rows_per_sample, const void* residual, int epi, void* d) {
+  return tsd_gemm_fwd_gn(stream, a0, a1, c0, c1, M, w, N, bias, row_bias, rows_per_sample, residual, epi, d, nullptr);
+}
+extern "C" int tsd_gemm_fwd_gn(void* stream, const void* a0, const void* a1, int c0, int c1, int M,
+                               const void* w, int N, const float* bias, const float* row_bias,
+                               int rows_per_sample, const void* residual, int epi, void* d, float* gn_part) {
   const int K = c0 + c1;
   TSD_CHECK(M > 0 && N % 128 == 0 && K % 64 == 0 && c0 % 64 == 0, "gemm_fwd: bad shape M=%d N=%d K=%d c0=%d", M, N, K, c0);
   TSD_CHECK(c1 == 0 || a1 != nullptr, "gemm_fwd: second source missing");
@@ -50,6 +58,7 @@ extern "C" int tsd_gemm_fwd(void* stream, const void* a0, const void* a1, int c0
   p.num_kb = K / 64; p.kb_per_split = p.num_kb;
   p.a_mode = A_K2D; p.a_c0 = c0; p.b_mode = B_K2D;
   p.epi = epi; p.act = act; p.bias = bias; p.row_bias = row_bias; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : 1;
+  p.gn_part = gn_part;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = N;
   TSD_CHECK(!(epi == EPI_GEGLU && (residual || row_bias)), "gemm_fwd: GEGLU epilogue takes no residual/row bias");
   return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA0, tA1, tB, tB, tD, p);
@@ -73,18 +82,26 @@ extern "C" int tsd_gemm_geglu_bwd(void* stream, const void* a, int M, int K, con
   return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA, tA, tB, tB, tD, p);
 }
 
+extern "C" int tsd_conv3x3_fwd_gn(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
+                                  int H, int W, int stride, const void* w, int cout, const float* bias,
+                                  const float* row_bias, int rows_per_sample, const void* residual, int act, void* d,
+                                  float* gn_part);
 extern "C" int tsd_conv3x3_fwd_act(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
                                    int H, int W, int stride, const void* w, int cout, const float* bias,
-                                   const float* row_bias, int rows_per_sample, const void* residual, int act, void* d);
+                                   const float* row_bias, int rows_per_sample, const void* residual, int act, void* d) {
+  return tsd_conv3x3_fwd_gn(stream, x0, x1, c0, c1, n_img, H, W, stride, w, cout, bias, row_bias, rows_per_sample,
+                            residual, act, d, nullptr);
+}
 extern "C" int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
                                int H, int W, int stride, const void* w, int cout, const float* bias,
                                const float* row_bias, int rows_per_sample, const void* residual, void* d) {
   return tsd_conv3x3_fwd_act(stream, x0, x1, c0, c1, n_img, H, W, stride, w, cout, bias, row_bias, rows_per_sample,
                              residual, 0, d);
 }
-extern "C" int tsd_conv3x3_fwd_act(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
-                                   int H, int W, int stride, const void* w, int cout, const float* bias,
-                                   const float* row_bias, int rows_per_sample, const void* residual, int act, void* d) {
+extern "C" int tsd_conv3x3_fwd_gn(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img,
+                                  int H, int W, int stride, const void* w, int cout, const float* bias,
+                                  const float* row_bias, int rows_per_sample, const void* residual, int act, void* d,
+                                  float* gn_part) {
   const int cin = c0 + c1;
   TSD_CHECK(act == 0 || (act >= TSD_EPI_LRELU && act <= TSD_EPI_TANH), "conv3x3_fwd_act: unknown activation %d", act);
   TSD_CHECK(stride == 1 || stride == 2, "conv3x3_fwd: stride must be 1 or 2");
@@ -107,6 +124,7 @@ extern "C" int tsd_conv3x3_fwd_act(void* stream, const void* x0, const void* x1,
   p.bias = bias; p.row_bias = row_bias; p.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : Ho * Wo;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = cout;
   p.act = act ? act - TSD_EPI_LRELU + ACT_LRELU : ACT_NONE;
+  p.gn_part = gn_part;
   return launch_gemm((cudaStream_t)stream, 0, 0, 0, tA0, tA1, tB, tB, tD, p);
 }
 

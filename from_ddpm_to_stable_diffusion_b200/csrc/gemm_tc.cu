@@ -419,6 +419,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // (the next tile's residual prefetch and, one tile later, its result are written there)
       if (!OUT_F32 && ep_leader) tma_store_wait_read<0>();
       named_bar_sync(1, EPI_THREADS);
+      if (!OUT_F32 && p.gn_part) {
+        // GroupNorm statistics of the tensor being written, as a by-product: per-channel sum and sum of squares of each
+        // 64-row half of the finished tile, read back from the staging buffer (thread = one column of one half; the
+        // bf16-rounded values, i.e. exactly what a later pass over the tensor would read).  Partials are stored, not
+        // accumulated: the consumer reduces them in a fixed order, so the statistics stay bit-reproducible.
+        const int et = (warp - 4) * 32 + lane;
+        const int col = et & 127, rh = et >> 7;
+        if (m0 + rh * 64 < p.M) {
+          const uint8_t* base = staging + (col >> 6) * (BM * 128) + (col & 7) * 2;
+          const int cc = (col & 63) >> 3;
+          float sm = 0.f, sq = 0.f;
+#pragma unroll 8
+          for (int r = rh * 64; r < rh * 64 + 64; ++r) {
+            const uint16_t v = *reinterpret_cast<const uint16_t*>(base + r * 128 + ((cc ^ (r & 7)) << 4));
+            const float f = __uint_as_float(static_cast<uint32_t>(v) << 16);
+            sm += f;
+            sq = fmaf(f, f, sq);
+          }
+          *reinterpret_cast<float2*>(p.gn_part + ((size_t)(m_blk * 2 + rh) * p.N + n0 + col) * 2) = make_float2(sm, sq);
+        }
+      }
       if (!OUT_F32 && p.epi == EPI_GEGLU_BWD && p.colsum) {
         // bias gradient of the C -> 8C linear as a by-product: column sums of the finished tile, read back from the
         // staging buffer (thread = one column of one 64-row half), kept per n-block in registers across the CTA's tiles
@@ -501,6 +522,8 @@ int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUte
     const int rcols = p.epi == EPI_GEGLU_BWD ? p.n_half : p.N;
     if (make_tmap_2d(&tmR, p.residual, 2, p.M, rcols, p.ldr, 64, 128)) return 1;
   }
+  TSD_CHECK(p.gn_part == nullptr || (!out_f32 && p.epi == EPI_NONE && p.M % 64 == 0),
+            "gemm: GroupNorm partials need a plain bf16 epilogue and M %% 64 == 0");
   TSD_CHECK(p.epi != EPI_GEGLU_BWD || (p.residual && !out_f32 && p.tiles_n <= 16 && p.n_half * 2 == p.N),
             "gemm: GEGLU backward epilogue needs d(gg), bf16 output and N = 2 * n_half <= 2048");
   TSD_CHECK(p.N % BN == 0, "gemm: N=%d must be a multiple of %d", p.N, BN);

@@ -51,6 +51,7 @@ struct GemmParams {
   int rows_per_sample;
   const bf16* residual;   // [M][ldr] or null
   int ldr;
+  float* gn_part;         // null, or [ceil(M/64)][N][2] fp32: per-channel (sum, sum of squares) of every 64-row half-tile
   float* colsum;          // EPI_GEGLU_BWD: bias gradient [N] (+=) or null
   int n_half;             // EPI_GEGLU_BWD: N / 2 (column offset of the gate half in the plain layout)
   int dbg;                // timing experiments only (TSD_GEMM_DBG): 1 = skip B loads, 2 = skip A loads after the ring fill

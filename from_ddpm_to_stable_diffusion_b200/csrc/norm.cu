@@ -109,6 +109,36 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, float* __rest
   stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
+// (mean, rstd) from the per-channel partials that the producing GEMM / convolution left behind (tsd_*_fwd_gn):
+// part_k [n_img * hw / 64][c_k][2] = (sum, sum of squares) of every 64-row half-tile.  One warp per (image, group):
+// lanes walk the (half-tile, channel) pairs in a fixed order, then a shuffle tree -- reproducible run to run.
+__global__ void __launch_bounds__(256) gn_finalize_parts_kernel(const float* __restrict__ part0, const float* __restrict__ part1,
+                                                                int c0, int c1, int n_img, int halves, float inv_cnt,
+                                                                float eps, float* __restrict__ stats) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n_img * GROUPS) return;
+  const int n = wid / GROUPS, g = wid - n * GROUPS;
+  const int C = c0 + c1, cpg = C / GROUPS;
+  const int ch0 = g * cpg;
+  const bool from0 = ch0 < c0;  // a group never straddles the two sources (c0 is a multiple of the group width)
+  const float* part = from0 ? part0 : part1;
+  const int cs = from0 ? c0 : c1, cb = from0 ? ch0 : ch0 - c0;
+  float s = 0.f, q = 0.f;
+  for (int i = lane; i < halves * cpg; i += 32) {
+    const int h = i / cpg, c = i - h * cpg;
+    const float2 v = *reinterpret_cast<const float2*>(part + ((size_t)(n * halves + h) * cs + cb + c) * 2);
+    s += v.x;
+    q += v.y;
+  }
+  warp_sum2(s, q);
+  if (lane == 0) {
+    const float mean = s * inv_cnt;
+    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+    stats[2 * wid] = mean;
+    stats[2 * wid + 1] = rsqrtf(var + eps);
+  }
+}
+
 // Keep/scale factors for the 8 consecutive elements starting at flat index ebase (ebase % 8 == 0): one Philox call,
 // one 16-bit uniform per element (keep probability quantised to 1/65536).  The backward kernels regenerate the mask.
 __device__ __forceinline__ void dropout_scales8(const Philox& rng, uint64_t ebase, uint64_t ctr_hi, float p,
@@ -627,6 +657,18 @@ extern "C" int tsd_gn_stats(void* stream, const void* x0, const void* x1, int c0
   const int count = n_img * GROUPS;
   gn_finalize_kernel<<<ceil_div(count, 256), 256, 0, (cudaStream_t)stream>>>(scratch, stats, count, gx,
                                                                             1.f / ((float)hw * (C / GROUPS)), eps);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tsd_gn_stats_from_parts(void* stream, const float* part0, const float* part1, int c0, int c1, int n_img,
+                                       int hw, float eps, float* stats) {
+  const int C = c0 + c1;
+  TSD_CHECK(C % GROUPS == 0 && hw % 64 == 0 && (c1 == 0 || c0 % (C / GROUPS) == 0) && (c1 == 0 || part1 != nullptr),
+            "gn_stats_from_parts: unsupported shape c0=%d c1=%d hw=%d", c0, c1, hw);
+  const int warps = n_img * GROUPS;
+  gn_finalize_parts_kernel<<<ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      part0, part1, c0, c1, n_img, hw / 64, 1.f / ((float)hw * (C / GROUPS)), eps, stats);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -316,8 +316,10 @@ class UNetEngine:
             st1 = ops.gn_stats(x0, n, hw, 1e-5, scratch, x1=x1)
             a1 = ops.gn_apply(x0, n, hw, st1, P[key + ".conv_1.0.weight"], P[key + ".conv_1.0.bias"], True, x1=x1)
             # row_bias row = output row / rps: per image in training, one shared time row when sampling
+            # (gn=True: the epilogue also leaves the GroupNorm partial sums of its output behind -- the statistics of the
+            # next GroupNorm then need no pass over the tensor)
             hmid = ops.conv3x3(a1, n, h, w, W[key + ".conv_1.2"], co, bias=P[key + ".conv_1.2.bias"],
-                               row_bias=tb, rows_per_sample=rps)
+                               row_bias=tb, rows_per_sample=rps, gn=True)
             st2 = ops.gn_stats(hmid, n, hw, 1e-5, scratch)
             seed = 0
             layer_no[0] += 1
@@ -329,7 +331,7 @@ class UNetEngine:
                 sc = ops.gemm(x0, W[key + ".residual_layer"], co, a1=x1, bias=P[key + ".residual_layer.bias"])
             else:
                 sc = x0
-            out = ops.conv3x3(a2, n, h, w, W[key + ".conv_2.3"], co, bias=P[key + ".conv_2.3.bias"], residual=sc)
+            out = ops.conv3x3(a2, n, h, w, W[key + ".conv_2.3"], co, bias=P[key + ".conv_2.3.bias"], residual=sc, gn=True)
             if save:
                 tape.append(_Rec("res", key, b=b, x0=x0, x1=x1, st1=st1, a1=a1, hmid=hmid, st2=st2, a2=a2,
                                  p_drop=p_drop, seed=seed, pos=drop_pos, h=h, w=w))
@@ -363,7 +365,7 @@ class UNetEngine:
                 h8 = None
                 gg = ops.gemm(l3, W[key + ".linear_1.geglu"], 8 * C, bias=W[key + ".linear_1.geglu_bias"], geglu=True)
             t3 = ops.gemm(gg, W[key + ".linear_2"], C, bias=P[key + ".linear_2.bias"], residual=t2)
-            out = ops.gemm(t3, W[key + ".conv_output"], C, bias=P[key + ".conv_output.bias"], residual=x0)
+            out = ops.gemm(t3, W[key + ".conv_output"], C, bias=P[key + ".conv_output.bias"], residual=x0, gn=True)
             if save:
                 tape.append(_Rec("attn", key, b=b, x0=x0, st=st, g=g, t0=t0, l1=l1, qkv=qkv, o=o, lse=lse, t2=t2, l3=l3,
                                  h8=h8, gg=gg, t3=t3, vv=vv, h=h, w=w))
@@ -377,13 +379,13 @@ class UNetEngine:
                     if save:
                         tape.append(_Rec("head", key, b=b))
                     return out, h, w
-                out = ops.conv3x3(x0, n, h, w, W[key], b[2], stride=b[3], bias=P[key + ".bias"])
+                out = ops.conv3x3(x0, n, h, w, W[key], b[2], stride=b[3], bias=P[key + ".bias"], gn=True)
                 if save:
                     tape.append(_Rec("conv", key, b=b, x0=x0, h=h, w=w))
                 return out, h // b[3], w // b[3]
             if b[0] == "up":
                 u = ops.upsample2_fwd(x0, n, h, w)
-                out = ops.conv3x3(u, n, 2 * h, 2 * w, W[key + ".conv"], b[1], bias=P[key + ".conv.bias"])
+                out = ops.conv3x3(u, n, 2 * h, 2 * w, W[key + ".conv"], b[1], bias=P[key + ".conv.bias"], gn=True)
                 if save:
                     tape.append(_Rec("up", key, b=b, u=u, h=h, w=w))
                 return out, 2 * h, 2 * w

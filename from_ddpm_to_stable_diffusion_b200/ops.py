@@ -22,10 +22,23 @@ def empty_bf16(*shape, like):
 
 
 # ------------------------------------------------------------------ dense contractions (tcgen05)
-def gemm(a0, w, n_out, a1=None, bias=None, row_bias=None, rows_per_sample=1, residual=None, geglu=False):
+def _gn_part_for(d, M, n_out):
+    """fp32 [M / 64][n_out][2] buffer for the GroupNorm partial sums the producing kernel leaves behind; attached to the
+    output tensor so that gn_stats() on it needs no pass over the data (lost, harmlessly, when the tensor is copied)."""
+    part = torch.empty(M // 64, n_out, 2, device=d.device, dtype=F32)
+    d._gn_part = part
+    return part
+
+
+def gemm(a0, w, n_out, a1=None, bias=None, row_bias=None, rows_per_sample=1, residual=None, geglu=False, gn=False):
+    """gn: also produce the GroupNorm partial sums of the output (plain epilogue, M % 64 == 0)"""
     M, c0 = a0.shape
     c1 = a1.shape[1] if a1 is not None else 0
     d = empty_bf16(M, n_out // 2 if geglu else n_out, like=a0)
+    if gn and not geglu and M % 64 == 0:
+        call("tsd_gemm_fwd_gn", _chk(a0, BF16), a1, c0, c1, M, _chk(w, BF16), n_out, bias, row_bias, rows_per_sample,
+             residual, 0, d, _gn_part_for(d, M, n_out))
+        return d
     call("tsd_gemm_fwd", _chk(a0, BF16), a1, c0, c1, M, _chk(w, BF16), n_out, bias, row_bias, rows_per_sample,
          residual, 1 if geglu else 0, d)
     return d
@@ -40,10 +53,17 @@ def gemm_geglu_bwd(a, w_geglu, bias_geglu, dgg, dbias=None):
     return dh8
 
 
-def conv3x3(x0, n_img, H, W, w, cout, x1=None, stride=1, bias=None, row_bias=None, rows_per_sample=0, residual=None):
+def conv3x3(x0, n_img, H, W, w, cout, x1=None, stride=1, bias=None, row_bias=None, rows_per_sample=0, residual=None,
+            gn=False):
+    """gn: also produce the GroupNorm partial sums of the output (output pixels per image a multiple of 64)"""
     c0 = x0.shape[1]
     c1 = x1.shape[1] if x1 is not None else 0
-    d = empty_bf16(n_img * (H // stride) * (W // stride), cout, like=x0)
+    hw_out = (H // stride) * (W // stride)
+    d = empty_bf16(n_img * hw_out, cout, like=x0)
+    if gn and hw_out % 64 == 0:
+        call("tsd_conv3x3_fwd_gn", _chk(x0, BF16), x1, c0, c1, n_img, H, W, stride, _chk(w, BF16), cout, bias, row_bias,
+             rows_per_sample, residual, 0, d, _gn_part_for(d, n_img * hw_out, cout))
+        return d
     call("tsd_conv3x3_fwd", _chk(x0, BF16), x1, c0, c1, n_img, H, W, stride, _chk(w, BF16), cout, bias, row_bias,
          rows_per_sample, residual, d)
     return d
@@ -78,10 +98,21 @@ def conv3x3_wgrad(dy, x0, n_img, H, W, dw_packed, x1=None, stride=1):
 
 
 # ------------------------------------------------------------------ norms
+GN_FROM_PARTS = bool(int(__import__("os").environ.get("TSD_GN_EPILOGUE_STATS", "1")))
+
+
 def gn_stats(x0, n_img, hw, eps, scratch, x1=None):
+    """(mean, rstd) per (image, group).  When the kernels that wrote x0 (and x1) left their per-channel partial sums
+    behind (gemm / conv3x3 with gn=True), the statistics come from those -- no pass over the tensors."""
     c0 = x0.shape[1]
     c1 = x1.shape[1] if x1 is not None else 0
     stats = torch.empty(n_img, 32, 2, device=x0.device, dtype=F32)
+    p0 = getattr(x0, "_gn_part", None)
+    p1 = getattr(x1, "_gn_part", None) if x1 is not None else None
+    if GN_FROM_PARTS and p0 is not None and (x1 is None or p1 is not None) and hw % 64 == 0 \
+            and (c1 == 0 or c0 % ((c0 + c1) // 32) == 0):
+        call("tsd_gn_stats_from_parts", p0, p1, c0, c1, n_img, hw, f32(eps), stats)
+        return stats
     call("tsd_gn_stats", _chk(x0, BF16), x1, c0, c1, n_img, hw, f32(eps), scratch, stats)
     return stats
 

@@ -67,6 +67,19 @@ int tsd_conv3x3_fwd(void* stream, const void* x0, const void* x1, int c0, int c1
  * written in the plain layout [d value (N/2) | d gate (N/2)]; dbias (optional, fp32 [N], +=) receives its column sums. */
 int tsd_gemm_geglu_bwd(void* stream, const void* a, int M, int K, const void* w_geglu, int N, const float* bias_geglu,
                        const void* dgg, void* dh8, float* dbias);
+/* GroupNorm statistics as a by-product of the kernel that writes the tensor (north star: norm fused into the producing
+ * epilogue).  tsd_gemm_fwd_gn / tsd_conv3x3_fwd_gn are tsd_gemm_fwd / tsd_conv3x3_fwd_act with one more output:
+ * gn_part fp32 [M / 64][N][2] = (sum, sum of squares) per channel of every 64-row half-tile of d (the bf16-rounded
+ * values; M % 64 == 0, plain epilogue).  tsd_gn_stats_from_parts reduces the partials of x0 (and x1, for a channel
+ * concat) to the (mean, rstd) of tsd_gn_stats in a fixed order, without reading the tensors (hw % 64 == 0). */
+int tsd_gemm_fwd_gn(void* stream, const void* a0, const void* a1, int c0, int c1, int M, const void* w, int N,
+                    const float* bias, const float* row_bias, int rows_per_sample, const void* residual, int epi, void* d,
+                    float* gn_part);
+int tsd_conv3x3_fwd_gn(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int H, int W,
+                       int stride, const void* w, int cout, const float* bias, const float* row_bias,
+                       int rows_per_sample, const void* residual, int act, void* d, float* gn_part);
+int tsd_gn_stats_from_parts(void* stream, const float* part0, const float* part1, int c0, int c1, int n_img, int hw,
+                            float eps, float* stats);
 /* tsd_conv3x3_fwd with a pointwise activation (0 or TSD_EPI_LRELU / RELU / TANH) on the finished value */
 int tsd_conv3x3_fwd_act(void* stream, const void* x0, const void* x1, int c0, int c1, int n_img, int H, int W,
                         int stride, const void* w, int cout, const float* bias, const float* row_bias,

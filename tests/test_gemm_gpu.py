@@ -68,6 +68,37 @@ def test_gemm_geglu(cuda):
     _close(d, ref)
 
 
+@pytest.mark.parametrize("n,H,c0,c1,cout", [(3, 16, 128, 0, 128), (2, 8, 128, 128, 256), (5, 32, 64, 0, 128)])
+def test_groupnorm_statistics_from_the_producing_epilogue(cuda, n, H, c0, c1, cout):
+    """conv3x3 / GEMM with gn=True leave per-channel partial sums of their output behind; GroupNorm statistics from those
+    partials (no pass over the tensor) equal the stand-alone statistics kernel, also for a channel concat of two such
+    tensors (decoder skip connections)."""
+    from from_ddpm_to_stable_diffusion_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n * H + cout)
+    hw = H * H
+    x0 = _bf(torch.randn(n * hw, c0, device=cuda, generator=g))
+    x1 = _bf(torch.randn(n * hw, c1, device=cuda, generator=g)) if c1 else None
+    w = pack_conv(torch.randn(cout, c0 + c1, 3, 3, device=cuda, generator=g) * 0.05)
+    bias = torch.randn(cout, device=cuda, generator=g)
+    res = _bf(torch.randn(n * hw, cout, device=cuda, generator=g))
+    y = ops.conv3x3(x0, n, H, H, w, cout, x1=x1, bias=bias, residual=res, gn=True)
+    assert torch.equal(y, ops.conv3x3(x0, n, H, H, w, cout, x1=x1, bias=bias, residual=res))  # the by-product changes nothing
+    wl = _bf(torch.randn(cout, cout, device=cuda, generator=g) * 0.1)
+    z = ops.gemm(y, wl, cout, bias=bias, residual=y, gn=True)
+    scratch = torch.zeros(ops.gn_scratch_floats(n), device=cuda)
+    for (a0, a1) in ((y, None), (z, None), (y, z)):
+        got = ops.gn_stats(a0, n, hw, 1e-5, scratch, x1=a1)          # from the partials
+        b0 = a0.clone()
+        b1 = a1.clone() if a1 is not None else None                  # clones carry no partials: the stand-alone kernel
+        ref = ops.gn_stats(b0, n, hw, 1e-5, scratch, x1=b1)
+        assert hasattr(a0, "_gn_part") and not hasattr(b0, "_gn_part")
+        assert (got[..., 0] - ref[..., 0]).abs().max().item() < 1e-5
+        assert ((got[..., 1] - ref[..., 1]).abs() / ref[..., 1]).max().item() < 1e-5
+        full = a0.float() if a1 is None else torch.cat([a0, a1], 1).float()
+        m_ref = full.view(n, hw, 32, -1).permute(0, 2, 1, 3).reshape(n, 32, -1).mean(-1)
+        assert (got[..., 0] - m_ref).abs().max().item() < 1e-3
+
+
 @pytest.mark.parametrize("M,C", [(1000, 128), (4096, 256), (77, 128)])
 def test_gemm_geglu_bwd_recompute(cuda, M, C):
     """Backward of value * gelu(gate) with the pre-activations recomputed inside the GEMM (no stored 8C-wide tensor)
