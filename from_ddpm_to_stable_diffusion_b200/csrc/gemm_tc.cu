@@ -419,6 +419,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // (the next tile's residual prefetch and, one tile later, its result are written there)
       if (!OUT_F32 && ep_leader) tma_store_wait_read<0>();
       named_bar_sync(1, EPI_THREADS);
+      if (ep_leader) {
+        if (OUT_F32) {
+#pragma unroll
+          for (int ch = 0; ch < BN / 32; ++ch)
+            tma_reduce_add_2d(&tmD, smem_staging + ch * (BM * 128), n0 + ch * 32, m0);
+        } else {
+          // the other staging buffer was the source of tile it-1's store: once that has been read it can take
+          // the next tile's residual (prefetch) and, one tile later, the next result
+          if (has_res && tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + gridDim.x, sbuf ^ 1);
+          if (p.epi == EPI_GEGLU) {
+            tma_store_2d(&tmD, staging_s, n0 / 2, m0);
+          } else if (p.epi == EPI_GEGLU_BWD) {  // dh8 in the plain layout: [d value (n_half) | d gate (n_half)]
+            tma_store_2d(&tmD, staging_s, n0 / 2, m0);
+            tma_store_2d(&tmD, staging_s + BM * 128, p.n_half + n0 / 2, m0);
+          } else {
+            tma_store_2d(&tmD, staging_s, n0, m0);
+            tma_store_2d(&tmD, staging_s + BM * 128, n0 + 64, m0);
+          }
+        }
+        tma_store_commit();
+      }
+      // by-products computed from the finished staging tile AFTER the leader has issued the store and the next residual
+      // prefetch (doing them first delayed both by a microsecond per tile and made the epilogue the critical path)
       if (!OUT_F32 && p.gn_part) {
         // GroupNorm statistics of the tensor being written, as a by-product: per-channel sum and sum of squares of each
         // 64-row half of the finished tile, read back from the staging buffer (thread = one column of one half; the
@@ -453,27 +476,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           part += __uint_as_float(static_cast<uint32_t>(v) << 16);
         }
         cs_acc[n_blk & 15] += part;
-      }
-      if (ep_leader) {
-        if (OUT_F32) {
-#pragma unroll
-          for (int ch = 0; ch < BN / 32; ++ch)
-            tma_reduce_add_2d(&tmD, smem_staging + ch * (BM * 128), n0 + ch * 32, m0);
-        } else {
-          // the other staging buffer was the source of tile it-1's store: once that has been read it can take
-          // the next tile's residual (prefetch) and, one tile later, the next result
-          if (has_res && tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + gridDim.x, sbuf ^ 1);
-          if (p.epi == EPI_GEGLU) {
-            tma_store_2d(&tmD, staging_s, n0 / 2, m0);
-          } else if (p.epi == EPI_GEGLU_BWD) {  // dh8 in the plain layout: [d value (n_half) | d gate (n_half)]
-            tma_store_2d(&tmD, staging_s, n0 / 2, m0);
-            tma_store_2d(&tmD, staging_s + BM * 128, p.n_half + n0 / 2, m0);
-          } else {
-            tma_store_2d(&tmD, staging_s, n0, m0);
-            tma_store_2d(&tmD, staging_s + BM * 128, n0 + 64, m0);
-          }
-        }
-        tma_store_commit();
       }
     }
     if (ep_leader) tma_store_wait_all<0>();

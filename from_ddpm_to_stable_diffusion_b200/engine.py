@@ -166,11 +166,16 @@ class UNetEngine:
                     lin(key + "." + n, f"{key}.{n}.weight")
                 if which == "train":  # plain: the B operand of the data gradient dl3 = dh8 W1
                     lin(key + ".linear_1", key + ".linear_1.weight")
-                if which == "infer" or self.fused_geglu_train:
+                if which == "infer" or self._geglu_fused(b[1]):
                     lin(key + ".linear_1.geglu", key + ".linear_1.weight", ops.PACK_LINEAR_GEGLU)
                     b1 = P[key + ".linear_1.bias"]
                     E.append((key + ".linear_1.geglu_bias", b1, ops.PACK_GEGLU_BIAS, b1.shape[0], 1, (b1.shape[0],), F32))
         return E
+
+    def _geglu_fused(self, C):
+        """training GEGLU through the fused forward epilogue + recomputing backward GEMM (8C <= 2048: its per-thread
+        bias-gradient partials cover 16 n-blocks); wider blocks keep the stored pre-activations"""
+        return self.fused_geglu_train and 8 * C <= 2048
 
     def _pack_set(self, P, which):
         """Packed copies of one set, refreshed by ONE kernel launch when any parameter changed.  The destination buffers
@@ -358,7 +363,7 @@ class UNetEngine:
             t2 = ops.gemm(o, W[key + ".atten_1.1.out_proj"], C, bias=P[key + ".atten_1.1.out_proj.bias"],
                           row_bias=cb, rows_per_sample=L, residual=t0)
             l3 = ops.ln_fwd(t2, P[key + ".norm_3.weight"], P[key + ".norm_3.bias"])
-            if save and not self.fused_geglu_train:
+            if save and not self._geglu_fused(C):
                 h8 = ops.gemm(l3, W[key + ".linear_1"], 8 * C, bias=P[key + ".linear_1.bias"])
                 gg = ops.geglu_fwd(h8)
             else:

@@ -41,12 +41,14 @@ else:
     s = SamplerDDPM(model, 0.0015, 0.0195, 1000, w=1.8).to(dev)
     xT = torch.randn(B, 3, 64, 64, device=dev)
     ys = torch.randint(1, 4, (B,), device=dev)
+    NS = int(os.environ.get("TSD_NCU_SAMPLE_STEPS", "3"))  # replays inside the profiled range (use ~40 for plain timing)
     s(xT, ys, steps=range(999, 993, -1))
+    s(xT, ys, steps=range(999, 996, -1))  # hoisted conditioning and graph are warm now
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStart()
     e0.record()
-    s(xT, ys, steps=range(999, 996, -1))  # 3 graph replays
+    s(xT, ys, steps=range(999, 999 - NS, -1))
     e1.record()
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
-    print(f"3 reverse steps, {B} images: {e0.elapsed_time(e1) / 3:.3f} ms per step")
+    print(f"{NS} reverse steps, {B} images: {e0.elapsed_time(e1) / NS:.3f} ms per step (includes the per-call conditioning set-up)")
