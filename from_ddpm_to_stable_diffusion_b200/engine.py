@@ -356,12 +356,22 @@ class UNetEngine:
             l1 = ops.ln_fwd(t0, P[key + ".atten_1.0.weight"], P[key + ".atten_1.0.bias"])
             qkv = ops.gemm(l1, W[key + ".atten_1.1.in_proj"], 3 * C)
             o, lse = ops.attn_fwd(qkv, n, L, C, m.N_HEAD, need_lse=save)
-            if key == first_attn:  # the cross-attention vector is the first label-dependent term: widen to all rows
+            widen = key == first_attn
+            if widen:
+                # the cross-attention vector is the first label-dependent term: from here on all n_full rows exist.  o,
+                # t0 and the block input x0 are not duplicated: the two halves of t2 (and of the block output below) are
+                # produced by two GEMM calls that read the same n rows; only the skip tensors are copied
+                nh = n
                 n = n_full
-                o, t0, x0 = torch.cat([o, o]), torch.cat([t0, t0]), torch.cat([x0, x0])
                 skips[:] = [torch.cat([sk, sk]) for sk in skips]
-            t2 = ops.gemm(o, W[key + ".atten_1.1.out_proj"], C, bias=P[key + ".atten_1.1.out_proj.bias"],
-                          row_bias=cb, rows_per_sample=L, residual=t0)
+                t2 = ops.empty_bf16(n * L, C, like=o)
+                for hf in range(2):
+                    ops.gemm(o, W[key + ".atten_1.1.out_proj"], C, bias=P[key + ".atten_1.1.out_proj.bias"],
+                             row_bias=cb[hf * nh:(hf + 1) * nh], rows_per_sample=L, residual=t0,
+                             out=t2[hf * nh * L:(hf + 1) * nh * L])
+            else:
+                t2 = ops.gemm(o, W[key + ".atten_1.1.out_proj"], C, bias=P[key + ".atten_1.1.out_proj.bias"],
+                              row_bias=cb, rows_per_sample=L, residual=t0)
             l3 = ops.ln_fwd(t2, P[key + ".norm_3.weight"], P[key + ".norm_3.bias"])
             if save and not self._geglu_fused(C):
                 h8 = ops.gemm(l3, W[key + ".linear_1"], 8 * C, bias=P[key + ".linear_1.bias"])
@@ -370,7 +380,15 @@ class UNetEngine:
                 h8 = None
                 gg = ops.gemm(l3, W[key + ".linear_1.geglu"], 8 * C, bias=W[key + ".linear_1.geglu_bias"], geglu=True)
             t3 = ops.gemm(gg, W[key + ".linear_2"], C, bias=P[key + ".linear_2.bias"], residual=t2)
-            out = ops.gemm(t3, W[key + ".conv_output"], C, bias=P[key + ".conv_output.bias"], residual=x0, gn=True)
+            if widen:  # both halves add the same (un-duplicated) block input
+                out = ops.empty_bf16(n * L, C, like=t3)
+                part = ops._gn_part_for(out, n * L, C) if L % 64 == 0 else None
+                for hf in range(2):
+                    rows = slice(hf * nh * L, (hf + 1) * nh * L)
+                    ops.gemm(t3[rows], W[key + ".conv_output"], C, bias=P[key + ".conv_output.bias"], residual=x0,
+                             out=out[rows], gn_part=None if part is None else part[hf * nh * L // 64:(hf + 1) * nh * L // 64])
+            else:
+                out = ops.gemm(t3, W[key + ".conv_output"], C, bias=P[key + ".conv_output.bias"], residual=x0, gn=True)
             if save:
                 tape.append(_Rec("attn", key, b=b, x0=x0, st=st, g=g, t0=t0, l1=l1, qkv=qkv, o=o, lse=lse, t2=t2, l3=l3,
                                  h8=h8, gg=gg, t3=t3, vv=vv, h=h, w=w))

@@ -30,11 +30,17 @@ def _gn_part_for(d, M, n_out):
     return part
 
 
-def gemm(a0, w, n_out, a1=None, bias=None, row_bias=None, rows_per_sample=1, residual=None, geglu=False, gn=False):
-    """gn: also produce the GroupNorm partial sums of the output (plain epilogue, M % 64 == 0)"""
+def gemm(a0, w, n_out, a1=None, bias=None, row_bias=None, rows_per_sample=1, residual=None, geglu=False, gn=False,
+         out=None, gn_part=None):
+    """gn: also produce the GroupNorm partial sums of the output (plain epilogue, M % 64 == 0).  out / gn_part: write
+    into caller-provided (row-slices of) buffers instead of allocating."""
     M, c0 = a0.shape
     c1 = a1.shape[1] if a1 is not None else 0
-    d = empty_bf16(M, n_out // 2 if geglu else n_out, like=a0)
+    d = empty_bf16(M, n_out // 2 if geglu else n_out, like=a0) if out is None else _chk(out, BF16)
+    if gn_part is not None:
+        call("tsd_gemm_fwd_gn", _chk(a0, BF16), a1, c0, c1, M, _chk(w, BF16), n_out, bias, row_bias, rows_per_sample,
+             residual, 0, d, _chk(gn_part, F32))
+        return d
     if gn and not geglu and M % 64 == 0:
         call("tsd_gemm_fwd_gn", _chk(a0, BF16), a1, c0, c1, M, _chk(w, BF16), n_out, bias, row_bias, rows_per_sample,
              residual, 0, d, _gn_part_for(d, M, n_out))
