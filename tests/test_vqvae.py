@@ -115,3 +115,30 @@ def test_image_to_latent_to_image_with_denoiser(cuda):
     z0 = sampler(lat, torch.tensor([1, 2], device=cuda), steps=range(20, -1, -1))  # last 21 reverse steps from the latents
     img = m.decode(z0)
     assert img.shape == (2, 3, 64, 64) and torch.isfinite(img).all() and float(img.abs().max()) <= 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("in_ch,D,K,hidden,img", [(3, 8, 64, [32, 64], 32), (1, 4, 96, [64, 128, 256], 64), (3, 16, 512, [128], 16)])
+def test_codec_other_geometries_vs_oracle(cuda, in_ch, D, K, hidden, img):
+    """Hidden widths that are not multiples of the GEMM tile (zero-padded channels), one / three down-sampling stages,
+    a codebook larger than one shared-memory tile: encode, quantise and decode against the oracle on the same weights."""
+    sd = V.init_state_dict(3, in_ch, D, K, hidden)
+    cfg = dict(in_channels=in_ch, embedding_dim=D, num_embeddings=K, hidden_dims=hidden)
+    m = _module(cuda, sd, cfg)
+    g = torch.Generator().manual_seed(img)
+    x = torch.randn(3, in_ch, img, img, generator=g).clamp(-2.5, 2.5)
+    nh = len(hidden)
+    with torch.no_grad():
+        lat_ref = V.encode(sd, x, nh)
+        zq_ref, loss_ref, idx_ref, dist = V.quantize({k: v.double() for k, v in sd.items()}, lat_ref.double())
+        rec_ref = V.decode(sd, zq_ref.float(), nh)
+    lat = m.encode(x.to(cuda))[0]
+    assert lat.shape == lat_ref.shape and _rel(lat, lat_ref) < 2e-2
+    zq, loss, idx = m.quantize(lat_ref.to(cuda))
+    diff = (idx.cpu() != idx_ref).nonzero().flatten()
+    for i in diff.tolist():  # only near-ties may differ from the fp64 oracle
+        d = dist[i]
+        assert abs(d[idx[i].item()] - d[idx_ref[i]]) < 1e-5 * max(1.0, float(d.abs().max())), i
+    assert diff.numel() <= 2 and abs(loss.item() - loss_ref.item()) / loss_ref.item() < 1e-3
+    rec = m.decode(zq_ref.float().to(cuda))
+    assert rec.shape == (3, 3, img, img) and _rel(rec, rec_ref) < 2e-2
