@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtinysd_b200.so")
+LIB_PATH = os.environ.get("TSD_LIB") or os.path.join(_HERE, "libtinysd_b200.so")  # TSD_LIB: an alternative build (A/B runs)
 
 _lib = None
 

@@ -10,8 +10,24 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 16 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
-constexpr int EPI_THREADS = 256;
+// Epilogue warps: EPI_Q per TMEM sub-partition, each draining 128 / EPI_Q accumulator columns.  Measured (same box,
+// alternating builds): 16 epilogue warps of 96 registers (-DTSD_EPI_Q=4) against 8 of 168 -- training step 136.4 vs
+// 135.8 ms, reverse step 77.7 vs 77.2 ms: the epilogue-heavy K = 128 layers are not short of warps, and the HBM-bound
+// ones lose a little.  8 it stays.
+#ifndef TSD_EPI_Q
+#define TSD_EPI_Q 2
+#endif
+constexpr int EPI_Q = TSD_EPI_Q;
+constexpr int EPI_THREADS = 4 * EPI_Q * 32;
+constexpr int NUM_THREADS = 128 + EPI_THREADS;  // 4 control warps + the epilogue warps
+constexpr int EPI_CH = 4 / EPI_Q;               // 32-column chunks per epilogue warp (plain / fp32 paths)
+constexpr int EPI_PAIRS = 64 / EPI_Q;           // (value, gate) pairs per thread (GEGLU paths)
+constexpr int GN_ROWS = 128 * 128 / EPI_THREADS;  // rows per thread of the column-wise by-products (32)
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
+  if constexpr (N == 32) tmem_ld32(taddr, r);
+  else tmem_ld16(taddr, r);
+}
 constexpr int TMEM_COLS = 256;  // two 128-column fp32 accumulators
 
 template <int OUT_F32>
@@ -218,9 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp >= 4) {
     // =========================================================== epilogue
-    // Eight epilogue warps: warps w and w+4 share TMEM sub-partition (w % 4) and split the 128 columns.
+    // Epilogue warps w, w+4, ... share TMEM sub-partition (w % 4) and split the 128 columns into EPI_Q groups.
     const int ep_warp = (warp - 4) & 3;      // TMEM sub-partition
-    const int half = (warp - 4) >> 2;        // column half handled by this warp
+    const int half = (warp - 4) >> 2;        // column group handled by this warp (0 .. EPI_Q-1)
     const int ep_tid = ep_warp * 32 + lane;  // == TMEM lane == row inside the tile
     const bool ep_leader = (warp == 4 && lane == 0);
     const uint32_t lane_off = static_cast<uint32_t>(ep_warp * 32) << 16;
@@ -273,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int r7 = ep_tid & 7;
       if (OUT_F32) {
 #pragma unroll 1
-        for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
+        for (int ch = half * EPI_CH; ch < half * EPI_CH + EPI_CH; ++ch) {
           uint32_t v[32];
           tmem_ld32(t_addr + ch * 32, v);
           tmem_ld_wait();
@@ -290,15 +306,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // buffer: dx = d * gelu(g) goes back over d, dg = d * x * gelu'(g) into the second half; gelu in the tanh form of
         // the forward epilogue (geglu_fast_f), one MUFU per element for value and derivative together.
         const int ch = half;
-        uint32_t xv[32], gv[32];
-        tmem_ld32(t_addr + ch * 32, xv);
-        tmem_ld32(t_addr + 64 + ch * 32, gv);
+        uint32_t xv[EPI_PAIRS], gv[EPI_PAIRS];
+        tmem_ld_n<EPI_PAIRS>(t_addr + ch * EPI_PAIRS, xv);
+        tmem_ld_n<EPI_PAIRS>(t_addr + 64 + ch * EPI_PAIRS, gv);
         tmem_ld_wait();
         uint8_t* row_d = staging + ep_tid * 128;
         uint8_t* row_g = staging + BM * 128 + ep_tid * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int cj = ch * 4 + q;
+        for (int q = 0; q < EPI_PAIRS / 8; ++q) {
+          const int cj = ch * (EPI_PAIRS / 8) + q;
           const uint4 dv4 = *reinterpret_cast<const uint4*>(row_d + ((cj ^ r7) << 4));
           const uint32_t dw[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
           uint32_t ox[4], og[4];
@@ -308,8 +324,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             float x[2] = {__uint_as_float(xv[j]), __uint_as_float(xv[j + 1])};
             float g[2] = {__uint_as_float(gv[j]), __uint_as_float(gv[j + 1])};
             if (p.bias) {
-              const float2 bx = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + ch * 32 + j));
-              const float2 bg = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + 64 + ch * 32 + j));
+              const float2 bx = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + ch * EPI_PAIRS + j));
+              const float2 bg = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + 64 + ch * EPI_PAIRS + j));
               x[0] += bx.x; x[1] += bx.y; g[0] += bg.x; g[1] += bg.y;
             }
             const float2 d = unpack_bf16(dw[e]);
@@ -335,13 +351,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // columns [0,64) = value half, [64,128) = gate half (weights are packed that way)
         {
           const int ch = half;
-          uint32_t xv[32], gv[32];
-          tmem_ld32(t_addr + ch * 32, xv);
-          tmem_ld32(t_addr + 64 + ch * 32, gv);
+          uint32_t xv[EPI_PAIRS], gv[EPI_PAIRS];
+          tmem_ld_n<EPI_PAIRS>(t_addr + ch * EPI_PAIRS, xv);
+          tmem_ld_n<EPI_PAIRS>(t_addr + 64 + ch * EPI_PAIRS, gv);
           tmem_ld_wait();
           uint8_t* dst = staging + ep_tid * 128;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < EPI_PAIRS / 8; ++q) {
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -349,19 +365,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
               float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
               if (p.bias) {
-                const float2 bx = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + ch * 32 + j));
-                const float2 bg = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + 64 + ch * 32 + j));
+                const float2 bx = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + ch * EPI_PAIRS + j));
+                const float2 bg = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + 64 + ch * EPI_PAIRS + j));
                 x0 += bx.x; x1 += bx.y; g0 += bg.x; g1 += bg.y;
               }
               o[e] = pack_bf16(geglu_fast_f(x0, g0), geglu_fast_f(x1, g1));
             }
-            const int cj = ch * 4 + q;
+            const int cj = ch * (EPI_PAIRS / 8) + q;
             *reinterpret_cast<uint4*>(dst + ((cj ^ r7) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
       } else {
 #pragma unroll 1
-        for (int ch = half * 2; ch < half * 2 + 2; ++ch) {
+        for (int ch = half * EPI_CH; ch < half * EPI_CH + EPI_CH; ++ch) {
           uint32_t v[32];
           tmem_ld32(t_addr + ch * 32, v);
           tmem_ld_wait();
@@ -444,34 +460,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // prefetch (doing them first delayed both by a microsecond per tile and made the epilogue the critical path)
       if (!OUT_F32 && p.gn_part) {
         // GroupNorm statistics of the tensor being written, as a by-product: per-channel sum and sum of squares of each
-        // 64-row half of the finished tile, read back from the staging buffer (thread = one column of one half; the
+        // 32-row quarter of the finished tile, read back from the staging buffer (thread = one column of one half; the
         // bf16-rounded values, i.e. exactly what a later pass over the tensor would read).  Partials are stored, not
         // accumulated: the consumer reduces them in a fixed order, so the statistics stay bit-reproducible.
         const int et = (warp - 4) * 32 + lane;
         const int col = et & 127, rh = et >> 7;
-        if (m0 + rh * 64 < p.M) {
+        if (m0 + rh * GN_ROWS < p.M) {
           const uint8_t* base = staging + (col >> 6) * (BM * 128) + (col & 7) * 2;
           const int cc = (col & 63) >> 3;
-          float sm = 0.f, sq = 0.f;
+#pragma unroll
+          for (int sub = 0; sub < GN_ROWS / 32; ++sub) {  // partials have a fixed 32-row granularity
+            const int r0 = rh * GN_ROWS + sub * 32;
+            float sm = 0.f, sq = 0.f;
 #pragma unroll 8
-          for (int r = rh * 64; r < rh * 64 + 64; ++r) {
-            const uint16_t v = *reinterpret_cast<const uint16_t*>(base + r * 128 + ((cc ^ (r & 7)) << 4));
-            const float f = __uint_as_float(static_cast<uint32_t>(v) << 16);
-            sm += f;
-            sq = fmaf(f, f, sq);
+            for (int r = r0; r < r0 + 32; ++r) {
+              const uint16_t v = *reinterpret_cast<const uint16_t*>(base + r * 128 + ((cc ^ (r & 7)) << 4));
+              const float f = __uint_as_float(static_cast<uint32_t>(v) << 16);
+              sm += f;
+              sq = fmaf(f, f, sq);
+            }
+            if (m0 + r0 < p.M)
+              *reinterpret_cast<float2*>(p.gn_part + ((size_t)(m_blk * 4 + (r0 >> 5)) * p.N + n0 + col) * 2) = make_float2(sm, sq);
           }
-          *reinterpret_cast<float2*>(p.gn_part + ((size_t)(m_blk * 2 + rh) * p.N + n0 + col) * 2) = make_float2(sm, sq);
         }
       }
       if (!OUT_F32 && p.epi == EPI_GEGLU_BWD && p.colsum) {
         // bias gradient of the C -> 8C linear as a by-product: column sums of the finished tile, read back from the
         // staging buffer (thread = one column of one 64-row half), kept per n-block in registers across the CTA's tiles
         const int et = (warp - 4) * 32 + lane;
-        const int col = et & 63, which = (et >> 6) & 1, r_lo = (et >> 7) * 64;
+        const int col = et & 63, which = (et >> 6) & 1, r_lo = (et >> 7) * GN_ROWS;
         const uint8_t* base = staging + which * (BM * 128) + (col & 7) * 2;
         float part = 0.f;
 #pragma unroll 8
-        for (int r = r_lo; r < r_lo + 64; ++r) {
+        for (int r = r_lo; r < r_lo + GN_ROWS; ++r) {
           const uint16_t v = *reinterpret_cast<const uint16_t*>(base + r * 128 + (((col >> 3) ^ (r & 7)) << 4));
           part += __uint_as_float(static_cast<uint32_t>(v) << 16);
         }

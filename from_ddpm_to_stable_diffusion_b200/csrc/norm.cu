@@ -110,7 +110,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, float* __rest
 }
 
 // (mean, rstd) from the per-channel partials that the producing GEMM / convolution left behind (tsd_*_fwd_gn):
-// part_k [n_img * hw / 64][c_k][2] = (sum, sum of squares) of every 64-row half-tile.  One warp per (image, group):
+// part_k [n_img * hw / 32][c_k][2] = (sum, sum of squares) of every 32-row quarter-tile.  One warp per (image, group):
 // lanes walk the (half-tile, channel) pairs in a fixed order, then a shuffle tree -- reproducible run to run.
 __global__ void __launch_bounds__(256) gn_finalize_parts_kernel(const float* __restrict__ part0, const float* __restrict__ part1,
                                                                 int c0, int c1, int n_img, int halves, float inv_cnt,
@@ -668,7 +668,7 @@ extern "C" int tsd_gn_stats_from_parts(void* stream, const float* part0, const f
             "gn_stats_from_parts: unsupported shape c0=%d c1=%d hw=%d", c0, c1, hw);
   const int warps = n_img * GROUPS;
   gn_finalize_parts_kernel<<<ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      part0, part1, c0, c1, n_img, hw / 64, 1.f / ((float)hw * (C / GROUPS)), eps, stats);
+      part0, part1, c0, c1, n_img, hw / 32, 1.f / ((float)hw * (C / GROUPS)), eps, stats);
   TSD_LAUNCH_CHECK();
   return 0;
 }

@@ -386,7 +386,7 @@ class UNetEngine:
                 for hf in range(2):
                     rows = slice(hf * nh * L, (hf + 1) * nh * L)
                     ops.gemm(t3[rows], W[key + ".conv_output"], C, bias=P[key + ".conv_output.bias"], residual=x0,
-                             out=out[rows], gn_part=None if part is None else part[hf * nh * L // 64:(hf + 1) * nh * L // 64])
+                             out=out[rows], gn_part=None if part is None else part[hf * nh * L // 32:(hf + 1) * nh * L // 32])
             else:
                 out = ops.gemm(t3, W[key + ".conv_output"], C, bias=P[key + ".conv_output.bias"], residual=x0, gn=True)
             if save:

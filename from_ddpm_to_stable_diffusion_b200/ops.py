@@ -23,9 +23,9 @@ def empty_bf16(*shape, like):
 
 # ------------------------------------------------------------------ dense contractions (tcgen05)
 def _gn_part_for(d, M, n_out):
-    """fp32 [M / 64][n_out][2] buffer for the GroupNorm partial sums the producing kernel leaves behind; attached to the
+    """fp32 [M / 32][n_out][2] buffer for the GroupNorm partial sums the producing kernel leaves behind; attached to the
     output tensor so that gn_stats() on it needs no pass over the data (lost, harmlessly, when the tensor is copied)."""
-    part = torch.empty(M // 64, n_out, 2, device=d.device, dtype=F32)
+    part = torch.empty(M // 32, n_out, 2, device=d.device, dtype=F32)
     d._gn_part = part
     return part
 

@@ -69,7 +69,7 @@ int tsd_gemm_geglu_bwd(void* stream, const void* a, int M, int K, const void* w_
                        const void* dgg, void* dh8, float* dbias);
 /* GroupNorm statistics as a by-product of the kernel that writes the tensor (north star: norm fused into the producing
  * epilogue).  tsd_gemm_fwd_gn / tsd_conv3x3_fwd_gn are tsd_gemm_fwd / tsd_conv3x3_fwd_act with one more output:
- * gn_part fp32 [M / 64][N][2] = (sum, sum of squares) per channel of every 64-row half-tile of d (the bf16-rounded
+ * gn_part fp32 [M / 32][N][2] = (sum, sum of squares) per channel of every 32-row quarter-tile of d (the bf16-rounded
  * values; M % 64 == 0, plain epilogue).  tsd_gn_stats_from_parts reduces the partials of x0 (and x1, for a channel
  * concat) to the (mean, rstd) of tsd_gn_stats in a fixed order, without reading the tensors (hw % 64 == 0). */
 int tsd_gemm_fwd_gn(void* stream, const void* a0, const void* a1, int c0, int c1, int M, const void* w, int N,
