@@ -119,8 +119,10 @@ def test_graphed_iteration_matches_eager(cuda):
     assert opt1.step_count == opt2.step_count == 4
     assert tr1.rng.calls == tr2.rng.calls and m1._engine.rng.calls == m2._engine.rng.calls
     assert len(set(eager)) == 4  # every step drew new timesteps / noise
+    # dQ's arrival-order sums make two runs of the same step differ in the last bits; at lr 1e-4 the loss moves by 15 %
+    # per step, which amplifies that to ~1e-4 relative after one step (stale weights would show as ~1e-1)
     for a, b in zip(eager, graphed):
-        assert abs(a - b) / abs(a) < 1e-4, (eager, graphed)
+        assert abs(a - b) / abs(a) < 1e-3, (eager, graphed)
     # dQ partials are summed by the L2 in arrival order, so the two runs agree to fp32 re-association, not bit for bit;
     # Adam turns noise-level gradients into +-lr steps, so a few weights differ by O(lr) after four steps
     assert _rel(opt2.flat_p, opt1.flat_p) < 2e-3
@@ -249,4 +251,4 @@ def test_graph_is_recaptured_when_the_engine_replaces_its_buffers(cuda):
     m2, tr2, opt2 = _setup(cuda, 0.0)
     train_step(tr2, opt2, data[0][0].to(cuda), data[0][1].to(cuda), rng=_NoDrop)
     lb = train_step(tr2, opt2, data[1][0].to(cuda), data[1][1].to(cuda), rng=_NoDrop).item()
-    assert abs(la - lb) / abs(lb) < 1e-4, (la, lb)
+    assert abs(la - lb) / abs(lb) < 1e-3, (la, lb)
