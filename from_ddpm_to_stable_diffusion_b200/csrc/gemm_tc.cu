@@ -29,6 +29,38 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
   else tmem_ld16(taddr, r);
 }
 constexpr int TMEM_COLS = 256;  // two 128-column fp32 accumulators
+constexpr int MAX_RING = 8, MAX_ARING = 4;  // mbarrier pairs reserved for the operand rings
+
+// ---- halo mode of the 3x3 convolution (A_KHALO): the M tile is a 16-row x 8-pixel patch of ONE image, and the
+// activations of a 64-channel block are loaded once per patch instead of once per tap.  An 8-pixel image row of 64
+// channels is exactly one SWIZZLE_128B atom (8 x 128 B), so a K-major UMMA descriptor with SBO = one halo row walks down
+// the 16 patch rows, and a tap's vertical shift is a whole number of atoms:
+//   halo == 1: three x-shifted copies {64 ch, 8 px, 18 rows} (18 KB each, one ring slot per copy); tap (dy, dx) reads
+//              copy dx from row dy on -- every descriptor start stays 1024-byte aligned.  A traffic: 54 KB per patch and
+//              channel block instead of 9 x 16 KB.
+//   halo == 2: one copy {64 ch, 10 px, 18 rows} (22.5 KB); tap (dy, dx) starts dy rows + dx pixels in, i.e. NOT on an
+//              atom boundary -- correct as it stands, because TMA and UMMA both derive the swizzle phase from the
+//              absolute shared-memory address.  A traffic: 22.5 KB instead of 9 x 16 KB.  The default.
+// The weight tiles (16 KB per tap and channel block) keep streaming through their own ring.
+constexpr int HALO_TW = 8, HALO_TH = 16, HALO_ROWS = HALO_TH + 2;
+struct HaloCfg {
+  int taps_per_item;     // taps served by one ring slot of activations
+  int n_a, n_b;          // ring depths
+  uint32_t a_bytes;      // bytes one activation slot receives
+  uint32_t a_stage;      // slot pitch (1024-byte aligned)
+  uint32_t row_pitch;    // bytes between halo rows inside a slot (= SBO)
+};
+__device__ __forceinline__ HaloCfg halo_cfg(int mode) {
+  HaloCfg c;
+  if (mode == 1) {
+    c.taps_per_item = 3; c.n_a = 4; c.n_b = 5;
+    c.a_bytes = HALO_ROWS * HALO_TW * 128; c.a_stage = c.a_bytes; c.row_pitch = HALO_TW * 128;
+  } else {
+    c.taps_per_item = 9; c.n_a = 2; c.n_b = 7;
+    c.a_bytes = HALO_ROWS * (HALO_TW + 2) * 128; c.a_stage = 23 * 1024; c.row_pitch = (HALO_TW + 2) * 128;
+  }
+  return c;
+}
 
 template <int OUT_F32>
 struct Cfg {
@@ -53,13 +85,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t smem_stage0 = smem_base;
   const uint32_t smem_staging = smem_base + STAGES * STAGE_BYTES;
   const uint32_t bar_base = smem_staging + Cfg<OUT_F32>::STAGING_BYTES;
-  // barrier map (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+  // barrier map (8 bytes each): full[8], empty[8], tmem_full[2], tmem_empty[2], res[2], halo a_full[4], a_empty[4],
+  // then the tmem ptr.  The plain modes use STAGES of the full / empty pairs; the halo mode (below) uses up to 7 of
+  // them for its weight ring and the a_* pairs for its activation ring.
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  auto res_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 6);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_RING + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_RING + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_RING + 2 + s); };
+  auto res_bar = [&](int s) { return bar_base + 8u * (2 * MAX_RING + 4 + s); };
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * MAX_RING + 6 + s); };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_RING + 6 + MAX_ARING + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_RING + 6 + 2 * MAX_ARING);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to aligned base
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -79,9 +115,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < MAX_RING; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < MAX_ARING; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -99,7 +139,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_mn * p.splits;
 
-  if (warp == 0 && lane == 0) {
+  // Patch geometry of an M tile in halo mode: m_blk = (image, patch row, patch column).
+  auto halo_geom = [&](int m_blk, int& img, int& y0, int& x0) {
+    img = m_blk / p.halo_tpi;
+    const int r = m_blk - img * p.halo_tpi;
+    const int ty = r / p.halo_tx;
+    y0 = ty * HALO_TH;
+    x0 = (r - ty * p.halo_tx) * HALO_TW;
+  };
+  // One weight (B) k-block of the tile column starting at n0 into ring slot sb.
+  auto load_b = [&](int kb, uint32_t sb, uint32_t fb, int n0, int b_c, int b_tap, const CUtensorMap* b_map) {
+    if (B_MN == 0) {
+      tma_load_2d(sb, &tmB0, fb, kb * BK, n0);
+    } else if (p.b_mode == B_MN2D) {
+      const int tap = kb / p.b_cpt;
+      const int row = (kb - tap * p.b_cpt) * BK;
+      const int t = p.b_flip ? (p.b_ntaps - 1 - tap) : tap;
+      const int col = b_c + t * p.b_tapstride;
+      tma_load_2d(sb, b_map, fb, col, row);
+      tma_load_2d(sb + B_STAGE_BYTES / 2, b_map, fb, col + 64, row);
+    } else {  // B_MNCONV: 64 output pixels starting at kb*64, shifted by the tap
+      const int p0 = kb * BK;
+      const int hw = p.Ho * p.Wo;
+      const int n_i = p0 / hw;
+      const int rem = p0 - n_i * hw;
+      const int y = rem / p.Wo, x = rem - (rem / p.Wo) * p.Wo;
+      const int dy = b_tap / 3, dx = b_tap - dy * 3;
+      const int xs = x * p.stride + dx - 1, ys = y * p.stride + dy - 1;
+      tma_load_4d(sb, b_map, fb, b_c, xs, ys, n_i);
+      tma_load_4d(sb + B_STAGE_BYTES / 2, b_map, fb, b_c + 64, xs, ys, n_i);
+    }
+  };
+
+  if (p.halo && A_MN == 0 && warp == 3 && lane == 0) {
+    // =========================================================== halo mode: activation producer
+    const HaloCfg hc = halo_cfg(p.halo);
+    const int items = p.a_cpt * (9 / hc.taps_per_item);
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = (tile % tiles_mn) / p.tiles_n;
+      int img, y0, x0;
+      halo_geom(m_blk, img, y0, x0);
+      for (int item = 0; item < items; ++item) {
+        const int cb = hc.taps_per_item == 3 ? item / 3 : item;
+        const int dx = hc.taps_per_item == 3 ? item - cb * 3 : 0;
+        int c = cb * BK;
+        const CUtensorMap* m = &tmA0;
+        if (c >= p.a_c0) { c -= p.a_c0; m = &tmA1; }
+        mbar_wait(aempty_bar(as), aph ^ 1);
+        if (p.dbg == 2 && (item >= hc.n_a || tile != (int)blockIdx.x)) {  // timing experiment: no A loads
+          mbar_arrive(afull_bar(as));
+        } else {
+          mbar_arrive_expect_tx(afull_bar(as), hc.a_bytes);
+          tma_load_4d(smem_stage0 + as * hc.a_stage, m, afull_bar(as), c, x0 + dx - 1, y0 - 1, img);
+        }
+        if (++as == hc.n_a) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (p.halo && A_MN == 0 && warp == 0 && lane == 0) {
+    // =========================================================== halo mode: weight producer
+    const HaloCfg hc = halo_cfg(p.halo);
+    const int items = p.a_cpt * (9 / hc.taps_per_item);
+    const uint32_t smem_b0 = smem_stage0 + hc.n_a * hc.a_stage;
+    int bs = 0;
+    uint32_t bph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = ((tile % tiles_mn) % p.tiles_n) * BN;
+      for (int item = 0; item < items; ++item) {
+        const int cb = hc.taps_per_item == 3 ? item / 3 : item;
+        const int dx = hc.taps_per_item == 3 ? item - cb * 3 : 0;
+        for (int j = 0; j < hc.taps_per_item; ++j) {
+          const int tap = hc.taps_per_item == 3 ? j * 3 + dx : j;
+          mbar_wait(empty_bar(bs), bph ^ 1);
+          if (p.dbg == 1 && (item * hc.taps_per_item + j >= hc.n_b || tile != (int)blockIdx.x)) {  // no B loads
+            mbar_arrive(full_bar(bs));
+          } else {
+            mbar_arrive_expect_tx(full_bar(bs), B_STAGE_BYTES);
+            load_b(tap * p.a_cpt + cb, smem_b0 + bs * B_STAGE_BYTES, full_bar(bs), n0, n0, 0, &tmB0);
+          }
+          if (++bs == hc.n_b) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 0 && lane == 0 && !(p.halo && A_MN == 0)) {
     // =========================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -165,27 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           tma_load_2d(sa + A_STAGE_BYTES / 2, &tmA0, fb, m0 + 64, kb * BK);
         }
         // ---- B
-        if (skip_b) {
-        } else if (B_MN == 0) {
-          tma_load_2d(sb, &tmB0, fb, kb * BK, n0);
-        } else if (p.b_mode == B_MN2D) {
-          const int tap = kb / p.b_cpt;
-          const int row = (kb - tap * p.b_cpt) * BK;
-          const int t = p.b_flip ? (p.b_ntaps - 1 - tap) : tap;
-          const int col = b_c + t * p.b_tapstride;
-          tma_load_2d(sb, b_map, fb, col, row);
-          tma_load_2d(sb + B_STAGE_BYTES / 2, b_map, fb, col + 64, row);
-        } else {  // B_MNCONV: 64 output pixels starting at kb*64, shifted by the tap
-          const int p0 = kb * BK;
-          const int hw = p.Ho * p.Wo;
-          const int n_i = p0 / hw;
-          const int rem = p0 - n_i * hw;
-          const int y = rem / p.Wo, x = rem - (rem / p.Wo) * p.Wo;
-          const int dy = b_tap / 3, dx = b_tap - dy * 3;
-          const int xs = x * p.stride + dx - 1, ys = y * p.stride + dy - 1;
-          tma_load_4d(sb, b_map, fb, b_c, xs, ys, n_i);
-          tma_load_4d(sb + B_STAGE_BYTES / 2, b_map, fb, b_c + 64, xs, ys, n_i);
-        }
+        if (!skip_b) load_b(kb, sb, fb, n0, b_c, b_tap, b_map);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -200,6 +303,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    if (p.halo && A_MN == 0) {
+      // halo mode: the taps of an activation slot are shifted descriptors over the same shared-memory patch
+      const HaloCfg hc = halo_cfg(p.halo);
+      const int items = p.a_cpt * (9 / hc.taps_per_item);
+      const uint32_t smem_b0 = smem_stage0 + hc.n_a * hc.a_stage;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int item = 0; item < items; ++item) {
+          mbar_wait(afull_bar(as), aph);
+          const uint32_t sa = smem_stage0 + as * hc.a_stage;
+          for (int j = 0; j < hc.taps_per_item; ++j) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sb = smem_b0 + stage * B_STAGE_BYTES;
+            const uint32_t a0 = hc.taps_per_item == 3 ? sa + j * hc.row_pitch
+                                                      : sa + (j / 3) * hc.row_pitch + (j % 3) * 128;
+            if (elect_one()) {
+              uint64_t da = umma_smem_desc(a0, A_LBO, hc.row_pitch);
+              // (halo == 2: a0 is not on a 1024-byte atom boundary.  The swizzle is a function of the absolute
+              // shared-memory address, on the TMA side and on the UMMA side alike, so the descriptor's base-offset
+              // field stays 0 -- measured: with the field set to (a0 >> 7) & 7 the results are wrong.)
+              const uint64_t db = umma_smem_desc(sb, B_LBO, 1024);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16(d_tmem, da + (uint64_t)(k * (A_KSTEP / 16)), db + (uint64_t)(k * (B_KSTEP / 16)), idesc,
+                          (item > 0 || j > 0 || k > 0) ? 1u : 0u);
+              umma_commit(empty_bar(stage));
+              if (j + 1 == hc.taps_per_item) umma_commit(aempty_bar(as));
+              if (j + 1 == hc.taps_per_item && item + 1 == items) umma_commit(tfull_bar(acc));
+            }
+            __syncwarp();
+            if (++stage == hc.n_b) { stage = 0; phase ^= 1; }
+          }
+          if (++as == hc.n_a) { as = 0; aph ^= 1; }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int split = tile / tiles_mn;
       const int kb_begin = split * p.kb_per_split;
@@ -247,6 +393,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int t2r = tile_idx % tiles_mn;
       const int nb = t2r % p.tiles_n, mb = t2r / p.tiles_n;
       const uint32_t dst = smem_staging + bufsel * (BM * BN * 2);
+      if (p.halo) {  // the tile is a 16 x 8 pixel patch: same bytes in shared memory, 4-D box in global memory
+        int img, y0, x0;
+        halo_geom(mb, img, y0, x0);
+        mbar_arrive_expect_tx(res_bar(bufsel), BM * BN * 2);
+        tma_load_4d(dst, &tmR, res_bar(bufsel), nb * BN, x0, y0, img);
+        tma_load_4d(dst + BM * 128, &tmR, res_bar(bufsel), nb * BN + 64, x0, y0, img);
+        return;
+      }
       if (p.epi == EPI_GEGLU_BWD) {  // the 64 d(gg) columns that belong to this tile's 64 value + 64 gate columns
         mbar_arrive_expect_tx(res_bar(bufsel), BM * 64 * 2);
         tma_load_2d(dst, &tmR, res_bar(bufsel), nb * 64, mb * BM);
@@ -271,7 +425,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int row = m0 + ep_tid;
+      int h_img = 0, h_y0 = 0, h_x0 = 0;
+      if (p.halo) halo_geom(m_blk, h_img, h_y0, h_x0);
+      // halo mode: all 128 rows of the patch belong to image h_img
+      const int row = p.halo ? h_img * (p.Ho * p.Wo) : m0 + ep_tid;
       const bool row_ok = row < p.M;
       const int sample = (p.row_bias && row_ok) ? row / p.rows_per_sample : 0;
 
@@ -449,6 +606,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           } else if (p.epi == EPI_GEGLU_BWD) {  // dh8 in the plain layout: [d value (n_half) | d gate (n_half)]
             tma_store_2d(&tmD, staging_s, n0 / 2, m0);
             tma_store_2d(&tmD, staging_s + BM * 128, p.n_half + n0 / 2, m0);
+          } else if (p.halo) {
+            tma_store_4d(&tmD, staging_s, n0, h_x0, h_y0, h_img);
+            tma_store_4d(&tmD, staging_s + BM * 128, n0 + 64, h_x0, h_y0, h_img);
           } else {
             tma_store_2d(&tmD, staging_s, n0, m0);
             tma_store_2d(&tmD, staging_s + BM * 128, n0 + 64, m0);
@@ -540,7 +700,9 @@ int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUte
                 const CUtensorMap& tmD, const GemmParams& p) {
   // residual [M][ldr] bf16 is read through its own tensor map (same tiling as D)
   CUtensorMap tmR = tmD;
-  if (p.residual && !out_f32) {
+  if (p.residual && !out_f32 && p.halo) {
+    if (make_tmap_nhwc(&tmR, p.residual, p.M / (p.Ho * p.Wo), p.Ho, p.Wo, p.ldr, 64, HALO_TW, HALO_TH, 1, 1)) return 1;
+  } else if (p.residual && !out_f32) {
     // EPI_GEGLU_BWD: the "residual" operand is d(gg) [M][n_half], one 64-column box per tile
     const int rcols = p.epi == EPI_GEGLU_BWD ? p.n_half : p.N;
     if (make_tmap_2d(&tmR, p.residual, 2, p.M, rcols, p.ldr, 64, 128)) return 1;
@@ -550,6 +712,10 @@ int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUte
   TSD_CHECK(p.epi != EPI_GEGLU_BWD || (p.residual && !out_f32 && p.tiles_n <= 16 && p.n_half * 2 == p.N),
             "gemm: GEGLU backward epilogue needs d(gg), bf16 output and N = 2 * n_half <= 2048");
   TSD_CHECK(p.N % BN == 0, "gemm: N=%d must be a multiple of %d", p.N, BN);
+  TSD_CHECK(!p.halo || (!a_mn && !out_f32 && p.splits == 1 && p.stride == 1 && p.epi == EPI_NONE && p.Ho % HALO_TH == 0 &&
+                        p.Wo % HALO_TW == 0 && p.halo_tx == p.Wo / HALO_TW &&
+                        p.halo_tpi == (p.Ho / HALO_TH) * (p.Wo / HALO_TW)),
+            "gemm: halo mode needs a stride-1 3x3 convolution on a %d x %d pixel patch grid", HALO_TH, HALO_TW);
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("TSD_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
   GemmParams pd = p;

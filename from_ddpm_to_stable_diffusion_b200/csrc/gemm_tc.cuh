@@ -55,6 +55,8 @@ struct GemmParams {
   float* colsum;          // EPI_GEGLU_BWD: bias gradient [N] (+=) or null
   int n_half;             // EPI_GEGLU_BWD: N / 2 (column offset of the gate half in the plain layout)
   int dbg;                // timing experiments only (TSD_GEMM_DBG): 1 = skip B loads, 2 = skip A loads after the ring fill
+  int halo;               // 3x3 stride-1 convolution in halo mode (gemm_tc.cu): 0 off, 1 = three aligned copies, 2 = one copy
+  int halo_tx, halo_tpi;  // patches per image row / per image
   int act;                // ACT_*: pointwise activation on the finished value (codec convolutions, vqvae models.py:286-341)
 };
 

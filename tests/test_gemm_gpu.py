@@ -129,6 +129,7 @@ def test_gemm_geglu_bwd_recompute(cuda, M, C):
 @pytest.mark.parametrize("n,H,W,c0,c1,cout,stride", [
     (2, 16, 16, 64, 0, 128, 1), (3, 8, 8, 128, 128, 256, 1), (1, 64, 64, 64, 64, 128, 1),
     (2, 32, 32, 128, 0, 128, 2), (2, 16, 16, 64, 0, 128, 2), (4, 4, 4, 64, 0, 128, 1), (8, 2, 2, 64, 0, 128, 1),
+    (2, 32, 32, 128, 128, 256, 1), (3, 32, 64, 64, 0, 128, 1), (150, 32, 32, 64, 0, 128, 1), (3, 16, 32, 64, 64, 128, 1),  # halo-mode patches
 ])
 def test_conv3x3_fwd(cuda, n, H, W, c0, c1, cout, stride):
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -162,7 +163,8 @@ def test_gemm_dgrad(cuda):
     _close(dx, dy.float() @ w.float() + res.float())
 
 
-@pytest.mark.parametrize("n,H,W,cin,cout", [(2, 16, 16, 128, 64), (2, 8, 8, 256, 128), (1, 64, 64, 128, 128)])
+@pytest.mark.parametrize("n,H,W,cin,cout", [(2, 16, 16, 128, 64), (2, 8, 8, 256, 128), (1, 64, 64, 128, 128),
+                                            (3, 32, 32, 256, 128), (2, 64, 32, 128, 64)])
 def test_conv3x3_dgrad(cuda, n, H, W, cin, cout):
     g = torch.Generator(device="cuda").manual_seed(5)
     dy = _bf(torch.randn(n, H, W, cout, device=cuda, generator=g))
