@@ -244,6 +244,30 @@ extern "C" int tsd_conv3x3_wgrad(void* stream, const void* dy, const void* x0, c
   TSD_CHECK(cin % 128 == 0 && c0 % 128 == 0 && cout % 64 == 0, "conv3x3_wgrad: bad channels c0=%d c1=%d cout=%d", c0, c1, cout);
   const int Ho = H / stride, Wo = W / stride;
   const int M = n_img * Ho * Wo;
+  static int wg_mode = -1;  // TSD_WGRAD_HALO=0: tap-by-tap boxes for every shape (A/B switch)
+  if (wg_mode < 0) { const char* e = getenv("TSD_WGRAD_HALO"); wg_mode = e ? atoi(e) : 1; }
+  if (wg_mode && stride == 1 && H % 8 == 0 && W % 8 == 0 && cout % 128 == 0) {
+    // patch mode (gemm_tc.cu): k-blocks are 8 x 8 pixel patches, a work item = (kernel row, co block, ci block, pixel range)
+    CUtensorMap tA, tB0, tB1, tD;
+    if (make_tmap_nhwc(&tA, dy, n_img, H, W, cout, 64, 8, 8, 1, 1)) return 1;
+    if (make_tmap_nhwc(&tB0, x0, n_img, H, W, c0, 64, 10, 8, 1, 1)) return 1;
+    if (c1 > 0) { if (make_tmap_nhwc(&tB1, x1, n_img, H, W, c1, 64, 10, 8, 1, 1)) return 1; } else tB1 = tB0;
+    if (make_tmap_2d(&tD, dw, 4, cout, 9 * cin, 9 * cin, 32, 128)) return 1;
+    GemmParams p; zero_params(p);
+    p.M = cout; p.N = 9 * cin; p.tiles_m = cout / 128; p.tiles_n = 3 * (cin / 128);
+    p.num_kb = n_img * (H / 8) * (W / 8);
+    p.a_mode = A_MN2D; p.b_mode = B_MNCONV; p.b_c0 = c0; p.b_ctot = cin;
+    p.Ho = H; p.Wo = W; p.stride = 1; p.rows_per_sample = 1;
+    p.wg_halo = 1; p.halo_tx = W / 8; p.halo_tpi = (H / 8) * (W / 8);
+    // one round of work items over the SMs: every item ends with three 64 KB reduce-adds, so fewer, longer items
+    const int tiles = p.tiles_m * p.tiles_n;
+    int want = num_sms() / tiles;
+    if (want < 1) want = 1;
+    if (want > p.num_kb) want = p.num_kb;
+    p.kb_per_split = ceil_div(p.num_kb, want);
+    p.splits = ceil_div(p.num_kb, p.kb_per_split);
+    return launch_gemm((cudaStream_t)stream, 1, 1, 1, tA, tA, tB0, tB1, tD, p);
+  }
   uint32_t bw, bh, bn;
   if (pixel_box(Ho, Wo, 64, &bw, &bh, &bn)) return 1;
   CUtensorMap tA, tB0, tB1, tD;

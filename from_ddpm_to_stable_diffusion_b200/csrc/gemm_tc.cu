@@ -28,7 +28,8 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
   if constexpr (N == 32) tmem_ld32(taddr, r);
   else tmem_ld16(taddr, r);
 }
-constexpr int TMEM_COLS = 256;  // two 128-column fp32 accumulators
+constexpr int TMEM_COLS = 256;     // two 128-column fp32 accumulators
+constexpr int TMEM_COLS_WG = 512;  // weight-gradient instantiation: room for the three tap accumulators of the patch mode
 constexpr int MAX_RING = 8, MAX_ARING = 4;  // mbarrier pairs reserved for the operand rings
 
 // ---- halo mode of the 3x3 convolution (A_KHALO): the M tile is a 16-row x 8-pixel patch of ONE image, and the
@@ -43,6 +44,15 @@ constexpr int MAX_RING = 8, MAX_ARING = 4;  // mbarrier pairs reserved for the o
 //              absolute shared-memory address.  A traffic: 22.5 KB instead of 9 x 16 KB.  The default.
 // The weight tiles (16 KB per tap and channel block) keep streaming through their own ring.
 constexpr int HALO_TW = 8, HALO_TH = 16, HALO_ROWS = HALO_TH + 2;
+// ---- patch mode of the 3x3 weight gradient (p.wg_halo, instantiation <1,1,1>): a k-block is an 8 x 8 pixel patch of one
+// image.  A work item owns one kernel ROW dy of a (128 co x 128 ci) block and keeps the three taps dx = 0, 1, 2 in three
+// TMEM accumulators: dY of the patch (16 KB) and the input rows y + dy - 1 with a one-pixel margin left and right
+// ({64 ci, 10 px, 8 rows} per 64-channel chunk, 20 KB) are loaded once and serve all three taps -- the tap is a
+// 128-byte shift of the MN-major B descriptor.  Operand traffic per tap and 64 pixels: 12 KB instead of 32 KB.
+constexpr int WG_A_BYTES = 64 * 128 * 2;             // dY patch: two 64-channel chunks of [64 px][128 B]
+constexpr int WG_B_CHUNK = 8 * (HALO_TW + 2) * 128;  // one 64-channel chunk of the input rows: 10 KB
+constexpr int WG_STAGE = WG_A_BYTES + 2 * WG_B_CHUNK;  // 36 KB
+constexpr int WG_STAGES = 4;
 struct HaloCfg {
   int taps_per_item;     // taps served by one ring slot of activations
   int n_a, n_b;          // ring depths
@@ -130,7 +140,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  constexpr int kTmemCols = OUT_F32 ? TMEM_COLS_WG : TMEM_COLS;
+  constexpr bool kWG = A_MN && B_MN && OUT_F32;  // the instantiation that carries the patch-mode 3x3 weight gradient
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -222,6 +234,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
+  } else if (kWG && p.wg_halo && warp == 0 && lane == 0) {
+    // =========================================================== patch-mode weight gradient: producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / tiles_mn;
+      const int t2 = tile - split * tiles_mn;
+      const int n_blk = t2 % p.tiles_n;           // (kernel row dy, 128-channel block of the input)
+      const int m0 = (t2 / p.tiles_n) * BM;
+      const int ci_blocks = p.tiles_n / 3;
+      const int dy = n_blk / ci_blocks;
+      int b_c = (n_blk - dy * ci_blocks) * BN;
+      const CUtensorMap* b_map = &tmB0;
+      if (b_c >= p.b_c0) { b_c -= p.b_c0; b_map = &tmB1; }
+      const int kb_begin = split * p.kb_per_split;
+      const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        int img, y0, x0;
+        halo_geom(kb, img, y0, x0);
+        y0 >>= 1;  // halo_geom counts 16-row patches; these are 8 rows tall
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = smem_stage0 + stage * WG_STAGE;
+        const uint32_t sb = sa + WG_A_BYTES;
+        const uint32_t fb = full_bar(stage);
+        mbar_arrive_expect_tx(fb, WG_STAGE);
+        tma_load_4d(sa, &tmA0, fb, m0, x0, y0, img);
+        tma_load_4d(sa + WG_A_BYTES / 2, &tmA0, fb, m0 + 64, x0, y0, img);
+        tma_load_4d(sb, b_map, fb, b_c, x0 - 1, y0 + dy - 1, img);
+        tma_load_4d(sb + WG_B_CHUNK, b_map, fb, b_c + 64, x0 - 1, y0 + dy - 1, img);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
   } else if (warp == 0 && lane == 0 && !(p.halo && A_MN == 0)) {
     // =========================================================== TMA producer
     int stage = 0;
@@ -303,7 +347,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    if (p.halo && A_MN == 0) {
+    if (kWG && p.wg_halo) {
+      // patch-mode weight gradient: three taps (dx) of one kernel row accumulate side by side in TMEM
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int split = tile / tiles_mn;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+        mbar_wait(tempty_bar(0), (it & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_stage0 + stage * WG_STAGE;
+          const uint32_t sb = sa + WG_A_BYTES;
+          if (elect_one()) {
+            const uint64_t da = umma_smem_desc(sa, WG_A_BYTES / 2, 1024);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              // B rows are pixels of the margin-extended input rows: 8-pixel groups one image row (10 pixels) apart,
+              // the tap's horizontal shift is dx pixels into the row (not on an atom boundary: see the halo mode)
+              const uint64_t db = umma_smem_desc(sb + dx * 128, WG_B_CHUNK, (HALO_TW + 2) * 128);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)  // 16 pixels = two image rows of the patch per step
+                umma_bf16(tmem_base + dx * BN, da + (uint64_t)(k * (2048 / 16)),
+                          db + (uint64_t)(k * (2 * (HALO_TW + 2) * 128 / 16)), idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));
+            if (kb + 1 == kb_end) umma_commit(tfull_bar(0));
+          }
+          __syncwarp();
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (kb_end <= kb_begin) {
+          if (elect_one()) umma_commit(tfull_bar(0));
+          __syncwarp();
+        }
+      }
+    } else if (p.halo && A_MN == 0) {
       // halo mode: the taps of an activation slot are shifted descriptors over the same shared-memory patch
       const HaloCfg hc = halo_cfg(p.halo);
       const int items = p.a_cpt * (9 / hc.taps_per_item);
@@ -415,6 +495,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int i = 0; i < 16; ++i) cs_acc[i] = 0.f;
     if (has_res && ep_leader && (int)blockIdx.x < total_tiles) prefetch_residual(blockIdx.x, 0);
     int it = 0;
+    if (kWG && p.wg_halo) {
+      // patch-mode weight gradient: the item's three tap accumulators leave one after the other through the single
+      // fp32 staging tile (TMA reduce-add into dW[co][(dy*3 + dx) * cin + ci])
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int t2 = tile % tiles_mn;
+        const int n_blk = t2 % p.tiles_n;
+        const int m0 = (t2 / p.tiles_n) * BM;
+        const int ci_blocks = p.tiles_n / 3;
+        const int dy = n_blk / ci_blocks;
+        const int ci0 = (n_blk - dy * ci_blocks) * BN;
+        mbar_wait(tfull_bar(0), it & 1);
+        tc_fence_after();
+        const int r7 = ep_tid & 7;
+#pragma unroll 1
+        for (int dx = 0; dx < 3; ++dx) {
+          if (ep_leader) tma_store_wait_read<0>();  // the previous reduce-add has read the staging tile
+          named_bar_sync(1, EPI_THREADS);
+          const uint32_t t_addr = tmem_base + lane_off + dx * BN;
+#pragma unroll 1
+          for (int ch = half * EPI_CH; ch < half * EPI_CH + EPI_CH; ++ch) {
+            uint32_t v[32];
+            tmem_ld32(t_addr + ch * 32, v);
+            tmem_ld_wait();
+            uint8_t* dst = staging0 + ch * (BM * 128) + ep_tid * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              uint4 o = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              *reinterpret_cast<uint4*>(dst + ((q ^ r7) << 4)) = o;
+            }
+          }
+          if (dx == 2) {
+            tc_fence_before();
+            mbar_arrive(tempty_bar(0));
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, EPI_THREADS);
+          if (ep_leader) {
+            const int col0 = (dy * 3 + dx) * p.b_ctot + ci0;
+#pragma unroll
+            for (int ch = 0; ch < BN / 32; ++ch)
+              tma_reduce_add_2d(&tmD, smem_staging + ch * (BM * 128), col0 + ch * 32, m0);
+            tma_store_commit();
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int sbuf = OUT_F32 ? 0 : (it & 1);
       uint8_t* staging = staging0 + sbuf * (BM * BN * 2);
@@ -673,7 +799,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -712,6 +838,9 @@ int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUte
   TSD_CHECK(p.epi != EPI_GEGLU_BWD || (p.residual && !out_f32 && p.tiles_n <= 16 && p.n_half * 2 == p.N),
             "gemm: GEGLU backward epilogue needs d(gg), bf16 output and N = 2 * n_half <= 2048");
   TSD_CHECK(p.N % BN == 0, "gemm: N=%d must be a multiple of %d", p.N, BN);
+  TSD_CHECK(!p.wg_halo || (a_mn && b_mn && out_f32 && p.stride == 1 && p.tiles_n % 3 == 0 && p.Ho % 8 == 0 && p.Wo % 8 == 0 &&
+                           p.halo_tx == p.Wo / 8 && p.halo_tpi == (p.Ho / 8) * (p.Wo / 8) && p.b_ctot == (p.tiles_n / 3) * BN),
+            "gemm: patch-mode weight gradient needs a stride-1 3x3 convolution on an 8 x 8 pixel patch grid");
   TSD_CHECK(!p.halo || (!a_mn && !out_f32 && p.splits == 1 && p.stride == 1 && p.epi == EPI_NONE && p.Ho % HALO_TH == 0 &&
                         p.Wo % HALO_TW == 0 && p.halo_tx == p.Wo / HALO_TW &&
                         p.halo_tpi == (p.Ho / HALO_TH) * (p.Wo / HALO_TW)),

@@ -57,6 +57,7 @@ struct GemmParams {
   int dbg;                // timing experiments only (TSD_GEMM_DBG): 1 = skip B loads, 2 = skip A loads after the ring fill
   int halo;               // 3x3 stride-1 convolution in halo mode (gemm_tc.cu): 0 off, 1 = three aligned copies, 2 = one copy
   int halo_tx, halo_tpi;  // patches per image row / per image
+  int wg_halo;            // 3x3 stride-1 weight gradient in patch mode (gemm_tc.cu); halo_tx / halo_tpi count 8 x 8 patches
   int act;                // ACT_*: pointwise activation on the finished value (codec convolutions, vqvae models.py:286-341)
 };
 

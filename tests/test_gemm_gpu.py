@@ -191,6 +191,7 @@ def test_gemm_wgrad(cuda):
 
 @pytest.mark.parametrize("n,H,W,c0,c1,cout,stride", [
     (2, 16, 16, 128, 0, 128, 1), (4, 8, 8, 128, 128, 256, 1), (1, 64, 64, 128, 0, 128, 1), (2, 32, 32, 128, 0, 128, 2),
+    (3, 32, 16, 128, 128, 256, 1), (40, 32, 32, 256, 0, 128, 1), (2, 8, 8, 128, 0, 64, 1),
 ])
 def test_conv3x3_wgrad(cuda, n, H, W, c0, c1, cout, stride):
     g = torch.Generator(device="cuda").manual_seed(7)
