@@ -28,26 +28,27 @@ int pixel_box(int Ho, int Wo, int P, uint32_t* bw, uint32_t* bh, uint32_t* bn) {
   return 0;
 }
 
-// Halo mode of the stride-1 3x3 convolutions (gemm_tc.cu): the M tile becomes a 16 x 8 pixel patch whose activations
-// are loaded once per channel block instead of once per tap.  TSD_CONV_HALO: 0 = off (tap-by-tap boxes), 1 = three
-// aligned x-shifted copies, 2 = one 10-pixel-wide copy with unaligned descriptor starts (default) -- A/B switches for
-// the measurements in DESIGN.md.  TSD_CONV_HALO_MINH: smallest image height that takes the halo path.
+// Halo mode of the stride-1 3x3 convolutions (gemm_tc.cu): the M tile becomes a 16 x 8 pixel patch (or two of them side
+// by side) whose activations are loaded once per channel block instead of once per tap.  TSD_CONV_HALO: 0 = off
+// (tap-by-tap boxes), 1 = three aligned x-shifted copies, 2 = one 10-pixel-wide copy with unaligned descriptor starts,
+// 3 = two patches per tile (default; widths that are not a multiple of 16 fall back to 2) -- A/B switches for the
+// measurements in DESIGN.md.  TSD_CONV_HALO_MINH: smallest image height that takes the halo path.
 int halo_mode(int H, int W, int stride) {
   static int mode = -1, min_h = 16;
   if (mode < 0) {
     const char* e = getenv("TSD_CONV_HALO");
-    mode = e ? atoi(e) : 2;
-    if (mode < 0 || mode > 2) mode = 2;
+    mode = e ? atoi(e) : 3;
+    if (mode < 0 || mode > 3) mode = 3;
     const char* h = getenv("TSD_CONV_HALO_MINH");
     if (h) min_h = atoi(h);
   }
   if (!mode || stride != 1 || H % 16 != 0 || W % 8 != 0 || H < min_h) return 0;
-  return mode;
+  return (mode == 3 && W % 16 != 0) ? 2 : mode;
 }
 // Tensor maps and tile geometry of a halo-mode convolution: a0 / a1 = the (up to two) NHWC sources, d = NHWC output.
 int setup_halo(GemmParams& p, int mode, CUtensorMap* tA0, CUtensorMap* tA1, CUtensorMap* tD, const void* a0, const void* a1,
                int c0, int c1, void* d, int n_img, int H, int W, int cout) {
-  const uint32_t bw = mode == 1 ? 8 : 10;
+  const uint32_t bw = mode == 1 ? 8 : mode == 2 ? 10 : 18;
   if (make_tmap_nhwc(tA0, a0, n_img, H, W, c0, 64, bw, 18, 1, 1)) return 1;
   if (c1 > 0) { if (make_tmap_nhwc(tA1, a1, n_img, H, W, c1, 64, bw, 18, 1, 1)) return 1; } else *tA1 = *tA0;
   if (make_tmap_nhwc(tD, d, n_img, H, W, cout, 64, 8, 16, 1, 1)) return 1;
@@ -140,17 +141,19 @@ extern "C" int tsd_conv3x3_fwd_gn(void* stream, const void* x0, const void* x1, 
   TSD_CHECK(H % stride == 0 && W % stride == 0, "conv3x3_fwd: H, W must be multiples of the stride");
   const int Ho = H / stride, Wo = W / stride;
   const int M = n_img * Ho * Wo;
-  uint32_t bw, bh, bn;
-  if (pixel_box(Ho, Wo, 128, &bw, &bh, &bn)) return 1;
   CUtensorMap tA0, tA1, tB, tD;
-  if (make_tmap_nhwc(&tA0, x0, n_img, H, W, c0, 64, bw, bh, bn, stride)) return 1;
-  if (c1 > 0) { if (make_tmap_nhwc(&tA1, x1, n_img, H, W, c1, 64, bw, bh, bn, stride)) return 1; } else tA1 = tA0;
-  if (make_tmap_2d(&tB, w, 2, cout, 9 * cin, 9 * cin, 64, 128)) return 1;
-  if (make_tmap_2d(&tD, d, 2, M, cout, cout, 64, 128)) return 1;
   GemmParams p; zero_params(p);
-  if (const int hm = halo_mode(H, W, stride))
+  if (make_tmap_2d(&tB, w, 2, cout, 9 * cin, 9 * cin, 64, 128)) return 1;
+  if (const int hm = halo_mode(H, W, stride)) {
     if (setup_halo(p, hm, &tA0, &tA1, &tD, x0, x1, c0, c1, d, n_img, H, W, cout)) return 1;
-  p.M = M; p.N = cout; p.tiles_m = ceil_div(M, 128); p.tiles_n = cout / 128;
+  } else {
+    uint32_t bw, bh, bn;
+    if (pixel_box(Ho, Wo, 128, &bw, &bh, &bn)) return 1;
+    if (make_tmap_nhwc(&tA0, x0, n_img, H, W, c0, 64, bw, bh, bn, stride)) return 1;
+    if (c1 > 0) { if (make_tmap_nhwc(&tA1, x1, n_img, H, W, c1, 64, bw, bh, bn, stride)) return 1; } else tA1 = tA0;
+    if (make_tmap_2d(&tD, d, 2, M, cout, cout, 64, 128)) return 1;
+  }
+  p.M = M; p.N = cout; p.tiles_m = p.halo == 3 ? M / 256 : ceil_div(M, 128); p.tiles_n = cout / 128;
   p.a_mode = A_KCONV; p.a_c0 = c0; p.a_cpt = cin / 64;
   p.num_kb = 9 * p.a_cpt; p.kb_per_split = p.num_kb;
   p.Ho = Ho; p.Wo = Wo; p.stride = stride; p.b_mode = B_K2D;
@@ -185,18 +188,19 @@ extern "C" int tsd_conv3x3_dgrad(void* stream, const void* dy, int n_img, int H,
                                  const void* w, int cin, const void* residual, void* dx) {
   TSD_CHECK(cout % 64 == 0 && cin % 128 == 0, "conv3x3_dgrad: bad channels cin=%d cout=%d", cin, cout);
   const int M = n_img * H * W;
-  uint32_t bw, bh, bn;
-  if (pixel_box(H, W, 128, &bw, &bh, &bn)) return 1;
   CUtensorMap tA, tB, tD;
-  if (make_tmap_nhwc(&tA, dy, n_img, H, W, cout, 64, bw, bh, bn, 1)) return 1;
-  if (make_tmap_2d(&tB, w, 2, cout, 9 * cin, 9 * cin, 64, 64)) return 1;
-  if (make_tmap_2d(&tD, dx, 2, M, cin, cin, 64, 128)) return 1;
   GemmParams p; zero_params(p);
+  if (make_tmap_2d(&tB, w, 2, cout, 9 * cin, 9 * cin, 64, 64)) return 1;
   if (const int hm = halo_mode(H, W, 1)) {
     CUtensorMap tA1;
     if (setup_halo(p, hm, &tA, &tA1, &tD, dy, nullptr, cout, 0, dx, n_img, H, W, cin)) return 1;
+  } else {
+    uint32_t bw, bh, bn;
+    if (pixel_box(H, W, 128, &bw, &bh, &bn)) return 1;
+    if (make_tmap_nhwc(&tA, dy, n_img, H, W, cout, 64, bw, bh, bn, 1)) return 1;
+    if (make_tmap_2d(&tD, dx, 2, M, cin, cin, 64, 128)) return 1;
   }
-  p.M = M; p.N = cin; p.tiles_m = ceil_div(M, 128); p.tiles_n = cin / 128;
+  p.M = M; p.N = cin; p.tiles_m = p.halo == 3 ? M / 256 : ceil_div(M, 128); p.tiles_n = cin / 128;
   p.a_mode = A_KCONV; p.a_c0 = cout; p.a_cpt = cout / 64;
   p.num_kb = 9 * p.a_cpt; p.kb_per_split = p.num_kb;
   p.Ho = H; p.Wo = W; p.stride = 1;

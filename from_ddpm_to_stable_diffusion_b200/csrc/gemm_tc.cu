@@ -41,7 +41,11 @@ constexpr int MAX_RING = 8, MAX_ARING = 4;  // mbarrier pairs reserved for the o
 //              channel block instead of 9 x 16 KB.
 //   halo == 2: one copy {64 ch, 10 px, 18 rows} (22.5 KB); tap (dy, dx) starts dy rows + dx pixels in, i.e. NOT on an
 //              atom boundary -- correct as it stands, because TMA and UMMA both derive the swizzle phase from the
-//              absolute shared-memory address.  A traffic: 22.5 KB instead of 9 x 16 KB.  The default.
+//              absolute shared-memory address.  A traffic: 22.5 KB instead of 9 x 16 KB.
+//   halo == 3: the tile is TWO such patches side by side (16 rows x 16 pixels, one copy {64 ch, 18 px, 18 rows}, 40.5 KB)
+//              with one accumulator each: every weight tile now feeds eight UMMAs instead of four, which halves the
+//              weight stream and the per-k-block issue overhead of the MMA warp (measured: that overhead, not the
+//              operand streams, bounded halo == 2).  The default where the width is a multiple of 16.
 // The weight tiles (16 KB per tap and channel block) keep streaming through their own ring.
 constexpr int HALO_TW = 8, HALO_TH = 16, HALO_ROWS = HALO_TH + 2;
 // ---- patch mode of the 3x3 weight gradient (p.wg_halo, instantiation <1,1,1>): a k-block is an 8 x 8 pixel patch of one
@@ -65,9 +69,12 @@ __device__ __forceinline__ HaloCfg halo_cfg(int mode) {
   if (mode == 1) {
     c.taps_per_item = 3; c.n_a = 4; c.n_b = 5;
     c.a_bytes = HALO_ROWS * HALO_TW * 128; c.a_stage = c.a_bytes; c.row_pitch = HALO_TW * 128;
-  } else {
+  } else if (mode == 2) {
     c.taps_per_item = 9; c.n_a = 2; c.n_b = 7;
     c.a_bytes = HALO_ROWS * (HALO_TW + 2) * 128; c.a_stage = 23 * 1024; c.row_pitch = (HALO_TW + 2) * 128;
+  } else {  // 3: two patches side by side (16 rows x 16 pixels, M = 256 in two accumulators)
+    c.taps_per_item = 9; c.n_a = 2; c.n_b = 4;
+    c.a_bytes = HALO_ROWS * (2 * HALO_TW + 2) * 128; c.a_stage = 41 * 1024; c.row_pitch = (2 * HALO_TW + 2) * 128;
   }
   return c;
 }
@@ -140,7 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     fence_mbar_init();
   }
-  constexpr int kTmemCols = OUT_F32 ? TMEM_COLS_WG : TMEM_COLS;
+  constexpr int kTmemCols = TMEM_COLS_WG;  // four accumulators (halo == 3: two pairs; patch-mode weight gradient: three)
   constexpr bool kWG = A_MN && B_MN && OUT_F32;  // the instantiation that carries the patch-mode 3x3 weight gradient
   if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
@@ -190,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = (tile % tiles_mn) / p.tiles_n;
+      const int m_blk = ((tile % tiles_mn) / p.tiles_n) * (p.halo == 3 ? 2 : 1);  // (first) 16 x 8 patch of the tile
       int img, y0, x0;
       halo_geom(m_blk, img, y0, x0);
       for (int item = 0; item < items; ++item) {
@@ -200,7 +207,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const CUtensorMap* m = &tmA0;
         if (c >= p.a_c0) { c -= p.a_c0; m = &tmA1; }
         mbar_wait(aempty_bar(as), aph ^ 1);
-        if (p.dbg == 2 && (item >= hc.n_a || tile != (int)blockIdx.x)) {  // timing experiment: no A loads
+        if ((p.dbg == 2 || p.dbg == 5) && (item >= hc.n_a || tile != (int)blockIdx.x)) {  // timing experiment: no A loads
           mbar_arrive(afull_bar(as));
         } else {
           mbar_arrive_expect_tx(afull_bar(as), hc.a_bytes);
@@ -224,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int j = 0; j < hc.taps_per_item; ++j) {
           const int tap = hc.taps_per_item == 3 ? j * 3 + dx : j;
           mbar_wait(empty_bar(bs), bph ^ 1);
-          if (p.dbg == 1 && (item * hc.taps_per_item + j >= hc.n_b || tile != (int)blockIdx.x)) {  // no B loads
+          if ((p.dbg == 1 || p.dbg == 5) && (item * hc.taps_per_item + j >= hc.n_b || tile != (int)blockIdx.x)) {  // no B loads
             mbar_arrive(full_bar(bs));
           } else {
             mbar_arrive_expect_tx(full_bar(bs), B_STAGE_BYTES);
@@ -395,26 +402,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const int subs = p.halo == 3 ? 2 : 1;
+        const uint32_t d_tmem = tmem_base + acc * subs * BN;
         for (int item = 0; item < items; ++item) {
           mbar_wait(afull_bar(as), aph);
           const uint32_t sa = smem_stage0 + as * hc.a_stage;
           for (int j = 0; j < hc.taps_per_item; ++j) {
-            mbar_wait(full_bar(stage), phase);
+            if (p.dbg != 4) mbar_wait(full_bar(stage), phase);  // (4: timing experiment, issue without waiting)
             tc_fence_after();
             const uint32_t sb = smem_b0 + stage * B_STAGE_BYTES;
             const uint32_t a0 = hc.taps_per_item == 3 ? sa + j * hc.row_pitch
                                                       : sa + (j / 3) * hc.row_pitch + (j % 3) * 128;
             if (elect_one()) {
-              uint64_t da = umma_smem_desc(a0, A_LBO, hc.row_pitch);
-              // (halo == 2: a0 is not on a 1024-byte atom boundary.  The swizzle is a function of the absolute
+              const uint64_t da = umma_smem_desc(a0, A_LBO, hc.row_pitch);
+              // (halo >= 2: a0 is not on a 1024-byte atom boundary.  The swizzle is a function of the absolute
               // shared-memory address, on the TMA side and on the UMMA side alike, so the descriptor's base-offset
               // field stays 0 -- measured: with the field set to (a0 >> 7) & 7 the results are wrong.)
               const uint64_t db = umma_smem_desc(sb, B_LBO, 1024);
+              for (int h = 0; h < subs; ++h) {  // halo == 3: the second patch starts 8 pixels to the right
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_bf16(d_tmem, da + (uint64_t)(k * (A_KSTEP / 16)), db + (uint64_t)(k * (B_KSTEP / 16)), idesc,
-                          (item > 0 || j > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  umma_bf16(d_tmem + h * BN, da + (uint64_t)(h * (HALO_TW * 128 / 16) + k * (A_KSTEP / 16)),
+                            db + (uint64_t)(k * (B_KSTEP / 16)), idesc, (item > 0 || j > 0 || k > 0) ? 1u : 0u);
+              }
               umma_commit(empty_bar(stage));
               if (j + 1 == hc.taps_per_item) umma_commit(aempty_bar(as));
               if (j + 1 == hc.taps_per_item && item + 1 == items) umma_commit(tfull_bar(acc));
@@ -469,9 +479,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint8_t* staging0 = smem_gen + (smem_staging - smem_base);
     const bool has_res = (!OUT_F32) && p.residual != nullptr;
     // residual tile of (m0, n0): two 64-column boxes, prefetched by TMA into a staging buffer
-    auto prefetch_residual = [&](int tile_idx, int bufsel) {
+    const int subs = (!OUT_F32 && p.halo == 3) ? 2 : 1;  // 128-row sub-tiles (accumulators) per tile
+    auto prefetch_residual = [&](int tile_idx, int hsub, int bufsel) {
       const int t2r = tile_idx % tiles_mn;
-      const int nb = t2r % p.tiles_n, mb = t2r / p.tiles_n;
+      const int nb = t2r % p.tiles_n, mb = (t2r / p.tiles_n) * subs + hsub;
       const uint32_t dst = smem_staging + bufsel * (BM * BN * 2);
       if (p.halo) {  // the tile is a 16 x 8 pixel patch: same bytes in shared memory, 4-D box in global memory
         int img, y0, x0;
@@ -493,7 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     float cs_acc[16];  // EPI_GEGLU_BWD: this thread's column-sum partials per n-block (bias gradient), flushed at the end
 #pragma unroll
     for (int i = 0; i < 16; ++i) cs_acc[i] = 0.f;
-    if (has_res && ep_leader && (int)blockIdx.x < total_tiles) prefetch_residual(blockIdx.x, 0);
+    if (has_res && ep_leader && (int)blockIdx.x < total_tiles) prefetch_residual(blockIdx.x, 0, 0);
     int it = 0;
     if (kWG && p.wg_halo) {
       // patch-mode weight gradient: the item's three tap accumulators leave one after the other through the single
@@ -541,13 +552,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     } else
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int sbuf = OUT_F32 ? 0 : (it & 1);
+    for (int tile = blockIdx.x, sit = 0; tile < total_tiles; tile += gridDim.x, ++it)
+    for (int hsub = 0; hsub < subs; ++hsub, ++sit) {  // sit counts sub-tiles: staging buffers / residual barriers alternate
+      const int sbuf = OUT_F32 ? 0 : (sit & 1);
       uint8_t* staging = staging0 + sbuf * (BM * BN * 2);
       const uint32_t staging_s = smem_staging + sbuf * (BM * BN * 2);
       const int t2 = tile % tiles_mn;
       const int n_blk = t2 % p.tiles_n;
-      const int m_blk = t2 / p.tiles_n;
+      const int m_blk = (t2 / p.tiles_n) * subs + hsub;  // index of the 128-row sub-tile
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -558,17 +570,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const bool row_ok = row < p.M;
       const int sample = (p.row_bias && row_ok) ? row / p.rows_per_sample : 0;
 
-      mbar_wait(tfull_bar(acc), acc_phase);
+      if (hsub == 0) mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (p.dbg == 3) {  // timing experiment: no epilogue work at all
+        tc_fence_before();
+        if (hsub == subs - 1) mbar_arrive(tempty_bar(acc));
+        continue;
+      }
       if (OUT_F32) {
         // single staging tile: it must have been fully read by the previous tile's TMA reduce-add
         if (ep_leader) tma_store_wait_read<0>();
         named_bar_sync(1, EPI_THREADS);
       } else if (has_res) {
-        mbar_wait(res_bar(sbuf), (it >> 1) & 1);  // residual tile has landed in this staging buffer
+        mbar_wait(res_bar(sbuf), (sit >> 1) & 1);  // residual tile has landed in this staging buffer
       }
 
-      const uint32_t t_addr = tmem_base + lane_off + acc * BN;
+      const uint32_t t_addr = tmem_base + lane_off + (acc * subs + hsub) * BN;
       const int r7 = ep_tid & 7;
       if (OUT_F32) {
 #pragma unroll 1
@@ -709,9 +726,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
-      // TMEM accumulator drained -> hand it back to the MMA warp.
+      // TMEM accumulator (pair) drained -> hand it back to the MMA warp.
       tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if (hsub == subs - 1) mbar_arrive(tempty_bar(acc));
       // smem writes (generic proxy) -> visible to the TMA engine (async proxy).
       fence_proxy_async_smem();
       // bf16: before anyone moves on, the store of tile it-1 must have finished reading the OTHER staging buffer
@@ -726,7 +743,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         } else {
           // the other staging buffer was the source of tile it-1's store: once that has been read it can take
           // the next tile's residual (prefetch) and, one tile later, the next result
-          if (has_res && tile + (int)gridDim.x < total_tiles) prefetch_residual(tile + gridDim.x, sbuf ^ 1);
+          const int ntile = hsub + 1 < subs ? tile : tile + (int)gridDim.x;
+          if (has_res && ntile < total_tiles) prefetch_residual(ntile, hsub + 1 < subs ? hsub + 1 : 0, sbuf ^ 1);
           if (p.epi == EPI_GEGLU) {
             tma_store_2d(&tmD, staging_s, n0 / 2, m0);
           } else if (p.epi == EPI_GEGLU_BWD) {  // dh8 in the plain layout: [d value (n_half) | d gate (n_half)]
@@ -841,6 +859,7 @@ int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUte
   TSD_CHECK(!p.wg_halo || (a_mn && b_mn && out_f32 && p.stride == 1 && p.tiles_n % 3 == 0 && p.Ho % 8 == 0 && p.Wo % 8 == 0 &&
                            p.halo_tx == p.Wo / 8 && p.halo_tpi == (p.Ho / 8) * (p.Wo / 8) && p.b_ctot == (p.tiles_n / 3) * BN),
             "gemm: patch-mode weight gradient needs a stride-1 3x3 convolution on an 8 x 8 pixel patch grid");
+  TSD_CHECK(p.halo != 3 || (p.Wo % (2 * HALO_TW) == 0 && p.tiles_m * 2 * BM == p.M), "gemm: halo mode 3 needs a width multiple of 16");
   TSD_CHECK(!p.halo || (!a_mn && !out_f32 && p.splits == 1 && p.stride == 1 && p.epi == EPI_NONE && p.Ho % HALO_TH == 0 &&
                         p.Wo % HALO_TW == 0 && p.halo_tx == p.Wo / HALO_TW &&
                         p.halo_tpi == (p.Ho / HALO_TH) * (p.Wo / HALO_TW)),

@@ -129,7 +129,7 @@ def test_gemm_geglu_bwd_recompute(cuda, M, C):
 @pytest.mark.parametrize("n,H,W,c0,c1,cout,stride", [
     (2, 16, 16, 64, 0, 128, 1), (3, 8, 8, 128, 128, 256, 1), (1, 64, 64, 64, 64, 128, 1),
     (2, 32, 32, 128, 0, 128, 2), (2, 16, 16, 64, 0, 128, 2), (4, 4, 4, 64, 0, 128, 1), (8, 2, 2, 64, 0, 128, 1),
-    (2, 32, 32, 128, 128, 256, 1), (3, 32, 64, 64, 0, 128, 1), (150, 32, 32, 64, 0, 128, 1), (3, 16, 32, 64, 64, 128, 1),  # halo-mode patches
+    (2, 32, 32, 128, 128, 256, 1), (3, 32, 64, 64, 0, 128, 1), (150, 32, 32, 64, 0, 128, 1), (3, 16, 32, 64, 64, 128, 1), (2, 16, 24, 64, 0, 128, 1),  # halo-mode patches
 ])
 def test_conv3x3_fwd(cuda, n, H, W, c0, c1, cout, stride):
     g = torch.Generator(device="cuda").manual_seed(3)

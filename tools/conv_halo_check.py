@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from from_ddpm_to_stable_diffusion_b200 import ops
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-mode = os.environ.get("TSD_CONV_HALO", "1")
+mode = os.environ.get("TSD_CONV_HALO", "3 (default)")
 def timeit(fn, n=10):
     for _ in range(3): fn()
     torch.cuda.synchronize()
