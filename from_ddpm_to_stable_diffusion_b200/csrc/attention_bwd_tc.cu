@@ -301,7 +301,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_wait(ld_full(0), 0);
       // stagger: the second issuer's warpgroups start half a sub-tile after the first one's, so that the four softmax
       // warps of a scheduler are not all in the same phase (TMEM load / exponentials / stores) at the same time
-      if (stagger && si > 0) mbar_wait(s_free(0), 0);
+      if ((stagger & 0xff) && si > 0) mbar_wait(s_free(0), 0);
       tc_fence_after();
 #pragma unroll
       for (int gi = 0; gi < NWG / NSI; ++gi) issue_S(0, g_lo + gi);
@@ -330,6 +330,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       constexpr uint32_t idescKN = umma_idesc_bf16(KT, DH, 0, 1);   // A K-major (or TMEM), B MN-major
       constexpr uint32_t idescDQ = umma_idesc_bf16(QT, DH, 1, 1);   // A MN-major, B MN-major
       const int which = warp - W_P;
+      const int dbg = stagger >> 8;  // TSD_ATTN_BWD_TC_DBG (timing experiments, WRONG results): 1 / 2 / 4 = no dV / dK / dQ products
       mbar_wait(kv_full, 0);
       const uint64_t dKt = d32(sK);
       for (int t = 0; t < NT; ++t) {
@@ -339,7 +340,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         mbar_wait(pds_full(buf), (t >> 1) & 1);
         if (which == 2 && kh == 0 && j > 0) mbar_wait(dq_free, (j - 1) & 1);  // dQ of tile j - 1 has left TMEM
         tc_fence_after();
-        if (!elect_one()) {
+        if (!elect_one() || ((dbg >> which) & 1)) {
         } else if (which == 0) {
           const uint32_t tP = tmem_base + P_COL + buf * 64;
           const uint64_t db = d32(st + ST_DO);
@@ -404,6 +405,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const uint32_t ds_row = ((g * CW) >> 6) * (DS_BYTES / 2) + r * 128;
     const uint32_t u0 = ((g * CW) & 63) >> 3;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
+    const int dbg = stagger >> 8;  // 8 = no dS^T shared-memory stores, 16 = no exponentials (timing experiments)
     for (int t = 0; t < NT; ++t) {
       const int buf = t & 1;
       mbar_wait(s_full(gs), t & 1);
@@ -442,7 +444,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           // x = c (s - lse2 / c) <= 0 up to rounding: P <= 1
           float a0, a1;
           upk2(fmul2_(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2), a0, a1);
-          const float p0 = ex2f(a0), p1 = ex2f(a1);
+          const float p0 = (dbg & 16) ? a0 : ex2f(a0), p1 = (dbg & 16) ? a1 : ex2f(a1);
           float e0, e1;
           upk2(fmul2_(pk2(p0, p1), pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1]))), e0, e1);
           pP[i] = pack_bf16(p0, p1);
@@ -454,6 +456,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
         tmem_st8(lane_base + P_COL + buf * 64 + (g * CW + cc * 16) / 2, pP);
         const uint32_t drow = sDS(buf) + ds_row;
+        if (!(dbg & 8))
 #pragma unroll
         for (int i4 = 0; i4 < 2; ++i4)
           sts128(drow + (((u0 + cc * 2 + i4) ^ sw) << 4), pD[4 * i4], pD[4 * i4 + 1], pD[4 * i4 + 2], pD[4 * i4 + 3]);
@@ -568,6 +571,8 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
   if (stagger < 0) {
     const char* e = getenv("TSD_ATTN_BWD_TC_STAGGER");
     stagger = e ? atoi(e) : 0;
+    e = getenv("TSD_ATTN_BWD_TC_DBG");
+    if (e) stagger |= atoi(e) << 8;
     // 1: score products issued once per sub-tile for all warpgroups (N = 128).  Measured SLOWER (3.54 vs 3.05 ms per 64
     // samples at L = 4096): sharing the hand-off locks the four warpgroups into the same phase.  Kept for A/B runs.
     e = getenv("TSD_ATTN_BWD_TC_SHARED");

@@ -147,7 +147,10 @@ def test_attention_tc_forward_modes(cuda, mode):
 
 @pytest.mark.parametrize("n,hw,c0,c1,silu,eps", [(3, 4096, 128, 0, True, 1e-5), (2, 1024, 128, 128, True, 1e-5),
                                                  (4, 64, 256, 256, True, 1e-5), (2, 256, 256, 0, False, 1e-6),
-                                                 (5, 16, 256, 0, True, 1e-5), (2, 4, 256, 256, True, 1e-5)])
+                                                 (5, 16, 256, 0, True, 1e-5), (2, 4, 256, 256, True, 1e-5),
+                                                 # batches that fill the machine: backward as ONE cluster kernel
+                                                 (24, 1024, 128, 0, True, 1e-5), (20, 256, 256, 256, True, 1e-5),
+                                                 (40, 64, 256, 0, False, 1e-6), (32, 4096, 128, 128, True, 1e-5)])
 def test_groupnorm_fwd_bwd(cuda, n, hw, c0, c1, silu, eps):
     """GroupNorm(32) (+SiLU) over a (concatenated) channels-last tensor, forward and backward (diffusion.py:90-96,122)."""
     C = c0 + c1

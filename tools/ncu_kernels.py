@@ -1,6 +1,6 @@
 """One launch each of the three dominant kernels at the benchmark shapes inside a cudaProfilerStart/Stop range, for
   ncu --profile-from-start off --set full --clock-control none --import-source on -o gpurun_out/r02_kernels python tools/ncu_kernels.py
-(gemm_tc_kernel: conv3x3 128->128 @64x64, batch 256; attn_fwd_tc_kernel / attn_bwd_tc_kernel: L=4096, head_dim 16, batch B_ATT)."""
+(gemm_tc_kernel: conv3x3 128->128 @64x64 forward (halo mode) and weight gradient (patch mode), batch 256; attn_fwd_tc_kernel / attn_bwd_tc_kernel: L=4096, head_dim 16, batch B_ATT)."""
 import os
 import sys
 
@@ -17,13 +17,16 @@ H, C = 64, 128
 x = torch.randn(B * H * H, C, device=dev, generator=g).to(torch.bfloat16)
 w = (torch.randn(C, 9 * C, device=dev, generator=g) * 0.03).to(torch.bfloat16)
 bias = torch.zeros(C, device=dev)
+dyc = torch.randn(B * H * H, C, device=dev, generator=g).to(torch.bfloat16)
+dw = torch.zeros(C, 9 * C, device=dev)
 L = 4096
 qkv = (torch.randn(B_ATT * L, 3 * C, device=dev, generator=g) * 1.3).to(torch.bfloat16)
 dout = torch.randn(B_ATT * L, C, device=dev, generator=g).to(torch.bfloat16)
 
 
 def run():
-    ops.conv3x3(x, B, H, H, w, C, bias=bias)
+    ops.conv3x3(x, B, H, H, w, C, bias=bias)       # gemm_tc_kernel<0,0,0>, halo mode
+    ops.conv3x3_wgrad(dyc, x, B, H, H, dw)         # gemm_tc_kernel<1,1,1>, patch mode
     out, lse = ops.attn_fwd(qkv, B_ATT, L, C, 8, need_lse=True)
     ops.attn_bwd(qkv, out, dout, lse, B_ATT, L, C, 8)
 
