@@ -89,7 +89,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
 };
 
-template <int A_MN, int B_MN, int OUT_F32>
+template <int A_MN, int B_MN, int OUT_F32, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -160,9 +160,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   // Patch geometry of an M tile in halo mode: m_blk = (image, patch row, patch column).
   auto halo_geom = [&](int m_blk, int& img, int& y0, int& x0) {
-    img = m_blk / p.halo_tpi;
+    img = fdiv(m_blk, p.fd_tpi);
     const int r = m_blk - img * p.halo_tpi;
-    const int ty = r / p.halo_tx;
+    const int ty = fdiv(r, p.fd_tx);
     y0 = ty * HALO_TH;
     x0 = (r - ty * p.halo_tx) * HALO_TW;
   };
@@ -197,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = ((tile % tiles_mn) / p.tiles_n) * (p.halo == 3 ? 2 : 1);  // (first) 16 x 8 patch of the tile
+      const int m_blk = fdiv(tile - fdiv(tile, p.fd_tiles_mn) * tiles_mn, p.fd_tiles_n) * (p.halo == 3 ? 2 : 1);  // (first) 16 x 8 patch
       int img, y0, x0;
       halo_geom(m_blk, img, y0, x0);
       for (int item = 0; item < items; ++item) {
@@ -224,7 +224,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int bs = 0;
     uint32_t bph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n0 = ((tile % tiles_mn) % p.tiles_n) * BN;
+      const int t2b = tile - fdiv(tile, p.fd_tiles_mn) * tiles_mn;
+      const int n0 = (t2b - fdiv(t2b, p.fd_tiles_n) * p.tiles_n) * BN;
       for (int item = 0; item < items; ++item) {
         const int cb = hc.taps_per_item == 3 ? item / 3 : item;
         const int dx = hc.taps_per_item == 3 ? item - cb * 3 : 0;
@@ -279,10 +280,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       // (m, n) tiles fastest, K split slowest: CTAs running together share operand tiles in L2.
-      const int split = tile / tiles_mn;
+      const int split = fdiv(tile, p.fd_tiles_mn);
       const int t2 = tile - split * tiles_mn;
-      const int n_blk = t2 % p.tiles_n;
-      const int m_blk = t2 / p.tiles_n;
+      const int m_blk = fdiv(t2, p.fd_tiles_n);
+      const int n_blk = t2 - m_blk * p.tiles_n;
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int kb_begin = split * p.kb_per_split;
       const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
@@ -481,8 +482,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // residual tile of (m0, n0): two 64-column boxes, prefetched by TMA into a staging buffer
     const int subs = (!OUT_F32 && p.halo == 3) ? 2 : 1;  // 128-row sub-tiles (accumulators) per tile
     auto prefetch_residual = [&](int tile_idx, int hsub, int bufsel) {
-      const int t2r = tile_idx % tiles_mn;
-      const int nb = t2r % p.tiles_n, mb = (t2r / p.tiles_n) * subs + hsub;
+      const int t2r = tile_idx - fdiv(tile_idx, p.fd_tiles_mn) * tiles_mn;
+      const int mq = fdiv(t2r, p.fd_tiles_n);
+      const int nb = t2r - mq * p.tiles_n, mb = mq * subs + hsub;
       const uint32_t dst = smem_staging + bufsel * (BM * BN * 2);
       if (p.halo) {  // the tile is a 16 x 8 pixel patch: same bytes in shared memory, 4-D box in global memory
         int img, y0, x0;
@@ -492,7 +494,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tma_load_4d(dst + BM * 128, &tmR, res_bar(bufsel), nb * BN + 64, x0, y0, img);
         return;
       }
-      if (p.epi == EPI_GEGLU_BWD) {  // the 64 d(gg) columns that belong to this tile's 64 value + 64 gate columns
+      if (EPI == EPI_GEGLU_BWD) {  // the 64 d(gg) columns that belong to this tile's 64 value + 64 gate columns
         mbar_arrive_expect_tx(res_bar(bufsel), BM * 64 * 2);
         tma_load_2d(dst, &tmR, res_bar(bufsel), nb * 64, mb * BM);
         return;
@@ -557,9 +559,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int sbuf = OUT_F32 ? 0 : (sit & 1);
       uint8_t* staging = staging0 + sbuf * (BM * BN * 2);
       const uint32_t staging_s = smem_staging + sbuf * (BM * BN * 2);
-      const int t2 = tile % tiles_mn;
-      const int n_blk = t2 % p.tiles_n;
-      const int m_blk = (t2 / p.tiles_n) * subs + hsub;  // index of the 128-row sub-tile
+      // (no integer divisions per tile: with K = 128 the epilogue is the critical path, and the division sequences of
+      // all 256 epilogue threads were a quarter of its instructions)
+      const int t2 = tile - fdiv(tile, p.fd_tiles_mn) * tiles_mn;
+      const int mq = fdiv(t2, p.fd_tiles_n);
+      const int n_blk = t2 - mq * p.tiles_n;
+      const int m_blk = mq * subs + hsub;  // index of the 128-row sub-tile
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -568,7 +573,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // halo mode: all 128 rows of the patch belong to image h_img
       const int row = p.halo ? h_img * (p.Ho * p.Wo) : m0 + ep_tid;
       const bool row_ok = row < p.M;
-      const int sample = (p.row_bias && row_ok) ? row / p.rows_per_sample : 0;
+      const int sample = (p.row_bias && row_ok) ? fdiv(row, p.fd_rps) : 0;
 
       if (hsub == 0) mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -600,7 +605,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             *reinterpret_cast<uint4*>(dst + ((q ^ r7) << 4)) = o;
           }
         }
-      } else if (p.epi == EPI_GEGLU_BWD) {
+      } else if (EPI == EPI_GEGLU_BWD) {
         // Backward of value * gelu(gate) with the pre-activations RECOMPUTED by this GEMM (accumulator columns [0,64) =
         // value x, [64,128) = gate g, same packing as the forward) and d(gg) of the tile TMA-loaded into the staging
         // buffer: dx = d * gelu(g) goes back over d, dg = d * x * gelu'(g) into the second half; gelu in the tanh form of
@@ -647,7 +652,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           *reinterpret_cast<uint4*>(row_d + ((cj ^ r7) << 4)) = make_uint4(ox[0], ox[1], ox[2], ox[3]);
           *reinterpret_cast<uint4*>(row_g + ((cj ^ r7) << 4)) = make_uint4(og[0], og[1], og[2], og[3]);
         }
-      } else if (p.epi == EPI_GEGLU) {
+      } else if (EPI == EPI_GEGLU) {
         // columns [0,64) = value half, [64,128) = gate half (weights are packed that way)
         {
           const int ch = half;
@@ -745,9 +750,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           // the next tile's residual (prefetch) and, one tile later, the next result
           const int ntile = hsub + 1 < subs ? tile : tile + (int)gridDim.x;
           if (has_res && ntile < total_tiles) prefetch_residual(ntile, hsub + 1 < subs ? hsub + 1 : 0, sbuf ^ 1);
-          if (p.epi == EPI_GEGLU) {
+          if (EPI == EPI_GEGLU) {
             tma_store_2d(&tmD, staging_s, n0 / 2, m0);
-          } else if (p.epi == EPI_GEGLU_BWD) {  // dh8 in the plain layout: [d value (n_half) | d gate (n_half)]
+          } else if (EPI == EPI_GEGLU_BWD) {  // dh8 in the plain layout: [d value (n_half) | d gate (n_half)]
             tma_store_2d(&tmD, staging_s, n0 / 2, m0);
             tma_store_2d(&tmD, staging_s + BM * 128, p.n_half + n0 / 2, m0);
           } else if (p.halo) {
@@ -788,7 +793,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
-      if (!OUT_F32 && p.epi == EPI_GEGLU_BWD && p.colsum) {
+      if (!OUT_F32 && EPI == EPI_GEGLU_BWD && p.colsum) {
         // bias gradient of the C -> 8C linear as a by-product: column sums of the finished tile, read back from the
         // staging buffer (thread = one column of one 64-row half), kept per n-block in registers across the CTA's tiles
         const int et = (warp - 4) * 32 + lane;
@@ -804,7 +809,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
     if (ep_leader) tma_store_wait_all<0>();
-    if (!OUT_F32 && p.epi == EPI_GEGLU_BWD && p.colsum) {
+    if (!OUT_F32 && EPI == EPI_GEGLU_BWD && p.colsum) {
       const int et = (warp - 4) * 32 + lane;
       const int col = et & 63, which = (et >> 6) & 1;
       for (int nb = 0; nb < p.tiles_n && nb < 16; ++nb)
@@ -821,11 +826,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
 }
 
-template <int A_MN, int B_MN, int OUT_F32>
+template <int A_MN, int B_MN, int OUT_F32, int EPI>
 static int launch_t(cudaStream_t stream, const CUtensorMap& tmA0, const CUtensorMap& tmA1,
                     const CUtensorMap& tmB0, const CUtensorMap& tmB1, const CUtensorMap& tmD,
                     const CUtensorMap& tmR, const GemmParams& p) {
-  auto kern = gemm_tc_kernel<A_MN, B_MN, OUT_F32>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, OUT_F32, EPI>;
   constexpr int smem = Cfg<OUT_F32>::SMEM_BYTES;
   static tsd::PerDeviceFlag configured;
   if (!configured.cur()) {
@@ -870,9 +875,17 @@ int launch_gemm(cudaStream_t stream, int a_mn, int b_mn, int out_f32, const CUte
   pd.dbg = dbg;
   const GemmParams& p2 = pd;
   TSD_CHECK(p.num_kb > 0 && p.splits > 0 && p.kb_per_split > 0, "gemm: empty K loop");
-  if (!a_mn && !b_mn && !out_f32) return launch_t<0, 0, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
-  if (!a_mn && b_mn && !out_f32) return launch_t<0, 1, 0>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
-  if (a_mn && b_mn && out_f32) return launch_t<1, 1, 1>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
+  pd.fd_tiles_mn = make_fastdiv(p.tiles_m * p.tiles_n);
+  pd.fd_tiles_n = make_fastdiv(p.tiles_n);
+  pd.fd_rps = make_fastdiv(p.rows_per_sample > 0 ? p.rows_per_sample : 1);
+  pd.fd_tpi = make_fastdiv(p.halo_tpi > 0 ? p.halo_tpi : 1);
+  pd.fd_tx = make_fastdiv(p.halo_tx > 0 ? p.halo_tx : 1);
+  // the epilogue kind is a template parameter: each instantiation carries only its own epilogue code
+  if (!a_mn && !b_mn && !out_f32 && p.epi == EPI_NONE) return launch_t<0, 0, 0, EPI_NONE>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
+  if (!a_mn && !b_mn && !out_f32 && p.epi == EPI_GEGLU) return launch_t<0, 0, 0, EPI_GEGLU>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
+  if (!a_mn && !b_mn && !out_f32 && p.epi == EPI_GEGLU_BWD) return launch_t<0, 0, 0, EPI_GEGLU_BWD>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
+  if (!a_mn && b_mn && !out_f32 && p.epi == EPI_NONE) return launch_t<0, 1, 0, EPI_NONE>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
+  if (a_mn && b_mn && out_f32 && p.epi == EPI_NONE) return launch_t<1, 1, 1, EPI_NONE>(stream, tmA0, tmA1, tmB0, tmB1, tmD, tmR, p2);
   set_error("gemm: unsupported operand-major / output combination (%d,%d,%d)", a_mn, b_mn, out_f32);
   return 1;
 }

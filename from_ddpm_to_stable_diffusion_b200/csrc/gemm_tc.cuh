@@ -26,6 +26,21 @@ enum : int { B_K2D = 0, B_MN2D = 1, B_MNCONV = 2 };
 enum : int { EPI_NONE = 0, EPI_GEGLU = 1, EPI_GEGLU_BWD = 2 };
 enum : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2, ACT_TANH = 3 };  // applied last: act(acc + bias + residual)
 
+// n / d for 0 <= n < 2^31 as one wide multiply and a shift (d >= 1, set up on the host)
+struct FastDiv { uint32_t mul, sh; };
+inline FastDiv make_fastdiv(int d) {
+  int l = 0;
+  while ((1ll << l) < d) ++l;
+  const int p = 31 + l;
+  FastDiv f;
+  f.mul = static_cast<uint32_t>(((1ull << p) + static_cast<uint64_t>(d) - 1) / static_cast<uint64_t>(d));
+  f.sh = static_cast<uint32_t>(p);
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, FastDiv f) {
+  return static_cast<int>((static_cast<uint64_t>(static_cast<uint32_t>(n)) * f.mul) >> f.sh);
+}
+
 struct GemmParams {
   int M, N;              // rows / cols of D (GEGLU: N counts the 2x-wide pre-activation columns)
   int tiles_m, tiles_n;
@@ -58,6 +73,7 @@ struct GemmParams {
   int halo;               // 3x3 stride-1 convolution in halo mode (gemm_tc.cu): 0 off, 1 = three aligned copies, 2 = one copy
   int halo_tx, halo_tpi;  // patches per image row / per image
   int wg_halo;            // 3x3 stride-1 weight gradient in patch mode (gemm_tc.cu); halo_tx / halo_tpi count 8 x 8 patches
+  FastDiv fd_tiles_mn, fd_tiles_n, fd_rps, fd_tpi, fd_tx;  // filled in by launch_gemm
   int act;                // ACT_*: pointwise activation on the finished value (codec convolutions, vqvae models.py:286-341)
 };
 
