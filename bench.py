@@ -359,7 +359,7 @@ def run_ours(args):
     n1, t1 = fam("tsd_conv3x3_fwd", lambda k: k[0] == 128 and k[1] == 0 and k[3] == 64 and k[6] == 128)
     if n1:
         fl = 2.0 * B * 64 * 64 * 128 * 9 * 128
-        extra.append({"kernel": "gemm_tc_kernel<0,0,0> conv3x3 128->128 @64x64 (tcgen05 implicit GEMM)", "bound": "tensor",
+        extra.append({"kernel": "gemm_tc_kernel<0,0,0,0> conv3x3 128->128 @64x64 (tcgen05 implicit GEMM, halo mode)", "bound": "tensor",
                       "achieved": fl * n1 / (t1 * 1e-3) / 1e12, "peak": tf, "unit": "TFLOP/s",
                       "frac": fl * n1 / (t1 * 1e-3) / 1e12 / tf, "launches": n1})
     n2, t2 = fam("tsd_gn_apply", lambda k: k[0] == 128 and k[1] == 0 and k[3] == 4096)
