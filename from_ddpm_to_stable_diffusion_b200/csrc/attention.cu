@@ -1369,20 +1369,23 @@ attn_bwd_fused_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dou
   }
 }
 
-// dq workspace fp32 [B][H][L][16] -> bf16 dq columns of dqkv [B*L][3C]; one thread per (row, head)
+// dq workspace fp32 [B][H][L][DH] -> bf16 dq columns of dqkv [B*L][3C]; one thread per (row, head)
+template <int DH>
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ ws, bf16* __restrict__ dqkv, int B,
                                                               int L, int C) {
-  const int H = C / 16;
+  const int H = C / DH;
   const size_t total = (size_t)B * L * H;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int h = (int)(i % H);
-    const size_t row = i / H;  // b * L + l: consecutive threads write consecutive 32-byte head slices of one row
+    const size_t row = i / H;  // b * L + l: consecutive threads write consecutive head slices of one row
     const size_t bb = row / L, l = row - bb * L;
-    const float4* src = reinterpret_cast<const float4*>(ws + (((bb * H + h) * L) + l) * 16);
-    const float4 a = src[0], b4 = src[1], c = src[2], d = src[3];
-    uint4* dst = reinterpret_cast<uint4*>(dqkv + row * 3 * C + h * 16);
-    dst[0] = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b4.x, b4.y), pack_bf16(b4.z, b4.w));
-    dst[1] = make_uint4(pack_bf16(c.x, c.y), pack_bf16(c.z, c.w), pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
+    const float4* src = reinterpret_cast<const float4*>(ws + (((bb * H + h) * L) + l) * DH);
+    uint4* dst = reinterpret_cast<uint4*>(dqkv + row * 3 * C + h * DH);
+#pragma unroll
+    for (int q = 0; q < DH / 8; ++q) {
+      const float4 a = src[2 * q], b4 = src[2 * q + 1];
+      dst[q] = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b4.x, b4.y), pack_bf16(b4.z, b4.w));
+    }
   }
 }
 
@@ -1580,7 +1583,17 @@ static int attn_bwd_impl(void* stream, const void* qkv, const void* out, const v
     if (launch_attn_bwd_tc(st, qkv, dout, lse2, delta, dqkv, ws, B, L, C, heads)) return 1;
     int cg = (int)((total + 255) / 256);
     if (cg > num_sms() * 16) cg = num_sms() * 16;
-    attn_dq_convert_kernel<<<cg, 256, 0, st>>>(ws, (bf16*)dqkv, B, L, C);
+    attn_dq_convert_kernel<16><<<cg, 256, 0, st>>>(ws, (bf16*)dqkv, B, L, C);
+    TSD_LAUNCH_CHECK();
+    return 0;
+  }
+  if (bwd_tc && ws != nullptr && attn_bwd_tc32_supported(L, C, heads)) {
+    // the same for head_dim 32 (attention_bwd_tc32.cu): one 128-key block per CTA, workspace [B][heads][L][32]
+    TSD_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)B * L * C, st));
+    if (launch_attn_bwd_tc32(st, qkv, dout, lse2, delta, dqkv, ws, B, L, C, heads)) return 1;
+    int cg = (int)((total + 255) / 256);
+    if (cg > num_sms() * 16) cg = num_sms() * 16;
+    attn_dq_convert_kernel<32><<<cg, 256, 0, st>>>(ws, (bf16*)dqkv, B, L, C);
     TSD_LAUNCH_CHECK();
     return 0;
   }
@@ -1597,7 +1610,7 @@ static int attn_bwd_impl(void* stream, const void* qkv, const void* out, const v
     TSD_LAUNCH_CHECK();
     int cg = (int)((total + 255) / 256);
     if (cg > num_sms() * 16) cg = num_sms() * 16;
-    attn_dq_convert_kernel<<<cg, 256, 0, st>>>(ws, (bf16*)dqkv, B, L, C);
+    attn_dq_convert_kernel<16><<<cg, 256, 0, st>>>(ws, (bf16*)dqkv, B, L, C);
     TSD_LAUNCH_CHECK();
     return 0;
   }

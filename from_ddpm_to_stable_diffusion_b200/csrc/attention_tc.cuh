@@ -16,4 +16,9 @@ bool attn_bwd_tc_supported(int L, int C, int heads);
 int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const float* lse2, const float* delta,
                        void* dqkv, float* ws, int B, int L, int C, int heads);
 
+// the same for head_dim 32 and L a multiple of 128, L >= 256 (attention_bwd_tc32.cu); ws = zeroed fp32 [B][heads][L][32]
+bool attn_bwd_tc32_supported(int L, int C, int heads);
+int launch_attn_bwd_tc32(cudaStream_t st, const void* qkv, const void* dout, const float* lse2, const float* delta,
+                         void* dqkv, float* ws, int B, int L, int C, int heads);
+
 }  // namespace tsd

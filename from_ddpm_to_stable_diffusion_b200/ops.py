@@ -170,8 +170,10 @@ def attn_fwd(qkv, B, L, C, heads=8, need_lse=False):
 def attn_bwd(qkv, out, dout, lse, B, L, C, heads=8):
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, heads, L, device=qkv.device, dtype=F32)
-    # fp32 scratch for the one-pass backward (head_dim 16, L % 256 == 0): dQ partials are reduced there
-    ws = torch.empty(B * L * C, device=qkv.device, dtype=F32) if (C // heads == 16 and L % 256 == 0) else None
+    # fp32 scratch for the one-pass backward (head_dim 16, L % 256 == 0; head_dim 32, L % 128 == 0): dQ partials are reduced there
+    dh = C // heads
+    ws = torch.empty(B * L * C, device=qkv.device, dtype=F32) \
+        if ((dh == 16 and L % 256 == 0) or (dh == 32 and L % 128 == 0 and L >= 256)) else None
     call("tsd_attn_bwd_ws", qkv, out, _chk(dout, BF16), lse, delta, dqkv, ws, B, L, C, heads)
     return dqkv
 

@@ -89,6 +89,30 @@ def test_attention_backward_tc_shapes(cuda, shape):
         assert _rel(d[:, sl], ref_d[:, sl]) < 1.5e-2
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 256), (2, 1024, 256), (1, 384, 256), (3, 4096, 256)])
+def test_attention_backward_tc_head_dim_32(cuda, shape):
+    """The tcgen05 backward for head_dim 32 (one 128-key block per CTA, K as a shared-memory A operand, 64-byte rows):
+    two query tiles, the 32x32 sequence of the C = 256 blocks (diffusion.py:212), a sequence that is a multiple of 128
+    but not of 256, and 32 key blocks reducing into the same dQ rows."""
+    B, L, C = shape
+    H = C // 32
+    g = torch.Generator(device="cuda").manual_seed(13)
+    qkv = (torch.randn(B * L, 3 * C, device=cuda, generator=g) * 1.1).to(BF)
+    qkv[: L // 2, :C] *= 2.5  # peaked rows: large lse2, P close to one-hot
+    dout = (torch.randn(B * L, C, device=cuda, generator=g) * 4.0).to(BF)
+    out, lse = ops.attn_fwd(qkv, B, L, C, H, need_lse=True)
+    d = ops.attn_bwd(qkv, out, dout, lse, B, L, C, H)
+    x = qkv.float().view(B, L, 3, H, 32).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+    ref = F.scaled_dot_product_attention(x[0], x[1], x[2])
+    ref.backward(dout.float().view(B, L, H, 32).permute(0, 2, 1, 3))
+    ref_d = x.grad.permute(1, 3, 0, 2, 4).reshape(B * L, 3 * C)
+    assert torch.isfinite(d).all()
+    for sl in (slice(0, C), slice(C, 2 * C), slice(2 * C, 3 * C)):
+        assert _rel(d[:, sl], ref_d[:, sl]) < 1.5e-2
+    d2 = ops.attn_bwd(qkv, out, dout, lse, B, L, C, H)  # run-to-run: dK / dV exact, dQ to fp32 summation order
+    assert torch.equal(d[:, C:], d2[:, C:]) and _rel(d[:, :C], d2[:, :C]) < 8e-3
+
+
 def test_attention_backward_mma_sync_one_pass_subprocess(cuda):
     """The mma.sync one-pass kernel (TSD_ATTN_BWD_TC=0) stays the fallback for the same shapes; the switch is read once
     per process, so it is exercised in a child process."""
