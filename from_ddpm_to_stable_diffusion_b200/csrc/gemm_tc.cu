@@ -28,6 +28,31 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
   if constexpr (N == 32) tmem_ld32(taddr, r);
   else tmem_ld16(taddr, r);
 }
+// packed fp32 pairs (one FMUL2 / FFMA2 / FADD2 issue slot for two values): the GEGLU epilogues are bound by instruction
+// issue -- 8 epilogue warps, ~20 instructions per output element pair in scalar form
+__device__ __forceinline__ uint64_t pk2f(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2f(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2f(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2f(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 constexpr int TMEM_COLS = 256;     // two 128-column fp32 accumulators
 constexpr int TMEM_COLS_WG = 512;  // weight-gradient instantiation: room for the three tap accumulators of the patch mode
 constexpr int MAX_RING = 8, MAX_ARING = 4;  // mbarrier pairs reserved for the operand rings
@@ -626,28 +651,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = q * 8 + e * 2;
-            float x[2] = {__uint_as_float(xv[j]), __uint_as_float(xv[j + 1])};
-            float g[2] = {__uint_as_float(gv[j]), __uint_as_float(gv[j + 1])};
+            uint64_t X = pk2f(__uint_as_float(xv[j]), __uint_as_float(xv[j + 1]));
+            uint64_t G = pk2f(__uint_as_float(gv[j]), __uint_as_float(gv[j + 1]));
             if (p.bias) {
               const float2 bx = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + ch * EPI_PAIRS + j));
               const float2 bg = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + 64 + ch * EPI_PAIRS + j));
-              x[0] += bx.x; x[1] += bx.y; g[0] += bg.x; g[1] += bg.y;
+              X = add2f(X, pk2f(bx.x, bx.y));
+              G = add2f(G, pk2f(bg.x, bg.y));
             }
             const float2 d = unpack_bf16(dw[e]);
-            const float dd[2] = {d.x, d.y};
-            float rx[2], rg[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float t = g[u] * g[u];
-              const float th = tanh_fast(g[u] * fmaf(0.0347008941f, t, 0.8001570768f));
-              const float hp = fmaf(0.5f, th, 0.5f);                        // 0.5 (1 + tanh z)
-              const float dz = fmaf(0.1041026823f, t, 0.8001570768f);       // dz/dg = a + 3 b g^2
-              const float gp = fmaf(0.5f * g[u] * dz, fmaf(-th, th, 1.f), hp);  // gelu'(g)
-              rx[u] = dd[u] * (g[u] * hp);
-              rg[u] = dd[u] * x[u] * gp;
-            }
-            ox[e] = pack_bf16(rx[0], rx[1]);
-            og[e] = pack_bf16(rg[0], rg[1]);
+            const uint64_t D = pk2f(d.x, d.y);
+            // two columns per instruction: th = tanh(g (a + b g^2)), hp = 0.5 (1 + th), gelu'(g) = hp + 0.5 g (a + 3 b g^2) (1 - th^2)
+            const uint64_t T = mul2f(G, G);
+            const uint64_t Z = mul2f(G, fma2f(pk2f(0.0347008941f, 0.0347008941f), T, pk2f(0.8001570768f, 0.8001570768f)));
+            float z0, z1;
+            upk2f(Z, z0, z1);
+            const uint64_t TH = pk2f(tanh_fast(z0), tanh_fast(z1));
+            const uint64_t HALF = pk2f(0.5f, 0.5f);
+            const uint64_t HP = fma2f(HALF, TH, HALF);
+            const uint64_t DZ = fma2f(pk2f(0.1041026823f, 0.1041026823f), T, pk2f(0.8001570768f, 0.8001570768f));
+            const uint64_t SECH = fma2f(mul2f(TH, pk2f(-1.f, -1.f)), TH, pk2f(1.f, 1.f));
+            const uint64_t GP = fma2f(mul2f(mul2f(HALF, G), DZ), SECH, HP);
+            float rx0, rx1, rg0, rg1;
+            upk2f(mul2f(D, mul2f(G, HP)), rx0, rx1);
+            upk2f(mul2f(mul2f(D, X), GP), rg0, rg1);
+            ox[e] = pack_bf16(rx0, rx1);
+            og[e] = pack_bf16(rg0, rg1);
           }
           *reinterpret_cast<uint4*>(row_d + ((cj ^ r7) << 4)) = make_uint4(ox[0], ox[1], ox[2], ox[3]);
           *reinterpret_cast<uint4*>(row_g + ((cj ^ r7) << 4)) = make_uint4(og[0], og[1], og[2], og[3]);
@@ -666,15 +695,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
+              // value * gelu(gate) in the tanh form of geglu_fast_f, two columns per instruction
               const int j = q * 8 + e * 2;
-              float x0 = __uint_as_float(xv[j]), x1 = __uint_as_float(xv[j + 1]);
-              float g0 = __uint_as_float(gv[j]), g1 = __uint_as_float(gv[j + 1]);
+              uint64_t X = pk2f(__uint_as_float(xv[j]), __uint_as_float(xv[j + 1]));
+              uint64_t G = pk2f(__uint_as_float(gv[j]), __uint_as_float(gv[j + 1]));
               if (p.bias) {
                 const float2 bx = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + ch * EPI_PAIRS + j));
                 const float2 bg = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + 64 + ch * EPI_PAIRS + j));
-                x0 += bx.x; x1 += bx.y; g0 += bg.x; g1 += bg.y;
+                X = add2f(X, pk2f(bx.x, bx.y));
+                G = add2f(G, pk2f(bg.x, bg.y));
               }
-              o[e] = pack_bf16(geglu_fast_f(x0, g0), geglu_fast_f(x1, g1));
+              const uint64_t T = mul2f(G, G);
+              const uint64_t Z = mul2f(G, fma2f(pk2f(0.0347008941f, 0.0347008941f), T, pk2f(0.8001570768f, 0.8001570768f)));
+              const uint64_t HG = mul2f(mul2f(X, pk2f(0.5f, 0.5f)), G);
+              float z0, z1;
+              upk2f(Z, z0, z1);
+              float r0, r1;
+              upk2f(fma2f(HG, pk2f(tanh_fast(z0), tanh_fast(z1)), HG), r0, r1);
+              o[e] = pack_bf16(r0, r1);
             }
             const int cj = ch * (EPI_PAIRS / 8) + q;
             *reinterpret_cast<uint4*>(dst + ((cj ^ r7) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
