@@ -405,7 +405,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const uint32_t ds_row = ((g * CW) >> 6) * (DS_BYTES / 2) + r * 128;
     const uint32_t u0 = ((g * CW) & 63) >> 3;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    const int dbg = stagger >> 8;  // 8 = no dS^T shared-memory stores, 16 = no exponentials (timing experiments)
+    const int dbg = stagger >> 8;  // 8 = no dS^T shared-memory stores, 16 = no exponentials (timing experiments), 32 = late s_free in PIPE mode
     for (int t = 0; t < NT; ++t) {
       const int buf = t & 1;
       mbar_wait(s_full(gs), t & 1);
@@ -421,8 +421,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           tmem_ld16(tDP + cc * 16, dvp[cc]);
         }
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(s_free(gs));
+        if (!(dbg & 32)) {
+          tc_fence_before();
+          mbar_arrive(s_free(gs));
+        }
       }
 #pragma unroll
       for (int cc = 0; cc < NCH; ++cc) {
@@ -449,6 +451,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           upk2(fmul2_(pk2(p0, p1), pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1]))), e0, e1);
           pP[i] = pack_bf16(p0, p1);
           pD[i] = pack_bf16(e0, e1);
+        }
+        if (PIPE && (dbg & 32) && cc == 0) {  // A/B: whole-sub-tile load, but the score buffer goes back where the default does
+          tc_fence_before();
+          mbar_arrive(s_free(gs));
         }
         if (cc == 0 && t >= 2) {  // P^T / dS^T buffers of sub-tile t - 2 have been consumed
           mbar_wait(mma_done(buf), ((t >> 1) & 1) ^ 1);
