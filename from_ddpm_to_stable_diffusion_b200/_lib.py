@@ -44,6 +44,7 @@ def stream_ptr():
 
 
 PROFILE = bool(int(os.environ.get("TSD_PROFILE", "0")))
+NVTX = bool(int(os.environ.get("TSD_NVTX", "0")))  # one NVTX range per C-ABI call (entry-point name) for nsys / ncu --nvtx
 _prof = []
 
 
@@ -53,7 +54,11 @@ def call(name, *args):
     if PROFILE:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+    if NVTX:
+        torch.cuda.nvtx.range_push(name)
     rc = fn(stream_ptr(), *[_as_arg(a) for a in args])
+    if NVTX:
+        torch.cuda.nvtx.range_pop()
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib().tsd_last_error().decode()}")
     if PROFILE:

@@ -7,6 +7,7 @@
 //   CFG combine + posterior update + Philox z + NaN flag                              (utils.py:149-167)
 #include "../../include/tinysd_b200.h"
 #include "common.cuh"
+#include "ptx.cuh"
 #include <cstdlib>
 
 using namespace tsd;
@@ -391,6 +392,287 @@ tail_conv_mma_kernel(const bf16* __restrict__ a, const float* __restrict__ w, co
   if (SAMPLE && bad) atomicOr(nan_flag, 1);
 }
 
+// ------------------------------------------------------------------------------------------ tail conv, per-pixel form
+// The same convolution (and the same fused sampling epilogue) with every input pixel read from shared memory ONCE:
+//   Y[p][tap * CO + o] = sum_c a[p][c] * w[o][c][tap]        one [pixels x 128] x [128 x 9 CO] product per halo pixel
+//   eps[q][o]          = bias[o] + sum_tap Y[q + off(tap)][tap * CO + o]
+// N = 27 (36) columns fill four (five) n8 tiles instead of 3 of 8 per tap, the weights live in registers as B
+// fragments for the CTA's life, and the nine taps no longer re-read the activation tile with ldmatrix (the kernel
+// above reads 9 x 256 B per pixel from shared memory and was bound by that, not by HBM).  Persistent CTAs walk over
+// 256-pixel tiles (TH = 256 / W rows + halo); the next tile's activations are in flight while the current one is
+// multiplied, summed and written: two TMA boxes [TH + 2][W + 2][64 channels] per tile (out-of-image pixels arrive as
+// zeros, 128-byte swizzle = the XOR pattern ldmatrix wants).  A first version staged the tile with cp.async: its
+// 25 copies per thread queued in front of the ldmatrix reads in the LSU and the load time added to the compute time
+// (TSD_TAIL_Y_DBG experiments: 60 us of loads + 42 us of compute = 102 us).  Y overlays the activation buffer it was
+// computed from.
+// V = 0: 256 threads, two activation buffers, one CTA per SM.  V = 1: 128 threads and ONE buffer, two CTAs per SM: the
+// phases of a tile (tensor pipe, shared-memory traffic, Philox / update arithmetic, global latency) are serial inside a
+// CTA, two independent CTAs overlap them.
+template <int CO, int SAMPLE, int W, int V>
+__global__ void __launch_bounds__(V ? 128 : 256, V ? 2 : 1)
+tail_conv_y_kernel(const __grid_constant__ CUtensorMap tmA, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ out, const int* __restrict__ step_ptr, const float* __restrict__ c1,
+                   const float* __restrict__ c2, const float* __restrict__ sigma, float wcfg,
+                   const float* __restrict__ noise_in, uint64_t seed, int* __restrict__ nan_flag,
+                   float* __restrict__ eps_out, int B, int H, int clip_last, const uint64_t* __restrict__ rng_dev,
+                   int n_tiles, int dbg) {
+  using namespace tcv;
+  constexpr int NTHR = V ? 128 : 256, NW = NTHR / 32, NBUF = V ? 1 : 2, PPT = 256 / NTHR;
+  constexpr int TH = 256 / W, HWP = W + 2, NP = (TH + 2) * HWP, MT = (NP + 15) / 16, MTW = (MT + NW - 1) / NW;
+  constexpr int NJ = 9 * CO, NT = (NJ + 7) / 8, YP = NJ | 1;  // odd pitch: conflict-free gathers
+  constexpr int HALFB = MT * 16 * 128;                        // one 64-channel half of a tile: [pixel][128 B], swizzled
+  constexpr int BUF = 2 * HALFB;                              // bytes per activation buffer
+  constexpr int NH = SAMPLE ? 2 : 1;
+  static_assert(NP * YP * 4 <= BUF, "Y must fit the buffer it overlays");
+  static_assert(HALFB % 1024 == 0, "swizzled TMA destinations need 1024-byte alignment");
+  extern __shared__ uint8_t smem_ty_raw[];
+  const uint32_t s0 = (smem_addr(smem_ty_raw) + 1023u) & ~1023u;
+  uint8_t* smem_ty = smem_ty_raw + (s0 - smem_addr(smem_ty_raw));
+  const uint32_t bar0 = s0 + NBUF * BUF;  // "tile landed" mbarriers, one per buffer
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int HW = H * W, tiles_per_img = HW / 256;
+  // ---- weights as B fragments: B[k = c][j = tap * CO + o] = w[o][c][tap] (OIHW fp32 -> bf16), zero for j >= 9 CO
+  uint32_t bfr[8][NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int j = nt * 8 + g;
+    const float* wj = w + (size_t)(j % CO) * C * 9 + j / CO;
+#pragma unroll
+    for (int kc = 0; kc < 8; ++kc) {
+      const int k0 = kc * 16 + 2 * t;
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+      if (j < NJ) {
+        v0 = __ldg(wj + (k0) * 9);
+        v1 = __ldg(wj + (k0 + 1) * 9);
+        v2 = __ldg(wj + (k0 + 8) * 9);
+        v3 = __ldg(wj + (k0 + 9) * 9);
+      }
+      bfr[kc][nt][0] = pack_bf16(v0, v1);
+      bfr[kc][nt][1] = pack_bf16(v2, v3);
+    }
+  }
+  float bv[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) bv[o] = bias[o];
+  const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int n_items = my_tiles * NH;
+  auto issue = [&](int it, int buf) {  // one thread
+    const int tile = blockIdx.x + (it / NH) * gridDim.x, hf = it % NH;
+    const int n = tile / tiles_per_img;
+    const int y0 = (tile - n * tiles_per_img) * TH;
+    const uint32_t bar = bar0 + 8u * buf, dst = s0 + buf * BUF;
+    if (dbg & 8) {
+      mbar_arrive(bar);
+      return;
+    }
+    fence_proxy_async_smem();  // the buffer was last touched through the generic proxy (ldmatrix, Y)
+    mbar_arrive_expect_tx(bar, 2 * NP * 128);
+    tma_load_4d(dst, &tmA, bar, 0, -1, y0 - 1, n + hf * B);
+    tma_load_4d(dst + HALFB, &tmA, bar, 64, -1, y0 - 1, n + hf * B);
+  };
+  if (tid == 0) {
+    tma_prefetch_desc(&tmA);
+    mbar_init(bar0, 1);
+    if (NBUF == 2) mbar_init(bar0 + 8u, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  int step = 0;
+  float k1 = 0.f, k2 = 0.f, sg = 0.f;
+  if (SAMPLE) {
+    step = *step_ptr;
+    k1 = c1[step]; k2 = c2[step]; sg = sigma[step];
+  }
+  const float w1 = 1.f + wcfg;
+  const Philox rng(seed);
+  const RngPos pos = load_rng_pos(rng_dev);
+  const uint64_t ctr_hi = ((uint64_t)step + 1) | (pos.calls << 16);
+  const uint64_t ebase = pos.sample0 * (uint64_t)(CO * HW);  // z depends on the GLOBAL sample index
+  bool bad = false;
+  float ec[PPT][CO];
+#pragma unroll
+  for (int r = 0; r < PPT; ++r)
+#pragma unroll
+    for (int o = 0; o < CO; ++o) ec[r][o] = 0.f;
+
+  if (n_items > 0 && tid == 0) issue(0, 0);
+  for (int it = 0; it < n_items; ++it) {
+    const int buf = NBUF == 2 ? (it & 1) : 0;
+    if (NBUF == 2) {
+      __syncthreads();  // nobody reads the other buffer (the previous tile's Y) any more
+      if (it + 1 < n_items && tid == 0) issue(it + 1, buf ^ 1);
+    }
+    mbar_wait(bar0 + 8u * buf, NBUF == 2 ? ((it >> 1) & 1) : (it & 1));  // tile `it` has landed
+    const uint32_t base = s0 + buf * BUF;
+    // ---- Y for this warp's m-tiles (16 halo pixels each)
+    float acc[MTW][NT][4];
+#pragma unroll
+    for (int m = 0; m < MTW; ++m) {
+      const int mt = warp + NW * m;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[m][nt][0] = acc[m][nt][1] = acc[m][nt][2] = acc[m][nt][3] = 0.f;
+      if (mt < MT && !(dbg & 1)) {
+        const int px = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;  // ldmatrix row of this lane
+        const uint32_t row = base + px * 128;
+        const uint32_t sw = static_cast<uint32_t>(px & 7), hi = static_cast<uint32_t>(lane >> 4);
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) {
+          uint32_t af[4];
+          ldsm4(af, row + (kc >> 2) * HALFB + (((2 * (kc & 3) + hi) ^ sw) << 4));
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) mma(acc[m][nt], af, bfr[kc][nt][0], bfr[kc][nt][1]);
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with the activations: Y may overwrite them
+    float* Y = reinterpret_cast<float*>(smem_ty + (size_t)buf * BUF);
+#pragma unroll
+    for (int m = 0; m < MTW; ++m) {
+      const int mt = warp + NW * m;
+      if (mt < MT && !(dbg & 2)) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int px = mt * 16 + g + 8 * r;
+          if (px < NP) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+              const int j = nt * 8 + 2 * t;
+              if (j < NJ) Y[px * YP + j] = acc[m][nt][2 * r];
+              if (j + 1 < NJ) Y[px * YP + j + 1] = acc[m][nt][2 * r + 1];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- thread = PPT output pixels: nine neighbours x CO columns each
+    const int tile = blockIdx.x + (it / NH) * gridDim.x, hf = it % NH;
+    const int n = tile / tiles_per_img;
+    const int rem0 = (tile - n * tiles_per_img) * 256;  // pixel index inside the image (tile rows are contiguous)
+    float ev[PPT][CO];
+#pragma unroll
+    for (int r = 0; r < PPT; ++r) {
+      const int q = tid + NTHR * r;
+      const int ty = q / W, tx = q - ty * W;
+      const int hp0 = ty * HWP + tx;
+#pragma unroll
+      for (int o = 0; o < CO; ++o) ev[r][o] = 0.f;
+      if (!(dbg & 2))
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float* yp = Y + (hp0 + (tap / 3) * HWP + (tap % 3)) * YP + tap * CO;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) ev[r][o] += yp[o];
+      }
+#pragma unroll
+      for (int o = 0; o < CO; ++o) ev[r][o] += bv[o];
+    }
+    if (NBUF == 1) {
+      __syncthreads();  // Y is dead: the next tile may land while this one is written out
+      if (it + 1 < n_items && tid == 0) issue(it + 1, 0);
+    }
+    if (!SAMPLE) {
+#pragma unroll
+      for (int r = 0; r < PPT; ++r)
+#pragma unroll
+        for (int o = 0; o < CO; ++o) out[((size_t)n * CO + o) * HW + rem0 + tid + NTHR * r] = ev[r][o];
+    } else if (hf == 0) {
+#pragma unroll
+      for (int r = 0; r < PPT; ++r)
+#pragma unroll
+        for (int o = 0; o < CO; ++o) ec[r][o] = ev[r][o];
+    } else if (!(dbg & 4)) {
+#pragma unroll
+      for (int r = 0; r < PPT; ++r)
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        const size_t e = ((size_t)n * CO + o) * HW + rem0 + tid + NTHR * r;
+        const float eu = ev[r][o];
+        if (eps_out) {
+          eps_out[e] = ec[r][o];
+          eps_out[(size_t)B * CO * HW + e] = eu;
+        }
+        float z = 0.f;
+        if (step > 0) {
+          if (noise_in) {
+            z = noise_in[e];
+          } else {
+            const uint4 rr = rng(ebase + e, ctr_hi);
+            z = box_muller(rr.x, rr.y).x;
+          }
+        }
+        const float ep = __fsub_rn(__fmul_rn(w1, ec[r][o]), __fmul_rn(wcfg, eu));
+        const float mean = __fsub_rn(__fmul_rn(k1, out[e]), __fmul_rn(k2, ep));
+        float v = __fadd_rn(mean, __fmul_rn(sg, z));
+        bad |= (v != v);
+        if (clip_last && step == 0) v = fminf(fmaxf(v, -1.f), 1.f);
+        out[e] = v;
+        out[(size_t)B * CO * HW + e] = v;  // the unconditional copy of the 2B batch
+      }
+    }
+  }
+  if (SAMPLE && bad) atomicOr(nan_flag, 1);
+}
+
+static int tail_y_variant() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TSD_TAIL_Y");  // 0: the tap-by-tap kernel above; 1: one 256-thread CTA per SM, two buffers; 2: two 128-thread CTAs
+    on = e ? atoi(e) : 2;
+  }
+  return on;
+}
+static bool tail_y_ok(int H, int W) {
+  return tail_y_variant() && (W == 16 || W == 32 || W == 64) && (H * W) % 256 == 0 && H % (256 / W) == 0;
+}
+template <int CO, int SAMPLE, int W, int V>
+static int launch_tail_y_v(cudaStream_t st, const bf16* a, const float* w, const float* bias, float* out,
+                           const int* step_ptr, const float* c1, const float* c2, const float* sigma, float wcfg,
+                           const float* noise_in, uint64_t seed, int* nan_flag, float* eps_out, int B, int H, int clip_last,
+                           const uint64_t* rng_dev) {
+  constexpr int NP = (256 / W + 2) * (W + 2), MT = (NP + 15) / 16;
+  constexpr int smem = (V ? 1 : 2) * MT * 16 * 256 + 1024 + 64;
+  CUtensorMap tmA;
+  if (make_tmap_nhwc(&tmA, a, (uint64_t)(SAMPLE ? 2 * B : B), H, W, 128, 64, W + 2, 256 / W + 2, 1, 1)) return 1;
+  static tsd::PerDeviceFlag cfgd;
+  if (!cfgd.cur()) {
+    TSD_CUDA(cudaFuncSetAttribute(tail_conv_y_kernel<CO, SAMPLE, W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cfgd.cur() = true;
+  }
+  const int n_tiles = B * (H * W / 256);
+  const int slots = (V ? 2 : 1) * num_sms();
+  const int grid = n_tiles < slots ? n_tiles : slots;
+  static int dbg = -1;  // TSD_TAIL_Y_DBG bit mask, timing experiments with WRONG results: 1 no MMAs, 2 no Y / gather, 4 no update, 8 no loads
+  if (dbg < 0) {
+    const char* e = getenv("TSD_TAIL_Y_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  tail_conv_y_kernel<CO, SAMPLE, W, V><<<grid, V ? 128 : 256, smem, st>>>(tmA, w, bias, out, step_ptr, c1, c2, sigma, wcfg, noise_in,
+                                                                          seed, nan_flag, eps_out, B, H, clip_last, rng_dev, n_tiles, dbg);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+template <int CO, int SAMPLE, int W>
+static int launch_tail_y(cudaStream_t st, const bf16* a, const float* w, const float* bias, float* out,
+                         const int* step_ptr, const float* c1, const float* c2, const float* sigma, float wcfg,
+                         const float* noise_in, uint64_t seed, int* nan_flag, float* eps_out, int B, int H, int clip_last,
+                         const uint64_t* rng_dev) {
+  if (tail_y_variant() == 1)
+    return launch_tail_y_v<CO, SAMPLE, W, 0>(st, a, w, bias, out, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, clip_last, rng_dev);
+  return launch_tail_y_v<CO, SAMPLE, W, 1>(st, a, w, bias, out, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, clip_last, rng_dev);
+}
+template <int CO, int SAMPLE>
+static int launch_tail_y_w(cudaStream_t st, int W, const bf16* a, const float* w, const float* bias, float* out,
+                           const int* step_ptr, const float* c1, const float* c2, const float* sigma, float wcfg,
+                           const float* noise_in, uint64_t seed, int* nan_flag, float* eps_out, int B, int H,
+                           int clip_last, const uint64_t* rng_dev) {
+  if (W == 64)
+    return launch_tail_y<CO, SAMPLE, 64>(st, a, w, bias, out, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, clip_last, rng_dev);
+  if (W == 32)
+    return launch_tail_y<CO, SAMPLE, 32>(st, a, w, bias, out, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, clip_last, rng_dev);
+  return launch_tail_y<CO, SAMPLE, 16>(st, a, w, bias, out, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, clip_last, rng_dev);
+}
+
 // the tail conv tiles an image into 128-pixel row blocks
 static bool tail_mma_ok(int H, int W) {
   return (W == 16 || W == 32 || W == 64) && (H * W) % 128 == 0 && H % (128 / W) == 0;
@@ -495,6 +777,11 @@ extern "C" int tsd_tail_conv_fwd(void* stream, const void* a, const float* w, co
   const int smem = tail_mma_smem(W);
   const int grid_tc = n_img * (H * W / 128);
   cudaStream_t st = (cudaStream_t)stream;
+  if (tail_y_ok(H, W)) {
+    if (co == 3)
+      return launch_tail_y_w<3, 0>(st, W, (const bf16*)a, w, bias, out, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, n_img, H, 0, nullptr);
+    return launch_tail_y_w<4, 0>(st, W, (const bf16*)a, w, bias, out, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, n_img, H, 0, nullptr);
+  }
   if (co == 3) {
     TSD_TAIL_SMEM_ATTR((tail_conv_mma_kernel<3, 0>));
     tail_conv_mma_kernel<3, 0><<<grid_tc, 256, smem, st>>>((const bf16*)a, w, bias, out, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, 0, nullptr, nullptr, 0, H, W, 0, nullptr);
@@ -566,6 +853,11 @@ extern "C" int tsd_tail_conv_sample(void* stream, const void* a, const float* w,
   const int smem = tail_mma_smem(W);
   const int grid_tc = B * (H * W / 128);
   cudaStream_t stt = (cudaStream_t)stream;
+  if (tail_y_ok(H, W)) {
+    if (co == 3)
+      return launch_tail_y_w<3, 1>(stt, W, (const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, clip_last, rng_dev);
+    return launch_tail_y_w<4, 1>(stt, W, (const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, clip_last, rng_dev);
+  }
   if (co == 3) {
     TSD_TAIL_SMEM_ATTR((tail_conv_mma_kernel<3, 1>));
     tail_conv_mma_kernel<3, 1><<<grid_tc, 256, smem, stt>>>((const bf16*)a, w, bias, x, step_ptr, c1, c2, sigma, wcfg, noise_in, seed, nan_flag, eps_out, B, H, W, clip_last, rng_dev);
