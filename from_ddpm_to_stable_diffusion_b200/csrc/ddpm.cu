@@ -81,6 +81,122 @@ __global__ void __launch_bounds__(256) head_conv_fwd_kernel(const float* __restr
 }
 
 
+// The same convolution as an implicit GEMM on warp-level TF32 MMA (m16n8k8): M = pixels, N = 128, K = 9 ci (27 / 36,
+// padded to 32 / 40).  x and w are rounded to TF32 (2^-11; the bf16 output rounds at 2^-9), accumulation in fp32.  The CUDA-core
+// kernel above needs 3 456 FMAs per pixel and was FMA-bound at a quarter of the HBM rate of its output.
+// DGRAD = 1 turns it into the DATA GRADIENT of the tail conv (128 -> co): da[p][c] = sum_{o,tap} dy[p - off(tap)][o] w[o][c][tap]
+// is the same contraction over (o, tap') with tap' = 8 - tap, no bias.
+// A persistent CTA walks over 256-pixel tiles; the fp32 halo tile (ci x (TH + 2) x (W + 2)) is staged in shared memory as TF32 and
+// every A fragment element is one shared-memory load at (k's tap offset) + (pixel offset); a warp owns 64 of the 128 output
+// channels (its B fragments stay in registers) and every fourth m-tile; the bf16 rows leave through a per-warp staging tile
+// as 16-byte stores.
+template <int CI, int W, int DGRAD>
+__global__ void __launch_bounds__(256, 2)
+in_conv_tf32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    bf16* __restrict__ out, int n_img, int H, int n_tiles) {
+  constexpr int TH = 256 / W, HWP = W + 2, HR = TH + 2, K = CI * 9, KC = (K + 7) / 8, CO = 128;
+  constexpr int XS = CI * HR * HWP;
+  __shared__ uint32_t xs[XS];
+  __shared__ __align__(16) uint32_t so[8][16][36];  // [warp][pixel][32 words of 2 bf16 + 4 pad]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int half = warp & 1, mq = warp >> 1;
+  auto tf32 = [](float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+  };
+  // B[k = c * 9 + tap][n]: forward w[n][c][tap] (OIHW); data gradient w[o = c][n][8 - tap]
+  uint32_t bfr[KC][8][2];
+  int aoff[KC][2];
+#pragma unroll
+  for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int k = kc * 8 + t + 4 * h2;
+      const bool valid = k < K;
+      const int c = valid ? k / 9 : 0, tap = valid ? k - c * 9 : 0;
+      aoff[kc][h2] = c * HR * HWP + (tap / 3) * HWP + (tap % 3);  // k >= K: any finite value, its B row is zero
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int n = half * 64 + nt * 8 + g;
+        float v = 0.f;
+        if (valid) v = DGRAD ? __ldg(w + ((size_t)c * CO + n) * 9 + 8 - tap) : __ldg(w + ((size_t)n * CI + c) * 9 + tap);
+        bfr[kc][nt][h2] = tf32(v);
+      }
+    }
+  __shared__ __align__(8) float sb[CO];
+  if (tid < CO) sb[tid] = DGRAD ? 0.f : bias[tid];
+  const int tiles_per_img = H * W / 256;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int n = tile / tiles_per_img;
+    const int y0 = (tile - n * tiles_per_img) * TH;
+    __syncthreads();  // the previous tile's fragments have been read
+    for (int i = tid; i < XS; i += 256) {
+      const int c = i / (HR * HWP), r = i - c * (HR * HWP);
+      const int hy = r / HWP, hx = r - hy * HWP;
+      const int yy = y0 + hy - 1, xx = hx - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      xs[i] = ok ? tf32(__ldg(x + (((size_t)n * CI + c) * H + yy) * W + xx)) : 0u;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int mi = 0; mi < 4; ++mi) {
+      const int mt = mq + 4 * mi;
+      const int p0 = mt * 16 + g, p1 = p0 + 8;
+      const int pb0 = (p0 / W) * HWP + (p0 % W), pb1 = (p1 / W) * HWP + (p1 % W);
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 b2 = *reinterpret_cast<const float2*>(&sb[half * 64 + nt * 8 + 2 * t]);
+        acc[nt][0] = acc[nt][2] = b2.x;
+        acc[nt][1] = acc[nt][3] = b2.y;
+      }
+#pragma unroll
+      for (int kc = 0; kc < KC; ++kc) {
+        const uint32_t a0 = xs[aoff[kc][0] + pb0], a1 = xs[aoff[kc][0] + pb1];
+        const uint32_t a2 = xs[aoff[kc][1] + pb0], a3 = xs[aoff[kc][1] + pb1];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bfr[kc][nt][0]), "r"(bfr[kc][nt][1]));
+      }
+      __syncwarp();  // the staging tile's previous rows have been read
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        so[warp][g][nt * 4 + t] = pack_bf16(acc[nt][0], acc[nt][1]);
+        so[warp][g + 8][nt * 4 + t] = pack_bf16(acc[nt][2], acc[nt][3]);
+      }
+      __syncwarp();
+      bf16* dst = out + ((size_t)tile * 256 + mt * 16) * CO + half * 64;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int id = lane + 32 * i, row = id >> 3, c16 = id & 7;
+        *reinterpret_cast<uint4*>(dst + (size_t)row * CO + c16 * 8) = *reinterpret_cast<const uint4*>(&so[warp][row][c16 * 4]);
+      }
+    }
+  }
+}
+static bool in_conv_tf32_ok(int ci, int H, int W, int co) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TSD_IN_CONV_TF32");  // 0: the CUDA-core kernels (A/B)
+    on = e ? atoi(e) : 1;
+  }
+  return on && co == 128 && (ci == 3 || ci == 4) && (W == 16 || W == 32 || W == 64) && (H * W) % 256 == 0 && H % (256 / W) == 0;
+}
+template <int CI, int DGRAD>
+static int launch_in_conv_tf32(cudaStream_t st, const float* x, const float* w, const float* bias, bf16* out, int n_img,
+                               int H, int W) {
+  const int n_tiles = n_img * (H * W / 256);
+  const int grid = n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms();
+  if (W == 64) in_conv_tf32_kernel<CI, 64, DGRAD><<<grid, 256, 0, st>>>(x, w, bias, out, n_img, H, n_tiles);
+  else if (W == 32) in_conv_tf32_kernel<CI, 32, DGRAD><<<grid, 256, 0, st>>>(x, w, bias, out, n_img, H, n_tiles);
+  else in_conv_tf32_kernel<CI, 16, DGRAD><<<grid, 256, 0, st>>>(x, w, bias, out, n_img, H, n_tiles);
+  TSD_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ tail conv
 // Data gradient of the tail conv: da[p][c] = sum_tap sum_co dy[p - off(tap)][co] * w[co][c][tap], register-blocked:
 // thread = (4 consecutive pixels of a row, 8 channels).  Every weight vector read from shared memory serves 4 pixels
@@ -756,6 +872,10 @@ inline int ew_grid(size_t items) {
 extern "C" int tsd_head_conv_fwd(void* stream, const float* x, const float* w, const float* bias, void* out, int n_img,
                                  int ci, int H, int W, int co) {
   TSD_CHECK(ci <= MAX_CI && co % 8 == 0 && W % 4 == 0, "head_conv_fwd: unsupported shape ci=%d co=%d W=%d", ci, co, W);
+  if (in_conv_tf32_ok(ci, H, W, co)) {
+    if (ci == 3) return launch_in_conv_tf32<3, 0>((cudaStream_t)stream, x, w, bias, (bf16*)out, n_img, H, W);
+    return launch_in_conv_tf32<4, 0>((cudaStream_t)stream, x, w, bias, (bf16*)out, n_img, H, W);
+  }
   const size_t smem = (size_t)(ci * 9 * co + co) * sizeof(float);
   const size_t total = (size_t)n_img * H * (W / 4) * (co / 8);
   head_conv_fwd_kernel<<<ew_grid(total), 256, smem, (cudaStream_t)stream>>>(x, w, bias, (bf16*)out, n_img, ci, H, W, co);
@@ -884,6 +1004,10 @@ extern "C" int tsd_tail_conv_dgrad(void* stream, const float* dy, const float* w
                                    int c_in, int co) {
   TSD_CHECK(c_in == 128 && (co == 3 || co == 4), "tail_conv_dgrad: unsupported channels c_in=%d co=%d", c_in, co);
   TSD_CHECK(W % 4 == 0, "tail_conv_dgrad: W=%d must be a multiple of 4", W);
+  if (in_conv_tf32_ok(co, H, W, c_in)) {
+    if (co == 3) return launch_in_conv_tf32<3, 1>((cudaStream_t)stream, dy, w, nullptr, (bf16*)da, n_img, H, W);
+    return launch_in_conv_tf32<4, 1>((cudaStream_t)stream, dy, w, nullptr, (bf16*)da, n_img, H, W);
+  }
   const size_t total = (size_t)n_img * H * W;
   if (co == 3) tail_conv_dgrad4_kernel<3><<<ew_grid(total * 4), 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
   else tail_conv_dgrad4_kernel<4><<<ew_grid(total * 4), 256, 0, (cudaStream_t)stream>>>(dy, w, (bf16*)da, n_img, H, W);
