@@ -423,6 +423,25 @@ def run_ours(args):
                     # block up to its self-attention) runs once for the conditional / unconditional pair
                     "gflop_per_image_step_executed": 2 * FWD_GF_PER_SAMPLE - 11.57,
                     "tflops": (2 * FWD_GF_PER_SAMPLE - 11.57) * Bs / (per / 1e3) / 1e3}
+        # the fused sampling tail (final conv + CFG + posterior update + Philox noise, the north star's "update kernel")
+        # against the HBM roofline: two eager reverse steps with per-call CUDA events
+        if rank == 0:
+            ug = getattr(sampler, "use_cuda_graph", True)
+            sampler.use_cuda_graph = False
+            _lib.PROFILE = True
+            _lib.profile_report()
+            sampler(xT, ys, steps=range(CFG["T"] - 1, CFG["T"] - 3, -1))
+            agg_s = _lib.profile_report()
+            _lib.PROFILE = False
+            sampler.use_cuda_graph = ug
+            nt_ = sum(v[0] for (nm, _k), v in agg_s.items() if nm == "tsd_tail_conv_sample")
+            tt_ = sum(v[1] for (nm, _k), v in agg_s.items() if nm == "tsd_tail_conv_sample")
+            if nt_:
+                hw_ = CFG["img"] * CFG["img"]
+                by = 2.0 * Bs * hw_ * 128 * 2 + 3.0 * Bs * CFG["channel_img"] * hw_ * 4
+                extra.append({"kernel": "tail_conv_y_kernel<3,1> fused sampling tail (128->3 conv + CFG + posterior update + "
+                              "Philox noise), %d image pairs" % Bs, "bound": "hbm", "achieved": by * nt_ / (tt_ * 1e-3) / 1e9,
+                              "peak": hbm, "unit": "GB/s", "frac": by * nt_ / (tt_ * 1e-3) / 1e9 / hbm, "launches": nt_})
         del sampler, out
         torch.cuda.empty_cache()
         # BASELINE configs[4]: latent-space DDPM, 4x16x16 latents, batch 4096 (sharded over the ranks), num_class 10
