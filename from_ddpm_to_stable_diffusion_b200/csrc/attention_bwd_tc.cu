@@ -90,6 +90,34 @@ __device__ __forceinline__ uint64_t fmul2_(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ uint64_t ffma2_(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2_(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for a packed pair on the FMA pipe (the forward kernel's Cody-Waite cubic, attention_tc.cu): |rel err| < 2e-4, far
+// under the bf16 rounding of P.  x <= 0 up to rounding here; clamped at -126 for the exponent insertion (2^-126 ~ 0).
+__device__ __forceinline__ void exp2_poly2_(uint64_t x, float& o0, float& o1) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  const uint64_t xc = pk2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t r = fadd2_(xc, pk2(12582912.f, 12582912.f));
+  const uint64_t fl = fadd2_(r, pk2(-12582912.f, -12582912.f));
+  const uint64_t f = ffma2_(fl, pk2(-1.f, -1.f), xc);
+  uint64_t pv = ffma2_(f, pk2(0.05550411f, 0.05550411f), pk2(0.24022651f, 0.24022651f));
+  pv = ffma2_(pv, f, pk2(0.69314718f, 0.69314718f));
+  pv = ffma2_(pv, f, pk2(1.f, 1.f));
+  float r0, r1, p0, p1;
+  upk2(r, r0, r1);
+  upk2(pv, p0, p1);
+  o0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -113,7 +141,8 @@ __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-template <bool SHARED, bool PIPE>
+// POLY > 0: every POLY-th pair of exponentials runs as a cubic on the FMA pipe instead of MUFU.EX2 (as in the forward).
+template <bool SHARED, bool PIPE, int POLY = 0>
 __global__ void __launch_bounds__(PIPE ? BT_THREADS_PIPE : BT_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse2, const float* __restrict__ delta, bf16* __restrict__ dqkv,
@@ -444,9 +473,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           // x = c (s - lse2 / c) <= 0 up to rounding: P <= 1
-          float a0, a1;
-          upk2(fmul2_(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2), a0, a1);
-          const float p0 = (dbg & 16) ? a0 : ex2f(a0), p1 = (dbg & 16) ? a1 : ex2f(a1);
+          float a0, a1, p0, p1;
+          const uint64_t a01 = fmul2_(pk2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2);
+          if (POLY > 0 && (i % (POLY > 0 ? POLY : 1)) == (POLY - 1)) {
+            exp2_poly2_(a01, p0, p1);
+          } else {
+            upk2(a01, a0, a1);
+            p0 = (dbg & 16) ? a0 : ex2f(a0);
+            p1 = (dbg & 16) ? a1 : ex2f(a1);
+          }
           float e0, e1;
           upk2(fmul2_(pk2(p0, p1), pk2(__uint_as_float(dv[2 * i]), __uint_as_float(dv[2 * i + 1]))), e0, e1);
           pP[i] = pack_bf16(p0, p1);
@@ -571,10 +606,16 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     configured.cur() = true;
   }
-  static int stagger = -1, shared = -1, pipe = -1;
+  static int stagger = -1, shared = -1, pipe = -1, poly = 4;
   if (stagger < 0) {
+    // every n-th pair of exponentials on the FMA pipe (n = 2, 4 or 8; 0 = all on MUFU.EX2).  64 x L = 4096, one box,
+    // alternating: 0: 3.297 ms, 8: 3.235, 4: 3.205 / 3.207, 2: 3.399 (gradients identical to the last digit printed)
+    if (const char* ep = getenv("TSD_ATTN_BWD_TC_POLY")) poly = atoi(ep);
     const char* e = getenv("TSD_ATTN_BWD_TC_STAGGER");
     stagger = e ? atoi(e) : 0;
     e = getenv("TSD_ATTN_BWD_TC_DBG");
@@ -596,6 +637,12 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
     attn_bwd_tc_kernel<true, false><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, sl2, stagger);
   else if (pipe)
     attn_bwd_tc_kernel<false, true><<<grid, BT_THREADS_PIPE, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, sl2, stagger);
+  else if (poly == 2)
+    attn_bwd_tc_kernel<false, false, 2><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, sl2, stagger);
+  else if (poly == 4)
+    attn_bwd_tc_kernel<false, false, 4><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, sl2, stagger);
+  else if (poly == 8)
+    attn_bwd_tc_kernel<false, false, 8><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, sl2, stagger);
   else
     attn_bwd_tc_kernel<false, false><<<grid, BT_THREADS, BT_SMEM, st>>>(tmQKV, tmDO, lse2, delta, (bf16*)dqkv, ws, L, C, scale, sl2, stagger);
   TSD_LAUNCH_CHECK();
