@@ -611,10 +611,12 @@ int launch_attn_bwd_tc(cudaStream_t st, const void* qkv, const void* dout, const
     TSD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     configured.cur() = true;
   }
-  static int stagger = -1, shared = -1, pipe = -1, poly = 4;
+  static int stagger = -1, shared = -1, pipe = -1, poly = 0;
   if (stagger < 0) {
-    // every n-th pair of exponentials on the FMA pipe (n = 2, 4 or 8; 0 = all on MUFU.EX2).  64 x L = 4096, one box,
-    // alternating: 0: 3.297 ms, 8: 3.235, 4: 3.205 / 3.207, 2: 3.399 (gradients identical to the last digit printed)
+    // every n-th pair of exponentials on the FMA pipe (n = 2, 4 or 8; 0 = all on MUFU.EX2, the default).  The kernel alone,
+    // 64 x L = 4096, one box, alternating: 0: 3.297 ms, 8: 3.235, 4: 3.205 / 3.207, 2: 3.399 (gradients identical) -- but
+    // the whole training step at batch 256 (power-capped, tools/ncu_step.py, alternating 4 / 0 / 4 / 0): 128.06 / 126.16 /
+    // 127.20 / 125.59 ms: the extra FMA-pipe work costs the step more than the shorter MUFU queue gains.  Kept for A/B.
     if (const char* ep = getenv("TSD_ATTN_BWD_TC_POLY")) poly = atoi(ep);
     const char* e = getenv("TSD_ATTN_BWD_TC_STAGGER");
     stagger = e ? atoi(e) : 0;
