@@ -6,7 +6,6 @@ same default initialisation under the same torch seed.  Everything below the mod
 sm_100a library: the torch sub-modules created here are *parameter holders only*; their forward
 methods are never called.  There is no CPU / eager fallback: a non-CUDA input raises.
 """
-import math
 from typing import List
 
 import torch

@@ -5,7 +5,6 @@ Normalize), :42-72 (``EMA``), :75-93 (``CosineWarmupScheduler``); 02_train_direc
 denormalize, save_image grid) and :64-74 (the step body).  Same names, arguments and behaviour; the device work is
 done by the library's kernels (csrc/imageio.cu, csrc/optim.cu) and there is no CPU fallback for it.
 """
-import math
 
 import numpy as np
 import torch

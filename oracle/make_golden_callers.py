@@ -3,7 +3,6 @@ copied) and torchvision itself.  Run in the build container only:  python oracle
 import os
 import sys
 
-import numpy as np
 import torch
 from torchvision import transforms
 from torchvision.utils import make_grid

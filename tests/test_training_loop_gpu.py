@@ -1,8 +1,5 @@
 """The training iteration as the caller runs it (02_train_direct.py:64-74) on the CUDA path: parity at the benchmark
 batch size, the captured-graph iteration against the eager one, micro-batch accumulation and resume parity."""
-import copy
-
-import numpy as np
 import pytest
 import torch
 
